@@ -1,0 +1,169 @@
+/*
+ * uoc.h -- C ABI of the B200-native UnseenObjectClustering inference hot path.
+ *
+ * The reference (NVlabs/UnseenObjectClustering @ f5a00c7) is pure Python/PyTorch and has no FFI
+ * of its own; its boundary for this path is Python-function level.  The entry
+ * points below are what a ctypes binding on the reference side binds to replace those functions;
+ * each one cites the reference interface it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - every function returns an int status (UOC_OK == 0); on failure uoc_last_error() returns a
+ *    thread-local, human readable message.  No exceptions cross the ABI, nothing calls exit().
+ *  - all `const float*` / `void*` data arguments are DEVICE pointers unless the name ends in
+ *    `_host`.  The library never allocates device memory behind the caller's back except for the
+ *    re-packed weights owned by a uoc_backbone handle; callers pass a workspace whose size the
+ *    matching *_workspace_bytes() function reports.
+ *  - work is enqueued on the caller's CUDA stream (`stream` is a cudaStream_t passed as void*);
+ *    functions return after enqueueing unless stated otherwise.
+ *  - there is no CPU fallback: without a Blackwell (sm_100) device every compute entry point fails
+ *    with UOC_ERR_UNSUPPORTED.
+ */
+#ifndef UOC_H_
+#define UOC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define UOC_API __declspec(dllexport)
+#else
+#define UOC_API __attribute__((visibility("default")))
+#endif
+
+enum {
+  UOC_OK = 0,
+  UOC_ERR_INVALID = 1,      /* bad argument (shape, alignment, null pointer)            */
+  UOC_ERR_CUDA = 2,         /* a CUDA runtime / driver call failed                      */
+  UOC_ERR_WORKSPACE = 3,    /* workspace too small                                      */
+  UOC_ERR_UNSUPPORTED = 4,  /* no sm_100 device, or a size outside the supported range  */
+  UOC_ERR_DEVICE = 5        /* a kernel reported an internal error (pipeline time-out)  */
+};
+
+/* flags (bit set) accepted by the compute entry points */
+enum {
+  UOC_FLAG_LOOP_SIMT = 1,   /* mean-shift iterations on the fp32 SIMT validation kernel instead of tcgen05 */
+  UOC_FLAG_CONV_SIMT = 2,   /* backbone convolutions on the fp32 SIMT validation kernel instead of tcgen05 */
+  UOC_FLAG_SYNC_CHECK = 4   /* synchronise the stream and read back the device error word before returning */
+};
+
+#define UOC_MAX_SEEDS 128   /* num_seeds upper bound: one tcgen05 M=128 accumulator tile */
+
+typedef void* uoc_stream_t;  /* cudaStream_t */
+
+UOC_API const char* uoc_last_error(void);
+UOC_API int uoc_version(void);
+/* sm count / compute capability of the current device; UOC_ERR_UNSUPPORTED if it is not sm_100. */
+UOC_API int uoc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Clustering: replaces utils.mean_shift.mean_shift_smart_init (lib/utils/mean_shift.py:192-229)
+ * as called per batch item by fcn.test_dataset.clustering_features (lib/fcn/test_dataset.py:44-59).
+ *
+ * X is the embedding field in the reference's own memory layout: for batch item b, point p,
+ * channel k the element is X[b*stride_b + k*stride_d + p] (planar NCHW: stride_d = H*W, points
+ * contiguous; the reference's `features[j].view(C,-1).t()` view, test_dataset.py:54-55).
+ * Rows must be unit-norm (the network emits F.normalize'd features, lib/networks/SEG.py:114).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Bytes of device workspace uoc_meanshift_cluster / the stage functions need. */
+UOC_API size_t uoc_meanshift_workspace_bytes(int batch, int64_t n, int d, int m);
+
+/*
+ * Whole clustering of `batch` independent fields: farthest-point seed selection -> `iters`
+ * mean-shift updates -> greedy seed labelling (epsilon) -> nearest-seed pixel labels with the
+ * "largest cluster is label 0" swap.
+ *   first_seed_host [batch]   the np.random.randint(0, n) draw of mean_shift.py:155, made by the caller
+ *   labels_out      [batch,n] int32 (device)    mean_shift_smart_init's cluster_labels
+ *   selected_out    [batch,m] int64 (device)    mean_shift_smart_init's selected_indices
+ *   seeds_out       [batch,m,d] fp32 (device) or NULL: the converged seeds Z
+ *   seed_labels_out [batch,m] int32 (device) or NULL: connected_components labels of the seeds
+ *   x_bf16          optional [batch,n,d] bf16 pixel-major copy of X (as written by
+ *                   uoc_backbone_forward); NULL -> made internally from X.
+ */
+UOC_API int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16,
+                                  int batch, int64_t n, int d, int m, float kappa, int iters, float epsilon,
+                                  const int64_t* first_seed_host, int32_t* labels_out, int64_t* selected_out,
+                                  float* seeds_out, int32_t* seed_labels_out, void* workspace, size_t workspace_bytes,
+                                  int flags, uoc_stream_t stream);
+
+/* Stage entry points (same semantics as the matching reference functions; used by the parity
+ * tests and by callers that want one stage only). */
+
+/* select_smart_seeds (lib/utils/mean_shift.py:128-189, cosine): selected_out [batch,m] int64,
+ * seeds_out [batch,m,d] fp32. */
+UOC_API int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
+                             const int64_t* first_seed_host, int64_t* selected_out, float* seeds_out,
+                             void* workspace, size_t workspace_bytes, uoc_stream_t stream);
+
+/* seed_hill_climbing_ball (lib/utils/mean_shift.py:79-109, cosine): Z [batch,m,d] fp32 updated in place. */
+UOC_API int uoc_hill_climb(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch,
+                           int64_t n, int d, int m, float kappa, int iters, float* Z, void* workspace,
+                           size_t workspace_bytes, int flags, uoc_stream_t stream);
+
+/* connected_components (lib/utils/mean_shift.py:41-76, cosine): seed_labels_out [batch,m] int32;
+ * num_unique_out [batch] int32 = len(unique(seed labels)) (mean_shift.py:218). */
+UOC_API int uoc_label_seeds(const float* Z, int batch, int m, int d, float epsilon, int32_t* seed_labels_out,
+                            int32_t* num_unique_out, uoc_stream_t stream);
+
+/* nearest-seed assignment + relabel (lib/utils/mean_shift.py:206-227): labels_out [batch,n] int32. */
+UOC_API int uoc_assign_labels(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
+                              const float* Z, const int32_t* seed_labels, const int32_t* num_unique,
+                              int32_t* labels_out, void* workspace, size_t workspace_bytes, uoc_stream_t stream);
+
+/* fp32 planar [batch][d][n] -> bf16 pixel-major [batch][n][d] (the layout the tcgen05 loop streams). */
+UOC_API int uoc_pack_bf16(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d,
+                          void* x_bf16_out, uoc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backbone: replaces networks.seg_resnet34_8s_embedding(...).forward for INPUT='RGBD',
+ * FUSION_TYPE='add' in eval mode (lib/networks/SEG.py:88-119, :173-176; trunk
+ * lib/networks/resnet_dilated.py:287-327 + lib/networks/resnet.py:236-270).
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct uoc_backbone uoc_backbone;
+
+/* One tensor of a reference-format state_dict (keys 'fcn.resnet34_8s.*', 'fcn_depth.resnet34_8s.*'
+ * after the 'module.' stripping of SEG.py:145-146); data_host is contiguous fp32 on the host. */
+typedef struct {
+  const char* name;
+  const float* data_host;
+  int64_t numel;
+} uoc_weight_desc;
+
+/* Folds eval-mode BatchNorm (eps 1e-5) into the convolutions, converts to bf16, re-packs to the
+ * K-major [Cout][tap][Cin] layout the implicit-GEMM kernel reads, uploads.  Blocking. */
+UOC_API int uoc_backbone_create(uoc_backbone** out, const uoc_weight_desc* tensors, int n_tensors, int num_units);
+UOC_API void uoc_backbone_destroy(uoc_backbone* bb);
+UOC_API size_t uoc_backbone_workspace_bytes(const uoc_backbone* bb, int N, int H, int W);
+
+/*
+ * rgb, xyz: [N,3,H,W] fp32 NCHW (image_color / depth of the reference sample dict,
+ * lib/fcn/test_dataset.py:235-239).  features_out: [N,num_units,H,W] fp32 NCHW, unit L2 norm over
+ * channels.  features_bf16_out (optional, may be NULL): [N,H*W,num_units] bf16 copy for
+ * uoc_meanshift_cluster.  H and W must be multiples of 8.
+ */
+UOC_API int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, int N, int H, int W,
+                                 float* features_out, void* features_bf16_out, void* workspace,
+                                 size_t workspace_bytes, int flags, uoc_stream_t stream);
+
+/* Debug / test hook: copy the trunk output of one branch (0 = rgb, 1 = depth), [N,num_units,H/8,W/8]
+ * fp32 NCHW, from the last uoc_backbone_forward's workspace. */
+UOC_API int uoc_backbone_read_trunk(uoc_backbone* bb, int branch, int N, int H, int W, const void* workspace,
+                                    float* out, uoc_stream_t stream);
+
+/* Generic single convolution on the tcgen05 implicit-GEMM kernel (test hook for the parity tests):
+ * x [N,H,W,Cin] bf16 NHWC, w [Cout,KH*KW,Cin] bf16, bias [Cout] fp32, residual (optional) and y
+ * [N,Ho,Wo,Cout] bf16 NHWC. Cin % 64 == 0, Cout % 64 == 0. */
+UOC_API int uoc_conv2d_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y, int N,
+                            int H, int W, int Cin, int Cout, int ksize, int stride, int dilation, int relu, int flags,
+                            uoc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UOC_H_ */

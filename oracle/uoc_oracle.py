@@ -1,0 +1,387 @@
+"""CPU oracle for the UnseenObjectClustering inference hot path  --  TEST INFRASTRUCTURE ONLY.
+
+A plain torch-CPU / numpy restatement of the reference algorithm (NVlabs/UnseenObjectClustering,
+commit f5a00c7).  It is the checker the parity tests compare the CUDA path against, and the
+`cpu_baseline` / `--impl reference` leg of bench.py.  Only tests/, __graft_entry__.smoke() and
+bench.py's CPU-baseline legs may import it; the product package never does.
+
+Pinning: the reference ships no tests or golden vectors for this path, so
+this file is pinned against the reference ITSELF, imported in the build container through
+oracle/ref_harness.py: tests/test_oracle_vs_reference.py (skipped where /root/reference is
+absent) and the fixtures under tests/golden/ written by oracle/make_golden.py.
+
+Each function cites the reference file:line it follows (paths relative to the reference root).
+The arithmetic deliberately uses the same library calls as the reference (torch.mm, torch.exp,
+F.normalize, torch.argmax ...) so that its CPU timing is representative of the reference's CPU
+path and its results are bit-identical to the reference on CPU.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+EMBEDDING_ALPHA = 0.02      # lib/fcn/config.py:254  (cfg.TRAIN.EMBEDDING_ALPHA)
+KAPPA = 20.0                # lib/fcn/test_dataset.py:51
+MAX_ITERS = 10              # lib/fcn/test_dataset.py:56
+NUM_SEEDS = 100             # lib/fcn/test_dataset.py:248 (stage 1) and :44 default (stage 2)
+CROP_SIZE = 224             # lib/fcn/config.py:129 (cfg.TRAIN.SYN_CROP_SIZE)
+BN_EPS = 1e-5               # torch.nn.BatchNorm2d default, lib/networks/resnet.py:50
+
+
+# --------------------------------------------------------------------------------------------
+# mean shift clustering  (lib/utils/mean_shift.py)
+# --------------------------------------------------------------------------------------------
+
+def cosine_kernel(Z, X, kappa):
+    """lib/utils/mean_shift.py:25-26  W = exp(kappa * Z X^T)   ([m,d],[n,d] -> [m,n])."""
+    return torch.exp(kappa * torch.mm(Z, X.t()))
+
+
+def label_mode(values):
+    """lib/utils/mean_shift.py:30-38  most frequent value, ties -> smallest value."""
+    vals, counts = np.unique(values, return_counts=True)
+    return int(vals[np.argmax(counts)])
+
+
+def label_seeds(Z, epsilon):
+    """lib/utils/mean_shift.py:41-76 (cosine branch).  Greedy, order dependent labelling of the
+    converged seeds: every still-unlabelled seed i claims all seeds within cosine distance epsilon
+    (fp32 `<=`); the claimed set takes the mode of its existing labels if any member is already
+    labelled, else a fresh label; the WHOLE claimed set is overwritten."""
+    m = Z.shape[0]
+    labels = torch.full((m,), -1, dtype=torch.long)
+    next_label = 0
+    for i in range(m):
+        if labels[i] != -1:
+            continue
+        dist = 0.5 * (1 - torch.mm(Z, Z[i:i + 1].t()))[:, 0]
+        comp = dist <= epsilon
+        current = labels[comp]
+        if torch.unique(current).shape[0] > 1:
+            cur = current.numpy()
+            lab = label_mode(cur[cur != -1])
+        else:
+            lab = next_label
+            next_label += 1
+        labels[comp] = lab
+    return labels
+
+
+def hill_climb(X, Z, kappa, max_iters):
+    """lib/utils/mean_shift.py:79-109 (cosine branch).  max_iters fixed-count mean-shift updates
+    Z <- normalize_rows(exp(kappa Z X^T) X); no convergence test."""
+    for _ in range(max_iters):
+        W = cosine_kernel(Z, X, kappa)
+        Z = F.normalize(torch.mm(W, X), p=2, dim=1)
+    return Z
+
+
+def select_seeds(X, num_seeds, first_index):
+    """lib/utils/mean_shift.py:128-189 (cosine branch).  Farthest point sampling.  `first_index`
+    is the value the reference draws with np.random.randint(0, n) (:155).  Returns
+    (seeds [m,d], selected_indices [m] int64)."""
+    n, d = X.shape
+    selected = -torch.ones(num_seeds, dtype=torch.long)
+    seeds = torch.empty((num_seeds, d))
+    distances = torch.empty((n, num_seeds))
+    selected[0] = int(first_index)
+    seeds[0] = X[int(first_index)]
+    distances[:, 0] = 0.5 * (1 - torch.mm(X, seeds[0].unsqueeze(1))[:, 0])
+    for i in range(1, num_seeds):
+        nearest = torch.min(distances[:, :i], dim=1)[0]
+        idx = torch.argmax(nearest)
+        selected[i] = idx
+        seeds[i] = X[idx]
+        distances[:, i] = 0.5 * (1 - torch.mm(X, seeds[i].unsqueeze(1))[:, 0])
+    return seeds, selected
+
+
+def assign_and_relabel(X, Z, seed_labels):
+    """lib/utils/mean_shift.py:206-227.  Nearest-seed assignment (argmin of 0.5(1 - x.z), first
+    minimum), then swap label 0 with the most populated label.  Reproduces the histogram quirk:
+    counts exist only for labels in range(len(unique(seed_labels)))."""
+    dist = 0.5 * (1 - torch.mm(X, Z.t()))
+    closest = torch.argmin(dist, dim=1)
+    labels = seed_labels[closest]
+    num = len(torch.unique(seed_labels))
+    count = torch.zeros(num, dtype=torch.long)
+    for i in range(num):
+        count[i] = (labels == i).sum()
+    label_max = int(torch.argmax(count))
+    if label_max != 0:
+        idx0 = labels == 0
+        idx1 = labels == label_max
+        labels[idx0] = label_max
+        labels[idx1] = 0
+    return labels
+
+
+def mean_shift_smart_init(X, kappa=KAPPA, num_seeds=NUM_SEEDS, max_iters=MAX_ITERS, first_index=None,
+                          return_all=False):
+    """lib/utils/mean_shift.py:192-229.  X: [n,d] unit rows (any strides).  `first_index` None ->
+    draw it from numpy's global RNG exactly like the reference (:155)."""
+    n = X.shape[0]
+    if first_index is None:
+        first_index = np.random.randint(0, n)
+    seeds, selected = select_seeds(X, num_seeds, first_index)
+    Z = hill_climb(X, seeds, kappa, max_iters)
+    seed_labels = label_seeds(Z, 2 * EMBEDDING_ALPHA)          # mean_shift.py:123
+    labels = assign_and_relabel(X, Z, seed_labels)
+    if return_all:
+        return labels, selected, seeds, Z, seed_labels
+    return labels, selected
+
+
+def clustering_features(features, num_seeds=NUM_SEEDS, first_indices=None):
+    """lib/fcn/test_dataset.py:44-59.  features [N,C,H,W] -> (labels float32 [N,H,W] CPU,
+    list of N int64 [num_seeds] tensors)."""
+    N, C, H, W = features.shape
+    out = torch.zeros((N, H, W))
+    picked = []
+    for j in range(N):
+        X = features[j].reshape(C, -1).t()
+        fi = None if first_indices is None else int(first_indices[j])
+        labels, sel = mean_shift_smart_init(X, KAPPA, num_seeds, MAX_ITERS, fi)
+        out[j] = labels.view(H, W)
+        picked.append(sel)
+    return out, picked
+
+
+# --------------------------------------------------------------------------------------------
+# two-stage plumbing  (lib/fcn/test_dataset.py, lib/utils/mask.py)
+# --------------------------------------------------------------------------------------------
+
+def filter_labels_depth(labels, depth, threshold):
+    """lib/fcn/test_dataset.py:183-198.  Zero every non-background id whose fraction of pixels
+    with Z > 0 (depth channel 2) is below `threshold`."""
+    out = labels.clone()
+    for i in range(labels.shape[0]):
+        ids = torch.unique(labels[i])
+        for mid in ids:
+            if mid == 0:
+                continue
+            sel = labels[i] == mid
+            frac = (depth[i, 2][sel] > 0).sum().float() / sel.sum().float()
+            if frac < threshold:
+                out[i][sel] = 0
+    return out
+
+
+def tight_box(mask):
+    """lib/utils/mask.py:180-187  -> (x_min, y_min, x_max, y_max) of the non-zeros."""
+    nz = torch.nonzero(mask)
+    return int(nz[:, 1].min()), int(nz[:, 0].min()), int(nz[:, 1].max()), int(nz[:, 0].max())
+
+
+def _round_half_even(v):
+    return int(torch.round(torch.tensor(float(v))).item())
+
+
+def crop_rois(rgb, initial_masks, depth, crop_size=CROP_SIZE):
+    """lib/fcn/test_dataset.py:62-112.  Only batch item 0 is cropped (:68,97,100).  ROI = tight
+    box padded by round(0.25 * extent) (torch.round: half to even, extent without +1), clamped;
+    rgb/depth resized bilinear align_corners=True, mask nearest (legacy floor)."""
+    N, H, W = initial_masks.shape
+    ids = torch.unique(initial_masks[0])
+    ids = ids[ids != 0] if (len(ids) and ids[0] == 0) else ids
+    K = ids.shape[0]
+    rgb_crops = torch.zeros((K, 3, crop_size, crop_size))
+    mask_crops = torch.zeros((K, crop_size, crop_size))
+    rois = torch.zeros((K, 4))
+    depth_crops = torch.zeros((K, 3, crop_size, crop_size)) if depth is not None else None
+    size = (crop_size, crop_size)
+    for k, mid in enumerate(ids):
+        mask = (initial_masks[0] == mid).float()
+        x0, y0, x1, y1 = tight_box(mask)
+        xp = _round_half_even((x1 - x0) * 0.25)
+        yp = _round_half_even((y1 - y0) * 0.25)
+        x0 = max(x0 - xp, 0); x1 = min(x1 + xp, W - 1)
+        y0 = max(y0 - yp, 0); y1 = min(y1 + yp, H - 1)
+        rois[k] = torch.tensor([x0, y0, x1, y1], dtype=torch.float32)
+        rgb_crops[k] = F.interpolate(rgb[0:1, :, y0:y1 + 1, x0:x1 + 1], size=size, mode="bilinear",
+                                     align_corners=True)[0]
+        mask_crops[k] = F.interpolate(mask[None, None, y0:y1 + 1, x0:x1 + 1], size=size, mode="nearest")[0, 0]
+        if depth is not None:
+            depth_crops[k] = F.interpolate(depth[0:1, :, y0:y1 + 1, x0:x1 + 1], size=size, mode="bilinear",
+                                           align_corners=True)[0]
+    return rgb_crops, mask_crops, rois, depth_crops
+
+
+def match_label_crop(initial_masks, labels_crop, mask_crops, rois, depth_crops):
+    """lib/fcn/test_dataset.py:116-179.  (i) drop (-1) crop clusters overlapping the stage-1 mask by
+    < 50 % of their area; (ii) order crops far -> near by mean Z of kept pixels with Z > 0 (ROI area
+    when no depth), descending; (iii) renumber kept clusters 1,2,3.. in that order, nearest-resize
+    to the ROI and paste the non-zeros, nearer crops overwriting.  Mutates labels_crop like the
+    reference (:125)."""
+    K = labels_crop.shape[0]
+    for i in range(K):
+        for mid in torch.unique(labels_crop[i]):
+            sel = labels_crop[i] == mid
+            frac = (sel.float() * mask_crops[i]).sum() / sel.float().sum()
+            if frac < 0.5:
+                labels_crop[i][sel] = -1
+    keyed = []
+    for i in range(K):
+        if depth_crops is not None:
+            kept = labels_crop[i] > -1
+            zs = depth_crops[i, 2][kept] if kept.sum() > 0 else depth_crops[i, 2]
+            keyed.append((i, torch.mean(zs[zs > 0])))
+        else:
+            keyed.append((i, (rois[i, 3] - rois[i, 1] + 1) * (rois[i, 2] - rois[i, 0] + 1)))
+    order = [i for i, _ in sorted(keyed, key=lambda t: t[1], reverse=True)]
+    refined = torch.zeros_like(initial_masks).float()
+    count = 0
+    for i in order:
+        ids = torch.unique(labels_crop[i])
+        ids = ids[1:] if ids[0] == -1 else ids
+        renum = torch.zeros_like(labels_crop[i])
+        for mid in ids:
+            count += 1
+            renum[labels_crop[i] == mid] = count
+        x0, y0, x1, y1 = (int(rois[i, j].item()) for j in range(4))
+        back = F.interpolate(renum[None, None].float(), size=(y1 - y0 + 1, x1 - x0 + 1), mode="nearest")[0, 0]
+        hh, ww = torch.nonzero(back).t()
+        refined[0, y0:y1 + 1, x0:x1 + 1][hh, ww] = back[hh, ww]
+    return refined, labels_crop
+
+
+def test_sample(image, depth, network, network_crop, first_indices=None, first_indices_crop=None):
+    """lib/fcn/test_dataset.py:232-267 on CPU tensors.  `network(image, None, depth)` must return
+    unit-norm [N,C,H,W] features.  Returns (out_label, out_label_refined | None)."""
+    features = network(image, None, depth).detach()
+    out_label, _ = clustering_features(features, NUM_SEEDS, first_indices)
+    if depth is not None:
+        out_label = filter_labels_depth(out_label, depth, 0.8)
+    refined = None
+    if network_crop is not None:
+        rgb_c, mask_c, rois, depth_c = crop_rois(image, out_label.clone(), depth)
+        if rgb_c.shape[0] > 0:
+            feats_c = network_crop(rgb_c, mask_c, depth_c).detach()
+            labels_c, _ = clustering_features(feats_c, NUM_SEEDS, first_indices_crop)
+            refined, _ = match_label_crop(out_label, labels_c, mask_c, rois, depth_c)
+    return out_label, refined
+
+
+# --------------------------------------------------------------------------------------------
+# backbone: ResNet34-8s two-branch RGB-D add-fusion  (lib/networks/{SEG,resnet_dilated,resnet}.py)
+# --------------------------------------------------------------------------------------------
+
+# (planes, blocks, first-block stride, dilation) after the output_stride=8 stride->dilation
+# conversion of lib/networks/resnet.py:188-234 (layer3/4: stride 1, dilation 2 / 4).
+RESNET34_8S_LAYERS = ((64, 3, 1, 1), (128, 4, 2, 1), (256, 6, 1, 2), (512, 3, 1, 4))
+
+
+def _bn(x, sd, p):
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        False, 0.0, BN_EPS)
+
+
+def resnet34_8s_trunk(x, sd, prefix):
+    """lib/networks/resnet.py:236-270 with fully_conv / remove_avg_pool_layer / output_stride=8
+    (lib/networks/resnet_dilated.py:296-303): stem 7x7 s2 -> BN -> ReLU -> maxpool 3x3 s2 ->
+    4 stages of BasicBlock (resnet.py:57-73) -> 1x1 conv `fc` with bias.  Eval-mode BN."""
+    p = prefix
+    x = F.conv2d(x, sd[p + "conv1.weight"], None, stride=2, padding=3)
+    x = F.relu(_bn(x, sd, p + "bn1"))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    for li, (planes, blocks, stride, dil) in enumerate(RESNET34_8S_LAYERS, start=1):
+        for b in range(blocks):
+            q = "%slayer%d.%d." % (p, li, b)
+            s = stride if b == 0 else 1
+            out = F.conv2d(x, sd[q + "conv1.weight"], None, stride=s, padding=dil, dilation=dil)
+            out = F.relu(_bn(out, sd, q + "bn1"))
+            out = F.conv2d(out, sd[q + "conv2.weight"], None, stride=1, padding=dil, dilation=dil)
+            out = _bn(out, sd, q + "bn2")
+            if (q + "downsample.0.weight") in sd:
+                res = _bn(F.conv2d(x, sd[q + "downsample.0.weight"], None, stride=s), sd, q + "downsample.1")
+            else:
+                res = x
+            x = F.relu(out + res)
+    return F.conv2d(x, sd[p + "fc.weight"], sd[p + "fc.bias"])
+
+
+def segnet_rgbd_add_forward(sd, img, depth):
+    """lib/networks/SEG.py:88-119 (INPUT='RGBD', FUSION_TYPE='add', eval): each branch = trunk ->
+    bilinear upsample to the input size with align_corners=True (resnet_dilated.py:325), add
+    (:108), F.normalize over channels (:114).  `sd` is a reference-format state_dict."""
+    size = img.shape[2:]
+    a = F.interpolate(resnet34_8s_trunk(img, sd, "fcn.resnet34_8s."), size=size, mode="bilinear", align_corners=True)
+    b = F.interpolate(resnet34_8s_trunk(depth, sd, "fcn_depth.resnet34_8s."), size=size, mode="bilinear",
+                      align_corners=True)
+    return F.normalize(a + b, p=2, dim=1)
+
+
+def normalize_state_dict(data):
+    """Key handling of lib/networks/SEG.py:130-159 and tools/test_net.py:111-112: unwrap
+    {'model': sd}, strip a leading 'module.'."""
+    if isinstance(data, dict) and "model" in data and not torch.is_tensor(data["model"]):
+        data = data["model"]
+    out = {}
+    for k, v in data.items():
+        out[k[7:] if k.startswith("module.") else k] = v
+    return out
+
+
+class OracleSegNet:
+    """Callable with the reference's network signature net(img, label, depth) -> features."""
+
+    def __init__(self, state_dict):
+        self.sd = {k: v.detach().float() for k, v in normalize_state_dict(state_dict).items()}
+
+    def __call__(self, img, label=None, depth=None):
+        with torch.no_grad():
+            return segnet_rgbd_add_forward(self.sd, img, depth)
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic inputs shared by tests / bench
+# --------------------------------------------------------------------------------------------
+
+def synthetic_clustered_features(H, W, d=64, num_objects=6, noise=0.05, seed=0):
+    """cfg2 generator: unit-norm embedding field [1,d,H,W] with num_objects axis-aligned rectangles
+    on a background; x = normalize(centre[label] + noise * randn).  Returns (features, gt [H,W])."""
+    g = torch.Generator().manual_seed(seed)
+    centres = F.normalize(torch.randn(num_objects + 1, d, generator=g), dim=1)
+    gt = torch.zeros(H, W, dtype=torch.long)
+    for k in range(1, num_objects + 1):
+        h = int(torch.randint(H // 8, H // 3, (1,), generator=g))
+        w = int(torch.randint(W // 8, W // 3, (1,), generator=g))
+        y = int(torch.randint(0, H - h, (1,), generator=g))
+        x = int(torch.randint(0, W - w, (1,), generator=g))
+        gt[y:y + h, x:x + w] = k
+    X = centres[gt.view(-1)] + noise * torch.randn(H * W, d, generator=g)
+    X = F.normalize(X, dim=1)
+    feats = X.t().contiguous().view(1, d, H, W)
+    return feats, gt
+
+
+def synthetic_rgbd_frame(H=480, W=640, seed=0):
+    """cfg1 generator: image ~ U(-0.5, 0.6); XYZ from Z ~ U(0.3, 1.5) m with the demo intrinsics
+    (data/demo/camera_params.json: fx 612.937 fy 613.173 cx 322.549 cy 248.158, scaled to HxW)."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(1, 3, H, W, generator=g) * 1.1 - 0.5
+    z = torch.rand(1, 1, H, W, generator=g) * 1.2 + 0.3
+    sx, sy = W / 640.0, H / 480.0
+    fx, fy, cx, cy = 612.937 * sx, 613.173 * sy, 322.549 * sx, 248.158 * sy
+    u = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+    v = torch.arange(H, dtype=torch.float32).view(1, 1, H, 1)
+    xyz = torch.cat([(u - cx) / fx * z, (v - cy) / fy * z, z], dim=1)
+    return img, xyz
+
+
+def labels_equal_up_to_permutation(a, b):
+    """True iff integer label maps a, b are identical up to a relabelling that fixes label 0
+    (0 = background / largest cluster is special downstream)."""
+    a = np.asarray(a).astype(np.int64).ravel()
+    b = np.asarray(b).astype(np.int64).ravel()
+    if a.shape != b.shape:
+        return False
+    if not np.array_equal(a == 0, b == 0):
+        return False
+    fwd, bwd = {}, {}
+    pairs = np.unique(np.stack([a, b], 1), axis=0)
+    for x, y in pairs:
+        if fwd.setdefault(int(x), int(y)) != int(y) or bwd.setdefault(int(y), int(x)) != int(x):
+            return False
+    return True

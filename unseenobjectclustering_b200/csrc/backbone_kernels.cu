@@ -1,0 +1,316 @@
+// SIMT kernels of the backbone: stem (7x7 s2 conv + BN + ReLU), max-pool, the fused head
+// (branch add -> bilinear x8 -> L2 normalise -> both output layouts), a layout helper, and the
+// fp32-accumulate validation convolution (UOC_FLAG_CONV_SIMT; not the product path).
+#include "conv.cuh"
+
+namespace uoc {
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// ----------------------------------------------------------------------------------------------
+// validation convolution: one thread per (output pixel, output channel)
+// ----------------------------------------------------------------------------------------------
+struct ConvSimtParams {
+  const __nv_bfloat16* x[2];
+  const __nv_bfloat16* w[2];
+  const float* bias[2];
+  const __nv_bfloat16* residual[2];
+  void* y[2];
+  int N, H, W, Cin, Cout, Ho, Wo, ksize, stride, dil, pad, relu, out_fp32;
+};
+
+__global__ void __launch_bounds__(256) conv_simt_kernel(ConvSimtParams p) {
+  const int g = blockIdx.z;
+  const long long total = (long long)p.N * p.Ho * p.Wo * p.Cout;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int co = int(idx % p.Cout);
+  long long pix = idx / p.Cout;
+  const int ox = int(pix % p.Wo);
+  const int oy = int((pix / p.Wo) % p.Ho);
+  const int n = int(pix / ((long long)p.Wo * p.Ho));
+  float acc = 0.f;
+  const int taps = p.ksize * p.ksize;
+  for (int r = 0; r < p.ksize; ++r) {
+    const int iy = oy * p.stride - p.pad + r * p.dil;
+    if (iy < 0 || iy >= p.H) continue;
+    for (int s = 0; s < p.ksize; ++s) {
+      const int ix = ox * p.stride - p.pad + s * p.dil;
+      if (ix < 0 || ix >= p.W) continue;
+      const uint4* xp = reinterpret_cast<const uint4*>(p.x[g] + ((size_t(n) * p.H + iy) * p.W + ix) * p.Cin);
+      const uint4* wp = reinterpret_cast<const uint4*>(p.w[g] + (size_t(co) * taps + (r * p.ksize + s)) * p.Cin);
+      for (int c8 = 0; c8 < p.Cin / 8; ++c8) {
+        const uint4 xv = __ldg(xp + c8), wv = __ldg(wp + c8);
+        acc = fmaf(bf16_lo(xv.x), bf16_lo(wv.x), acc); acc = fmaf(bf16_hi(xv.x), bf16_hi(wv.x), acc);
+        acc = fmaf(bf16_lo(xv.y), bf16_lo(wv.y), acc); acc = fmaf(bf16_hi(xv.y), bf16_hi(wv.y), acc);
+        acc = fmaf(bf16_lo(xv.z), bf16_lo(wv.z), acc); acc = fmaf(bf16_hi(xv.z), bf16_hi(wv.z), acc);
+        acc = fmaf(bf16_lo(xv.w), bf16_lo(wv.w), acc); acc = fmaf(bf16_hi(xv.w), bf16_hi(wv.w), acc);
+      }
+    }
+  }
+  acc += p.bias[g][co];
+  if (p.residual[g]) acc += __bfloat162float(p.residual[g][pix * p.Cout + co]);
+  if (p.relu) acc = fmaxf(acc, 0.f);
+  if (p.out_fp32) static_cast<float*>(p.y[g])[pix * p.Cout + co] = acc;
+  else static_cast<__nv_bfloat16*>(p.y[g])[pix * p.Cout + co] = __float2bfloat16_rn(acc);
+}
+
+int launch_conv_simt(const ConvProblem& c, cudaStream_t stream) {
+  if (c.Cin % 8 != 0) return fail(UOC_ERR_UNSUPPORTED, "conv_simt needs Cin % 8 == 0");
+  ConvSimtParams p;
+  for (int g = 0; g < 2; ++g) {
+    const int s = g < c.groups ? g : 0;
+    p.x[g] = static_cast<const __nv_bfloat16*>(c.g[s].x);
+    p.w[g] = static_cast<const __nv_bfloat16*>(c.g[s].w);
+    p.bias[g] = c.g[s].bias;
+    p.residual[g] = static_cast<const __nv_bfloat16*>(c.g[s].residual);
+    p.y[g] = c.g[s].y;
+  }
+  p.N = c.N; p.H = c.H; p.W = c.W; p.Cin = c.Cin; p.Cout = c.Cout;
+  p.ksize = c.ksize; p.stride = c.stride; p.dil = c.dilation; p.pad = (c.ksize == 3) ? c.dilation : 0;
+  p.Ho = conv_out_dim(c.H, c.ksize, c.stride, c.dilation);
+  p.Wo = conv_out_dim(c.W, c.ksize, c.stride, c.dilation);
+  p.relu = c.relu; p.out_fp32 = c.out_fp32;
+  const long long total = (long long)p.N * p.Ho * p.Wo * p.Cout;
+  conv_simt_kernel<<<dim3((unsigned int)((total + 255) / 256), 1, c.groups), 256, 0, stream>>>(p);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// stem: 7x7 stride-2 pad-3 convolution of the fp32 NCHW input (3 channels), folded BN, ReLU
+// (lib/networks/resnet.py:141-145, :237-239).  One block = 16x16 output pixels x 64 channels.
+// ----------------------------------------------------------------------------------------------
+struct StemParams {
+  StemGroup g[2];
+  int N, H, W, Ho, Wo;
+};
+
+constexpr int kStemPatch = 16 * 2 + 5;  // 37 input rows / cols per 16 output rows / cols
+
+__global__ void __launch_bounds__(256) stem_kernel(StemParams p) {
+  extern __shared__ float sm[];
+  float* wsm = sm;                               // [147][64]  (k-major so that 4 channels = one float4)
+  float* patch = sm + 147 * 64;                  // [3][37][38]
+  const int g = blockIdx.z / p.N, n = blockIdx.z % p.N;
+  const int tid = threadIdx.x;
+  const float* wg = p.g[g].w;
+  for (int e = tid; e < 147 * 64; e += 256) {
+    const int k = e >> 6, co = e & 63;
+    wsm[e] = __ldg(wg + co * 147 + k);
+  }
+  const int oy0 = blockIdx.y * 16, ox0 = blockIdx.x * 16;
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  const float* xg = p.g[g].x + size_t(n) * 3 * p.H * p.W;
+  for (int e = tid; e < 3 * kStemPatch * kStemPatch; e += 256) {
+    const int c = e / (kStemPatch * kStemPatch);
+    const int rem = e - c * kStemPatch * kStemPatch;
+    const int py = rem / kStemPatch, px = rem - py * kStemPatch;
+    const int iy = iy0 + py, ix = ix0 + px;
+    float v = 0.f;
+    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xg + (size_t(c) * p.H + iy) * p.W + ix);
+    patch[(c * kStemPatch + py) * 38 + px] = v;
+  }
+  __syncthreads();
+  const int ly = tid >> 4, lx = tid & 15;
+  float acc[64];
+#pragma unroll
+  for (int q = 0; q < 64; ++q) acc[q] = 0.f;
+  for (int r = 0; r < 7; ++r) {
+    for (int s = 0; s < 7; ++s) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float xv = patch[(c * kStemPatch + ly * 2 + r) * 38 + lx * 2 + s];
+        const float4* wk = reinterpret_cast<const float4*>(wsm + ((r * 7 + s) * 3 + c) * 64);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float4 wv = wk[q];
+          acc[4 * q + 0] = fmaf(xv, wv.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(xv, wv.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(xv, wv.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(xv, wv.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  const int oy = oy0 + ly, ox = ox0 + lx;
+  if (oy < p.Ho && ox < p.Wo) {
+    const float* bias = p.g[g].bias;
+    uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.g[g].y) + ((size_t(n) * p.Ho + oy) * p.Wo + ox) * 64);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float f[8];
+#pragma unroll
+      for (int h = 0; h < 8; ++h) f[h] = fmaxf(acc[8 * e + h] + __ldg(bias + 8 * e + h), 0.f);
+      op[e] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+  }
+}
+
+int launch_stem(const StemGroup* g, int groups, int N, int H, int W, cudaStream_t stream) {
+  StemParams p;
+  for (int i = 0; i < 2; ++i) p.g[i] = g[i < groups ? i : 0];
+  p.N = N; p.H = H; p.W = W;
+  p.Ho = (H + 6 - 7) / 2 + 1;
+  p.Wo = (W + 6 - 7) / 2 + 1;
+  const size_t smem = sizeof(float) * (147 * 64 + 3 * kStemPatch * 38);
+  static bool attr = false;
+  if (!attr) {
+    UOC_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr = true;
+  }
+  stem_kernel<<<dim3((p.Wo + 15) / 16, (p.Ho + 15) / 16, groups * N), 256, smem, stream>>>(p);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// max-pool 3x3 stride 2 pad 1 (lib/networks/resnet.py:145), bf16 NHWC, 8 channels per thread
+// ----------------------------------------------------------------------------------------------
+struct PoolParams {
+  const __nv_bfloat16* x[2];
+  __nv_bfloat16* y[2];
+  int N, H, W, C, Ho, Wo;
+};
+
+__global__ void __launch_bounds__(256) maxpool_kernel(PoolParams p) {
+  const int g = blockIdx.z;
+  const int c8n = p.C / 8;
+  const long long total = (long long)p.N * p.Ho * p.Wo * c8n;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = int(idx % c8n);
+  long long pix = idx / c8n;
+  const int ox = int(pix % p.Wo);
+  const int oy = int((pix / p.Wo) % p.Ho);
+  const int n = int(pix / ((long long)p.Wo * p.Ho));
+  float m[8];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) m[h] = -INFINITY;
+  for (int r = 0; r < 3; ++r) {
+    const int iy = oy * 2 - 1 + r;
+    if (iy < 0 || iy >= p.H) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int ix = ox * 2 - 1 + s;
+      if (ix < 0 || ix >= p.W) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.x[g] + ((size_t(n) * p.H + iy) * p.W + ix) * p.C) + c8);
+      m[0] = fmaxf(m[0], bf16_lo(v.x)); m[1] = fmaxf(m[1], bf16_hi(v.x));
+      m[2] = fmaxf(m[2], bf16_lo(v.y)); m[3] = fmaxf(m[3], bf16_hi(v.y));
+      m[4] = fmaxf(m[4], bf16_lo(v.z)); m[5] = fmaxf(m[5], bf16_hi(v.z));
+      m[6] = fmaxf(m[6], bf16_lo(v.w)); m[7] = fmaxf(m[7], bf16_hi(v.w));
+    }
+  }
+  reinterpret_cast<uint4*>(p.y[g] + pix * p.C)[c8] =
+      make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+}
+
+int launch_maxpool(const void* const* x, void* const* y, int groups, int N, int H, int W, int C, cudaStream_t stream) {
+  PoolParams p;
+  for (int i = 0; i < 2; ++i) {
+    p.x[i] = static_cast<const __nv_bfloat16*>(x[i < groups ? i : 0]);
+    p.y[i] = static_cast<__nv_bfloat16*>(y[i < groups ? i : 0]);
+  }
+  p.N = N; p.H = H; p.W = W; p.C = C;
+  p.Ho = (H + 2 - 3) / 2 + 1;
+  p.Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * p.Ho * p.Wo * (C / 8);
+  maxpool_kernel<<<dim3((unsigned int)((total + 255) / 256), 1, groups), 256, 0, stream>>>(p);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K2 head: f = up8(a + b); f /= max(||f||, 1e-12)     (SEG.py:105-108,:114; resnet_dilated.py:325)
+// Bilinear with align_corners=True, index arithmetic in fp32 like ATen's upsample_bilinear2d:
+//   scale = (in - 1) / (out - 1);  src = scale * dst;  i0 = (int)src;  lambda1 = src - i0.
+// Upsampling is linear, so adding the two low-resolution trunk outputs first differs from the
+// reference's "upsample each, then add" by rounding only.
+// One thread per output pixel, channels in registers.
+// ----------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w,
+                                                   int H, int W, float sy, float sx, float* __restrict__ out_nchw,
+                                                   __nv_bfloat16* __restrict__ out_bf16) {
+  const int n = blockIdx.z;
+  const int oy = blockIdx.y;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= W) return;
+  const float fy = sy * float(oy), fx = sx * float(ox);
+  const int y0 = int(fy), x0 = int(fx);
+  const int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
+  const float ly1 = fy - float(y0), lx1 = fx - float(x0);
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const size_t base = size_t(n) * h * w;
+  const float4* a00 = reinterpret_cast<const float4*>(a + (base + size_t(y0) * w + x0) * D);
+  const float4* a01 = reinterpret_cast<const float4*>(a + (base + size_t(y0) * w + x1) * D);
+  const float4* a10 = reinterpret_cast<const float4*>(a + (base + size_t(y1) * w + x0) * D);
+  const float4* a11 = reinterpret_cast<const float4*>(a + (base + size_t(y1) * w + x1) * D);
+  const float4* b00 = reinterpret_cast<const float4*>(b + (base + size_t(y0) * w + x0) * D);
+  const float4* b01 = reinterpret_cast<const float4*>(b + (base + size_t(y0) * w + x1) * D);
+  const float4* b10 = reinterpret_cast<const float4*>(b + (base + size_t(y1) * w + x0) * D);
+  const float4* b11 = reinterpret_cast<const float4*>(b + (base + size_t(y1) * w + x1) * D);
+  float f[D];
+  float ss = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < D / 4; ++k4) {
+    float4 v00 = __ldg(a00 + k4), v01 = __ldg(a01 + k4), v10 = __ldg(a10 + k4), v11 = __ldg(a11 + k4);
+    const float4 u00 = __ldg(b00 + k4), u01 = __ldg(b01 + k4), u10 = __ldg(b10 + k4), u11 = __ldg(b11 + k4);
+    v00.x += u00.x; v00.y += u00.y; v00.z += u00.z; v00.w += u00.w;
+    v01.x += u01.x; v01.y += u01.y; v01.z += u01.z; v01.w += u01.w;
+    v10.x += u10.x; v10.y += u10.y; v10.z += u10.z; v10.w += u10.w;
+    v11.x += u11.x; v11.y += u11.y; v11.z += u11.z; v11.w += u11.w;
+    f[4 * k4 + 0] = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+    f[4 * k4 + 1] = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+    f[4 * k4 + 2] = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+    f[4 * k4 + 3] = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+    ss = fmaf(f[4 * k4 + 0], f[4 * k4 + 0], ss); ss = fmaf(f[4 * k4 + 1], f[4 * k4 + 1], ss);
+    ss = fmaf(f[4 * k4 + 2], f[4 * k4 + 2], ss); ss = fmaf(f[4 * k4 + 3], f[4 * k4 + 3], ss);
+  }
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  const size_t HW = size_t(H) * W;
+  const size_t pix = size_t(oy) * W + ox;
+  float* o = out_nchw + size_t(n) * D * HW + pix;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    f[k] *= inv;
+    __stcs(o + size_t(k) * HW, f[k]);
+  }
+  if (out_bf16) {
+    uint4* ob = reinterpret_cast<uint4*>(out_bf16 + (size_t(n) * HW + pix) * D);
+#pragma unroll
+    for (int e = 0; e < D / 8; ++e)
+      ob[e] = make_uint4(pack_bf16x2(f[8 * e + 0], f[8 * e + 1]), pack_bf16x2(f[8 * e + 2], f[8 * e + 3]),
+                         pack_bf16x2(f[8 * e + 4], f[8 * e + 5]), pack_bf16x2(f[8 * e + 6], f[8 * e + 7]));
+  }
+}
+
+int launch_head(const float* a, const float* b, int N, int h, int w, int d, int H, int W, float* out_nchw, void* out_bf16,
+                cudaStream_t stream) {
+  const float sy = (H > 1) ? float(h - 1) / float(H - 1) : 0.f;
+  const float sx = (W > 1) ? float(w - 1) / float(W - 1) : 0.f;
+  const dim3 grid((W + 127) / 128, H, N);
+  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  if (d == 64) head_kernel<64><<<grid, 128, 0, stream>>>(a, b, h, w, H, W, sy, sx, out_nchw, ob);
+  else if (d == 128) head_kernel<128><<<grid, 128, 0, stream>>>(a, b, h, w, H, W, sy, sx, out_nchw, ob);
+  else return fail(UOC_ERR_UNSUPPORTED, "head supports num_units = 64 or 128");
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ in, int hw, int d, float* __restrict__ out) {
+  const int n = blockIdx.y;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)hw * d) return;
+  const int k = int(idx / hw), pp = int(idx % hw);
+  out[size_t(n) * hw * d + idx] = in[(size_t(n) * hw + pp) * d + k];
+}
+
+int launch_nhwc_to_nchw(const float* in, int N, int h, int w, int d, float* out, cudaStream_t stream) {
+  const long long total = (long long)h * w * d;
+  nhwc_to_nchw_kernel<<<dim3((unsigned int)((total + 255) / 256), N), 256, 0, stream>>>(in, h * w, d, out);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+}  // namespace uoc

@@ -1,0 +1,155 @@
+// C-ABI entry points of the clustering path (declared in include/uoc.h).
+#include "cluster.cuh"
+
+namespace uoc {
+
+static int check_shape(const float* X, int batch, int64_t n, int d, int m, int64_t stride_b, int64_t stride_d) {
+  if (!X) return fail(UOC_ERR_INVALID, "X is null");
+  if (batch < 1 || n < 1 || d < 1 || m < 1) return fail(UOC_ERR_INVALID, "batch, n, d, m must be positive");
+  if (m > UOC_MAX_SEEDS) return fail(UOC_ERR_UNSUPPORTED, "num_seeds > 128 is not supported");
+  if (d > 256 || d % 2 != 0) return fail(UOC_ERR_UNSUPPORTED, "d must be even and <= 256");
+  if (n >= (int64_t(1) << 31)) return fail(UOC_ERR_UNSUPPORTED, "n must be < 2^31");
+  if (stride_d < n) return fail(UOC_ERR_INVALID, "stride_d must be >= n (points contiguous, planar layout)");
+  if (batch > 1 && stride_b < int64_t(d) * stride_d && stride_b != 0)
+    return fail(UOC_ERR_INVALID, "stride_b overlaps batch items");
+  return UOC_OK;
+}
+
+static int upload_first(const int64_t* first_host, int batch, int64_t n, const ClusterWorkspace& w, cudaStream_t st) {
+  if (!first_host) return fail(UOC_ERR_INVALID, "first_seed_host is null");
+  for (int b = 0; b < batch; ++b)
+    if (first_host[b] < 0 || first_host[b] >= n) return fail(UOC_ERR_INVALID, "first seed index out of range");
+  UOC_CUDA(cudaMemcpyAsync(w.first, first_host, sizeof(int64_t) * batch, cudaMemcpyHostToDevice, st));
+  return UOC_OK;
+}
+
+static int hill_climb(const float* X, const void* x_bf16, const ClusterShape& s, const ClusterWorkspace& w, float* Z,
+                      float kappa, int iters, int flags, cudaStream_t st) {
+  if (flags & UOC_FLAG_LOOP_SIMT) return launch_hill_climb_simt(X, s, w, Z, kappa, iters, st);
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x_bf16);
+  if (!xb) {
+    int rc = launch_pack_bf16(X, s, w.xb, st);
+    if (rc != UOC_OK) return rc;
+    xb = w.xb;
+  }
+  return launch_hill_climb_tc(xb, s, w, Z, kappa, iters, st);
+}
+
+}  // namespace uoc
+
+using namespace uoc;
+
+extern "C" {
+
+size_t uoc_meanshift_workspace_bytes(int batch, int64_t n, int d, int m) {
+  if (batch < 1 || n < 1 || d < 1 || m < 1) return 0;
+  return cluster_workspace_bytes(batch, n, d, m);
+}
+
+int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n,
+                          int d, int m, float kappa, int iters, float epsilon, const int64_t* first_seed_host,
+                          int32_t* labels_out, int64_t* selected_out, float* seeds_out, int32_t* seed_labels_out,
+                          void* workspace, size_t workspace_bytes, int flags, uoc_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != UOC_OK) return rc;
+  rc = check_shape(X, batch, n, d, m, stride_b, stride_d);
+  if (rc != UOC_OK) return rc;
+  if (!labels_out || !selected_out) return fail(UOC_ERR_INVALID, "labels_out / selected_out is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ClusterWorkspace w;
+  rc = carve_cluster_workspace(workspace, workspace_bytes, batch, n, d, m, &w);
+  if (rc != UOC_OK) return rc;
+  ClusterShape s{batch, n, d, m, stride_b, stride_d};
+  rc = upload_first(first_seed_host, batch, n, w, st);
+  if (rc != UOC_OK) return rc;
+  rc = launch_select_seeds(X, s, w, selected_out, w.Z, st);
+  if (rc != UOC_OK) return rc;
+  rc = hill_climb(X, x_bf16, s, w, w.Z, kappa, iters, flags, st);
+  if (rc != UOC_OK) return rc;
+  rc = launch_label_seeds(w.Z, batch, m, d, epsilon, w.seed_labels, w.num_unique, st);
+  if (rc != UOC_OK) return rc;
+  rc = launch_assign(X, s, w.Z, w.seed_labels, w.num_unique, w.hist, w.labels_tmp, labels_out, st);
+  if (rc != UOC_OK) return rc;
+  if (seeds_out)
+    UOC_CUDA(cudaMemcpyAsync(seeds_out, w.Z, sizeof(float) * size_t(batch) * m * d, cudaMemcpyDeviceToDevice, st));
+  if (seed_labels_out)
+    UOC_CUDA(cudaMemcpyAsync(seed_labels_out, w.seed_labels, sizeof(int) * size_t(batch) * m, cudaMemcpyDeviceToDevice, st));
+  if (flags & UOC_FLAG_SYNC_CHECK) return check_device_error(st);
+  return UOC_OK;
+}
+
+int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
+                     const int64_t* first_seed_host, int64_t* selected_out, float* seeds_out, void* workspace,
+                     size_t workspace_bytes, uoc_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != UOC_OK) return rc;
+  rc = check_shape(X, batch, n, d, m, stride_b, stride_d);
+  if (rc != UOC_OK) return rc;
+  if (!selected_out || !seeds_out) return fail(UOC_ERR_INVALID, "selected_out / seeds_out is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ClusterWorkspace w;
+  rc = carve_cluster_workspace(workspace, workspace_bytes, batch, n, d, m, &w);
+  if (rc != UOC_OK) return rc;
+  ClusterShape s{batch, n, d, m, stride_b, stride_d};
+  rc = upload_first(first_seed_host, batch, n, w, st);
+  if (rc != UOC_OK) return rc;
+  rc = launch_select_seeds(X, s, w, selected_out, seeds_out, st);
+  if (rc != UOC_OK) return rc;
+  return check_device_error(st);
+}
+
+int uoc_hill_climb(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n, int d,
+                   int m, float kappa, int iters, float* Z, void* workspace, size_t workspace_bytes, int flags,
+                   uoc_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != UOC_OK) return rc;
+  rc = check_shape(X, batch, n, d, m, stride_b, stride_d);
+  if (rc != UOC_OK) return rc;
+  if (!Z) return fail(UOC_ERR_INVALID, "Z is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ClusterWorkspace w;
+  rc = carve_cluster_workspace(workspace, workspace_bytes, batch, n, d, m, &w);
+  if (rc != UOC_OK) return rc;
+  ClusterShape s{batch, n, d, m, stride_b, stride_d};
+  rc = hill_climb(X, x_bf16, s, w, Z, kappa, iters, flags, st);
+  if (rc != UOC_OK) return rc;
+  if (flags & UOC_FLAG_SYNC_CHECK) return check_device_error(st);
+  return UOC_OK;
+}
+
+int uoc_label_seeds(const float* Z, int batch, int m, int d, float epsilon, int32_t* seed_labels_out,
+                    int32_t* num_unique_out, uoc_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != UOC_OK) return rc;
+  if (!Z || !seed_labels_out || !num_unique_out) return fail(UOC_ERR_INVALID, "null pointer");
+  if (batch < 1 || m < 1 || m > UOC_MAX_SEEDS || d < 1 || d > 256) return fail(UOC_ERR_INVALID, "bad batch / m / d");
+  return launch_label_seeds(Z, batch, m, d, epsilon, seed_labels_out, num_unique_out, static_cast<cudaStream_t>(stream));
+}
+
+int uoc_assign_labels(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
+                      const float* Z, const int32_t* seed_labels, const int32_t* num_unique, int32_t* labels_out,
+                      void* workspace, size_t workspace_bytes, uoc_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != UOC_OK) return rc;
+  rc = check_shape(X, batch, n, d, m, stride_b, stride_d);
+  if (rc != UOC_OK) return rc;
+  if (!Z || !seed_labels || !num_unique || !labels_out) return fail(UOC_ERR_INVALID, "null pointer");
+  ClusterWorkspace w;
+  rc = carve_cluster_workspace(workspace, workspace_bytes, batch, n, d, m, &w);
+  if (rc != UOC_OK) return rc;
+  ClusterShape s{batch, n, d, m, stride_b, stride_d};
+  return launch_assign(X, s, Z, seed_labels, num_unique, w.hist, w.labels_tmp, labels_out, static_cast<cudaStream_t>(stream));
+}
+
+int uoc_pack_bf16(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, void* x_bf16_out,
+                  uoc_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != UOC_OK) return rc;
+  rc = check_shape(X, batch, n, d, 1, stride_b, stride_d);
+  if (rc != UOC_OK) return rc;
+  if (!x_bf16_out) return fail(UOC_ERR_INVALID, "output is null");
+  ClusterShape s{batch, n, d, 1, stride_b, stride_d};
+  return launch_pack_bf16(X, s, static_cast<__nv_bfloat16*>(x_bf16_out), static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,618 @@
+// SIMT kernels of the clustering path (everything except the tcgen05 mean-shift loop):
+//   K3  farthest point sampling       -- persistent cooperative kernel, one grid barrier per seed
+//   K4' mean-shift iteration, fp32    -- validation kernel (UOC_FLAG_LOOP_SIMT), not the product path
+//   K4r partial-sum reduce + L2 normalise
+//   K5a greedy seed labelling         -- one CTA per field
+//   K5b nearest-seed assignment, label histogram, label-0 swap
+//   pack fp32 planar -> bf16 pixel-major
+//
+// Canonical fp32 arithmetic (mirrored bit for bit by oracle/uoc_oracle_c.c): every dot product that
+// feeds a discrete decision (arg-max of the sampling, epsilon threshold of the labelling, arg-min
+// of the assignment) is one sequential fused-multiply-add chain over the channels k = 0..d-1
+// starting from +0, and the cosine distance is 0.5f * (1.0f - dot).
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
+#include "cluster.cuh"
+
+namespace uoc {
+
+// ----------------------------------------------------------------------------------------------
+// workspace
+// ----------------------------------------------------------------------------------------------
+static int partial_capacity(int batch) {
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int P = (sms + batch - 1) / batch;
+  return P < 1 ? 1 : P;
+}
+
+static size_t carve(size_t& off, size_t bytes) {
+  size_t at = off;
+  off = align_up(off + bytes, 256);
+  return at;
+}
+
+struct WsLayout {
+  size_t r, keys, barrier, first, Z, partials, seed_labels, num_unique, hist, labels_tmp, xb, total;
+  int P;
+};
+
+static WsLayout ws_layout(int batch, int64_t n, int d, int m) {
+  WsLayout L;
+  size_t off = 0;
+  L.P = partial_capacity(batch);
+  L.r = carve(off, sizeof(float) * size_t(batch) * n);
+  L.keys = carve(off, sizeof(unsigned long long) * size_t(batch) * m);
+  L.barrier = carve(off, 256);
+  L.first = carve(off, sizeof(long long) * size_t(batch));
+  L.Z = carve(off, sizeof(float) * size_t(batch) * m * d);
+  L.partials = carve(off, sizeof(float) * size_t(batch) * L.P * 128 * d);
+  L.seed_labels = carve(off, sizeof(int) * size_t(batch) * m);
+  L.num_unique = carve(off, sizeof(int) * size_t(batch));
+  L.hist = carve(off, sizeof(int) * size_t(batch) * m);
+  L.labels_tmp = carve(off, sizeof(int) * size_t(batch) * n);
+  L.xb = carve(off, sizeof(__nv_bfloat16) * size_t(batch) * n * d);
+  L.total = off;
+  return L;
+}
+
+size_t cluster_workspace_bytes(int batch, int64_t n, int d, int m) { return ws_layout(batch, n, d, m).total; }
+
+int carve_cluster_workspace(void* ws, size_t ws_bytes, int batch, int64_t n, int d, int m, ClusterWorkspace* out) {
+  if (!ws) return fail(UOC_ERR_INVALID, "workspace pointer is null");
+  if (reinterpret_cast<uintptr_t>(ws) % 256 != 0) return fail(UOC_ERR_INVALID, "workspace must be 256-byte aligned");
+  WsLayout L = ws_layout(batch, n, d, m);
+  if (ws_bytes < L.total) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "workspace too small: need %zu bytes, got %zu", L.total, ws_bytes);
+    return fail(UOC_ERR_WORKSPACE, buf);
+  }
+  char* base = static_cast<char*>(ws);
+  out->r = reinterpret_cast<float*>(base + L.r);
+  out->keys = reinterpret_cast<unsigned long long*>(base + L.keys);
+  out->barrier = reinterpret_cast<unsigned int*>(base + L.barrier);
+  out->first = reinterpret_cast<long long*>(base + L.first);
+  out->Z = reinterpret_cast<float*>(base + L.Z);
+  out->partials = reinterpret_cast<float*>(base + L.partials);
+  out->seed_labels = reinterpret_cast<int*>(base + L.seed_labels);
+  out->num_unique = reinterpret_cast<int*>(base + L.num_unique);
+  out->hist = reinterpret_cast<int*>(base + L.hist);
+  out->labels_tmp = reinterpret_cast<int*>(base + L.labels_tmp);
+  out->xb = reinterpret_cast<__nv_bfloat16*>(base + L.xb);
+  out->max_partials = L.P;
+  return UOC_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K3: farthest point sampling
+// ----------------------------------------------------------------------------------------------
+struct FpsParams {
+  const float* X;
+  long long sb, sd;
+  long long n;
+  int d, m, batch;
+  const long long* first;
+  float* r;
+  unsigned long long* keys;
+  unsigned int* barrier;
+  long long* selected_out;
+  float* seeds_out;
+  unsigned int* err;
+};
+
+__device__ __forceinline__ unsigned int orderable(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ unsigned long long pack_key(float r, unsigned int idx) {
+  return (static_cast<unsigned long long>(orderable(r)) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - idx);
+}
+
+__device__ __forceinline__ bool grid_barrier(unsigned int* counter, unsigned int target, unsigned int* err) {
+  __syncthreads();
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    int ok = 0;
+    for (unsigned int it = 0; it < (1u << 27); ++it) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= target) { ok = 1; break; }
+    }
+    if (!ok) atomicOr(err, ERR_GRID_BARRIER_TIMEOUT);
+    s_ok = ok;
+    __threadfence();
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) fps_kernel(FpsParams p) {
+  extern __shared__ float s_seed[];  // d floats
+  __shared__ unsigned long long s_red[8];
+  const int tid = threadIdx.x;
+  const int G = gridDim.x;
+  // block -> item mapping: with G >= batch every item owns nb = G / batch blocks
+  const int nb = (G >= p.batch) ? (G / p.batch) : 1;
+  const int my_first_item = (G >= p.batch) ? (int(blockIdx.x) / nb) : int(blockIdx.x);
+  const int item_step = (G >= p.batch) ? p.batch : G;  // one item per block when G >= batch
+  const int rank = (G >= p.batch) ? (int(blockIdx.x) % nb) : 0;
+  const long long ngroups = p.n / VEC;
+  unsigned int target = 0;
+
+  for (int i = 0; i < p.m; ++i) {
+    for (int b = my_first_item; b < p.batch; b += item_step) {
+      long long idx;
+      if (i == 0) {
+        idx = p.first[b];
+      } else {
+        unsigned long long key = __ldcg(p.keys + size_t(b) * p.m + i);
+        idx = static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(key & 0xFFFFFFFFull));
+      }
+      const float* Xb = p.X + b * p.sb;
+      for (int k = tid; k < p.d; k += blockDim.x) s_seed[k] = __ldg(Xb + k * p.sd + idx);
+      __syncthreads();
+      if (rank == 0) {
+        if (tid == 0) p.selected_out[size_t(b) * p.m + i] = idx;
+        for (int k = tid; k < p.d; k += blockDim.x) p.seeds_out[(size_t(b) * p.m + i) * p.d + k] = s_seed[k];
+      }
+      if (i + 1 < p.m) {
+        unsigned long long best = 0ull;
+        float* rb = p.r + size_t(b) * p.n;
+        for (long long g = (long long)rank * blockDim.x + tid; g < ngroups; g += (long long)nb * blockDim.x) {
+          const float* xp = Xb + g * VEC;
+          float acc[VEC];
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+#pragma unroll 8
+          for (int k = 0; k < p.d; ++k) {
+            const float sk = s_seed[k];
+            if (VEC == 4) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(xp + k * p.sd));
+              acc[0] = fmaf(v.x, sk, acc[0]);
+              acc[1 % VEC] = fmaf(v.y, sk, acc[1 % VEC]);
+              acc[2 % VEC] = fmaf(v.z, sk, acc[2 % VEC]);
+              acc[3 % VEC] = fmaf(v.w, sk, acc[3 % VEC]);
+            } else {
+              acc[0] = fmaf(__ldg(xp + k * p.sd), sk, acc[0]);
+            }
+          }
+          float rn[VEC];
+          if (i == 0) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) rn[j] = 0.5f * (1.0f - acc[j]);
+          } else {
+            float ro[VEC];
+            if (VEC == 4) {
+              const float4 o = *reinterpret_cast<const float4*>(rb + g * VEC);
+              ro[0] = o.x; ro[1 % VEC] = o.y; ro[2 % VEC] = o.z; ro[3 % VEC] = o.w;
+            } else {
+              ro[0] = rb[g];
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+              const float dj = 0.5f * (1.0f - acc[j]);
+              rn[j] = dj < ro[j] ? dj : ro[j];
+            }
+          }
+          if (VEC == 4) {
+            *reinterpret_cast<float4*>(rb + g * VEC) = make_float4(rn[0], rn[1 % VEC], rn[2 % VEC], rn[3 % VEC]);
+          } else {
+            rb[g] = rn[0];
+          }
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const unsigned long long key = pack_key(rn[j], static_cast<unsigned int>(g * VEC + j));
+            best = key > best ? key : best;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+          best = other > best ? other : best;
+        }
+        if ((tid & 31) == 0) s_red[tid >> 5] = best;
+        __syncthreads();
+        if (tid < 32) {
+          unsigned long long v = (tid < (blockDim.x >> 5)) ? s_red[tid] : 0ull;
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+            v = other > v ? other : v;
+          }
+          if (tid == 0 && v != 0ull) atomicMax(p.keys + size_t(b) * p.m + i + 1, v);
+        }
+      }
+      __syncthreads();  // s_seed / s_red reuse
+    }
+    if (i + 1 < p.m) {
+      target += gridDim.x;
+      if (!grid_barrier(p.barrier, target, p.err)) return;
+    }
+  }
+}
+
+int launch_select_seeds(const float* X, const ClusterShape& s, const ClusterWorkspace& w, int64_t* selected_out,
+                        float* seeds_out, cudaStream_t stream) {
+  FpsParams p;
+  p.X = X; p.sb = s.stride_b; p.sd = s.stride_d; p.n = s.n; p.d = s.d; p.m = s.m; p.batch = s.batch;
+  p.first = w.first; p.r = w.r; p.keys = w.keys; p.barrier = w.barrier;
+  p.selected_out = reinterpret_cast<long long*>(selected_out);
+  p.seeds_out = seeds_out;
+  p.err = device_error_word();
+  if (!p.err) return fail(UOC_ERR_CUDA, "no device error word");
+  UOC_CUDA(cudaMemsetAsync(w.keys, 0, sizeof(unsigned long long) * size_t(s.batch) * s.m, stream));
+  UOC_CUDA(cudaMemsetAsync(w.barrier, 0, sizeof(unsigned int), stream));
+  const bool vec4 = (s.n % 4 == 0) && (s.stride_d % 4 == 0) && (s.stride_b % 4 == 0) &&
+                    (reinterpret_cast<uintptr_t>(X) % 16 == 0);
+  void* kern = vec4 ? reinterpret_cast<void*>(&fps_kernel<4>) : reinterpret_cast<void*>(&fps_kernel<1>);
+  const int threads = 256;
+  const size_t smem = sizeof(float) * size_t(s.d);
+  int per_sm = 0;
+  UOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) return fail(UOC_ERR_CUDA, "fps kernel does not fit on an SM");
+  int want = 2;
+  if (const char* e = getenv("UOC_FPS_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
+  if (want > per_sm) want = per_sm;
+  const int sms = sm_count();
+  long long groups_total = (s.n / (vec4 ? 4 : 1)) * (long long)s.batch;
+  int grid = sms * want;
+  long long needed = (groups_total + threads - 1) / threads;
+  if (needed < grid) grid = int(needed < 1 ? 1 : needed);
+  if (grid < s.batch && s.batch <= sms * per_sm) grid = s.batch;
+  void* args[] = {&p};
+  UOC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, stream));
+  return UOC_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K4': fp32 SIMT mean-shift iteration (validation path)
+// ----------------------------------------------------------------------------------------------
+// grid (P, m, batch); each block accumulates sum_p exp(kappa * x_p.z_j) * x_p over its point slice.
+__global__ void __launch_bounds__(256) meanshift_simt_kernel(const float* __restrict__ X, long long sb, long long sd,
+                                                             long long n, int d, int m, const float* __restrict__ Z,
+                                                             float kappa, float* __restrict__ partials, int P) {
+  extern __shared__ float sm[];  // z[d] + red[8][32]
+  float* z = sm;
+  float* red = sm + d;
+  const int part = blockIdx.x, j = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x;
+  const float* Xb = X + b * sb;
+  for (int k = tid; k < d; k += blockDim.x) z[k] = Z[(size_t(b) * m + j) * d + k];
+  __syncthreads();
+  const long long chunk = (n + P - 1) / P;
+  const long long p0 = part * chunk;
+  const long long p1 = (p0 + chunk < n) ? p0 + chunk : n;
+  float* out = partials + ((size_t(b) * P + part) * 128 + j) * d;
+  for (int kc = 0; kc < d; kc += 32) {
+    float acc[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) acc[q] = 0.f;
+    for (long long pnt = p0 + tid; pnt < p1; pnt += blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < d; ++k) s = fmaf(__ldg(Xb + k * sd + pnt), z[k], s);
+      const float wgt = expf(kappa * s);
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (kc + q < d) acc[q] = fmaf(wgt, __ldg(Xb + (kc + q) * sd + pnt), acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      float v = acc[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0) red[(tid >> 5) * 32 + q] = v;
+    }
+    __syncthreads();
+    if (tid < 32 && kc + tid < d) {
+      float v = 0.f;
+      for (int wq = 0; wq < int(blockDim.x >> 5); ++wq) v += red[wq * 32 + tid];
+      out[kc + tid] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// grid (m, batch), block 128: Z[b][j][:] = normalize(sum_part partials[b][part][j][:])
+__global__ void __launch_bounds__(128) reduce_normalize_kernel(const float* __restrict__ partials, int P, int m, int d,
+                                                               int row_stride, float* __restrict__ Z) {
+  __shared__ float s_sq[4];
+  const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  float v[2] = {0.f, 0.f};  // d <= 256
+  for (int part = 0; part < P; ++part) {
+    const float* src = partials + ((size_t(b) * P + part) * row_stride + j) * d;
+    if (tid < d) v[0] += src[tid];
+    if (tid + 128 < d) v[1] += src[tid + 128];
+  }
+  float sq = v[0] * v[0] + v[1] * v[1];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((tid & 31) == 0) s_sq[tid >> 5] = sq;
+  __syncthreads();
+  const float tot = (s_sq[0] + s_sq[1]) + (s_sq[2] + s_sq[3]);
+  const float denom = fmaxf(sqrtf(tot), 1e-12f);  // F.normalize eps (lib/utils/mean_shift.py:107)
+  float* dst = Z + (size_t(b) * m + j) * d;
+  if (tid < d) dst[tid] = v[0] / denom;
+  if (tid + 128 < d) dst[tid + 128] = v[1] / denom;
+}
+
+int launch_reduce_normalize(const float* partials, int batch, int P, int m, int d, int row_stride, float* Z,
+                            cudaStream_t stream) {
+  if (d > 256) return fail(UOC_ERR_UNSUPPORTED, "d > 256 is not supported");
+  reduce_normalize_kernel<<<dim3(m, batch), 128, 0, stream>>>(partials, P, m, d, row_stride, Z);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+int launch_hill_climb_simt(const float* X, const ClusterShape& s, const ClusterWorkspace& w, float* Z, float kappa,
+                           int iters, cudaStream_t stream) {
+  int P = w.max_partials;
+  const long long min_pts = 2048;
+  long long maxP = (s.n + min_pts - 1) / min_pts;
+  if (P > maxP) P = int(maxP);
+  if (P < 1) P = 1;
+  const size_t smem = sizeof(float) * (size_t(s.d) + 8 * 32);
+  for (int it = 0; it < iters; ++it) {
+    meanshift_simt_kernel<<<dim3(P, s.m, s.batch), 256, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, Z,
+                                                                       kappa, w.partials, P);
+    UOC_CHECK_LAUNCH();
+    int rc = launch_reduce_normalize(w.partials, s.batch, P, s.m, s.d, 128, Z, stream);
+    if (rc != UOC_OK) return rc;
+  }
+  return UOC_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K5a: greedy seed labelling, one CTA (512 threads) per field
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restrict__ Z, int m, int d, float eps,
+                                                          int* __restrict__ seed_labels, int* __restrict__ num_unique) {
+  extern __shared__ float zs[];  // [m][d+1]
+  __shared__ unsigned int adj[UOC_MAX_SEEDS][4];
+  __shared__ int labels[UOC_MAX_SEEDS];
+  __shared__ int cnt[UOC_MAX_SEEDS];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int ld = d + 1;
+  const float* Zb = Z + size_t(b) * m * d;
+  for (int e = tid; e < m * d; e += blockDim.x) zs[(e / d) * ld + (e % d)] = Zb[e];
+  if (tid < UOC_MAX_SEEDS) { labels[tid] = -1; cnt[tid] = 0; }
+  __syncthreads();
+  // adjacency: bit j of adj[i] <=> 0.5 * (1 - z_j . z_i) <= eps      (mean_shift.py:62-63)
+  {
+    const int j = tid & 127, iq = tid >> 7, w4 = (tid >> 5) & 3;
+    for (int i = iq; i < m; i += 4) {
+      bool in = false;
+      if (j < m) {
+        float acc = 0.f;
+        for (int k = 0; k < d; ++k) acc = fmaf(zs[j * ld + k], zs[i * ld + k], acc);
+        in = (0.5f * (1.0f - acc)) <= eps;
+      }
+      const unsigned int bits = __ballot_sync(0xffffffffu, in);
+      if ((tid & 31) == 0) adj[i][w4] = bits;
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int lane = tid;
+    int K = 0;
+    for (int i = 0; i < m; ++i) {
+      if (labels[i] != -1) continue;
+      for (int l = lane; l < K; l += 32) cnt[l] = 0;
+      __syncwarp();
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = lane + 32 * q;
+        const bool in = (j < m) && ((adj[i][q] >> lane) & 1u);
+        if (in && labels[j] != -1) { atomicAdd(&cnt[labels[j]], 1); any = true; }
+      }
+      any = __any_sync(0xffffffffu, any);
+      __syncwarp();
+      int lab;
+      if (any) {
+        // mode of the labelled members, ties -> smallest label (mean_shift.py:30-38)
+        unsigned int bestkey = 0;
+        for (int l = lane; l < K; l += 32) {
+          const unsigned int key = (static_cast<unsigned int>(cnt[l]) << 8) | static_cast<unsigned int>(255 - l);
+          bestkey = key > bestkey ? key : bestkey;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned int other = __shfl_xor_sync(0xffffffffu, bestkey, o);
+          bestkey = other > bestkey ? other : bestkey;
+        }
+        lab = 255 - int(bestkey & 0xFFu);
+      } else {
+        lab = K;
+        K += 1;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = lane + 32 * q;
+        if ((j < m) && ((adj[i][q] >> lane) & 1u)) labels[j] = lab;   // overwrite, labelled or not (:74)
+      }
+      __syncwarp();
+    }
+    // len(unique(labels))  (mean_shift.py:218)
+    for (int l = lane; l < UOC_MAX_SEEDS; l += 32) cnt[l] = 0;
+    __syncwarp();
+    for (int j = lane; j < m; j += 32) cnt[labels[j]] = 1;
+    __syncwarp();
+    int c = 0;
+    for (int l = lane; l < UOC_MAX_SEEDS; l += 32) c += cnt[l];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) num_unique[b] = c;
+    for (int j = lane; j < m; j += 32) seed_labels[size_t(b) * m + j] = labels[j];
+  }
+}
+
+int launch_label_seeds(const float* Z, int batch, int m, int d, float epsilon, int* seed_labels, int* num_unique,
+                       cudaStream_t stream) {
+  const size_t smem = sizeof(float) * size_t(m) * (d + 1);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    UOC_CUDA(cudaFuncSetAttribute(label_seeds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    configured = smem;
+  }
+  label_seeds_kernel<<<batch, 512, smem, stream>>>(Z, m, d, epsilon, seed_labels, num_unique);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K5b: nearest-seed assignment + histogram, then the label-0 swap
+// ----------------------------------------------------------------------------------------------
+template <int D>  // D > 0: channels held in registers; D == 0: generic (re-reads x through L1)
+__global__ void __launch_bounds__(128) assign_kernel(const float* __restrict__ X, long long sb, long long sd, long long n,
+                                                     int d, int m, const float* __restrict__ Z,
+                                                     const int* __restrict__ seed_labels, int* __restrict__ hist,
+                                                     int* __restrict__ labels_tmp) {
+  extern __shared__ float zs[];  // [m][d]
+  __shared__ int s_lab[UOC_MAX_SEEDS];
+  __shared__ int s_hist[UOC_MAX_SEEDS];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const float* Zb = Z + size_t(b) * m * d;
+  for (int e = tid; e < m * d; e += blockDim.x) zs[e] = Zb[e];
+  if (tid < UOC_MAX_SEEDS) { s_lab[tid] = tid < m ? seed_labels[size_t(b) * m + tid] : 0; s_hist[tid] = 0; }
+  __syncthreads();
+  const float* Xb = X + b * sb;
+  const long long pnt = (long long)blockIdx.x * blockDim.x + tid;
+  int label = -1;
+  if (pnt < n) {
+    float best = 0.f;
+    int bj = 0;
+    if (D > 0) {
+      float x[D > 0 ? D : 1];
+#pragma unroll
+      for (int k = 0; k < D; ++k) x[k] = __ldg(Xb + k * sd + pnt);
+      for (int j = 0; j < m; ++j) {
+        const float4* zj = reinterpret_cast<const float4*>(zs + j * D);
+        float acc = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < D / 4; ++k4) {
+          const float4 zv = zj[k4];
+          acc = fmaf(x[4 * k4 + 0], zv.x, acc);
+          acc = fmaf(x[4 * k4 + 1], zv.y, acc);
+          acc = fmaf(x[4 * k4 + 2], zv.z, acc);
+          acc = fmaf(x[4 * k4 + 3], zv.w, acc);
+        }
+        const float dist = 0.5f * (1.0f - acc);
+        if (j == 0 || dist < best) { best = dist; bj = j; }   // first minimum (torch.argmin)
+      }
+    } else {
+      for (int j = 0; j < m; ++j) {
+        float acc = 0.f;
+        for (int k = 0; k < d; ++k) acc = fmaf(__ldg(Xb + k * sd + pnt), zs[j * d + k], acc);
+        const float dist = 0.5f * (1.0f - acc);
+        if (j == 0 || dist < best) { best = dist; bj = j; }
+      }
+    }
+    label = s_lab[bj];
+    labels_tmp[size_t(b) * n + pnt] = label;
+  }
+  // warp-aggregated histogram
+  const unsigned int active = __ballot_sync(0xffffffffu, label >= 0);
+  if (label >= 0) {
+    const unsigned int peers = __match_any_sync(active, label);
+    if ((tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[label], __popc(peers));
+  }
+  __syncthreads();
+  if (tid < UOC_MAX_SEEDS && s_hist[tid] != 0) atomicAdd(hist + size_t(b) * m + tid, s_hist[tid]);
+}
+
+// swap label 0 <-> argmax_i count[i], i in range(num_unique)   (mean_shift.py:217-227)
+__global__ void __launch_bounds__(256) relabel_kernel(const int* __restrict__ labels_tmp, const int* __restrict__ hist,
+                                                      const int* __restrict__ num_unique, long long n, int m,
+                                                      int* __restrict__ labels_out) {
+  __shared__ int s_max;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    int num = num_unique[b];
+    if (num > m) num = m;
+    int best = 0, bi = 0;
+    for (int i = 0; i < num; ++i) {
+      const int c = hist[size_t(b) * m + i];
+      if (i == 0 || c > best) { best = c; bi = i; }
+    }
+    s_max = bi;
+  }
+  __syncthreads();
+  const int lm = s_max;
+  const long long pnt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pnt < n) {
+    int l = labels_tmp[size_t(b) * n + pnt];
+    if (lm != 0) {
+      if (l == 0) l = lm;
+      else if (l == lm) l = 0;
+    }
+    labels_out[size_t(b) * n + pnt] = l;
+  }
+}
+
+int launch_assign(const float* X, const ClusterShape& s, const float* Z, const int* seed_labels, const int* num_unique,
+                  int* hist, int* labels_tmp, int* labels_out, cudaStream_t stream) {
+  UOC_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * size_t(s.batch) * s.m, stream));
+  const size_t smem = sizeof(float) * size_t(s.m) * s.d;
+  const dim3 grid(static_cast<unsigned int>((s.n + 127) / 128), s.batch);
+  static bool attr_done = false;
+  if (!attr_done) {
+    UOC_CUDA(cudaFuncSetAttribute(assign_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    UOC_CUDA(cudaFuncSetAttribute(assign_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    UOC_CUDA(cudaFuncSetAttribute(assign_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_done = true;
+  }
+  if (s.d == 64)
+    assign_kernel<64><<<grid, 128, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, Z, seed_labels, hist, labels_tmp);
+  else if (s.d == 128)
+    assign_kernel<128><<<grid, 128, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, Z, seed_labels, hist, labels_tmp);
+  else
+    assign_kernel<0><<<grid, 128, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, Z, seed_labels, hist, labels_tmp);
+  UOC_CHECK_LAUNCH();
+  const dim3 grid2(static_cast<unsigned int>((s.n + 255) / 256), s.batch);
+  relabel_kernel<<<grid2, 256, 0, stream>>>(labels_tmp, hist, num_unique, s.n, s.m, labels_out);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// pack: fp32 planar [d][n] -> bf16 pixel-major [n][d]
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict__ X, long long sb, long long sd,
+                                                        long long n, int d, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float tile[];  // [d][65]
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * 64;
+  const float* Xb = X + b * sb;
+  for (int e = tid; e < d * 64; e += blockDim.x) {
+    const int k = e >> 6, pp = e & 63;
+    tile[k * 65 + pp] = (p0 + pp < n) ? __ldg(Xb + k * sd + p0 + pp) : 0.f;
+  }
+  __syncthreads();
+  const int half = d >> 1;
+  uint32_t* o32 = reinterpret_cast<uint32_t*>(out + (size_t(b) * n + p0) * d);
+  for (int e = tid; e < half * 64; e += blockDim.x) {
+    const int pp = e / half, k2 = e % half;
+    if (p0 + pp < n) o32[size_t(pp) * half + k2] = pack_bf16x2(tile[(2 * k2) * 65 + pp], tile[(2 * k2 + 1) * 65 + pp]);
+  }
+}
+
+int launch_pack_bf16(const float* X, const ClusterShape& s, __nv_bfloat16* xb, cudaStream_t stream) {
+  if (s.d % 2 != 0) return fail(UOC_ERR_UNSUPPORTED, "d must be even");
+  const size_t smem = sizeof(float) * size_t(s.d) * 65;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    UOC_CUDA(cudaFuncSetAttribute(pack_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    configured = smem;
+  }
+  const dim3 grid(static_cast<unsigned int>((s.n + 63) / 64), s.batch);
+  pack_bf16_kernel<<<grid, 256, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, xb);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+}  // namespace uoc

@@ -1,0 +1,57 @@
+// Internal interface of the backbone kernels (conv_tc.cu, backbone_kernels.cu).
+#pragma once
+#include "uoc_common.cuh"
+
+namespace uoc {
+
+// One convolution problem on NHWC bf16 activations, evaluated as an implicit GEMM
+//   M = N*Ho*Wo output pixels (tiles of 8 rows x 16 cols), N = Cout, K = taps*Cin.
+// Up to two independent "groups" (the RGB and the depth branch, different weights and buffers, same
+// shapes) are evaluated by one launch (gridDim.z).
+struct ConvGroup {
+  const void* x;          // [N][H][W][Cin] bf16
+  const void* w;          // [Cout][taps][Cin] bf16 (BN folded)
+  const float* bias;      // [Cout] fp32 (BN folded / fc bias)
+  const void* residual;   // [N][Ho][Wo][Cout] bf16 or nullptr
+  void* y;                // [N][Ho][Wo][Cout] bf16 (or fp32 when out_fp32)
+};
+
+struct ConvProblem {
+  int groups;             // 1 or 2
+  ConvGroup g[2];
+  int N, H, W, Cin, Cout;
+  int ksize;              // 1 or 3
+  int stride;             // 1 or 2
+  int dilation;           // 1, 2, 4
+  int relu;               // apply ReLU in the epilogue
+  int out_fp32;           // write fp32 instead of bf16
+};
+
+static inline int conv_out_dim(int in, int ksize, int stride, int dilation) {
+  const int pad = (ksize == 3) ? dilation : 0;   // "full" padding of lib/networks/resnet.py:24-41
+  return (in + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1;
+}
+
+// tcgen05 implicit-GEMM convolution (Cin % 64 == 0, Cout % 64 == 0)
+int launch_conv_tc(const ConvProblem& p, cudaStream_t stream);
+// fp32-accumulate SIMT validation convolution, same interface and data types
+int launch_conv_simt(const ConvProblem& p, cudaStream_t stream);
+
+// stem: conv 7x7 s2 p3 (Cin = 3, fp32 NCHW input) + folded BN + ReLU -> bf16 NHWC [N][H/2][W/2][64]
+struct StemGroup {
+  const float* x;         // [N][3][H][W] fp32
+  const float* w;         // [64][7*7*3] fp32, k = (r*7 + s)*3 + c, BN folded
+  const float* bias;      // [64]
+  void* y;                // [N][H/2][W/2][64] bf16
+};
+int launch_stem(const StemGroup* g, int groups, int N, int H, int W, cudaStream_t stream);
+// maxpool 3x3 s2 p1 on bf16 NHWC, C = 64
+int launch_maxpool(const void* const* x, void* const* y, int groups, int N, int H, int W, int C, cudaStream_t stream);
+// head: (trunk_rgb + trunk_depth) [N][h][w][d] fp32 -> bilinear x8 (align_corners) -> L2 normalise
+//       -> fp32 NCHW [N][d][H][W]  and (optional) bf16 pixel-major [N][H*W][d]
+int launch_head(const float* a, const float* b, int N, int h, int w, int d, int H, int W, float* out_nchw,
+                void* out_bf16, cudaStream_t stream);
+// [N][h][w][d] fp32 NHWC -> [N][d][h][w] fp32 NCHW (debug / test hook)
+int launch_nhwc_to_nchw(const float* in, int N, int h, int w, int d, float* out, cudaStream_t stream);
+
+}  // namespace uoc
