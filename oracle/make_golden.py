@@ -1,0 +1,108 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference
+through oracle/ref_harness.py) on seeded synthetic inputs.  TEST INFRASTRUCTURE ONLY; run in the
+build container:  python oracle/make_golden.py
+
+The reference ships no golden vectors of its own, so these fixtures -- outputs of
+the reference itself -- are what pins the oracle and the CUDA path.  Inputs are regenerated from
+seeds by oracle/uoc_oracle.py's generators (deterministic torch CPU RNG), so the fixtures only store
+the seeds, small inputs and the reference outputs.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_harness as rh          # noqa: E402
+import uoc_oracle as O            # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CLUSTER_CASES = [
+    # name, H, W, d, objects, noise, seed, num_seeds, np_seed
+    ("cluster_a", 32, 48, 64, 4, 0.05, 11, 100, 3),
+    ("cluster_b", 40, 40, 64, 6, 0.04, 12, 100, 5),
+    ("cluster_c", 30, 44, 128, 3, 0.05, 13, 100, 7),
+    ("cluster_d", 24, 24, 64, 2, 0.05, 14, 40, 9),
+]
+
+
+def gen_cluster(ref):
+    for name, H, W, d, K, noise, seed, m, npseed in CLUSTER_CASES:
+        feats, gt = O.synthetic_clustered_features(H, W, d, K, noise, seed)
+        X = feats[0].view(d, -1).t()
+        np.random.seed(npseed)
+        first = np.random.randint(0, H * W)
+        np.random.seed(npseed)
+        labels, selected = ref.mean_shift.mean_shift_smart_init(X, kappa=20, num_seeds=m, max_iters=10, metric='cosine')
+        # intermediates through the reference's own sub-functions
+        np.random.seed(npseed)
+        seeds, sel2 = ref.mean_shift.select_smart_seeds(X, m, return_selected_indices=True, metric='cosine')
+        assert torch.equal(sel2, selected)
+        seed_labels, Z = ref.mean_shift.mean_shift_with_seeds(X, seeds, 20, max_iters=10, metric='cosine')
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), H=H, W=W, d=d, objects=K, noise=noise, seed=seed,
+                            num_seeds=m, first_index=first, features=feats.numpy(), gt=gt.numpy(),
+                            labels=labels.numpy(), selected=selected.numpy(), Z=Z.numpy(),
+                            seed_labels=seed_labels.numpy())
+        print(name, "labels", np.unique(labels.numpy()).tolist())
+
+
+def gen_two_stage(ref):
+    H, W = 96, 128
+    feats, gt = O.synthetic_clustered_features(H, W, 64, 4, 0.05, seed=21)
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed=22)
+    xyz[:, 2, :10, :] = 0          # some invalid depth so that filter_labels_depth has something to see
+
+    def net(i, l, dd):
+        return feats
+
+    def net_crop(i, l, dd):
+        return torch.cat([O.synthetic_clustered_features(224, 224, 64, 2, 0.05, seed=30 + k)[0] for k in range(i.shape[0])], 0)
+
+    np.random.seed(3)
+    n1 = [np.random.randint(0, H * W)]
+    np.random.seed(3)
+    with rh.cpu_cuda_identity():
+        rgb_c, mask_c, rois, depth_c = None, None, None, None
+        out_label, refined = ref.test_dataset.test_sample({'image_color': img, 'depth': xyz}, net, net_crop)
+    # also record the crop stage in isolation (reference functions)
+    rgb_c, mask_c, rois, depth_c = ref.test_dataset.crop_rois(img, out_label.clone(), xyz)
+    np.random.seed(3)
+    np.random.randint(0, H * W)
+    firsts_crop = [int(np.random.randint(0, 224 * 224)) for _ in range(rgb_c.shape[0])]
+    np.savez_compressed(os.path.join(OUT, "two_stage.npz"), H=H, W=W, feat_seed=21, frame_seed=22, crop_seed0=30,
+                        first_index=n1[0], first_indices_crop=np.array(firsts_crop), out_label=out_label.numpy(),
+                        refined=refined.numpy(), rois=rois.numpy(), mask_crops_sum=mask_c.sum((1, 2)).numpy(),
+                        rgb_crops_mean=rgb_c.mean((1, 2, 3)).numpy(), depth_crops_mean=depth_c.mean((1, 2, 3)).numpy())
+    print("two_stage", np.unique(out_label.numpy()).tolist(), np.unique(refined.numpy()).tolist(), rois.numpy().tolist())
+
+
+def gen_backbone(ref):
+    from unseenobjectclustering_b200.networks import random_state_dict
+    for name, H, W, wseed, fseed in (("backbone_a", 64, 96, 5, 6), ("backbone_b", 48, 80, 7, 8)):
+        sd = O.randomise_bn_(random_state_dict(64, seed=wseed), wseed + 1000)   # non-trivial BN: exercises the folding
+        net = rh.build_network(64, state_dict=sd)
+        missing = [k for k, v in net.state_dict().items() if k in sd and not torch.equal(v, sd[k])]
+        assert not missing, missing[:5]
+        img, xyz = O.synthetic_rgbd_frame(H, W, seed=fseed)
+        with torch.no_grad():
+            feats = net(img, None, xyz)
+            ta = net.fcn.resnet34_8s(img)
+            tb = net.fcn_depth.resnet34_8s(xyz)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), H=H, W=W, weight_seed=wseed, frame_seed=fseed,
+                            trunk_rgb=ta.numpy(), trunk_depth=tb.numpy(), features_sub=feats[:, :, ::4, ::4].numpy(),
+                            features_sum=feats.double().sum().item())
+        print(name, ta.shape, float(ta.abs().mean()), float(tb.abs().mean()))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    ref = rh.load()
+    gen_cluster(ref)
+    gen_two_stage(ref)
+    gen_backbone(ref)

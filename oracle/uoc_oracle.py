@@ -370,6 +370,22 @@ def synthetic_rgbd_frame(H=480, W=640, seed=0):
     return img, xyz
 
 
+def randomise_bn_(sd, seed):
+    """Give every BatchNorm of a reference-format state_dict non-trivial statistics / affine terms
+    (and the fc a bias) so that BN folding is exercised.  In place; returns sd."""
+    g = torch.Generator().manual_seed(int(seed))
+    for k in list(sd.keys()):
+        if k.endswith("running_mean"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.05
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(sd[k].shape, generator=g) * 0.5 + 0.75
+        elif k.endswith("bn1.weight") or k.endswith("bn2.weight") or k.endswith("downsample.1.weight"):
+            sd[k] = torch.rand(sd[k].shape, generator=g) * 0.4 + 0.8
+        elif k.endswith("bn1.bias") or k.endswith("bn2.bias") or k.endswith("downsample.1.bias") or k.endswith("fc.bias"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.05
+    return sd
+
+
 def labels_equal_up_to_permutation(a, b):
     """True iff integer label maps a, b are identical up to a relabelling that fixes label 0
     (0 = background / largest cluster is special downstream)."""

@@ -1,0 +1,130 @@
+"""GPU parity tests of the backbone: the tcgen05 implicit-GEMM convolution against torch's
+convolution on bf16-rounded operands, and the whole two-branch ResNet34-8s against the golden
+fixtures written by the unmodified reference (tolerance: 1e-3 cosine distance, BASELINE.json)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import uoc_oracle as O
+from conftest import GOLDEN
+from unseenobjectclustering_b200 import _lib
+from unseenobjectclustering_b200 import networks as NW
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CONV_CASES = [
+    # Cin, Cout, k, stride, dil, H, W, N
+    (64, 64, 3, 1, 1, 40, 56, 2),
+    (64, 64, 3, 1, 1, 30, 44, 1),      # ragged tiles (H % 8, W % 16 != 0)
+    (64, 128, 3, 2, 1, 40, 56, 2),     # stride 2 (TMA element strides)
+    (64, 128, 1, 2, 1, 40, 56, 2),     # 1x1 stride-2 downsample
+    (64, 128, 3, 2, 1, 31, 45, 1),     # stride 2, odd sizes
+    (128, 256, 3, 1, 2, 20, 28, 2),    # dilation 2
+    (256, 512, 3, 1, 4, 20, 28, 1),    # dilation 4
+    (128, 256, 1, 1, 1, 20, 28, 1),
+    (512, 64, 1, 1, 1, 20, 28, 2),     # fc shape
+    (512, 512, 3, 1, 4, 60, 80, 1),    # layer4 at 640x480
+]
+
+
+def _conv_call(x, w, bias, res, N, H, W, Cin, Cout, k, stride, dil, relu, flags):
+    lib = _lib.load()
+    pad = dil if k == 3 else 0
+    Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=DEV)
+    st = lib.uoc_conv2d_bf16(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(res), _lib.ptr(y), N, H, W, Cin, Cout, k,
+                             stride, dil, relu, flags | _lib.FLAG_SYNC_CHECK, _lib.stream_ptr(torch.device(DEV)))
+    _lib.check(st, "uoc_conv2d_bf16")
+    return y
+
+
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_CONV_SIMT], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
+def test_conv_matches_torch(case, flags):
+    Cin, Cout, k, stride, dil, H, W, N = case
+    g = torch.Generator().manual_seed(Cin + Cout + k + H)
+    x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(Cout, k * k, Cin, generator=g) * (1.0 / np.sqrt(k * k * Cin))).to(torch.bfloat16)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    pad = dil if k == 3 else 0
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().view(Cout, k, k, Cin).permute(0, 3, 1, 2), bias, stride=stride,
+                   padding=pad, dilation=dil)
+    res = (torch.randn(ref.shape, generator=g) * 0.5).to(torch.bfloat16)
+    ref_res = torch.relu(ref + res.float())
+    xd, wd, bd = x.to(DEV), w.to(DEV), bias.to(DEV)
+    y0 = _conv_call(xd, wd, bd, None, N, H, W, Cin, Cout, k, stride, dil, 0, flags).float().cpu().permute(0, 3, 1, 2)
+    err0 = (y0 - ref).abs().max().item()
+    assert err0 < 0.02 * max(1.0, ref.abs().max().item()), err0      # bf16 output rounding (2^-9 relative)
+    resd = res.permute(0, 2, 3, 1).contiguous().to(DEV)
+    y1 = _conv_call(xd, wd, bd, resd, N, H, W, Cin, Cout, k, stride, dil, 1, flags).float().cpu().permute(0, 3, 1, 2)
+    err1 = (y1 - ref_res).abs().max().item()
+    assert err1 < 0.02 * max(1.0, ref_res.abs().max().item()), err1
+    assert (y1 >= 0).all()
+
+
+def _golden_net(g, flags):
+    sd = O.randomise_bn_(NW.random_state_dict(64, seed=int(g["weight_seed"])), int(g["weight_seed"]) + 1000)
+    net = NW.seg_resnet34_8s_embedding(2, 64, sd).to(DEV)
+    net.flags = flags | _lib.FLAG_SYNC_CHECK
+    return net, sd
+
+
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_CONV_SIMT], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("name", ["backbone_a", "backbone_b"])
+def test_backbone_matches_reference_golden(name, flags):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    H, W = int(g["H"]), int(g["W"])
+    net, _ = _golden_net(g, flags)
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed=int(g["frame_seed"]))
+    f = net(img.to(DEV), None, xyz.to(DEV))
+    assert f.shape == (1, 64, H, W) and f.dtype == torch.float32 and f.is_cuda
+    ta = net.read_trunk(0, 1, H, W).cpu().numpy()
+    tb = net.read_trunk(1, 1, H, W).cpu().numpy()
+    for got, want in ((ta, g["trunk_rgb"]), (tb, g["trunk_depth"])):
+        rel = np.abs(got - want).max() / np.abs(want).max()
+        assert rel < 0.03, rel                                   # bf16 activations through 36 layers
+    fc = f.cpu()
+    assert (fc.norm(dim=1) - 1).abs().max() < 1e-4
+    sub = fc[:, :, ::4, ::4].numpy()
+    cosd = 1.0 - (sub * g["features_sub"]).sum(1)
+    assert np.abs(cosd).max() < 1e-3, np.abs(cosd).max()          # BASELINE.json tolerance
+
+
+def test_backbone_full_frame_vs_oracle_and_bf16_copy():
+    from unseenobjectclustering_b200 import mean_shift as MS
+    sd = O.randomise_bn_(NW.random_state_dict(64, seed=3), 1003)
+    net = NW.seg_resnet34_8s_embedding(2, 64, sd).to(DEV)
+    net.flags = _lib.FLAG_SYNC_CHECK
+    img, xyz = O.synthetic_rgbd_frame(480, 640, seed=1)
+    f = net(img.to(DEV), None, xyz.to(DEV))
+    want = O.OracleSegNet(sd)(img, None, xyz)
+    cosd = (1.0 - (f.cpu() * want).sum(1)).abs().max().item()
+    assert cosd < 1e-3, cosd
+    xb = MS._lookup_bf16(f)
+    assert xb is not None and xb.shape == (1, 480 * 640, 64)
+    back = xb.float().view(1, 480, 640, 64).permute(0, 3, 1, 2)
+    assert (back - f).abs().max().item() < 1e-2
+    # batch of 2 crops-like inputs == two single calls
+    i2, x2 = O.synthetic_rgbd_frame(224, 224, seed=2)
+    i3, x3 = O.synthetic_rgbd_frame(224, 224, seed=3)
+    fb = net(torch.cat([i2, i3]).to(DEV), None, torch.cat([x2, x3]).to(DEV)).cpu()
+    f2 = net(i2.to(DEV), None, x2.to(DEV)).cpu()
+    f3 = net(i3.to(DEV), None, x3.to(DEV)).cpu()
+    assert torch.equal(fb[0], f2[0]) and torch.equal(fb[1], f3[0])
+
+
+def test_module_drop_in_behaviour():
+    net = NW.seg_resnet34_8s_embedding(2, 64, None).cuda(0)
+    dp = torch.nn.DataParallel(net, device_ids=[0]).cuda(0)
+    dp.eval()
+    img, xyz = O.synthetic_rgbd_frame(64, 96, seed=0)
+    f = dp(img.cuda(), None, xyz.cuda()).detach()
+    assert f.shape == (1, 64, 64, 96)
+    assert (f.norm(dim=1) - 1).abs().max() < 1e-4
+    _ = f[0, 0::3]      # the indexing the reference's visualisation does

@@ -1,0 +1,182 @@
+"""GPU parity tests of the clustering path, through the C ABI (ctypes), against the oracles.
+Bit-exact for index / label work against the canonical-order C oracle; tolerance (stated per
+test) for the floating-point mean-shift loop; golden fixtures = outputs of the unmodified reference."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import uoc_oracle as O
+import uoc_oracle_c as C
+from conftest import GOLDEN
+from unseenobjectclustering_b200 import _lib
+from unseenobjectclustering_b200 import mean_shift as MS
+from unseenobjectclustering_b200 import test_dataset as TD
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _field(H, W, d, K, noise, seed):
+    feats, gt = O.synthetic_clustered_features(H, W, d, K, noise, seed)
+    return feats, gt
+
+
+@pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 100), (30, 44, 128, 100), (24, 24, 64, 40),
+                                     (60, 80, 32, 17), (120, 160, 64, 100)])
+def test_select_seeds_bit_exact(H, W, d, m):
+    feats, _ = _field(H, W, d, 4, 0.05, seed=H * 7 + d)
+    Xp = feats[0].reshape(d, -1).numpy()
+    first = (H * W) // 3
+    sel_o, seeds_o = C.select_seeds(Xp, m, first)
+    X = feats.to(DEV)[0].view(d, -1).t()
+    seeds, sel = MS.select_smart_seeds(X, m, return_selected_indices=True, first_index=first)
+    assert np.array_equal(sel.numpy(), sel_o)
+    assert np.array_equal(seeds.cpu().numpy(), seeds_o)
+    assert sel[0] == first and len(set(sel.tolist())) == m
+
+
+@pytest.mark.parametrize("flags,tol", [(0, 2e-5), (_lib.FLAG_LOOP_SIMT, 2e-6)])
+@pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 50), (30, 44, 128, 100), (96, 128, 64, 100)])
+def test_hill_climb_vs_double_oracle(H, W, d, m, flags, tol):
+    """Cosine distance between converged seeds and the double-precision oracle:
+    tcgen05 loop (bf16 operands, fp32 accumulate) <= 2e-5, fp32 SIMT loop <= 2e-6."""
+    feats, _ = _field(H, W, d, 4, 0.05, seed=3 + H)
+    Xp = feats[0].reshape(d, -1).numpy()
+    _, seeds = C.select_seeds(Xp, m, 5)
+    Zo = C.hill_climb(Xp, seeds, 20.0, 10)
+    X = feats.to(DEV)[0].view(d, -1).t()
+    Z = MS.seed_hill_climbing_ball(X, torch.from_numpy(seeds).to(DEV), 20.0, 10, flags=flags).cpu().numpy()
+    assert np.isfinite(Z).all()
+    cosd = 1.0 - (Z * Zo).sum(1)
+    assert np.abs(cosd).max() < tol, np.abs(cosd).max()
+    assert np.abs(np.linalg.norm(Z, axis=1) - 1).max() < 1e-5
+
+
+def test_hill_climb_one_iteration_matches_torch():
+    feats, _ = _field(64, 64, 64, 3, 0.05, seed=9)
+    X = feats[0].view(64, -1).t()
+    seeds, _ = O.select_seeds(X, 100, 7)
+    Zt = O.hill_climb(X, seeds, 20.0, 1)
+    Z = MS.seed_hill_climbing_ball(X.to(DEV), seeds.to(DEV), 20.0, 1).cpu()
+    assert (1 - (Z * Zt).sum(1)).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("m,d", [(100, 64), (100, 128), (37, 64), (128, 32)])
+def test_label_seeds_bit_exact(m, d):
+    rng = np.random.RandomState(m + d)
+    for trial in range(6):
+        base = rng.randn(6, d).astype(np.float32)
+        Z = base[rng.randint(0, 6, m)] + (0.02 + 0.03 * trial) * rng.randn(m, d).astype(np.float32)
+        Z /= np.linalg.norm(Z, axis=1, keepdims=True)
+        lo, uo = C.label_seeds(Z, 0.04)
+        lg, ug = MS.connected_components(torch.from_numpy(Z).to(DEV), 0.04, return_num_unique=True)
+        assert np.array_equal(lg.numpy(), lo), trial
+        assert ug == uo
+
+
+@pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 33), (30, 44, 128, 100), (20, 30, 32, 10)])
+def test_assign_bit_exact(H, W, d, m):
+    feats, _ = _field(H, W, d, 4, 0.05, seed=21 + d)
+    Xp = feats[0].reshape(d, -1).numpy()
+    _, seeds = C.select_seeds(Xp, m, 1)
+    Z = C.hill_climb(Xp, seeds, 20.0, 3)
+    sl, uniq = C.label_seeds(Z, 0.04)
+    lo = C.assign(Xp, Z, sl, uniq)
+    X = feats.to(DEV)[0].view(d, -1).t()
+    lg = MS.assign_labels(X, torch.from_numpy(Z).to(DEV), torch.from_numpy(sl), uniq)
+    assert np.array_equal(lg.numpy(), lo)
+    # gapped labels exercise the range(len(unique)) histogram quirk
+    sl2 = (sl * 2).astype(np.int32)
+    lo2 = C.assign(Xp, Z, sl2, uniq)
+    lg2 = MS.assign_labels(X, torch.from_numpy(Z).to(DEV), torch.from_numpy(sl2), uniq)
+    assert np.array_equal(lg2.numpy(), lo2)
+
+
+FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "cluster_*.npz")))
+
+
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_LOOP_SIMT])
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p) for p in FIXTURES])
+def test_full_clustering_matches_reference_golden(path, flags):
+    g = np.load(path)
+    feats = torch.from_numpy(g["features"]).to(DEV)
+    m = int(g["num_seeds"])
+    labels, sel, Z, sl = MS.cluster_fields(feats, m, first_indices=[int(g["first_index"])], flags=flags | _lib.FLAG_SYNC_CHECK,
+                                           return_seeds=True)
+    assert np.array_equal(sel[0].cpu().numpy(), g["selected"])
+    cosd = 1.0 - (Z[0].cpu().numpy() * g["Z"]).sum(1)
+    assert np.abs(cosd).max() < 2e-5
+    assert O.labels_equal_up_to_permutation(labels[0].cpu().numpy(), g["labels"])
+    # on these inputs even the ids agree
+    assert np.array_equal(sl[0].cpu().numpy(), g["seed_labels"])
+    assert np.array_equal(labels[0].cpu().numpy(), g["labels"])
+
+
+def test_reference_api_surface_types():
+    g = np.load(FIXTURES[0])
+    feats = torch.from_numpy(g["features"]).to(DEV)
+    np.random.seed(3)
+    expect_first = np.random.randint(0, feats.shape[2] * feats.shape[3])
+    np.random.seed(3)
+    out_label, picked = TD.clustering_features(feats, num_seeds=int(g["num_seeds"]))
+    assert out_label.dtype == torch.float32 and out_label.device.type == "cpu" and out_label.shape == (1, int(g["H"]), int(g["W"]))
+    assert len(picked) == 1 and picked[0].dtype == torch.int64 and picked[0].device.type == "cpu"
+    assert int(picked[0][0]) == expect_first == int(g["first_index"])
+    assert np.array_equal(out_label.numpy().ravel(), g["labels"].astype(np.float32))
+    X = feats[0].view(feats.shape[1], -1).t()
+    lab, sel = MS.mean_shift_smart_init(X, kappa=20, num_seeds=int(g["num_seeds"]), max_iters=10, metric='cosine',
+                                        first_index=int(g["first_index"]))
+    assert lab.dtype == torch.int64 and lab.device.type == "cpu" and np.array_equal(lab.numpy(), g["labels"])
+    # pixel-major input (non planar strides) is accepted too
+    lab2, _ = MS.mean_shift_smart_init(X.contiguous(), kappa=20, num_seeds=int(g["num_seeds"]), max_iters=10,
+                                       first_index=int(g["first_index"]))
+    assert torch.equal(lab, lab2)
+
+
+def test_batched_call_equals_per_item_calls():
+    fields = [_field(40, 56, 64, 3, 0.05, seed=40 + k)[0] for k in range(5)]
+    batch = torch.cat(fields, 0).to(DEV)
+    firsts = [11, 222, 333, 444, 555]
+    lb, sb = MS.cluster_fields(batch, 100, first_indices=firsts, flags=_lib.FLAG_SYNC_CHECK)
+    for k in range(5):
+        l1, s1 = MS.cluster_fields(fields[k].to(DEV), 100, first_indices=[firsts[k]], flags=_lib.FLAG_SYNC_CHECK)
+        assert torch.equal(lb[k], l1[0]) and torch.equal(sb[k], s1[0])
+
+
+def test_full_resolution_properties():
+    """640x480x64 (BASELINE config 2): ground-truth recovery up to permutation, determinism,
+    distinct seeds, label 0 = largest cluster."""
+    feats, gt = _field(480, 640, 64, 6, 0.05, seed=0)
+    f = feats.to(DEV)
+    l1, s1 = MS.cluster_fields(f, 100, first_indices=[71530], flags=_lib.FLAG_SYNC_CHECK)
+    l2, s2 = MS.cluster_fields(f, 100, first_indices=[71530], flags=_lib.FLAG_SYNC_CHECK)
+    assert torch.equal(l1, l2) and torch.equal(s1, s2)
+    lab = l1[0].cpu().numpy()
+    assert O.labels_equal_up_to_permutation(lab, gt.numpy().ravel())
+    counts = np.bincount(lab)
+    assert counts.argmax() == 0
+    sel = s1[0].cpu().numpy()
+    assert sel[0] == 71530 and len(set(sel.tolist())) == 100
+    # first 8 seeds agree with the canonical oracle (cheap partial check at full size)
+    sel_o, _ = C.select_seeds(feats[0].reshape(64, -1).numpy(), 8, 71530)
+    assert np.array_equal(sel[:8], sel_o)
+
+
+def test_high_res_128d_30_iters():
+    """BASELINE config 5 shape class (d = 128, 30 iterations) at reduced resolution."""
+    feats, gt = _field(180, 240, 128, 8, 0.04, seed=5)
+    l, s = MS.cluster_fields(feats.to(DEV), 100, max_iters=30, first_indices=[5], flags=_lib.FLAG_SYNC_CHECK)
+    assert O.labels_equal_up_to_permutation(l[0].cpu().numpy(), gt.numpy().ravel())
+
+
+def test_bad_arguments_fail_loudly():
+    f = torch.zeros(1, 64, 8, 8, device=DEV)
+    with pytest.raises(_lib.UocError):
+        MS.cluster_fields(f, 200)                      # > UOC_MAX_SEEDS
+    with pytest.raises(_lib.UocError):
+        MS.cluster_fields(f, 10, first_indices=[64])   # first seed out of range
+    with pytest.raises(_lib.UocError):
+        MS.cluster_fields(f.cpu(), 10)

@@ -1,0 +1,95 @@
+"""Host-side plumbing of the product package checked against the oracle on CPU tensors
+(these functions are device agnostic tensor plumbing; the CUDA kernels are covered by -m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+import uoc_oracle as O
+from unseenobjectclustering_b200 import networks as N
+from unseenobjectclustering_b200 import test_dataset as TD
+
+
+def _labels(H, W, K, seed):
+    _, gt = O.synthetic_clustered_features(H, W, 8, K, 0.05, seed)
+    return gt
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_filter_labels_depth_matches_oracle(seed):
+    H, W = 60, 80
+    lab = _labels(H, W, 5, seed).float()[None]
+    _, xyz = O.synthetic_rgbd_frame(H, W, seed)
+    g = torch.Generator().manual_seed(seed)
+    xyz[:, 2][torch.rand(1, H, W, generator=g) < 0.3] = 0
+    xyz[:, 2, : H // 2, : W // 2] = 0
+    for thr in (0.5, 0.8):
+        a = O.filter_labels_depth(lab, xyz, thr)
+        b = TD.filter_labels_depth(lab, xyz, thr)
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_crop_rois_matches_oracle(seed):
+    H, W = 96, 128
+    lab = _labels(H, W, 4, seed).float()[None]
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed)
+    ra, ma, roa, da = O.crop_rois(img, lab.clone(), xyz)
+    rb, mb, rob, db = TD.crop_rois(img, lab.clone(), xyz)
+    assert torch.equal(roa, rob)
+    assert torch.equal(ma, mb)
+    assert torch.allclose(ra, rb, atol=1e-6) and torch.allclose(da, db, atol=1e-6)
+    # no depth
+    ra, ma, roa, da = O.crop_rois(img, lab.clone(), None)
+    rb, mb, rob, db = TD.crop_rois(img, lab.clone(), None)
+    assert da is None and db is None and torch.equal(roa, rob)
+
+
+def test_crop_rois_empty():
+    img, xyz = O.synthetic_rgbd_frame(32, 48, 0)
+    r, m, rois, d = TD.crop_rois(img, torch.zeros(1, 32, 48), xyz)
+    assert r.shape[0] == 0 and rois.shape == (0, 4)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_match_label_crop_matches_oracle(seed):
+    H, W = 96, 128
+    lab = _labels(H, W, 4, seed).float()[None]
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed)
+    rgb_c, mask_c, rois, depth_c = O.crop_rois(img, lab.clone(), xyz)
+    K = rgb_c.shape[0]
+    crops = torch.stack([_labels(224, 224, 3, 50 + seed * 10 + k).float() for k in range(K)])
+    a, la = O.match_label_crop(lab, crops.clone(), mask_c, rois, depth_c)
+    b, lb = TD.match_label_crop(lab, crops.clone(), mask_c, rois, depth_c)
+    assert torch.equal(a, b)
+    assert torch.equal(la, lb)
+    a, _ = O.match_label_crop(lab, crops.clone(), mask_c, rois, None)
+    b, _ = TD.match_label_crop(lab, crops.clone(), mask_c, rois, None)
+    assert torch.equal(a, b)
+
+
+def test_module_state_dict_roundtrip_and_key_filter():
+    sd = O.randomise_bn_(N.random_state_dict(64, seed=1), 2)
+    net = N.seg_resnet34_8s_embedding(2, 64, sd)
+    out = net.state_dict()
+    assert list(out.keys()) == [k for k, _ in N.reference_state_dict_keys(64)]
+    for k in sd:
+        assert torch.equal(out[k], sd[k]), k
+    # 'module.' prefix, {'model': ...} wrapper, wrong shapes silently skipped (SEG.py:145-152)
+    wrapped = {"model": {"module." + k: v for k, v in sd.items()}}
+    wrapped["model"]["module.fcn.resnet34_8s.fc.weight"] = torch.zeros(3, 3)
+    net2 = N.seg_resnet34_8s_embedding(2, 64, wrapped)
+    out2 = net2.state_dict()
+    assert torch.equal(out2["fcn.resnet34_8s.conv1.weight"], sd["fcn.resnet34_8s.conv1.weight"])
+    assert out2["fcn.resnet34_8s.fc.weight"].shape == (64, 512, 1, 1)
+    assert not net.training
+    with pytest.raises(NotImplementedError):
+        net.train()
+    dp = torch.nn.DataParallel(net2, device_ids=None) if False else net2   # constructing DataParallel needs a GPU
+    assert dp is net2
+
+
+def test_inputs_must_be_cuda():
+    from unseenobjectclustering_b200 import _lib
+    net = N.seg_resnet34_8s_embedding(2, 64, None)
+    with pytest.raises(_lib.UocError):
+        net(torch.zeros(1, 3, 32, 32), None, torch.zeros(1, 3, 32, 32))

@@ -1,0 +1,163 @@
+"""Pin the oracles: torch oracle == golden fixtures (outputs of the unmodified reference), torch
+oracle == reference run live (only where /root/reference exists), C oracle == torch oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import uoc_oracle as O
+import uoc_oracle_c as C
+import ref_harness as rh
+from conftest import GOLDEN
+
+CLUSTER_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "cluster_*.npz")))
+
+
+def _load(path):
+    z = np.load(path)
+    return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("path", CLUSTER_FIXTURES, ids=[os.path.basename(p) for p in CLUSTER_FIXTURES])
+def test_torch_oracle_matches_golden_clustering(path):
+    g = _load(path)
+    feats = torch.from_numpy(g["features"])
+    d = int(g["d"])
+    X = feats[0].view(d, -1).t()
+    labels, sel, seeds, Z, sl = O.mean_shift_smart_init(X, num_seeds=int(g["num_seeds"]), first_index=int(g["first_index"]),
+                                                        return_all=True)
+    assert np.array_equal(sel.numpy(), g["selected"])
+    assert np.array_equal(labels.numpy(), g["labels"])           # bit-exact: same torch ops as the reference
+    assert np.array_equal(sl.numpy(), g["seed_labels"])
+    assert np.allclose(Z.numpy(), g["Z"], atol=1e-6)
+    # the synthetic generator is deterministic
+    f2, gt2 = O.synthetic_clustered_features(int(g["H"]), int(g["W"]), d, int(g["objects"]), float(g["noise"]), int(g["seed"]))
+    assert torch.equal(f2, feats)
+    assert O.labels_equal_up_to_permutation(labels.numpy(), gt2.numpy().ravel()) or int(g["objects"]) + 1 != len(np.unique(g["labels"]))
+
+
+@pytest.mark.parametrize("path", CLUSTER_FIXTURES, ids=[os.path.basename(p) for p in CLUSTER_FIXTURES])
+def test_c_oracle_matches_golden_clustering(path):
+    g = _load(path)
+    d = int(g["d"])
+    Xp = g["features"][0].reshape(d, -1)
+    res = C.cluster(Xp, int(g["num_seeds"]), int(g["first_index"]))
+    # farthest point sampling: identical indices on these inputs (margins >> fp32 rounding)
+    assert np.array_equal(res["selected"], g["selected"])
+    cosd = 1.0 - (res["Z"] * g["Z"]).sum(1)
+    assert np.abs(cosd).max() < 1e-5
+    assert np.array_equal(res["seed_labels"], g["seed_labels"])
+    assert np.array_equal(res["labels"], g["labels"])
+
+
+def test_two_stage_oracle_matches_golden():
+    g = _load(os.path.join(GOLDEN, "two_stage.npz"))
+    H, W = int(g["H"]), int(g["W"])
+    feats, _ = O.synthetic_clustered_features(H, W, 64, 4, 0.05, seed=int(g["feat_seed"]))
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed=int(g["frame_seed"]))
+    xyz[:, 2, :10, :] = 0
+
+    def net(i, l, dd):
+        return feats
+
+    def net_crop(i, l, dd):
+        return torch.cat([O.synthetic_clustered_features(224, 224, 64, 2, 0.05, seed=int(g["crop_seed0"]) + k)[0]
+                          for k in range(i.shape[0])], 0)
+
+    a, b = O.test_sample(img, xyz, net, net_crop, [int(g["first_index"])], g["first_indices_crop"].tolist())
+    assert np.array_equal(a.numpy(), g["out_label"])
+    assert np.array_equal(b.numpy(), g["refined"])
+    rgb_c, mask_c, rois, depth_c = O.crop_rois(img, a.clone(), xyz)
+    assert np.array_equal(rois.numpy(), g["rois"])
+    assert np.allclose(mask_c.sum((1, 2)).numpy(), g["mask_crops_sum"])
+    assert np.allclose(rgb_c.mean((1, 2, 3)).numpy(), g["rgb_crops_mean"], atol=1e-6)
+    assert np.allclose(depth_c.mean((1, 2, 3)).numpy(), g["depth_crops_mean"], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["backbone_a", "backbone_b"])
+def test_backbone_oracle_matches_golden(name):
+    from unseenobjectclustering_b200.networks import random_state_dict
+    g = _load(os.path.join(GOLDEN, name + ".npz"))
+    sd = O.randomise_bn_(random_state_dict(64, seed=int(g["weight_seed"])), int(g["weight_seed"]) + 1000)
+    img, xyz = O.synthetic_rgbd_frame(int(g["H"]), int(g["W"]), seed=int(g["frame_seed"]))
+    net = O.OracleSegNet(sd)
+    with torch.no_grad():
+        ta = O.resnet34_8s_trunk(img, net.sd, "fcn.resnet34_8s.")
+        tb = O.resnet34_8s_trunk(xyz, net.sd, "fcn_depth.resnet34_8s.")
+    assert np.allclose(ta.numpy(), g["trunk_rgb"], atol=2e-5, rtol=1e-4)
+    assert np.allclose(tb.numpy(), g["trunk_depth"], atol=2e-5, rtol=1e-4)
+    f = net(img, None, xyz)
+    assert np.allclose(f[:, :, ::4, ::4].numpy(), g["features_sub"], atol=1e-5)
+    assert abs(f.double().sum().item() - float(g["features_sum"])) < 1e-2
+
+
+def test_label_seeds_quirks():
+    """Order dependence, overwrite of already-labelled seeds and label gaps."""
+    def unit(v):
+        v = np.asarray(v, dtype=np.float32)
+        return v / np.linalg.norm(v)
+    # chain a - b - c where a~b and b~c within eps but a !~ c: greedy, not transitive closure
+    ang = [0.0, 0.35, 0.70, 2.0]      # cosine distance 0.5(1-cos 0.35) = 0.0303 <= 0.04 ; 0.5(1-cos 0.7)=0.1176
+    Z = np.stack([unit([np.cos(a), np.sin(a), 0, 0]) for a in ang])
+    t = O.label_seeds(torch.from_numpy(Z), 0.04).numpy()
+    c, uniq = C.label_seeds(Z, 0.04)
+    assert np.array_equal(t, c)
+    assert t.tolist() == [0, 0, 0, 1] or t.tolist() == [0, 0, 1, 2]
+    assert uniq == len(np.unique(t))
+    rng = np.random.RandomState(0)
+    for trial in range(20):
+        base = rng.randn(5, 16).astype(np.float32)
+        Zr = base[rng.randint(0, 5, 60)] + 0.12 * rng.randn(60, 16).astype(np.float32)
+        Zr /= np.linalg.norm(Zr, axis=1, keepdims=True)
+        t = O.label_seeds(torch.from_numpy(Zr), 0.04).numpy()
+        c, uniq = C.label_seeds(Zr, 0.04)
+        # identical unless some pair sits within fp32 rounding of the threshold
+        dots = Zr @ Zr.T
+        margin = np.abs(0.5 * (1 - dots) - 0.04).min()
+        if margin > 1e-6:
+            assert np.array_equal(t, c), trial
+            assert uniq == len(np.unique(t))
+
+
+def test_assign_histogram_quirk_with_label_gaps():
+    rng = np.random.RandomState(1)
+    d, n, m = 16, 500, 6
+    Z = rng.randn(m, d).astype(np.float32)
+    Z /= np.linalg.norm(Z, axis=1, keepdims=True)
+    X = Z[rng.randint(0, m, n)] + 0.05 * rng.randn(n, d).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    seed_labels = np.array([0, 2, 2, 5, 5, 5], dtype=np.int32)       # gaps: unique = {0,2,5} -> num = 3
+    t = O.assign_and_relabel(torch.from_numpy(X), torch.from_numpy(Z), torch.from_numpy(seed_labels.astype(np.int64))).numpy()
+    c = C.assign(np.ascontiguousarray(X.T), Z, seed_labels, 3)
+    assert np.array_equal(t, c)
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not present (GPU box)")
+def test_torch_oracle_is_bit_identical_to_the_live_reference():
+    ref = rh.load()
+    for seed, (H, W, K) in enumerate([(36, 52, 3), (48, 48, 5)]):
+        feats, _ = O.synthetic_clustered_features(H, W, 64, K, 0.05, seed=100 + seed)
+        X = feats[0].view(64, -1).t()
+        np.random.seed(seed)
+        lr, sr = ref.mean_shift.mean_shift_smart_init(X, kappa=20, num_seeds=100, max_iters=10, metric='cosine')
+        np.random.seed(seed)
+        lo, so = O.mean_shift_smart_init(X)
+        assert torch.equal(lr, lo) and torch.equal(sr, so)
+        np.random.seed(seed)
+        a, _ = ref.test_dataset.clustering_features(feats, num_seeds=50)
+        np.random.seed(seed)
+        b, _ = O.clustering_features(feats, num_seeds=50)
+        assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not present (GPU box)")
+def test_state_dict_keys_match_the_reference_module():
+    from unseenobjectclustering_b200.networks import reference_state_dict_keys
+    net = rh.build_network(64)
+    ref_sd = net.state_dict()
+    ours = reference_state_dict_keys(64)
+    assert [k for k, _ in ours] == list(ref_sd.keys())
+    for k, shape in ours:
+        assert tuple(ref_sd[k].shape) == tuple(shape), k

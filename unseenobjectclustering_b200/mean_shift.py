@@ -1,0 +1,207 @@
+"""Host-side mirror of the reference's lib/utils/mean_shift.py on top of the CUDA C ABI.
+
+Same function names, argument meaning and return types as the reference (cosine metric, which is
+what every shipped config uses -- experiments/cfgs/*.yml `EMBEDDING_METRIC: cosine`); the arithmetic
+runs in libuoc_b200.so (farthest point sampling, tcgen05 mean-shift loop, greedy seed labelling,
+nearest-seed assignment).  PyTorch is used for device memory and streams only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+EMBEDDING_ALPHA = 0.02   # cfg.TRAIN.EMBEDDING_ALPHA default, lib/fcn/config.py:254
+
+_workspaces = {}
+_bf16_registry = {}      # data_ptr of a feature tensor -> (bf16 pixel-major copy, shape) made by the backbone
+
+
+def _workspace(device, nbytes):
+    """Grow-only uint8 scratch tensor per device (256-byte aligned by the caching allocator)."""
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def register_bf16_copy(features, xb):
+    """Called by the backbone module: remember the bf16 [N, H*W, C] copy written next to `features`."""
+    _bf16_registry.clear()   # one live entry is enough (single-threaded callers)
+    _bf16_registry[features.data_ptr()] = (xb, tuple(features.shape))
+
+
+def _lookup_bf16(features):
+    ent = _bf16_registry.get(features.data_ptr())
+    if ent is not None and ent[1] == tuple(features.shape):
+        return ent[0]
+    return None
+
+
+def _epsilon(epsilon=None):
+    return float(2 * EMBEDDING_ALPHA) if epsilon is None else float(epsilon)   # mean_shift.py:123
+
+
+def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indices=None, epsilon=None, flags=0,
+                   return_seeds=False):
+    """Cluster a batch of embedding fields in ONE library call.
+
+    features: [N, C, H, W] float32 CUDA tensor, unit norm over C (any batch stride; each item must
+    be planar-contiguous like the reference's network output).
+    first_indices: the per-item first seed (np.random.randint(0, n) of mean_shift.py:155); drawn
+    here from numpy's global RNG, in item order, when None.
+    Returns (labels int32 [N, H*W] CUDA, selected int64 [N, num_seeds] CUDA[, seeds, seed_labels]).
+    """
+    if not features.is_cuda:
+        raise _lib.UocError("features must be a CUDA tensor: there is no CPU path in this package")
+    if features.dtype != torch.float32:
+        raise _lib.UocError("features must be float32")
+    N, C, H, W = features.shape
+    n = H * W
+    if not (features.stride(3) == 1 and features.stride(2) == W and features.stride(1) == n):
+        features = features.contiguous()
+    lib = _lib.load()
+    dev = features.device
+    if first_indices is None:
+        first_indices = [np.random.randint(0, n) for _ in range(N)]
+    first = (ctypes.c_int64 * N)(*[int(v) for v in first_indices])
+    xb = _lookup_bf16(features)
+    with torch.cuda.device(dev):
+        nbytes = lib.uoc_meanshift_workspace_bytes(N, n, C, num_seeds)
+        ws = _workspace(dev, nbytes)
+        labels = torch.empty((N, n), dtype=torch.int32, device=dev)
+        selected = torch.empty((N, num_seeds), dtype=torch.int64, device=dev)
+        seeds = torch.empty((N, num_seeds, C), dtype=torch.float32, device=dev) if return_seeds else None
+        seed_labels = torch.empty((N, num_seeds), dtype=torch.int32, device=dev) if return_seeds else None
+        st = lib.uoc_meanshift_cluster(
+            _lib.ptr(features), features.stride(0), features.stride(1), _lib.ptr(xb), N, n, C, num_seeds,
+            float(kappa), int(max_iters), _epsilon(epsilon), ctypes.cast(first, ctypes.c_void_p), _lib.ptr(labels),
+            _lib.ptr(selected), _lib.ptr(seeds), _lib.ptr(seed_labels), _lib.ptr(ws), ws.numel(), int(flags),
+            _lib.stream_ptr(dev))
+        _lib.check(st, "uoc_meanshift_cluster")
+    if return_seeds:
+        return labels, selected, seeds, seed_labels
+    return labels, selected
+
+
+def _as_planar(X):
+    """[n, d] tensor -> (tensor, stride_d) with points contiguous (the reference passes the
+    transposed view of an NCHW feature map, strides (1, n): lib/fcn/test_dataset.py:54-55)."""
+    if X.stride(0) == 1 and X.stride(1) >= X.shape[0]:
+        return X, X.stride(1)
+    Xp = X.t().contiguous()          # [d, n]
+    return Xp.t(), Xp.stride(0)
+
+
+def mean_shift_smart_init(X, kappa, num_seeds=100, max_iters=10, metric='cosine', first_index=None, flags=0):
+    """lib/utils/mean_shift.py:192-229.  X: [n, d] CUDA float32 unit rows.  Returns
+    (cluster_labels int64 [n] on the CPU, selected_indices int64 [num_seeds] on the CPU), like the
+    reference."""
+    if metric != 'cosine':
+        raise NotImplementedError("only the cosine metric is implemented (all shipped configs use it)")
+    n, d = X.shape
+    Xp, stride_d = _as_planar(X)
+    feats = torch.as_strided(Xp, (1, d, 1, n), (d * stride_d, stride_d, n, 1))
+    fi = None if first_index is None else [first_index]
+    labels, selected = cluster_fields(feats, num_seeds, kappa, max_iters, fi, flags=flags)
+    return labels[0].to(torch.int64).cpu(), selected[0].cpu()
+
+
+def select_smart_seeds(X, num_seeds, return_selected_indices=False, init_seeds=None, num_init_seeds=None,
+                       metric='cosine', first_index=None):
+    """lib/utils/mean_shift.py:128-189 (fresh start only: init_seeds is not supported)."""
+    if metric != 'cosine' or init_seeds is not None:
+        raise NotImplementedError("cosine metric without init_seeds only")
+    n, d = X.shape
+    Xp, stride_d = _as_planar(X)
+    lib = _lib.load()
+    dev = X.device
+    if first_index is None:
+        first_index = np.random.randint(0, n)
+    first = (ctypes.c_int64 * 1)(int(first_index))
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, lib.uoc_meanshift_workspace_bytes(1, n, d, num_seeds))
+        selected = torch.empty((num_seeds,), dtype=torch.int64, device=dev)
+        seeds = torch.empty((num_seeds, d), dtype=torch.float32, device=dev)
+        st = lib.uoc_select_seeds(_lib.ptr(Xp), d * stride_d, stride_d, 1, n, d, num_seeds,
+                                  ctypes.cast(first, ctypes.c_void_p), _lib.ptr(selected), _lib.ptr(seeds), _lib.ptr(ws),
+                                  ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(st, "uoc_select_seeds")
+    if return_selected_indices:
+        return seeds, selected.cpu()
+    return (seeds,)
+
+
+def seed_hill_climbing_ball(X, Z, kappa, max_iters=10, metric='cosine', flags=0):
+    """lib/utils/mean_shift.py:79-109.  Returns the updated seeds (new tensor)."""
+    if metric != 'cosine':
+        raise NotImplementedError("cosine metric only")
+    n, d = X.shape
+    m = Z.shape[0]
+    Xp, stride_d = _as_planar(X)
+    lib = _lib.load()
+    dev = X.device
+    Zc = Z.detach().to(torch.float32).contiguous().clone()
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, lib.uoc_meanshift_workspace_bytes(1, n, d, m))
+        st = lib.uoc_hill_climb(_lib.ptr(Xp), d * stride_d, stride_d, None, 1, n, d, m, float(kappa), int(max_iters),
+                                _lib.ptr(Zc), _lib.ptr(ws), ws.numel(), int(flags) | _lib.FLAG_SYNC_CHECK,
+                                _lib.stream_ptr(dev))
+        _lib.check(st, "uoc_hill_climb")
+    return Zc
+
+
+def connected_components(Z, epsilon, metric='cosine', return_num_unique=False):
+    """lib/utils/mean_shift.py:41-76.  Z: [m, d] CUDA float32.  Returns int64 labels on the CPU."""
+    if metric != 'cosine':
+        raise NotImplementedError("cosine metric only")
+    m, d = Z.shape
+    lib = _lib.load()
+    dev = Z.device
+    Zc = Z.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        labels = torch.empty((m,), dtype=torch.int32, device=dev)
+        num = torch.empty((1,), dtype=torch.int32, device=dev)
+        st = lib.uoc_label_seeds(_lib.ptr(Zc), 1, m, d, float(epsilon), _lib.ptr(labels), _lib.ptr(num),
+                                 _lib.stream_ptr(dev))
+        _lib.check(st, "uoc_label_seeds")
+    if return_num_unique:
+        return labels.to(torch.int64).cpu(), int(num.item())
+    return labels.to(torch.int64).cpu()
+
+
+def assign_labels(X, Z, seed_labels, num_unique=None):
+    """lib/utils/mean_shift.py:206-227: nearest-seed labels with the label-0 swap. int64 CPU [n]."""
+    n, d = X.shape
+    m = Z.shape[0]
+    Xp, stride_d = _as_planar(X)
+    lib = _lib.load()
+    dev = X.device
+    sl = seed_labels.to(device=dev, dtype=torch.int32).contiguous()
+    if num_unique is None:
+        num_unique = int(torch.unique(sl).numel())
+    nu = torch.tensor([num_unique], dtype=torch.int32, device=dev)
+    Zc = Z.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, lib.uoc_meanshift_workspace_bytes(1, n, d, m))
+        out = torch.empty((n,), dtype=torch.int32, device=dev)
+        st = lib.uoc_assign_labels(_lib.ptr(Xp), d * stride_d, stride_d, 1, n, d, m, _lib.ptr(Zc), _lib.ptr(sl),
+                                   _lib.ptr(nu), _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(st, "uoc_assign_labels")
+    return out.to(torch.int64).cpu()
+
+
+def pack_bf16(features):
+    """[N, C, H, W] fp32 planar -> [N, H*W, C] bf16 pixel-major (the layout the tcgen05 loop streams)."""
+    N, C, H, W = features.shape
+    features = features.contiguous()
+    lib = _lib.load()
+    dev = features.device
+    out = torch.empty((N, H * W, C), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        st = lib.uoc_pack_bf16(_lib.ptr(features), C * H * W, H * W, N, H * W, C, _lib.ptr(out), _lib.stream_ptr(dev))
+        _lib.check(st, "uoc_pack_bf16")
+    return out

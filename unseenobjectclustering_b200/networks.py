@@ -1,0 +1,208 @@
+"""Host-side mirror of the reference's network factory for the RGB-D add-fusion ResNet34-8s
+(lib/networks/SEG.py:173-176 `seg_resnet34_8s_embedding`, class SEGNET :26-119).
+
+The module keeps the weights as a reference-format state_dict (same keys, so reference
+checkpoints load unchanged and .state_dict()/.cuda()/DataParallel behave), and runs the forward
+pass through uoc_backbone_forward: BN-folded bf16 implicit-GEMM convolutions on tcgen05, fused
+add + bilinear x8 + L2-normalise head.  Inference only.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import mean_shift as _ms
+
+__all__ = ["seg_resnet34_8s_embedding", "SEGNET_B200", "reference_state_dict_keys", "random_state_dict"]
+
+_LAYERS = ((64, 3), (128, 4), (256, 6), (512, 3))
+
+
+def reference_state_dict_keys(num_units=64):
+    """(key, shape) for every tensor of the reference module's state_dict, in its order
+    (lib/networks/resnet.py:141-186: conv1, bn1, layer1..4, fc; num_batches_tracked included)."""
+    out = []
+
+    def bn(p, c):
+        out.extend([(p + ".weight", (c,)), (p + ".bias", (c,)), (p + ".running_mean", (c,)),
+                    (p + ".running_var", (c,)), (p + ".num_batches_tracked", ())])
+
+    for top in ("fcn", "fcn_depth"):
+        p = top + ".resnet34_8s."
+        out.append((p + "conv1.weight", (64, 3, 7, 7)))
+        bn(p + "bn1", 64)
+        inplanes = 64
+        for li, (planes, blocks) in enumerate(_LAYERS, start=1):
+            for b in range(blocks):
+                q = "%slayer%d.%d." % (p, li, b)
+                out.append((q + "conv1.weight", (planes, inplanes, 3, 3)))
+                bn(q + "bn1", planes)
+                out.append((q + "conv2.weight", (planes, planes, 3, 3)))
+                bn(q + "bn2", planes)
+                if b == 0 and li > 1:
+                    out.append((q + "downsample.0.weight", (planes, inplanes, 1, 1)))
+                    bn(q + "downsample.1", planes)
+                inplanes = planes
+        out.append((p + "fc.weight", (num_units, 512, 1, 1)))
+        out.append((p + "fc.bias", (num_units,)))
+    return out
+
+
+def random_state_dict(num_units=64, seed=None):
+    """Random initialisation in the spirit of SEGNET._initialize_weights (SEG.py:77-85): xavier-normal
+    convolutions, zero biases, BN weight 1 / bias 0 / running stats (0, 1)."""
+    gen = torch.Generator()
+    if seed is not None:
+        gen.manual_seed(int(seed))
+    else:
+        gen.seed()
+    sd = {}
+    for k, shape in reference_state_dict_keys(num_units):
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros((), dtype=torch.long)
+        elif len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            fan_out = shape[0] * shape[2] * shape[3]
+            std = math.sqrt(2.0 / (fan_in + fan_out))
+            sd[k] = torch.randn(shape, generator=gen) * std
+        elif k.endswith("running_var") or (k.endswith(".weight") and len(shape) == 1):
+            sd[k] = torch.ones(shape)
+        else:
+            sd[k] = torch.zeros(shape)
+    return sd
+
+
+def _normalize_keys(data):
+    """Key handling of SEG.py:130-159 and tools/test_net.py:111-112."""
+    if isinstance(data, dict) and "model" in data and not torch.is_tensor(data["model"]):
+        data = data["model"]
+    out = {}
+    for k, v in data.items():
+        out[k[7:] if k.startswith("module.") else k] = v
+    return out
+
+
+class SEGNET_B200(nn.Module):
+    """Drop-in for the reference SEGNET built by seg_resnet34_8s_embedding (INPUT='RGBD',
+    FUSION_TYPE='add', cosine metric, EMBEDDING_NORMALIZATION=True).  forward(img, label, depth)
+    returns unit-norm features [N, num_units, H, W] float32 on the input's device."""
+
+    def __init__(self, num_units=64, data=None, flags=0):
+        super().__init__()
+        self.num_units = int(num_units)
+        self.flags = int(flags)
+        sd = random_state_dict(num_units)
+        if data is not None:
+            given = _normalize_keys(data)
+            for k, v in given.items():          # same filter as SEG.py:152: name and shape must match
+                if k in sd and tuple(v.shape) == tuple(sd[k].shape):
+                    sd[k] = v.detach().clone().to(sd[k].dtype)
+        self._names = list(sd.keys())
+        for k, v in sd.items():
+            self.register_buffer(k.replace(".", "__"), v, persistent=True)
+        self._handle = None
+        self._handle_dev = None
+        self._ws = None
+        self.keep_bf16 = True
+        self.eval()
+
+    # reference-format state_dict -------------------------------------------------------------
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        return type(sd)((k.replace("__", "."), v) for k, v in sd.items())
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        given = _normalize_keys(state_dict)
+        mapped = {k.replace(".", "__"): v for k, v in given.items()}
+        res = super().load_state_dict(mapped, strict=strict, **kw)
+        self._release()
+        return res
+
+    def _release(self):
+        if self._handle is not None:
+            _lib.load().uoc_backbone_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _apply(self, fn, *a, **k):      # .cuda() / .to(): weights moved -> rebuild the handle lazily
+        self._release()
+        return super()._apply(fn, *a, **k)
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("SEGNET_B200 is inference only (the training path is out of scope)")
+        return super().train(False)
+
+    # handle ------------------------------------------------------------------------------------
+    def _ensure_handle(self, device):
+        if self._handle is not None and self._handle_dev == device:
+            return
+        self._release()
+        lib = _lib.load()
+        keep = []
+        descs = []
+        for k in self._names:
+            if k.endswith("num_batches_tracked"):
+                continue
+            t = getattr(self, k.replace(".", "__")).detach().to("cpu", torch.float32).contiguous()
+            keep.append(t)
+            descs.append(_lib.WeightDesc(k.encode(), ctypes.c_void_p(t.data_ptr()), t.numel()))
+        arr = (_lib.WeightDesc * len(descs))(*descs)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.uoc_backbone_create(ctypes.byref(h), arr, len(descs), self.num_units), "uoc_backbone_create")
+        self._handle = h
+        self._handle_dev = device
+
+    def forward(self, img, label=None, depth=None):
+        if depth is None:
+            raise _lib.UocError("this module implements INPUT='RGBD' (image + depth); depth is required")
+        if not img.is_cuda:
+            raise _lib.UocError("inputs must be CUDA tensors: there is no CPU path in this package")
+        dev = img.device
+        self._ensure_handle(dev)
+        lib = _lib.load()
+        img = img.detach().to(torch.float32).contiguous()
+        depth = depth.detach().to(device=dev, dtype=torch.float32).contiguous()
+        N, _, H, W = img.shape
+        with torch.cuda.device(dev):
+            nbytes = lib.uoc_backbone_workspace_bytes(self._handle, N, H, W)
+            if self._ws is None or self._ws.device != dev or self._ws.numel() < nbytes + 1024:
+                self._ws = torch.empty(nbytes + 2048, dtype=torch.uint8, device=dev)
+            off = (-self._ws.data_ptr()) % 1024
+            ws_ptr = ctypes.c_void_p(self._ws.data_ptr() + off)
+            out = torch.empty((N, self.num_units, H, W), dtype=torch.float32, device=dev)
+            xb = torch.empty((N, H * W, self.num_units), dtype=torch.bfloat16, device=dev) if self.keep_bf16 else None
+            st = lib.uoc_backbone_forward(self._handle, _lib.ptr(img), _lib.ptr(depth), N, H, W, _lib.ptr(out),
+                                          _lib.ptr(xb), ws_ptr, self._ws.numel() - off, self.flags,
+                                          _lib.stream_ptr(dev))
+            _lib.check(st, "uoc_backbone_forward")
+        if xb is not None:
+            _ms.register_bf16_copy(out, xb)
+        return out
+
+    def read_trunk(self, branch, N, H, W):
+        """Test hook: trunk output [N, num_units, H/8, W/8] of one branch from the last forward."""
+        lib = _lib.load()
+        dev = self._ws.device
+        h3 = ((((H - 1) // 2 + 1) - 1) // 2 + 1 - 1) // 2 + 1
+        w3 = ((((W - 1) // 2 + 1) - 1) // 2 + 1 - 1) // 2 + 1
+        out = torch.empty((N, self.num_units, h3, w3), dtype=torch.float32, device=dev)
+        off = (-self._ws.data_ptr()) % 1024
+        with torch.cuda.device(dev):
+            _lib.check(lib.uoc_backbone_read_trunk(self._handle, branch, N, H, W,
+                                                   ctypes.c_void_p(self._ws.data_ptr() + off), _lib.ptr(out),
+                                                   _lib.stream_ptr(dev)), "uoc_backbone_read_trunk")
+        return out
+
+
+def seg_resnet34_8s_embedding(num_classes=2, num_units=64, data=None):
+    """Same signature as lib/networks/SEG.py:173-176."""
+    return SEGNET_B200(num_units=num_units, data=data)
