@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the UnseenObjectClustering hot path (BASELINE.json metric) on N B200s.
+
+A "step" is one pass of the hot path over one synthetic 640x480 RGB-D frame per GPU:
+  backbone (two-branch ResNet34-8s, tcgen05 implicit-GEMM convs, fused head) -> stage-1 clustering
+  (farthest point sampling, 10 tcgen05 mean-shift updates, seed labelling, pixel labels)
+= BASELINE.json configs[1] ("640x480 RGB-D, 64-dim cosine embeddings, stage-1 mean-shift only").
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (N>1: launched by torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same
+through the public API with pinned HOST buffers (H2D of the frame + D2H of the labels inside the
+timed region); `roofline` = the mean-shift loop kernel (the kernel BASELINE.json's metric names)
+against the measured HBM peak; `cpu_baseline` = the oracle port on the host cores (N=1 only).
+Timing: CUDA events per step on the launching stream, L2 flushed (untimed 256 MiB memset) between
+steps, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, D, M, ITERS, KAPPA = 480, 640, 64, 100, 10, 20.0
+METRIC = "frames/sec 640x480 RGB-D seg"
+UNIT = "frames/s"
+WORKLOAD = "640x480 RGB-D, ResNet34-8s x2 (random init), 64-dim cosine embeddings, stage-1 mean-shift (100 seeds, 10 iters)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def cpu_reference_frames(steps, warmup, threads=None):
+    """The reference's CPU path through the oracle port (oracle/uoc_oracle.py: same torch CPU ops as
+    the reference, pinned bit-identically against it): backbone forward + clustering_features on one
+    640x480 frame per step.  Returns (frames/s, cores, seconds per frame)."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import uoc_oracle as O
+    from unseenobjectclustering_b200.networks import random_state_dict
+    if threads is None:
+        threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    net = O.OracleSegNet(random_state_dict(D, seed=0))
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed=0)
+    np.random.seed(3)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        feats = net(img, None, xyz)
+        O.clustering_features(feats, M)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per = sum(times) / len(times)
+    return 1.0 / per, torch.get_num_threads(), per
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = args.steps, min(args.warmup, 2)
+    budget_s = 240.0
+    t0 = time.perf_counter()
+    fps1, cores, per = cpu_reference_frames(1, 1)           # probe the per-frame cost
+    steps_eff = max(1, min(steps, int((budget_s - (time.perf_counter() - t0)) / max(per, 1e-3)) - warmup))
+    fps, cores, per = cpu_reference_frames(steps_eff, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_eff,
+        "warmup": warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CPU path: torch CPU ops of the oracle port on the host cores"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d timed full frames (backbone + stage-1 clustering) after %d warm-up" % (steps_eff, warmup)},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from unseenobjectclustering_b200 import _lib, networks, synthetic
+    from unseenobjectclustering_b200 import mean_shift as MS
+    from unseenobjectclustering_b200 import distributed as UD
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    net = networks.seg_resnet34_8s_embedding(2, D, networks.random_state_dict(D, seed=0)).to(dev)
+    n = H * W
+    nframes = 4                                            # distinct inputs, rotated
+    frames = [synthetic.rgbd_frame(H, W, seed=100 * rank + i) for i in range(nframes)]
+    dev_frames = [(a.to(dev), b.to(dev)) for a, b in frames]
+    pin_frames = [(a.pin_memory(), b.pin_memory()) for a, b in frames]
+    firsts = UD.draw_first_indices(warmup + 3 * steps + 16, n, seed=3 + rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gathered = torch.empty((world, n), dtype=torch.int32, device=dev) if world > 1 else None
+    out_pin = torch.empty((1, H, W), dtype=torch.float32).pin_memory()
+
+    def step_device(i):
+        a, b = dev_frames[i % nframes]
+        feats = net(a, None, b)
+        labels, _ = MS.cluster_fields(feats, M, KAPPA, ITERS, [firsts[i]])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, labels.view(-1))
+        return labels
+
+    def step_e2e(i):
+        a, b = pin_frames[i % nframes]
+        ad = a.to(dev, non_blocking=True)
+        bd = b.to(dev, non_blocking=True)
+        feats = net(ad, None, bd)
+        labels, _ = MS.cluster_fields(feats, M, KAPPA, ITERS, [firsts[i]])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, labels.view(-1))
+        out_pin.copy_(labels.view(1, H, W).to(torch.float32), non_blocking=True)   # float32 CPU labels: the reference API
+        return labels
+
+    def timed(fn, count, base):
+        evs = []
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for i in range(count):
+            flush.zero_()                                   # L2 flush, outside the event pair
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn(base + i)
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(warmup):
+        step_device(i)
+        step_e2e(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.uoc_launch_count()
+    ms_dev = timed(step_device, steps, warmup)
+    launches = int(lib.uoc_launch_count() - l0)
+    ms_e2e = timed(step_e2e, steps, warmup + steps)
+
+    # ---- stage split (same kernels through the stage entry points), rank-local, for the roofline ----
+    import ctypes
+    ws = MS._workspace(dev, lib.uoc_meanshift_workspace_bytes(1, n, D, M))
+    sel = torch.empty((1, M), dtype=torch.int64, device=dev)
+    Z = torch.empty((1, M, D), dtype=torch.float32, device=dev)
+    sl = torch.empty((1, M), dtype=torch.int32, device=dev)
+    nu = torch.empty((1,), dtype=torch.int32, device=dev)
+    lab = torch.empty((1, n), dtype=torch.int32, device=dev)
+    sp = _lib.stream_ptr(dev)
+    stage_ms = {"backbone": 0.0, "fps": 0.0, "loop": 0.0, "label_assign": 0.0}
+    reps = max(3, min(steps, 10))
+    for rep in range(reps + 1):
+        flush.zero_()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        a, b = dev_frames[rep % nframes]
+        ev[0].record()
+        feats = net(a, None, b)
+        xb = MS._lookup_bf16(feats)
+        ev[1].record()
+        first = (ctypes.c_int64 * 1)(firsts[rep])
+        _lib.check(lib.uoc_select_seeds(_lib.ptr(feats), D * n, n, 1, n, D, M, ctypes.cast(first, ctypes.c_void_p),
+                                        _lib.ptr(sel), _lib.ptr(Z), _lib.ptr(ws), ws.numel(), 0, sp), "select_seeds")
+        ev[2].record()
+        _lib.check(lib.uoc_hill_climb(_lib.ptr(feats), D * n, n, _lib.ptr(xb), 1, n, D, M, KAPPA, ITERS, _lib.ptr(Z),
+                                      _lib.ptr(ws), ws.numel(), 0, sp), "hill_climb")
+        ev[3].record()
+        _lib.check(lib.uoc_label_seeds(_lib.ptr(Z), 1, M, D, 0.04, _lib.ptr(sl), _lib.ptr(nu), sp), "label_seeds")
+        _lib.check(lib.uoc_assign_labels(_lib.ptr(feats), D * n, n, 1, n, D, M, _lib.ptr(Z), _lib.ptr(sl), _lib.ptr(nu),
+                                         _lib.ptr(lab), _lib.ptr(ws), ws.numel(), sp), "assign_labels")
+        ev[4].record()
+        torch.cuda.synchronize()
+        if rep == 0:
+            continue
+        for k, (x, y) in zip(("backbone", "fps", "loop", "label_assign"), zip(ev[:-1], ev[1:])):
+            stage_ms[k] += x.elapsed_time(y) / reps
+    clocks = sampler.stop() if rank == 0 else None
+    torch.cuda.synchronize()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = _peaks()
+    t_iter_s = stage_ms["loop"] * 1e-3 / ITERS                     # one update = tcgen05 kernel + reduce/normalise kernel
+    bytes_actual = n * D * 2                                       # bf16 pixel-major copy streamed per update
+    achieved = bytes_actual / t_iter_s / 1e9 if t_iter_s > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": world * steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": 1, "l2": "flushed between steps (256 MiB memset, untimed)",
+                   "timing": "CUDA events per step on the launching stream, max over ranks",
+                   "multi_gpu": "frames sharded, one NCCL all-gather of label maps per step" if world > 1 else "single GPU"},
+        "clocks": clocks,
+        "e2e": {"value": world * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 3 * H * W * 4,
+                "d2h_bytes_per_step": H * W * 4, "ms_per_step": ms_e2e / steps},
+        "gpu_launches": launches,
+        "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+        "roofline": {"kernel": "meanshift_tc_kernel<64> (+reduce_normalize_kernel), per mean-shift update",
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "traffic": None,
+                     "bytes_per_launch": bytes_actual, "fp32_equivalent_GBps": achieved * 2.0,
+                     "note": "algorithmic bytes = n*d*2 (bf16 copy actually streamed); fp32-equivalent (n*d*4) is 2x"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        fps, cores, per = cpu_reference_frames(3, 1)
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "3 timed full frames (oracle backbone + stage-1 clustering) after 1 warm-up, %.1f s"
+                                          % (time.perf_counter() - t0)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

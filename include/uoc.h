@@ -57,6 +57,8 @@ typedef void* uoc_stream_t;  /* cudaStream_t */
 
 UOC_API const char* uoc_last_error(void);
 UOC_API int uoc_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+UOC_API unsigned long long uoc_launch_count(void);
 /* sm count / compute capability of the current device; UOC_ERR_UNSUPPORTED if it is not sm_100. */
 UOC_API int uoc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -98,7 +100,7 @@ UOC_API int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stri
  * seeds_out [batch,m,d] fp32. */
 UOC_API int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
                              const int64_t* first_seed_host, int64_t* selected_out, float* seeds_out,
-                             void* workspace, size_t workspace_bytes, uoc_stream_t stream);
+                             void* workspace, size_t workspace_bytes, int flags, uoc_stream_t stream);
 
 /* seed_hill_climbing_ball (lib/utils/mean_shift.py:79-109, cosine): Z [batch,m,d] fp32 updated in place. */
 UOC_API int uoc_hill_climb(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch,

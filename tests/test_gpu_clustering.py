@@ -38,11 +38,11 @@ def test_select_seeds_bit_exact(H, W, d, m):
     assert sel[0] == first and len(set(sel.tolist())) == m
 
 
-@pytest.mark.parametrize("flags,tol", [(0, 2e-5), (_lib.FLAG_LOOP_SIMT, 2e-6)])
+@pytest.mark.parametrize("flags,tol", [(0, 5e-5), (_lib.FLAG_LOOP_SIMT, 2e-6)])
 @pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 50), (30, 44, 128, 100), (96, 128, 64, 100)])
 def test_hill_climb_vs_double_oracle(H, W, d, m, flags, tol):
     """Cosine distance between converged seeds and the double-precision oracle:
-    tcgen05 loop (bf16 operands, fp32 accumulate) <= 2e-5, fp32 SIMT loop <= 2e-6."""
+    tcgen05 loop (bf16 operands, fp32 accumulate) <= 5e-5, fp32 SIMT loop <= 2e-6."""
     feats, _ = _field(H, W, d, 4, 0.05, seed=3 + H)
     Xp = feats[0].reshape(d, -1).numpy()
     _, seeds = C.select_seeds(Xp, m, 5)

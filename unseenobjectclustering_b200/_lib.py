@@ -30,11 +30,12 @@ _vp, _i, _i64, _f, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_siz
 SIGNATURES = {
     "uoc_last_error": (_c.c_char_p, []),
     "uoc_version": (_i, []),
+    "uoc_launch_count": (_c.c_uint64, []),
     "uoc_device_info": (_i, [_c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
     "uoc_meanshift_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "uoc_meanshift_cluster": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                    _i, _vp]),
-    "uoc_select_seeds": (_i, [_vp, _i64, _i64, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "uoc_select_seeds": (_i, [_vp, _i64, _i64, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "uoc_hill_climb": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _f, _i, _vp, _vp, _sz, _i, _vp]),
     "uoc_label_seeds": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "uoc_assign_labels": (_i, [_vp, _i64, _i64, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -80,7 +80,7 @@ int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stride_d, co
 
 int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
                      const int64_t* first_seed_host, int64_t* selected_out, float* seeds_out, void* workspace,
-                     size_t workspace_bytes, uoc_stream_t stream) {
+                     size_t workspace_bytes, int flags, uoc_stream_t stream) {
   int rc = require_sm100();
   if (rc != UOC_OK) return rc;
   rc = check_shape(X, batch, n, d, m, stride_b, stride_d);
@@ -95,7 +95,8 @@ int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, int bat
   if (rc != UOC_OK) return rc;
   rc = launch_select_seeds(X, s, w, selected_out, seeds_out, st);
   if (rc != UOC_OK) return rc;
-  return check_device_error(st);
+  if (flags & UOC_FLAG_SYNC_CHECK) return check_device_error(st);
+  return UOC_OK;
 }
 
 int uoc_hill_climb(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n, int d,

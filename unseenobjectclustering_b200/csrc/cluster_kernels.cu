@@ -266,6 +266,7 @@ int launch_select_seeds(const float* X, const ClusterShape& s, const ClusterWork
   if (grid < s.batch && s.batch <= sms * per_sm) grid = s.batch;
   void* args[] = {&p};
   UOC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, stream));
+  count_launch();
   return UOC_OK;
 }
 

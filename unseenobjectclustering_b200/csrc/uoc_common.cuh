@@ -26,7 +26,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (_e != cudaSuccess) return ::uoc::cuda_fail(_e, #expr, __FILE__, __LINE__); \
   } while (0)
 
-#define UOC_CHECK_LAUNCH() UOC_CUDA(cudaGetLastError())
+void count_launch();        // every kernel launch of this library is counted (uoc_launch_count)
+#define UOC_CHECK_LAUNCH()            \
+  do {                                \
+    ::uoc::count_launch();            \
+    UOC_CUDA(cudaGetLastError());     \
+  } while (0)
 
 int require_sm100();       // UOC_OK iff current device is compute capability 10.x
 int sm_count();            // cached multiProcessorCount of the current device

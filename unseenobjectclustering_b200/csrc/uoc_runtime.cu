@@ -2,12 +2,16 @@
 // capability gate (sm_100 only -- there is no fallback), device error word, tensor-map encoding.
 #include "uoc_common.cuh"
 
+#include <atomic>
 #include <cstdio>
 #include <mutex>
 
 namespace uoc {
 
 static thread_local std::string g_last_error;
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -148,6 +152,8 @@ extern "C" {
 const char* uoc_last_error(void) { return uoc::g_last_error.c_str(); }
 
 int uoc_version(void) { return 100; }
+
+unsigned long long uoc_launch_count(void) { return uoc::g_launches.load(); }
 
 int uoc_device_info(int* sm_count_out, int* cc_major, int* cc_minor) {
   int rc = uoc::query_device();

@@ -128,7 +128,7 @@ def select_smart_seeds(X, num_seeds, return_selected_indices=False, init_seeds=N
         seeds = torch.empty((num_seeds, d), dtype=torch.float32, device=dev)
         st = lib.uoc_select_seeds(_lib.ptr(Xp), d * stride_d, stride_d, 1, n, d, num_seeds,
                                   ctypes.cast(first, ctypes.c_void_p), _lib.ptr(selected), _lib.ptr(seeds), _lib.ptr(ws),
-                                  ws.numel(), _lib.stream_ptr(dev))
+                                  ws.numel(), _lib.FLAG_SYNC_CHECK, _lib.stream_ptr(dev))
         _lib.check(st, "uoc_select_seeds")
     if return_selected_indices:
         return seeds, selected.cpu()
