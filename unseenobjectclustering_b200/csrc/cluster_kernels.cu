@@ -13,6 +13,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "cluster.cuh"
 
@@ -236,6 +237,138 @@ __global__ void __launch_bounds__(256) fps_kernel(FpsParams p) {
   }
 }
 
+// Second-generation sampling kernel: one CTA per SM, every CTA owns a FIXED contiguous slice of points for
+// all m passes.  (1) the running min r[] of a thread's points lives in registers, (2) as much of the
+// slice as fits (~200 KB) is copied once into shared memory and re-read from there in every pass --
+// only the rest is streamed from L2 -- (3) the slice is split evenly so that no thread runs a second
+// trip.  Same canonical arithmetic as fps_kernel (bit-identical results).
+template <int GPT>   // float4 groups (4 consecutive points) per thread
+__global__ void __launch_bounds__(1024, 1) fps2_kernel(FpsParams p, int nb, int chunk, int rg) {
+  extern __shared__ float4 xs4[];                       // [d][rg] resident slice, then d floats of the current seed
+  float* s_seed = reinterpret_cast<float*>(xs4 + size_t(p.d) * rg);
+  __shared__ unsigned long long s_red[32];
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int b = blockIdx.x / nb, rank = blockIdx.x % nb;
+  const long long ngroups = p.n / 4;
+  const long long g0 = (long long)rank * chunk;
+  const long long g1 = (g0 + chunk < ngroups) ? g0 + chunk : ngroups;
+  const float* Xb = p.X + b * p.sb;
+  for (int lg = tid; lg < rg && g0 + lg < g1; lg += T) {
+    const float* xp = Xb + (g0 + lg) * 4;
+#pragma unroll 8
+    for (int k = 0; k < p.d; ++k) xs4[size_t(k) * rg + lg] = __ldg(reinterpret_cast<const float4*>(xp + k * p.sd));
+  }
+  float r[GPT][4];
+#pragma unroll
+  for (int q = 0; q < GPT; ++q) { r[q][0] = r[q][1] = r[q][2] = r[q][3] = 0.f; }
+  unsigned int target = 0;
+  for (int i = 0; i < p.m; ++i) {
+    long long idx;
+    if (i == 0) {
+      idx = p.first[b];
+    } else {
+      const unsigned long long key = __ldcg(p.keys + size_t(b) * p.m + i);
+      idx = static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(key & 0xFFFFFFFFull));
+    }
+    for (int k = tid; k < p.d; k += T) s_seed[k] = __ldg(Xb + k * p.sd + idx);
+    __syncthreads();
+    if (rank == 0) {
+      if (tid == 0) p.selected_out[size_t(b) * p.m + i] = idx;
+      for (int k = tid; k < p.d; k += T) p.seeds_out[(size_t(b) * p.m + i) * p.d + k] = s_seed[k];
+    }
+    if (i + 1 < p.m) {
+      unsigned long long best = 0ull;
+#pragma unroll
+      for (int q = 0; q < GPT; ++q) {
+        const int lg = tid + q * T;
+        const long long g = g0 + lg;
+        if (g < g1) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          if (lg < rg) {
+            const float4* xp = xs4 + lg;
+#pragma unroll 8
+            for (int k = 0; k < p.d; ++k) {
+              const float4 v = xp[size_t(k) * rg];
+              const float sk = s_seed[k];
+              a0 = fmaf(v.x, sk, a0); a1 = fmaf(v.y, sk, a1); a2 = fmaf(v.z, sk, a2); a3 = fmaf(v.w, sk, a3);
+            }
+          } else {
+            const float* xp = Xb + g * 4;
+#pragma unroll 8
+            for (int k = 0; k < p.d; ++k) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(xp + k * p.sd));
+              const float sk = s_seed[k];
+              a0 = fmaf(v.x, sk, a0); a1 = fmaf(v.y, sk, a1); a2 = fmaf(v.z, sk, a2); a3 = fmaf(v.w, sk, a3);
+            }
+          }
+          const float d0 = 0.5f * (1.0f - a0), d1 = 0.5f * (1.0f - a1), d2 = 0.5f * (1.0f - a2), d3 = 0.5f * (1.0f - a3);
+          if (i == 0) {
+            r[q][0] = d0; r[q][1] = d1; r[q][2] = d2; r[q][3] = d3;
+          } else {
+            r[q][0] = d0 < r[q][0] ? d0 : r[q][0];
+            r[q][1] = d1 < r[q][1] ? d1 : r[q][1];
+            r[q][2] = d2 < r[q][2] ? d2 : r[q][2];
+            r[q][3] = d3 < r[q][3] ? d3 : r[q][3];
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const unsigned long long key = pack_key(r[q][jj], static_cast<unsigned int>(g * 4 + jj));
+            best = key > best ? key : best;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+      }
+      if ((tid & 31) == 0) s_red[tid >> 5] = best;
+      __syncthreads();
+      if (tid < 32) {
+        unsigned long long v = (tid < (T >> 5)) ? s_red[tid] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+          v = other > v ? other : v;
+        }
+        if (tid == 0 && v != 0ull) atomicMax(p.keys + size_t(b) * p.m + i + 1, v);
+      }
+      target += gridDim.x;
+      if (!grid_barrier(p.barrier, target, p.err)) return;
+    }
+  }
+}
+
+static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, cudaStream_t stream, bool* used) {
+  *used = false;
+  const int sms = sm_count();
+  if (sms <= 0 || s.batch > sms) return UOC_OK;
+  if (const char* e = getenv("UOC_FPS_V1")) { if (atoi(e) != 0) return UOC_OK; }
+  const int nb = sms / s.batch;
+  const long long ngroups = s.n / 4;
+  const long long chunk_ll = (ngroups + nb - 1) / nb;
+  if (chunk_ll > 4096) return UOC_OK;
+  const int chunk = int(chunk_ll);
+  const int gpt = (chunk + 1023) / 1024;
+  const int gpt_t = gpt <= 1 ? 1 : (gpt <= 2 ? 2 : 4);
+  int threads = ((chunk + gpt_t - 1) / gpt_t + 31) / 32 * 32;
+  if (threads < 64) threads = 64;
+  size_t budget = 200 * 1024;
+  if (const char* e = getenv("UOC_FPS_SMEM_KB")) budget = size_t(atoi(e)) * 1024;
+  int rg = int(budget / (16 * size_t(s.d)));
+  if (rg > chunk) rg = chunk;
+  const size_t smem = size_t(rg) * s.d * 16 + size_t(s.d) * 4 + 16;
+  void* kern = gpt_t == 1 ? reinterpret_cast<void*>(&fps2_kernel<1>)
+                          : (gpt_t == 2 ? reinterpret_cast<void*>(&fps2_kernel<2>) : reinterpret_cast<void*>(&fps2_kernel<4>));
+  UOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int nb_i = nb, chunk_i = chunk, rg_i = rg;
+  void* args[] = {&p, &nb_i, &chunk_i, &rg_i};
+  UOC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(nb * s.batch), dim3(threads), args, smem, stream));
+  count_launch();
+  *used = true;
+  return UOC_OK;
+}
+
 int launch_select_seeds(const float* X, const ClusterShape& s, const ClusterWorkspace& w, int64_t* selected_out,
                         float* seeds_out, cudaStream_t stream) {
   FpsParams p;
@@ -249,6 +382,11 @@ int launch_select_seeds(const float* X, const ClusterShape& s, const ClusterWork
   UOC_CUDA(cudaMemsetAsync(w.barrier, 0, sizeof(unsigned int), stream));
   const bool vec4 = (s.n % 4 == 0) && (s.stride_d % 4 == 0) && (s.stride_b % 4 == 0) &&
                     (reinterpret_cast<uintptr_t>(X) % 16 == 0);
+  if (vec4) {
+    bool used = false;
+    int rc = launch_select_seeds_v2(p, s, stream, &used);
+    if (rc != UOC_OK || used) return rc;
+  }
   void* kern = vec4 ? reinterpret_cast<void*>(&fps_kernel<4>) : reinterpret_cast<void*>(&fps_kernel<1>);
   const int threads = 256;
   const size_t smem = sizeof(float) * size_t(s.d);
@@ -318,34 +456,60 @@ __global__ void __launch_bounds__(256) meanshift_simt_kernel(const float* __rest
   }
 }
 
-// grid (m, batch), block 128: Z[b][j][:] = normalize(sum_part partials[b][part][j][:])
-__global__ void __launch_bounds__(128) reduce_normalize_kernel(const float* __restrict__ partials, int P, int m, int d,
+// grid (m, batch), block 256 (8 warps): Z[b][j][:] = normalize(sum_part partials[b][part][j][:]).
+// Warp w adds parts w, w+8, w+16, ... (each a coalesced row read), the 8 warp sums are combined in a
+// fixed order -> deterministic.  Lane l owns channels l, l+32, ... (d <= 256).
+__global__ void __launch_bounds__(256) reduce_normalize_kernel(const float* __restrict__ partials, int P, int m, int d,
                                                                int row_stride, float* __restrict__ Z) {
-  __shared__ float s_sq[4];
-  const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  float v[2] = {0.f, 0.f};  // d <= 256
-  for (int part = 0; part < P; ++part) {
+  __shared__ float s_part[8][256];
+  __shared__ float s_sq[8];
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: partials are complete
+  const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float v[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = 0.f;
+  for (int part = warp; part < P; part += 8) {
     const float* src = partials + ((size_t(b) * P + part) * row_stride + j) * d;
-    if (tid < d) v[0] += src[tid];
-    if (tid + 128 < d) v[1] += src[tid + 128];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (lane + 32 * q < d) v[q] += __ldcg(src + lane + 32 * q);
   }
-  float sq = v[0] * v[0] + v[1] * v[1];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s_part[warp][lane + 32 * q] = v[q];
+  __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  float tot = 0.f;
+  if (tid < d) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_part[w][tid];
+  }
+  float sq = tot * tot;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  if ((tid & 31) == 0) s_sq[tid >> 5] = sq;
+  if (lane == 0) s_sq[warp] = sq;
   __syncthreads();
-  const float tot = (s_sq[0] + s_sq[1]) + (s_sq[2] + s_sq[3]);
-  const float denom = fmaxf(sqrtf(tot), 1e-12f);  // F.normalize eps (lib/utils/mean_shift.py:107)
-  float* dst = Z + (size_t(b) * m + j) * d;
-  if (tid < d) dst[tid] = v[0] / denom;
-  if (tid + 128 < d) dst[tid + 128] = v[1] / denom;
+  float all = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) all += s_sq[w];
+  const float denom = fmaxf(sqrtf(all), 1e-12f);  // F.normalize eps (lib/utils/mean_shift.py:107)
+  if (tid < d) Z[(size_t(b) * m + j) * d + tid] = tot / denom;
 }
 
 int launch_reduce_normalize(const float* partials, int batch, int P, int m, int d, int row_stride, float* Z,
                             cudaStream_t stream) {
   if (d > 256) return fail(UOC_ERR_UNSUPPORTED, "d > 256 is not supported");
-  reduce_normalize_kernel<<<dim3(m, batch), 128, 0, stream>>>(partials, P, m, d, row_stride, Z);
-  UOC_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(m, batch);
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  UOC_CUDA(cudaLaunchKernelEx(&cfg, reduce_normalize_kernel, partials, P, m, d, row_stride, Z));
+  count_launch();
   return UOC_OK;
 }
 

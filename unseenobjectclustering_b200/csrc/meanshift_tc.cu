@@ -7,13 +7,17 @@
 //     warp 0      TMA producer   : X tiles -> shared-memory ring (mbarrier full/empty)
 //     warp 1      MMA issuer     : GEMM1  S[128 seeds x 128 pts]  = Zs (smem, K-major) . Xtile^T (smem, K-major)
 //                                   GEMM2  O[128 seeds x d]      += P (TMEM, bf16)     . Xtile   (smem, MN-major)
-//     warps 2..5  weight warps   : S (TMEM fp32) -> ex2(kappa*log2e*(s-1)) -> P (bf16x2, TMEM, aliasing S)
-//                                   and the epilogue O (TMEM) -> per-CTA partial sums in global memory
+//     warps 2..9  weight warps   : S (TMEM fp32) -> ex2(kappa*log2e*(s-1)) -> P (bf16x2, TMEM, aliasing S)
+//                                   two groups of 4 warps ping-pong on even / odd tiles (one S buffer each) so that
+//                                   one group's TMEM round trips hide behind the other's MUFU work;
+//                                   then the epilogue O (TMEM) -> per-CTA partial sums in global memory
 //   S is double buffered in TMEM (2 x 128 columns), O occupies d columns; 512 columns are allocated.
 //   A second tiny kernel (reduce_normalize_kernel) adds the per-CTA partials and normalises the rows.
 // The factor exp(-kappa) common to all weights cancels in the row normalisation.
 //
 // Algorithmic traffic per update: n*d*2 bytes of bf16 X (fp32-equivalent: n*d*4), see DESIGN.md.
+#include <cstring>
+
 #include "cluster.cuh"
 
 namespace uoc {
@@ -21,7 +25,7 @@ namespace uoc {
 namespace {
 
 constexpr int kTile = 128;          // points per tile
-constexpr int kThreads = 192;       // 6 warps
+constexpr int kThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-5 weight group 0 (even tiles), warps 6-9 group 1 (odd tiles)
 constexpr int kBoxBytes = 128 * 128;  // one [128 x 64ch] bf16 box, 16 KiB
 
 template <int D>
@@ -69,12 +73,14 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: Z (and the bf16 field) of the previous kernel are complete
   if (warp >= 2) {
     // stage the seeds: fp32 [m][D] -> bf16, K-major 128B-swizzled rows (row r, 16B chunk c -> c ^ (r & 7))
-    const int r = threadIdx.x - 64;  // 0..127
+    const int r = (threadIdx.x - 64) & 127;        // 0..127
+    const int half = (threadIdx.x - 64) >> 7;      // each weight group stages half of the chunks
     const float* zr = Z + (size_t(b) * m + (r < m ? r : 0)) * D;
 #pragma unroll
-    for (int c = 0; c < D / 8; ++c) {
+    for (int c = half * (D / 16); c < (half + 1) * (D / 16); ++c) {
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (r < m) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(zr + c * 8));
@@ -91,6 +97,7 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {
@@ -147,11 +154,12 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
     }
   } else {
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int grp = (warp - 2) >> 2;        // weight group: 0 -> even tiles / S buffer 0, 1 -> odd tiles / S buffer 1
     const int row = q * 32 + lane;          // seed index
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
     bool ok = true;
-    for (int j = 0; j < T; ++j) {
-      const int buf = j & 1;
+    for (int j = grp; j < T; j += 2) {
+      const int buf = grp;
       if (!mbar_wait(&s_full[buf], (j >> 1) & 1, err)) { ok = false; break; }
       tc_fence_after();
       const uint32_t sa = lane_addr + (buf ? Cfg::kColS1 : Cfg::kColS0);
@@ -177,7 +185,7 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
       tc_fence_after();
       float* dst = partials + ((size_t(b) * P + cta) * 128 + row) * D;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = grp * (D / 64); c < (grp + 1) * (D / 64); ++c) {   // each group drains half of the columns
         uint32_t v[32];
         tmem_ld_32x32b_x32(lane_addr + Cfg::kColO + c * 32, v);
         tmem_wait_ld();
@@ -204,9 +212,24 @@ int launch_iter(const CUtensorMap& tmap, const ClusterShape& s, const ClusterWor
     attr = true;
   }
   const float c1 = kappa * 1.4426950408889634f;
-  meanshift_tc_kernel<D><<<dim3(P, s.batch), kThreads, Cfg::kSmemBytes, stream>>>(tmap, Z, w.partials, s.m, s.n, c1, P,
-                                                                                 device_error_word());
-  UOC_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(P, s.batch);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the previous kernel's tail
+  lattr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = lattr;
+  cfg.numAttrs = 1;
+  const float* Zc = Z;
+  float* partials = w.partials;
+  int m = s.m;
+  long long n = s.n;
+  unsigned int* err = device_error_word();
+  UOC_CUDA(cudaLaunchKernelEx(&cfg, meanshift_tc_kernel<D>, tmap, Zc, partials, m, n, c1, P, err));
+  count_launch();
   return UOC_OK;
 }
 
