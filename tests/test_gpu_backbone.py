@@ -44,10 +44,17 @@ def _conv_call(x, w, bias, res, N, H, W, Cin, Cout, k, stride, dil, relu, flags)
     return y
 
 
-@pytest.mark.parametrize("flags", [0, _lib.FLAG_CONV_SIMT], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("variant", ["tc_cluster4", "tc_cluster1", "tc_cluster8", "tc_cluster2_n128", "simt"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
-def test_conv_matches_torch(case, flags):
+def test_conv_matches_torch(case, variant, monkeypatch):
+    """tcgen05 implicit GEMM with every cluster-multicast width (the library reads UOC_CONV_CLUSTER /
+    UOC_CONV_MAX_BLOCK_N at each launch) and the SIMT validation kernel, against torch's convolution."""
     Cin, Cout, k, stride, dil, H, W, N = case
+    flags = _lib.FLAG_CONV_SIMT if variant == "simt" else 0
+    if variant.startswith("tc_cluster"):
+        monkeypatch.setenv("UOC_CONV_CLUSTER", variant[len("tc_cluster")])
+    if variant.endswith("_n128"):
+        monkeypatch.setenv("UOC_CONV_MAX_BLOCK_N", "128")
     g = torch.Generator().manual_seed(Cin + Cout + k + H)
     x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(torch.bfloat16)
     w = (torch.randn(Cout, k * k, Cin, generator=g) * (1.0 / np.sqrt(k * k * Cin))).to(torch.bfloat16)

@@ -17,6 +17,8 @@ struct ClusterShape {
 struct ClusterWorkspace {
   float* r;                       // [batch][n] running min distance of the farthest point sampling
   unsigned long long* keys;       // [batch][m] packed (distance, index) arg-max keys, one slot per pass
+  unsigned long long* slots;      // [batch][m][CTAs per item] per-CTA arg-max keys of the second-generation sampler
+  size_t slot_bytes;
   unsigned int* barrier;          // grid barrier counter
   long long* first;               // [batch] first seed index (device copy of the caller's host array)
   float* Z;                       // [batch][m][d] current seeds

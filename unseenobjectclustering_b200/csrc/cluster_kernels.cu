@@ -36,7 +36,8 @@ static size_t carve(size_t& off, size_t bytes) {
 }
 
 struct WsLayout {
-  size_t r, keys, barrier, first, Z, partials, seed_labels, num_unique, hist, labels_tmp, xb, total;
+  size_t r, keys, slots, barrier, first, Z, partials, seed_labels, num_unique, hist, labels_tmp, xb, total;
+  size_t slot_bytes;
   int P;
 };
 
@@ -46,6 +47,13 @@ static WsLayout ws_layout(int batch, int64_t n, int d, int m) {
   L.P = partial_capacity(batch);
   L.r = carve(off, sizeof(float) * size_t(batch) * n);
   L.keys = carve(off, sizeof(unsigned long long) * size_t(batch) * m);
+  {
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    const int nb = batch <= sms ? sms / batch : 1;
+    L.slot_bytes = sizeof(unsigned long long) * size_t(batch) * m * nb;
+    L.slots = carve(off, L.slot_bytes);
+  }
   L.barrier = carve(off, 256);
   L.first = carve(off, sizeof(long long) * size_t(batch));
   L.Z = carve(off, sizeof(float) * size_t(batch) * m * d);
@@ -73,6 +81,8 @@ int carve_cluster_workspace(void* ws, size_t ws_bytes, int batch, int64_t n, int
   char* base = static_cast<char*>(ws);
   out->r = reinterpret_cast<float*>(base + L.r);
   out->keys = reinterpret_cast<unsigned long long*>(base + L.keys);
+  out->slots = reinterpret_cast<unsigned long long*>(base + L.slots);
+  out->slot_bytes = L.slot_bytes;
   out->barrier = reinterpret_cast<unsigned int*>(base + L.barrier);
   out->first = reinterpret_cast<long long*>(base + L.first);
   out->Z = reinterpret_cast<float*>(base + L.Z);
@@ -238,21 +248,29 @@ __global__ void __launch_bounds__(256) fps_kernel(FpsParams p) {
 }
 
 // Second-generation sampling kernel: one CTA per SM, every CTA owns a FIXED contiguous slice of points for
-// all m passes.  (1) the running min r[] of a thread's points lives in registers, (2) as much of the
-// slice as fits (~200 KB) is copied once into shared memory and re-read from there in every pass --
-// only the rest is streamed from L2 -- (3) the slice is split evenly so that no thread runs a second
-// trip.  Same canonical arithmetic as fps_kernel (bit-identical results).
-template <int GPT>   // float4 groups (4 consecutive points) per thread
-__global__ void __launch_bounds__(1024, 1) fps2_kernel(FpsParams p, int nb, int chunk, int rg) {
+// all m passes.
+//  (1) the running min r[] of a thread's points lives in registers;
+//  (2) as much of the slice as fits (~200 KB) is copied once into shared memory and re-read from there in
+//      every pass -- only the rest is streamed from L2;
+//  (3) the slice is split evenly (no thread runs a second trip) and 16 channel loads are in flight per thread;
+//  (4) no atomics and no grid barrier: each CTA publishes its packed (distance, index) arg-max key in its own
+//      slot keys[item][pass][rank]; warp 0 of every CTA polls the nb slots of its item, takes the maximum
+//      and thereby learns the next seed.  The slots double as the inter-CTA barrier (a non-zero slot means
+//      "this CTA has finished pass i"), batch items never wait for each other.
+// Same canonical arithmetic as fps_kernel (bit-identical results).
+template <int GPT, int MAXT>   // float4 groups (4 consecutive points) per thread, max threads per CTA
+__global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int chunk, int rg, unsigned long long* slots) {
   extern __shared__ float4 xs4[];                       // [d][rg] resident slice, then d floats of the current seed
   float* s_seed = reinterpret_cast<float*>(xs4 + size_t(p.d) * rg);
   __shared__ unsigned long long s_red[32];
+  __shared__ long long s_idx;
   const int tid = threadIdx.x, T = blockDim.x;
   const int b = blockIdx.x / nb, rank = blockIdx.x % nb;
   const long long ngroups = p.n / 4;
   const long long g0 = (long long)rank * chunk;
   const long long g1 = (g0 + chunk < ngroups) ? g0 + chunk : ngroups;
   const float* Xb = p.X + b * p.sb;
+  unsigned long long* my_slots = slots + size_t(b) * p.m * nb;      // [pass][rank]
   for (int lg = tid; lg < rg && g0 + lg < g1; lg += T) {
     const float* xp = Xb + (g0 + lg) * 4;
 #pragma unroll 8
@@ -261,85 +279,102 @@ __global__ void __launch_bounds__(1024, 1) fps2_kernel(FpsParams p, int nb, int 
   float r[GPT][4];
 #pragma unroll
   for (int q = 0; q < GPT; ++q) { r[q][0] = r[q][1] = r[q][2] = r[q][3] = 0.f; }
-  unsigned int target = 0;
+  long long idx = p.first[b];
   for (int i = 0; i < p.m; ++i) {
-    long long idx;
-    if (i == 0) {
-      idx = p.first[b];
-    } else {
-      const unsigned long long key = __ldcg(p.keys + size_t(b) * p.m + i);
-      idx = static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(key & 0xFFFFFFFFull));
-    }
     for (int k = tid; k < p.d; k += T) s_seed[k] = __ldg(Xb + k * p.sd + idx);
     __syncthreads();
     if (rank == 0) {
       if (tid == 0) p.selected_out[size_t(b) * p.m + i] = idx;
       for (int k = tid; k < p.d; k += T) p.seeds_out[(size_t(b) * p.m + i) * p.d + k] = s_seed[k];
     }
-    if (i + 1 < p.m) {
-      unsigned long long best = 0ull;
+    if (i + 1 == p.m) break;
+    unsigned long long best = 1ull;                      // non-zero sentinel: an empty slice still signals arrival
 #pragma unroll
-      for (int q = 0; q < GPT; ++q) {
-        const int lg = tid + q * T;
-        const long long g = g0 + lg;
-        if (g < g1) {
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-          if (lg < rg) {
-            const float4* xp = xs4 + lg;
-#pragma unroll 8
-            for (int k = 0; k < p.d; ++k) {
-              const float4 v = xp[size_t(k) * rg];
-              const float sk = s_seed[k];
-              a0 = fmaf(v.x, sk, a0); a1 = fmaf(v.y, sk, a1); a2 = fmaf(v.z, sk, a2); a3 = fmaf(v.w, sk, a3);
-            }
-          } else {
-            const float* xp = Xb + g * 4;
-#pragma unroll 8
-            for (int k = 0; k < p.d; ++k) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(xp + k * p.sd));
-              const float sk = s_seed[k];
-              a0 = fmaf(v.x, sk, a0); a1 = fmaf(v.y, sk, a1); a2 = fmaf(v.z, sk, a2); a3 = fmaf(v.w, sk, a3);
-            }
+    for (int q = 0; q < GPT; ++q) {
+      const int lg = tid + q * T;
+      const long long g = g0 + lg;
+      if (g < g1) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (lg < rg) {
+          const float4* xp = xs4 + lg;
+#pragma unroll 16
+          for (int k = 0; k < p.d; ++k) {
+            const float4 v = xp[size_t(k) * rg];
+            const float sk = s_seed[k];
+            a0 = fmaf(v.x, sk, a0); a1 = fmaf(v.y, sk, a1); a2 = fmaf(v.z, sk, a2); a3 = fmaf(v.w, sk, a3);
           }
-          const float d0 = 0.5f * (1.0f - a0), d1 = 0.5f * (1.0f - a1), d2 = 0.5f * (1.0f - a2), d3 = 0.5f * (1.0f - a3);
-          if (i == 0) {
-            r[q][0] = d0; r[q][1] = d1; r[q][2] = d2; r[q][3] = d3;
-          } else {
-            r[q][0] = d0 < r[q][0] ? d0 : r[q][0];
-            r[q][1] = d1 < r[q][1] ? d1 : r[q][1];
-            r[q][2] = d2 < r[q][2] ? d2 : r[q][2];
-            r[q][3] = d3 < r[q][3] ? d3 : r[q][3];
-          }
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const unsigned long long key = pack_key(r[q][jj], static_cast<unsigned int>(g * 4 + jj));
-            best = key > best ? key : best;
+        } else {
+          const float* xp = Xb + g * 4;
+#pragma unroll 16
+          for (int k = 0; k < p.d; ++k) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xp + k * p.sd));
+            const float sk = s_seed[k];
+            a0 = fmaf(v.x, sk, a0); a1 = fmaf(v.y, sk, a1); a2 = fmaf(v.z, sk, a2); a3 = fmaf(v.w, sk, a3);
           }
         }
+        const float d0 = 0.5f * (1.0f - a0), d1 = 0.5f * (1.0f - a1), d2 = 0.5f * (1.0f - a2), d3 = 0.5f * (1.0f - a3);
+        if (i == 0) {
+          r[q][0] = d0; r[q][1] = d1; r[q][2] = d2; r[q][3] = d3;
+        } else {
+          r[q][0] = d0 < r[q][0] ? d0 : r[q][0];
+          r[q][1] = d1 < r[q][1] ? d1 : r[q][1];
+          r[q][2] = d2 < r[q][2] ? d2 : r[q][2];
+          r[q][3] = d3 < r[q][3] ? d3 : r[q][3];
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const unsigned long long key = pack_key(r[q][jj], static_cast<unsigned int>(g * 4 + jj));
+          best = key > best ? key : best;
+        }
       }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if ((tid & 31) == 0) s_red[tid >> 5] = best;
+    __syncthreads();
+    if (tid < 32) {
+      unsigned long long v = (tid < (T >> 5)) ? s_red[tid] : 0ull;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-        best = other > best ? other : best;
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
       }
-      if ((tid & 31) == 0) s_red[tid >> 5] = best;
-      __syncthreads();
-      if (tid < 32) {
-        unsigned long long v = (tid < (T >> 5)) ? s_red[tid] : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
-          v = other > v ? other : v;
+      unsigned long long* row = my_slots + size_t(i + 1) * nb;
+      if (tid == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(row + rank), "l"(v) : "memory");
+      // poll the nb slots of this item: every slot non-zero <=> every CTA of the item finished pass i
+      unsigned long long gmax = 0ull;
+      bool done = false;
+      for (unsigned int it = 0; it < (1u << 24) && !done; ++it) {
+        bool all = true;
+        gmax = 0ull;
+        for (int c = tid; c < nb; c += 32) {
+          unsigned long long kv;
+          asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(kv) : "l"(row + c) : "memory");
+          all = all && (kv != 0ull);
+          gmax = kv > gmax ? kv : gmax;
         }
-        if (tid == 0 && v != 0ull) atomicMax(p.keys + size_t(b) * p.m + i + 1, v);
+        done = __all_sync(0xffffffffu, all);
       }
-      target += gridDim.x;
-      if (!grid_barrier(p.barrier, target, p.err)) return;
+      if (!done && tid == 0) atomicOr(p.err, ERR_GRID_BARRIER_TIMEOUT);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, gmax, o);
+        gmax = other > gmax ? other : gmax;
+      }
+      if (tid == 0) s_idx = done ? static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(gmax & 0xFFFFFFFFull)) : -1;
     }
+    __syncthreads();
+    idx = s_idx;
+    if (idx < 0) return;     // time-out: error word is set
   }
 }
 
-static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, cudaStream_t stream, bool* used) {
+
+static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned long long* slots, size_t slot_bytes,
+                                  cudaStream_t stream, bool* used) {
   *used = false;
   const int sms = sm_count();
   if (sms <= 0 || s.batch > sms) return UOC_OK;
@@ -349,8 +384,14 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, cudaStream
   const long long chunk_ll = (ngroups + nb - 1) / nb;
   if (chunk_ll > 4096) return UOC_OK;
   const int chunk = int(chunk_ll);
-  const int gpt = (chunk + 1023) / 1024;
-  const int gpt_t = gpt <= 1 ? 1 : (gpt <= 2 ? 2 : 4);
+  if (size_t(s.batch) * s.m * nb * sizeof(unsigned long long) > slot_bytes) return UOC_OK;
+  // threads: one float4 group per thread when the slice fits 512 threads (112 registers available -> 16 loads in
+  // flight), otherwise up to 1024 threads / several groups per thread
+  int gpt_t, maxt;
+  if (chunk <= 576) { gpt_t = 1; maxt = 576; }
+  else if (chunk <= 1024) { gpt_t = 1; maxt = 1024; }
+  else if (chunk <= 2048) { gpt_t = 2; maxt = 1024; }
+  else { gpt_t = 4; maxt = 1024; }
   int threads = ((chunk + gpt_t - 1) / gpt_t + 31) / 32 * 32;
   if (threads < 64) threads = 64;
   size_t budget = 200 * 1024;
@@ -358,11 +399,15 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, cudaStream
   int rg = int(budget / (16 * size_t(s.d)));
   if (rg > chunk) rg = chunk;
   const size_t smem = size_t(rg) * s.d * 16 + size_t(s.d) * 4 + 16;
-  void* kern = gpt_t == 1 ? reinterpret_cast<void*>(&fps2_kernel<1>)
-                          : (gpt_t == 2 ? reinterpret_cast<void*>(&fps2_kernel<2>) : reinterpret_cast<void*>(&fps2_kernel<4>));
+  void* kern;
+  if (maxt == 576) kern = reinterpret_cast<void*>(&fps2_kernel<1, 576>);
+  else if (gpt_t == 1) kern = reinterpret_cast<void*>(&fps2_kernel<1, 1024>);
+  else if (gpt_t == 2) kern = reinterpret_cast<void*>(&fps2_kernel<2, 1024>);
+  else kern = reinterpret_cast<void*>(&fps2_kernel<4, 1024>);
   UOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  UOC_CUDA(cudaMemsetAsync(slots, 0, size_t(s.batch) * s.m * nb * sizeof(unsigned long long), stream));
   int nb_i = nb, chunk_i = chunk, rg_i = rg;
-  void* args[] = {&p, &nb_i, &chunk_i, &rg_i};
+  void* args[] = {&p, &nb_i, &chunk_i, &rg_i, &slots};
   UOC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(nb * s.batch), dim3(threads), args, smem, stream));
   count_launch();
   *used = true;
@@ -384,7 +429,7 @@ int launch_select_seeds(const float* X, const ClusterShape& s, const ClusterWork
                     (reinterpret_cast<uintptr_t>(X) % 16 == 0);
   if (vec4) {
     bool used = false;
-    int rc = launch_select_seeds_v2(p, s, stream, &used);
+    int rc = launch_select_seeds_v2(p, s, w.slots, w.slot_bytes, stream, &used);
     if (rc != UOC_OK || used) return rc;
   }
   void* kern = vec4 ? reinterpret_cast<void*>(&fps_kernel<4>) : reinterpret_cast<void*>(&fps_kernel<1>);

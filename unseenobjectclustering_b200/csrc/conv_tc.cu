@@ -10,6 +10,15 @@
 //   K-major layout the UMMA descriptor expects; no im2col buffer exists anywhere.
 //   warp 0: TMA producer, warp 1: MMA issuer (one thread), warps 2-5: epilogue
 //   (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/fp32 -> global).
+//
+//   The path is L2->SMEM bandwidth bound at batch 1 (every M tile re-reads the whole weight slab of its
+//   N tile), so CLUSTER consecutive M tiles form a thread-block cluster that shares ONE copy of the
+//   weight tile per K block: each CTA fetches BLOCK_N/CLUSTER rows and TMA-multicasts them into all
+//   CLUSTER shared memories; a stage is recycled only when every CTA of the cluster has consumed it
+//   (tcgen05.commit multicast onto all CTAs' empty barriers).
+#include <cstdlib>
+#include <cstring>
+
 #include "conv.cuh"
 
 namespace uoc {
@@ -25,7 +34,7 @@ struct ConvTcParams {
   const float* bias[2];
   const void* residual[2];
   void* y[2];
-  int Ho, Wo, Cin, Cout;
+  int N, Ho, Wo, Cin, Cout;
   int tiles_x, tiles_y, n_tiles;
   int ksize, stride, dil, pad;
   int relu, out_fp32;
@@ -41,10 +50,13 @@ struct ConvCfg {
   static constexpr uint32_t kTmemCols = BLOCK_N;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CLUSTER>
 __global__ void __launch_bounds__(kThreads)
 conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
+  constexpr int kSliceRows = BLOCK_N / CLUSTER;
+  constexpr uint16_t kMask = uint16_t((1u << CLUSTER) - 1u);
+  static_assert(kSliceRows >= 8 && kSliceRows % 8 == 0, "weight slice must be whole 8-row swizzle atoms");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -55,8 +67,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.z;
-  const int n_tile = blockIdx.x % p.n_tiles;
-  int m_tile = blockIdx.x / p.n_tiles;
+  // blockIdx.x = ((m_cluster * n_tiles) + n_tile) * CLUSTER + rank ; the CLUSTER CTAs of a cluster share n_tile
+  const int rank = int(blockIdx.x) % CLUSTER;
+  const int cl = int(blockIdx.x) / CLUSTER;
+  const int n_tile = cl % p.n_tiles;
+  int m_tile = (cl / p.n_tiles) * CLUSTER + rank;       // may exceed the real tile count (padding CTAs): all-zero A, no stores
   const int tx = m_tile % p.tiles_x; m_tile /= p.tiles_x;
   const int ty = m_tile % p.tiles_y;
   const int img = m_tile / p.tiles_y;
@@ -67,7 +82,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_x[g]);
     tma_prefetch_desc(&p.tmap_w[g]);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CLUSTER); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -78,6 +93,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CLUSTER > 1) cluster_sync_all();     // every CTA's barriers are initialised before any remote arrive / multicast
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -92,7 +108,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
         uint8_t* st = smem + s * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
         tma_load_4d(st, &p.tmap_x[g], &full[s], cb * 64, x_base + sx * p.dil, y_base + r * p.dil, img);
-        tma_load_2d(st + kABytes, &p.tmap_w[g], &full[s], kb * 64, n0);
+        if (CLUSTER == 1)
+          tma_load_2d(st + kABytes, &p.tmap_w[g], &full[s], kb * 64, n0);
+        else
+          tma_load_2d_mc(st + kABytes + rank * kSliceRows * 128, &p.tmap_w[g], &full[s], kb * 64, n0 + rank * kSliceRows, kMask);
       }
     }
   } else if (warp == 1) {
@@ -111,7 +130,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
           const uint64_t bd = make_smem_desc_sw128(b_addr + ks * 32, 16, 1024);
           umma_ss_f16(tmem_base, ad, bd, idesc, (kb | ks) ? 1u : 0u);
         }
-        umma_commit(&empty[s]);
+        if (CLUSTER == 1) umma_commit(&empty[s]);
+        else umma_commit_mc(&empty[s], kMask);
       }
       if (ok) umma_commit(acc_full);
     }
@@ -119,7 +139,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int oy = ty * 8 + (row >> 4), ox = tx * 16 + (row & 15);
-    const bool inb = (oy < p.Ho) && (ox < p.Wo);
+    const bool inb = (oy < p.Ho) && (ox < p.Wo) && (img < p.N);
     const size_t pix = (size_t(img) * p.Ho + oy) * p.Wo + ox;
     const float* bias = p.bias[g] + n0;
     if (mbar_wait(acc_full, 0, p.err)) {
@@ -175,20 +195,45 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();     // no CTA leaves while peers may still multicast into it / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CLUSTER>
 int launch(const ConvTcParams& prm, int m_tiles, int groups, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
   static bool attr = false;
   if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    UOC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr = true;
   }
-  conv_tc_kernel<BLOCK_N><<<dim3(m_tiles * prm.n_tiles, 1, groups), kThreads, Cfg::kSmemBytes, stream>>>(prm);
-  UOC_CHECK_LAUNCH();
+  const int m_clusters = (m_tiles + CLUSTER - 1) / CLUSTER;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(m_clusters * prm.n_tiles * CLUSTER, 1, groups);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = CLUSTER;
+  lattr[0].val.clusterDim.y = 1;
+  lattr[0].val.clusterDim.z = 1;
+  cfg.attrs = lattr;
+  cfg.numAttrs = 1;
+  UOC_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, CLUSTER>, prm));
+  count_launch();
   return UOC_OK;
+}
+
+template <int BLOCK_N>
+int launch_n(const ConvTcParams& prm, int cluster, int m_tiles, int groups, cudaStream_t stream) {
+  switch (cluster) {
+    case 8: if (BLOCK_N >= 64) return launch<BLOCK_N, 8>(prm, m_tiles, groups, stream);
+    case 4: return launch<BLOCK_N, 4>(prm, m_tiles, groups, stream);
+    case 2: return launch<BLOCK_N, 2>(prm, m_tiles, groups, stream);
+    default: return launch<BLOCK_N, 1>(prm, m_tiles, groups, stream);
+  }
 }
 
 }  // namespace
@@ -203,10 +248,14 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
   const int pad = (p.ksize == 3) ? p.dilation : 0;
   prm.Ho = conv_out_dim(p.H, p.ksize, p.stride, p.dilation);
   prm.Wo = conv_out_dim(p.W, p.ksize, p.stride, p.dilation);
-  prm.Cin = p.Cin; prm.Cout = p.Cout;
+  prm.Cin = p.Cin; prm.Cout = p.Cout; prm.N = p.N;
   prm.tiles_x = (prm.Wo + 15) / 16;
   prm.tiles_y = (prm.Ho + 7) / 8;
-  const int block_n = (p.Cout % 128 == 0) ? 128 : 64;
+  int block_n = (p.Cout % 256 == 0) ? 256 : ((p.Cout % 128 == 0) ? 128 : 64);
+  int cluster = 4;
+  if (const char* e = getenv("UOC_CONV_CLUSTER")) cluster = atoi(e);
+  if (const char* e = getenv("UOC_CONV_MAX_BLOCK_N")) { int mx = atoi(e); while (block_n > mx && block_n > 64) block_n /= 2; }
+  if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = 1;
   prm.n_tiles = p.Cout / block_n;
   prm.ksize = p.ksize; prm.stride = p.stride; prm.dil = p.dilation; prm.pad = pad;
   prm.relu = p.relu; prm.out_fp32 = p.out_fp32;
@@ -222,7 +271,7 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
     if (rc != UOC_OK) return rc;
     const uint64_t wd[2] = {uint64_t(taps) * p.Cin, uint64_t(p.Cout)};
     const uint64_t wsb[1] = {uint64_t(taps) * p.Cin * 2};
-    const uint32_t wb[2] = {64, uint32_t(block_n)};
+    const uint32_t wb[2] = {64, uint32_t(block_n / cluster)};   // each CTA of a cluster fetches (and multicasts) one slice
     rc = make_tmap_bf16(&prm.tmap_w[g], p.g[g].w, 2, wd, wsb, wb, nullptr);
     if (rc != UOC_OK) return rc;
     prm.bias[g] = p.g[g].bias;
@@ -230,7 +279,9 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
     prm.y[g] = p.g[g].y;
   }
   const int m_tiles = p.N * prm.tiles_y * prm.tiles_x;
-  return (block_n == 128) ? launch<128>(prm, m_tiles, p.groups, stream) : launch<64>(prm, m_tiles, p.groups, stream);
+  if (block_n == 256) return launch_n<256>(prm, cluster, m_tiles, p.groups, stream);
+  if (block_n == 128) return launch_n<128>(prm, cluster, m_tiles, p.groups, stream);
+  return launch_n<64>(prm, cluster, m_tiles, p.groups, stream);
 }
 
 }  // namespace uoc
