@@ -51,7 +51,9 @@ static WsLayout ws_layout(int batch, int64_t n, int d, int m) {
     int sms = sm_count();
     if (sms <= 0) sms = 148;
     const int nb = batch <= sms ? sms / batch : 1;
-    L.slot_bytes = sizeof(unsigned long long) * size_t(batch) * m * nb;
+    size_t per_pass = size_t(nb) * 128;                               // leader protocol: one line per CTA
+    if (size_t(nb) * nb * 8 > per_pass) per_pass = size_t(nb) * nb * 8;   // all-to-all protocol: nb x nb key matrix
+    L.slot_bytes = size_t(batch) * m * per_pass + size_t(batch) * m * d * 8;   // key slots + seed mailboxes
     L.slots = carve(off, L.slot_bytes);
   }
   L.barrier = carve(off, 256);
@@ -111,6 +113,8 @@ struct FpsParams {
   long long* selected_out;
   float* seeds_out;
   unsigned int* err;
+  long long* trace;       // optional (debug): per pass {start, after local arg-max, after exchange} clock64 of CTA `trace_cta`
+  int trace_cta;
 };
 
 __device__ __forceinline__ unsigned int orderable(float f) {
@@ -252,25 +256,30 @@ __global__ void __launch_bounds__(256) fps_kernel(FpsParams p) {
 //  (1) the running min r[] of a thread's points lives in registers;
 //  (2) as much of the slice as fits (~200 KB) is copied once into shared memory and re-read from there in
 //      every pass -- only the rest is streamed from L2;
-//  (3) the slice is split evenly (no thread runs a second trip) and 16 channel loads are in flight per thread;
-//  (4) no atomics and no grid barrier: each CTA publishes its packed (distance, index) arg-max key in its own
-//      slot keys[item][pass][rank]; warp 0 of every CTA polls the nb slots of its item, takes the maximum
-//      and thereby learns the next seed.  The slots double as the inter-CTA barrier (a non-zero slot means
-//      "this CTA has finished pass i"), batch items never wait for each other.
+//  (3) the slice is split evenly (no thread runs a second trip), UNROLL channel loads in flight per thread;
+//  (4) SYNC == 0: contention-free exchange without atomics or fences.  Each CTA stores its packed
+//      (distance, index) arg-max key into its OWN 128-byte slot; warp 0 of the item's rank-0 CTA (the leader)
+//      polls the nb slots, takes the maximum, gathers the winning point's channels and publishes them as d
+//      self-validating 64-bit words {pass tag, float bits} in a per-pass mailbox; all CTAs poll the mailbox
+//      words they need.  Every word carries its own validity (non-zero key / matching tag), so no ordering
+//      between stores is required, nothing is ever reset inside the kernel and batch items never wait for
+//      each other.   SYNC == 1: atomicMax + counting grid barrier (first-generation protocol).
 // Same canonical arithmetic as fps_kernel (bit-identical results).
-template <int GPT, int MAXT>   // float4 groups (4 consecutive points) per thread, max threads per CTA
-__global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int chunk, int rg, unsigned long long* slots) {
+template <int GPT, int MAXT, int UNROLL, int SYNC>
+__global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int chunk, int rg, unsigned long long* slots,
+                                                       unsigned long long* mail) {
   extern __shared__ float4 xs4[];                       // [d][rg] resident slice, then d floats of the current seed
   float* s_seed = reinterpret_cast<float*>(xs4 + size_t(p.d) * rg);
   __shared__ unsigned long long s_red[32];
   __shared__ long long s_idx;
+  __shared__ int s_fail;
   const int tid = threadIdx.x, T = blockDim.x;
   const int b = blockIdx.x / nb, rank = blockIdx.x % nb;
   const long long ngroups = p.n / 4;
   const long long g0 = (long long)rank * chunk;
   const long long g1 = (g0 + chunk < ngroups) ? g0 + chunk : ngroups;
   const float* Xb = p.X + b * p.sb;
-  unsigned long long* my_slots = slots + size_t(b) * p.m * nb;      // [pass][rank]
+  if (tid == 0) s_fail = 0;
   for (int lg = tid; lg < rg && g0 + lg < g1; lg += T) {
     const float* xp = Xb + (g0 + lg) * 4;
 #pragma unroll 8
@@ -280,14 +289,15 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
 #pragma unroll
   for (int q = 0; q < GPT; ++q) { r[q][0] = r[q][1] = r[q][2] = r[q][3] = 0.f; }
   long long idx = p.first[b];
+  for (int k = tid; k < p.d; k += T) s_seed[k] = __ldg(Xb + k * p.sd + idx);
+  __syncthreads();
   for (int i = 0; i < p.m; ++i) {
-    for (int k = tid; k < p.d; k += T) s_seed[k] = __ldg(Xb + k * p.sd + idx);
-    __syncthreads();
     if (rank == 0) {
       if (tid == 0) p.selected_out[size_t(b) * p.m + i] = idx;
       for (int k = tid; k < p.d; k += T) p.seeds_out[(size_t(b) * p.m + i) * p.d + k] = s_seed[k];
     }
     if (i + 1 == p.m) break;
+    if (p.trace && int(blockIdx.x) == p.trace_cta && tid == 0) p.trace[i * 3 + 0] = clock64();
     unsigned long long best = 1ull;                      // non-zero sentinel: an empty slice still signals arrival
 #pragma unroll
     for (int q = 0; q < GPT; ++q) {
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if (lg < rg) {
           const float4* xp = xs4 + lg;
-#pragma unroll 16
+#pragma unroll UNROLL
           for (int k = 0; k < p.d; ++k) {
             const float4 v = xp[size_t(k) * rg];
             const float sk = s_seed[k];
@@ -305,7 +315,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
           }
         } else {
           const float* xp = Xb + g * 4;
-#pragma unroll 16
+#pragma unroll UNROLL
           for (int k = 0; k < p.d; ++k) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(xp + k * p.sd));
             const float sk = s_seed[k];
@@ -334,7 +344,8 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
       best = other > best ? other : best;
     }
     if ((tid & 31) == 0) s_red[tid >> 5] = best;
-    __syncthreads();
+    __syncthreads();                                     // also: everybody is done reading s_seed of this pass
+    if (p.trace && int(blockIdx.x) == p.trace_cta && tid == 0) p.trace[i * 3 + 1] = clock64();
     if (tid < 32) {
       unsigned long long v = (tid < (T >> 5)) ? s_red[tid] : 0ull;
 #pragma unroll
@@ -342,36 +353,126 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
         v = other > v ? other : v;
       }
-      unsigned long long* row = my_slots + size_t(i + 1) * nb;
-      if (tid == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(row + rank), "l"(v) : "memory");
-      // poll the nb slots of this item: every slot non-zero <=> every CTA of the item finished pass i
-      unsigned long long gmax = 0ull;
-      bool done = false;
-      for (unsigned int it = 0; it < (1u << 24) && !done; ++it) {
-        bool all = true;
-        gmax = 0ull;
-        for (int c = tid; c < nb; c += 32) {
-          unsigned long long kv;
-          asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(kv) : "l"(row + c) : "memory");
-          all = all && (kv != 0ull);
-          gmax = kv > gmax ? kv : gmax;
-        }
-        done = __all_sync(0xffffffffu, all);
-      }
-      if (!done && tid == 0) atomicOr(p.err, ERR_GRID_BARRIER_TIMEOUT);
+      if (SYNC == 0) {
+        unsigned long long* row = slots + (size_t(b) * p.m + (i + 1)) * nb * 16;     // one 128-byte line per CTA
+        if (tid == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(row + size_t(rank) * 16), "l"(v) : "memory");
+        if (rank == 0) {
+          // leader: wait for every CTA of the item, arg-max, gather the winner's channels, publish
+          unsigned long long gmax = 0ull;
+          bool done = false;
+          for (unsigned int it = 0; it < (1u << 22) && !done; ++it) {
+            unsigned long long kv[5];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, gmax, o);
-        gmax = other > gmax ? other : gmax;
+            for (int sidx = 0; sidx < 5; ++sidx) {
+              const int c = tid + 32 * sidx;
+              kv[sidx] = 1ull;
+              if (c < nb) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(kv[sidx]) : "l"(row + size_t(c) * 16));
+            }
+            bool all = true;
+            gmax = 0ull;
+#pragma unroll
+            for (int sidx = 0; sidx < 5; ++sidx) {
+              all = all && (kv[sidx] != 0ull);
+              gmax = kv[sidx] > gmax ? kv[sidx] : gmax;
+            }
+            done = __all_sync(0xffffffffu, all);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, gmax, o);
+            gmax = other > gmax ? other : gmax;
+          }
+          const long long widx = static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(gmax & 0xFFFFFFFFull));
+          if (tid == 0) s_idx = widx;
+          unsigned long long* mrow = mail + (size_t(b) * p.m + (i + 1)) * p.d;
+          const unsigned long long tag = done ? (static_cast<unsigned long long>(i + 1) << 32)
+                                              : (0xFFFFFFFFull << 32);            // poison tag: readers give up too
+          for (int k = tid; k < p.d; k += 32) {
+            const float val = done ? __ldg(Xb + k * p.sd + widx) : 0.f;
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mrow + k), "l"(tag | __float_as_uint(val)) : "memory");
+          }
+          if (!done && tid == 0) atomicOr(p.err, ERR_GRID_BARRIER_TIMEOUT);
+        }
+      } else if (SYNC == 2) {
+        // all-to-all: this CTA's key goes into column `rank` of EVERY CTA's private row; then poll the own row
+        unsigned long long* mat = slots + (size_t(b) * p.m + (i + 1)) * nb * nb;
+#pragma unroll
+        for (int sidx = 0; sidx < 5; ++sidx) {
+          const int c = tid + 32 * sidx;
+          if (c < nb) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mat + size_t(c) * nb + rank), "l"(v) : "memory");
+        }
+        const unsigned long long* row = mat + size_t(rank) * nb;
+        unsigned long long gmax = 0ull;
+        bool done = false;
+        for (unsigned int it = 0; it < (1u << 22) && !done; ++it) {
+          unsigned long long kv[5];
+#pragma unroll
+          for (int sidx = 0; sidx < 5; ++sidx) {
+            const int c = tid + 32 * sidx;
+            kv[sidx] = 1ull;
+            if (c < nb) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(kv[sidx]) : "l"(row + c));
+          }
+          bool all = true;
+          gmax = 0ull;
+#pragma unroll
+          for (int sidx = 0; sidx < 5; ++sidx) {
+            all = all && (kv[sidx] != 0ull);
+            gmax = kv[sidx] > gmax ? kv[sidx] : gmax;
+          }
+          done = __all_sync(0xffffffffu, all);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, gmax, o);
+          gmax = other > gmax ? other : gmax;
+        }
+        if (tid == 0) {
+          s_idx = done ? static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(gmax & 0xFFFFFFFFull)) : -1;
+          if (!done) atomicOr(p.err, ERR_GRID_BARRIER_TIMEOUT);
+        }
+      } else {
+        if (tid == 0) atomicMax(p.keys + size_t(b) * p.m + i + 1, v);
       }
-      if (tid == 0) s_idx = done ? static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(gmax & 0xFFFFFFFFull)) : -1;
     }
-    __syncthreads();
-    idx = s_idx;
-    if (idx < 0) return;     // time-out: error word is set
+    if (SYNC == 2) {
+      __syncthreads();
+      idx = s_idx;
+      if (idx < 0) return;
+      for (int k = tid; k < p.d; k += T) s_seed[k] = __ldg(Xb + k * p.sd + idx);
+      __syncthreads();
+      if (p.trace && int(blockIdx.x) == p.trace_cta && tid == 0) p.trace[i * 3 + 2] = clock64();
+    } else if (SYNC == 0) {
+      // every CTA: fetch the new seed from the mailbox (each word validates itself by its tag)
+      const unsigned long long* mrow = mail + (size_t(b) * p.m + (i + 1)) * p.d;
+      for (int k = tid; k < p.d; k += T) {
+        unsigned long long w = 0ull;
+        unsigned int it = 0;
+        for (; it < (1u << 22); ++it) {
+          asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(mrow + k));
+          if (static_cast<unsigned int>(w >> 32) == static_cast<unsigned int>(i + 1)) break;
+          if (static_cast<unsigned int>(w >> 32) == 0xFFFFFFFFu) { it = 1u << 22; break; }
+        }
+        if (it >= (1u << 22)) s_fail = 1;
+        s_seed[k] = __uint_as_float(static_cast<unsigned int>(w & 0xFFFFFFFFull));
+      }
+      __syncthreads();
+      if (s_fail) { if (tid == 0) atomicOr(p.err, ERR_GRID_BARRIER_TIMEOUT); return; }
+      idx = s_idx;                                       // meaningful on the leader only (it alone writes the outputs)
+      if (p.trace && int(blockIdx.x) == p.trace_cta && tid == 0) p.trace[i * 3 + 2] = clock64();
+    } else {
+      if (!grid_barrier(p.barrier, (unsigned int)(i + 1) * gridDim.x, p.err)) return;
+      if (tid == 0) {
+        const unsigned long long key = __ldcg(p.keys + size_t(b) * p.m + i + 1);
+        s_idx = static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(key & 0xFFFFFFFFull));
+      }
+      __syncthreads();
+      idx = s_idx;
+      for (int k = tid; k < p.d; k += T) s_seed[k] = __ldg(Xb + k * p.sd + idx);
+      __syncthreads();
+      if (p.trace && int(blockIdx.x) == p.trace_cta && tid == 0) p.trace[i * 3 + 2] = clock64();
+    }
   }
 }
-
 
 static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned long long* slots, size_t slot_bytes,
                                   cudaStream_t stream, bool* used) {
@@ -380,12 +481,18 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
   if (sms <= 0 || s.batch > sms) return UOC_OK;
   if (const char* e = getenv("UOC_FPS_V1")) { if (atoi(e) != 0) return UOC_OK; }
   const int nb = sms / s.batch;
+  if (nb > 160) return UOC_OK;                      // the leader's poll loop reads at most 5 slots per lane
   const long long ngroups = s.n / 4;
   const long long chunk_ll = (ngroups + nb - 1) / nb;
   if (chunk_ll > 4096) return UOC_OK;
   const int chunk = int(chunk_ll);
-  if (size_t(s.batch) * s.m * nb * sizeof(unsigned long long) > slot_bytes) return UOC_OK;
-  // threads: one float4 group per thread when the slice fits 512 threads (112 registers available -> 16 loads in
+  int variant = 2;   // 0: leader + mailbox, 1: atomicMax + grid barrier, 2: all-to-all key exchange   (A/B knob)
+  if (const char* e = getenv("UOC_FPS_VARIANT")) variant = atoi(e);
+  const size_t slot_need = (variant == 2) ? size_t(s.batch) * s.m * nb * nb * 8 : size_t(s.batch) * s.m * nb * 128;
+  const size_t mail_need = size_t(s.batch) * s.m * s.d * 8;
+  if (slot_need + mail_need > slot_bytes) return UOC_OK;
+  unsigned long long* mail = slots + slot_need / 8;
+  // threads: one float4 group per thread when the slice fits 576 threads (112 registers available -> 16 loads in
   // flight), otherwise up to 1024 threads / several groups per thread
   int gpt_t, maxt;
   if (chunk <= 576) { gpt_t = 1; maxt = 576; }
@@ -400,14 +507,23 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
   if (rg > chunk) rg = chunk;
   const size_t smem = size_t(rg) * s.d * 16 + size_t(s.d) * 4 + 16;
   void* kern;
-  if (maxt == 576) kern = reinterpret_cast<void*>(&fps2_kernel<1, 576>);
-  else if (gpt_t == 1) kern = reinterpret_cast<void*>(&fps2_kernel<1, 1024>);
-  else if (gpt_t == 2) kern = reinterpret_cast<void*>(&fps2_kernel<2, 1024>);
-  else kern = reinterpret_cast<void*>(&fps2_kernel<4, 1024>);
+#define UOC_FPS_PICK(G, MT, U) (variant == 0 ? reinterpret_cast<void*>(&fps2_kernel<G, MT, U, 0>) \
+                               : (variant == 1 ? reinterpret_cast<void*>(&fps2_kernel<G, MT, U, 1>) \
+                                               : reinterpret_cast<void*>(&fps2_kernel<G, MT, U, 2>)))
+  if (maxt == 576) kern = UOC_FPS_PICK(1, 576, 16);
+  else if (gpt_t == 1) kern = UOC_FPS_PICK(1, 1024, 8);
+  else if (gpt_t == 2) kern = UOC_FPS_PICK(2, 1024, 8);
+  else kern = UOC_FPS_PICK(4, 1024, 8);
+#undef UOC_FPS_PICK
   UOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  UOC_CUDA(cudaMemsetAsync(slots, 0, size_t(s.batch) * s.m * nb * sizeof(unsigned long long), stream));
+  if (variant == 0 || variant == 2) {
+    UOC_CUDA(cudaMemsetAsync(slots, 0, slot_need + (variant == 0 ? mail_need : 0), stream));
+  } else {
+    UOC_CUDA(cudaMemsetAsync(p.keys, 0, sizeof(unsigned long long) * size_t(s.batch) * s.m, stream));
+    UOC_CUDA(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), stream));
+  }
   int nb_i = nb, chunk_i = chunk, rg_i = rg;
-  void* args[] = {&p, &nb_i, &chunk_i, &rg_i, &slots};
+  void* args[] = {&p, &nb_i, &chunk_i, &rg_i, &slots, &mail};
   UOC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(nb * s.batch), dim3(threads), args, smem, stream));
   count_launch();
   *used = true;
@@ -423,6 +539,13 @@ int launch_select_seeds(const float* X, const ClusterShape& s, const ClusterWork
   p.seeds_out = seeds_out;
   p.err = device_error_word();
   if (!p.err) return fail(UOC_ERR_CUDA, "no device error word");
+  p.trace = nullptr;
+  p.trace_cta = 0;
+  if (const char* e = getenv("UOC_FPS_TRACE")) {
+    // debug: the first 3*m int64 of the r[] scratch (unused by the second-generation kernel) receive the time stamps
+    p.trace = reinterpret_cast<long long*>(w.r);
+    p.trace_cta = atoi(e);
+  }
   UOC_CUDA(cudaMemsetAsync(w.keys, 0, sizeof(unsigned long long) * size_t(s.batch) * s.m, stream));
   UOC_CUDA(cudaMemsetAsync(w.barrier, 0, sizeof(unsigned int), stream));
   const bool vec4 = (s.n % 4 == 0) && (s.stride_d % 4 == 0) && (s.stride_b % 4 == 0) &&

@@ -97,7 +97,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {    // one elected lane: lets the compiler keep descriptors / barriers in uniform registers
       const int x_base = tx * 16 * p.stride - p.pad;
       const int y_base = ty * 8 * p.stride - p.pad;
       for (int kb = 0; kb < KB; ++kb) {
@@ -115,7 +115,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {    // one elected lane: lets the compiler keep descriptors / barriers in uniform registers
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
       bool ok = true;
       for (int kb = 0; kb < KB; ++kb) {
@@ -251,8 +251,11 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
   prm.Cin = p.Cin; prm.Cout = p.Cout; prm.N = p.N;
   prm.tiles_x = (prm.Wo + 15) / 16;
   prm.tiles_y = (prm.Ho + 7) / 8;
-  int block_n = (p.Cout % 256 == 0) ? 256 : ((p.Cout % 128 == 0) ? 128 : 64);
-  int cluster = 4;
+  // Measured on B200 (profiles/r01_conv_notes.md): the kernel is bound by the ~48 B/clk/SM TMA ingest rate, which
+  // multicast does not relieve (the bytes still enter every SM), so the defaults are the plain 128-wide tiles, 2 CTAs/SM.
+  int block_n = (p.Cout % 128 == 0) ? 128 : 64;
+  if (const char* e = getenv("UOC_CONV_BLOCK_N")) { if (atoi(e) == 256 && p.Cout % 256 == 0) block_n = 256; }
+  int cluster = 1;
   if (const char* e = getenv("UOC_CONV_CLUSTER")) cluster = atoi(e);
   if (const char* e = getenv("UOC_CONV_MAX_BLOCK_N")) { int mx = atoi(e); while (block_n > mx && block_n > 64) block_n /= 2; }
   if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = 1;

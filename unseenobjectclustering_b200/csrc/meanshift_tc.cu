@@ -100,7 +100,7 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {    // one elected lane: lets the compiler keep descriptors / barriers in uniform registers
       for (int j = 0; j < T; ++j) {
         const int s = j % Cfg::kStages;
         const uint32_t ph = (j / Cfg::kStages) & 1;
@@ -113,7 +113,7 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {    // one elected lane: lets the compiler keep descriptors / barriers in uniform registers
       constexpr uint32_t idesc1 = make_idesc_bf16(128, kTile, 0, 0);
       constexpr uint32_t idesc2 = make_idesc_bf16(128, D, 0, 1);
       const uint32_t zs_addr = smem_u32(zs);
