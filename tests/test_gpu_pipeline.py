@@ -59,3 +59,29 @@ def test_end_to_end_with_real_backbone_runs():
     img, xyz = O.synthetic_rgbd_frame(240, 320, seed=0)
     out_label, refined = TD.test_sample({'image_color': img, 'depth': xyz}, net, None, [17])
     assert out_label.shape == (1, 240, 320) and refined is None
+
+
+def test_frame_pipeline_equals_serial_calls():
+    """Frames in flight on two streams (pipeline.py) give exactly the labels of one-at-a-time calls."""
+    from unseenobjectclustering_b200 import mean_shift as MS
+    from unseenobjectclustering_b200.pipeline import FramePipeline
+    H, W = 96, 128
+    fields = [O.synthetic_clustered_features(H, W, 64, 3, 0.05, seed=70 + k)[0].to(DEV) for k in range(5)]
+    firsts = [5, 50, 500, 5000, 11]
+    it = iter(fields)
+
+    def net(i, l, d):
+        return next(it).clone()
+
+    pipe = FramePipeline(net, H, W, depth=2)
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed=0)
+    outs = []
+    for k in range(5):
+        pipe.submit(img, xyz, firsts[k])
+        if len(pipe.pending) == 2:
+            outs.append(pipe.collect_one()[0].clone())
+    outs.extend(o[0].clone() for o in pipe.drain())
+    assert len(outs) == 5
+    for k in range(5):
+        want, _ = MS.cluster_fields(fields[k], 100, first_indices=[firsts[k]], flags=_lib.FLAG_SYNC_CHECK)
+        assert torch.equal(outs[k].view(-1).to(torch.int32), want[0].cpu())

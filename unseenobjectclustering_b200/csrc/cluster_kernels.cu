@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) fps_kernel(FpsParams p) {
 //      each other.   SYNC == 1: atomicMax + counting grid barrier (first-generation protocol).
 // Same canonical arithmetic as fps_kernel (bit-identical results).
 template <int GPT, int MAXT, int UNROLL, int SYNC>
-__global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int chunk, int rg, unsigned long long* slots,
+__global__ void __launch_bounds__(MAXT, (MAXT <= 320 ? 2 : 1)) fps2_kernel(FpsParams p, int nb, int chunk, int rg, unsigned long long* slots,
                                                        unsigned long long* mail) {
   extern __shared__ float4 xs4[];                       // [d][rg] resident slice, then d floats of the current seed
   float* s_seed = reinterpret_cast<float*>(xs4 + size_t(p.d) * rg);
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
       for (int k = tid; k < p.d; k += T) p.seeds_out[(size_t(b) * p.m + i) * p.d + k] = s_seed[k];
     }
     if (i + 1 == p.m) break;
-    if (p.trace && int(blockIdx.x) == p.trace_cta && tid == 0) p.trace[i * 3 + 0] = clock64();
+    if (p.trace && tid == 0) { if (int(blockIdx.x) == p.trace_cta) p.trace[i * 3 + 0] = clock64(); else if (p.trace_cta < 0 && i == 50) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); p.trace[blockIdx.x * 8 + 0] = clock64(); p.trace[blockIdx.x * 8 + 3] = smid; } }
     unsigned long long best = 1ull;                      // non-zero sentinel: an empty slice still signals arrival
 #pragma unroll
     for (int q = 0; q < GPT; ++q) {
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
     }
     if ((tid & 31) == 0) s_red[tid >> 5] = best;
     __syncthreads();                                     // also: everybody is done reading s_seed of this pass
-    if (p.trace && int(blockIdx.x) == p.trace_cta && tid == 0) p.trace[i * 3 + 1] = clock64();
+    if (p.trace && tid == 0) { if (int(blockIdx.x) == p.trace_cta) p.trace[i * 3 + 1] = clock64(); else if (p.trace_cta < 0 && i == 50) p.trace[blockIdx.x * 8 + 1] = clock64(); }
     if (tid < 32) {
       unsigned long long v = (tid < (T >> 5)) ? s_red[tid] : 0ull;
 #pragma unroll
@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
           if (c < nb) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mat + size_t(c) * nb + rank), "l"(v) : "memory");
         }
         const unsigned long long* row = mat + size_t(rank) * nb;
+        if (p.trace && p.trace_cta < 0 && i == 50 && tid == 0) p.trace[blockIdx.x * 8 + 4] = clock64();
         unsigned long long gmax = 0ull;
         bool done = false;
         for (unsigned int it = 0; it < (1u << 22) && !done; ++it) {
@@ -429,6 +430,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
         if (tid == 0) {
           s_idx = done ? static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(gmax & 0xFFFFFFFFull)) : -1;
           if (!done) atomicOr(p.err, ERR_GRID_BARRIER_TIMEOUT);
+          if (p.trace && p.trace_cta < 0 && i == 50) p.trace[blockIdx.x * 8 + 5] = clock64();
         }
       } else {
         if (tid == 0) atomicMax(p.keys + size_t(b) * p.m + i + 1, v);
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
       if (idx < 0) return;
       for (int k = tid; k < p.d; k += T) s_seed[k] = __ldg(Xb + k * p.sd + idx);
       __syncthreads();
-      if (p.trace && int(blockIdx.x) == p.trace_cta && tid == 0) p.trace[i * 3 + 2] = clock64();
+      if (p.trace && tid == 0) { if (int(blockIdx.x) == p.trace_cta) p.trace[i * 3 + 2] = clock64(); else if (p.trace_cta < 0 && i == 50) p.trace[blockIdx.x * 8 + 2] = clock64(); }
     } else if (SYNC == 0) {
       // every CTA: fetch the new seed from the mailbox (each word validates itself by its tag)
       const unsigned long long* mrow = mail + (size_t(b) * p.m + (i + 1)) * p.d;
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
       __syncthreads();
       if (s_fail) { if (tid == 0) atomicOr(p.err, ERR_GRID_BARRIER_TIMEOUT); return; }
       idx = s_idx;                                       // meaningful on the leader only (it alone writes the outputs)
-      if (p.trace && int(blockIdx.x) == p.trace_cta && tid == 0) p.trace[i * 3 + 2] = clock64();
+      if (p.trace && tid == 0) { if (int(blockIdx.x) == p.trace_cta) p.trace[i * 3 + 2] = clock64(); else if (p.trace_cta < 0 && i == 50) p.trace[blockIdx.x * 8 + 2] = clock64(); }
     } else {
       if (!grid_barrier(p.barrier, (unsigned int)(i + 1) * gridDim.x, p.err)) return;
       if (tid == 0) {
@@ -469,7 +471,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps2_kernel(FpsParams p, int nb, int 
       idx = s_idx;
       for (int k = tid; k < p.d; k += T) s_seed[k] = __ldg(Xb + k * p.sd + idx);
       __syncthreads();
-      if (p.trace && int(blockIdx.x) == p.trace_cta && tid == 0) p.trace[i * 3 + 2] = clock64();
+      if (p.trace && tid == 0) { if (int(blockIdx.x) == p.trace_cta) p.trace[i * 3 + 2] = clock64(); else if (p.trace_cta < 0 && i == 50) p.trace[blockIdx.x * 8 + 2] = clock64(); }
     }
   }
 }
@@ -492,16 +494,20 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
   const size_t mail_need = size_t(s.batch) * s.m * s.d * 8;
   if (slot_need + mail_need > slot_bytes) return UOC_OK;
   unsigned long long* mail = slots + slot_need / 8;
-  // threads: one float4 group per thread when the slice fits 576 threads (112 registers available -> 16 loads in
-  // flight), otherwise up to 1024 threads / several groups per thread
+  // Footprint: the pass time is dominated by the inter-CTA exchange latency, not by the streaming loop, so the default
+  // is a LIGHT CTA (<= 320 threads, <= 96 KB shared memory) that leaves room on every SM for the kernels of another
+  // frame running on a second stream (see pipeline.py).  UOC_FPS_HEAVY=1 selects the widest configuration instead.
+  bool heavy = false;
+  if (const char* e = getenv("UOC_FPS_HEAVY")) heavy = atoi(e) != 0;
   int gpt_t, maxt;
-  if (chunk <= 576) { gpt_t = 1; maxt = 576; }
+  if (!heavy && chunk <= 640) { gpt_t = 2; maxt = 320; }
+  else if (chunk <= 576) { gpt_t = 1; maxt = 576; }
   else if (chunk <= 1024) { gpt_t = 1; maxt = 1024; }
   else if (chunk <= 2048) { gpt_t = 2; maxt = 1024; }
   else { gpt_t = 4; maxt = 1024; }
   int threads = ((chunk + gpt_t - 1) / gpt_t + 31) / 32 * 32;
   if (threads < 64) threads = 64;
-  size_t budget = 200 * 1024;
+  size_t budget = (maxt == 320) ? 96 * 1024 : 200 * 1024;
   if (const char* e = getenv("UOC_FPS_SMEM_KB")) budget = size_t(atoi(e)) * 1024;
   int rg = int(budget / (16 * size_t(s.d)));
   if (rg > chunk) rg = chunk;
@@ -510,7 +516,8 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
 #define UOC_FPS_PICK(G, MT, U) (variant == 0 ? reinterpret_cast<void*>(&fps2_kernel<G, MT, U, 0>) \
                                : (variant == 1 ? reinterpret_cast<void*>(&fps2_kernel<G, MT, U, 1>) \
                                                : reinterpret_cast<void*>(&fps2_kernel<G, MT, U, 2>)))
-  if (maxt == 576) kern = UOC_FPS_PICK(1, 576, 16);
+  if (maxt == 320) kern = UOC_FPS_PICK(2, 320, 8);
+  else if (maxt == 576) kern = UOC_FPS_PICK(1, 576, 16);
   else if (gpt_t == 1) kern = UOC_FPS_PICK(1, 1024, 8);
   else if (gpt_t == 2) kern = UOC_FPS_PICK(2, 1024, 8);
   else kern = UOC_FPS_PICK(4, 1024, 8);

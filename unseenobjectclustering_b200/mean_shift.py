@@ -19,8 +19,10 @@ _bf16_registry = {}      # data_ptr of a feature tensor -> (bf16 pixel-major cop
 
 
 def _workspace(device, nbytes):
-    """Grow-only uint8 scratch tensor per device (256-byte aligned by the caching allocator)."""
-    key = (device.type, device.index)
+    """Grow-only uint8 scratch tensor per (device, current stream): frames in flight on different
+    streams (pipeline.py) must not share scratch.  256-byte aligned by the caching allocator."""
+    sid = torch.cuda.current_stream(device).cuda_stream
+    key = (device.type, device.index) if sid == 0 else (device.type, device.index, sid)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
@@ -30,7 +32,8 @@ def _workspace(device, nbytes):
 
 def register_bf16_copy(features, xb):
     """Called by the backbone module: remember the bf16 [N, H*W, C] copy written next to `features`."""
-    _bf16_registry.clear()   # one live entry is enough (single-threaded callers, SURVEY section 8b)
+    while len(_bf16_registry) >= 8:          # a handful of live entries is enough (frames in flight)
+        _bf16_registry.pop(next(iter(_bf16_registry)))
     _bf16_registry[features.data_ptr()] = (xb, tuple(features.shape))
 
 
@@ -46,7 +49,7 @@ def _epsilon(epsilon=None):
 
 
 def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indices=None, epsilon=None, flags=0,
-                   return_seeds=False):
+                   return_seeds=False, on_sampling_done=None):
     """Cluster a batch of embedding fields in ONE library call.
 
     features: [N, C, H, W] float32 CUDA tensor, unit norm over C (any batch stride; each item must
@@ -74,6 +77,29 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
         ws = _workspace(dev, nbytes)
         labels = torch.empty((N, n), dtype=torch.int32, device=dev)
         selected = torch.empty((N, num_seeds), dtype=torch.int64, device=dev)
+        if on_sampling_done is not None:
+            # staged form (same kernels through the stage entry points): lets the caller record an event right after
+            # the cooperative sampling kernel so that the next frame's sampling may start (pipeline.py)
+            sp = _lib.stream_ptr(dev)
+            fptr = ctypes.cast(first, ctypes.c_void_p)
+            seeds = torch.empty((N, num_seeds, C), dtype=torch.float32, device=dev)
+            seed_labels = torch.empty((N, num_seeds), dtype=torch.int32, device=dev)
+            nuniq = torch.empty((N,), dtype=torch.int32, device=dev)
+            sb, sd_ = features.stride(0), features.stride(1)
+            _lib.check(lib.uoc_select_seeds(_lib.ptr(features), sb, sd_, N, n, C, num_seeds, fptr, _lib.ptr(selected),
+                                            _lib.ptr(seeds), _lib.ptr(ws), ws.numel(), 0, sp), "uoc_select_seeds")
+            on_sampling_done()
+            _lib.check(lib.uoc_hill_climb(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, float(kappa),
+                                          int(max_iters), _lib.ptr(seeds), _lib.ptr(ws), ws.numel(), int(flags), sp),
+                       "uoc_hill_climb")
+            _lib.check(lib.uoc_label_seeds(_lib.ptr(seeds), N, num_seeds, C, _epsilon(epsilon), _lib.ptr(seed_labels),
+                                           _lib.ptr(nuniq), sp), "uoc_label_seeds")
+            _lib.check(lib.uoc_assign_labels(_lib.ptr(features), sb, sd_, N, n, C, num_seeds, _lib.ptr(seeds),
+                                             _lib.ptr(seed_labels), _lib.ptr(nuniq), _lib.ptr(labels), _lib.ptr(ws),
+                                             ws.numel(), sp), "uoc_assign_labels")
+            if return_seeds:
+                return labels, selected, seeds, seed_labels
+            return labels, selected
         seeds = torch.empty((N, num_seeds, C), dtype=torch.float32, device=dev) if return_seeds else None
         seed_labels = torch.empty((N, num_seeds), dtype=torch.int32, device=dev) if return_seeds else None
         st = lib.uoc_meanshift_cluster(

@@ -105,6 +105,7 @@ class SEGNET_B200(nn.Module):
         self._handle = None
         self._handle_dev = None
         self._ws = None
+        self._ws_by_stream = {}
         self.keep_bf16 = True
         self.eval()
 
@@ -133,6 +134,8 @@ class SEGNET_B200(nn.Module):
 
     def _apply(self, fn, *a, **k):      # .cuda() / .to(): weights moved -> rebuild the handle lazily
         self._release()
+        self._ws = None
+        self._ws_by_stream = {}
         return super()._apply(fn, *a, **k)
 
     def train(self, mode=True):
@@ -174,8 +177,11 @@ class SEGNET_B200(nn.Module):
         N, _, H, W = img.shape
         with torch.cuda.device(dev):
             nbytes = lib.uoc_backbone_workspace_bytes(self._handle, N, H, W)
+            sid = torch.cuda.current_stream(dev).cuda_stream       # one activation workspace per stream in flight
+            self._ws = self._ws_by_stream.get(sid)
             if self._ws is None or self._ws.device != dev or self._ws.numel() < nbytes + 1024:
                 self._ws = torch.empty(nbytes + 2048, dtype=torch.uint8, device=dev)
+                self._ws_by_stream[sid] = self._ws
             off = (-self._ws.data_ptr()) % 1024
             ws_ptr = ctypes.c_void_p(self._ws.data_ptr() + off)
             out = torch.empty((N, self.num_units, H, W), dtype=torch.float32, device=dev)
