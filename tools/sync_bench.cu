@@ -7,6 +7,12 @@
 __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_cg(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.global.cg.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_weak(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
@@ -37,7 +43,7 @@ __global__ void pingpong(unsigned long long* flags, int iters, long long* out, i
 }
 
 // proto 0: atomic counter barrier; proto 1: all-to-all matrix [dst][src]; proto 2: one slot per CTA (own line), everybody polls all slots
-__global__ void exchange(unsigned long long* buf, unsigned int* counter, int iters, long long* out, int proto) {
+__global__ void exchange(unsigned long long* buf, unsigned int* counter, int iters, long long* out, int proto, int stmode) {
   const int nb = gridDim.x, rank = blockIdx.x, tid = threadIdx.x;
   long long t0 = clock64();
   for (int i = 1; i <= iters; ++i) {
@@ -50,7 +56,11 @@ __global__ void exchange(unsigned long long* buf, unsigned int* counter, int ite
       }
     } else if (proto == 1) {
       if (tid < 32) {
-        for (int c = tid; c < nb; c += 32) st_relaxed(buf + (size_t)c * nb + rank, i);
+        for (int c = tid; c < nb; c += 32) {
+          if (stmode == 0) st_relaxed(buf + (size_t)c * nb + rank, i);
+          else if (stmode == 1) st_cg(buf + (size_t)c * nb + rank, i);
+          else st_weak(buf + (size_t)c * nb + rank, i);
+        }
         bool done = false;
         while (!done) {
           bool all = true;
@@ -94,10 +104,23 @@ int main() {
     printf("ping-pong (%s poll): %.0f clk per round trip (2 hops)\n", mode ? "ld.volatile" : "ld.relaxed.gpu", h / 2000.0);
   }
   const char* names[3] = {"atomic counter barrier", "all-to-all matrix", "slot per CTA, all poll all"};
+  const char* stn[3] = {"st.relaxed.gpu", "st.global.cg", "st.global (weak)"};
+  for (int grid : {148}) {
+    for (int stmode = 0; stmode < 3; ++stmode) {
+      int proto = 1;
+      cudaMemset(buf, 0, 148 * 148 * 8 + 4096); cudaMemset(counter, 0, 4);
+      void* args[] = {&buf, &counter, nullptr, &out, &proto, &stmode};
+      int iters = 2000; args[2] = &iters;
+      cudaLaunchCooperativeKernel((void*)exchange, dim3(grid), dim3(128), args, 0, 0);
+      cudaDeviceSynchronize(); cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
+      printf("grid %3d all-to-all with %-18s: %.0f clk per exchange\n", grid, stn[stmode], h / 2000.0);
+    }
+  }
   for (int grid : {8, 32, 148}) {
     for (int proto = 0; proto < 3; ++proto) {
+      int stmode = 0;
       cudaMemset(buf, 0, 148 * 148 * 8 + 4096); cudaMemset(counter, 0, 4);
-      void* args[] = {&buf, &counter, nullptr, &out, &proto};
+      void* args[] = {&buf, &counter, nullptr, &out, &proto, &stmode};
       int iters = 2000; args[2] = &iters;
       cudaError_t e = cudaLaunchCooperativeKernel((void*)exchange, dim3(grid), dim3(128), args, 0, 0);
       cudaError_t e2 = cudaDeviceSynchronize(); cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);

@@ -115,6 +115,7 @@ struct FpsParams {
   unsigned int* err;
   long long* trace;       // optional (debug): per pass {start, after local arg-max, after exchange} clock64 of CTA `trace_cta`
   int trace_cta;
+  int debug_mode;         // 0 normal; 1 = skip the inter-CTA exchange (each CTA follows its own arg-max); 2 = skip the streaming loop
 };
 
 __device__ __forceinline__ unsigned int orderable(float f) {
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 320 ? 2 : 1)) fps2_kernel(FpsPa
     for (int q = 0; q < GPT; ++q) {
       const int lg = tid + q * T;
       const long long g = g0 + lg;
-      if (g < g1) {
+      if (g < g1 && p.debug_mode != 2) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if (lg < rg) {
           const float4* xp = xs4 + lg;
@@ -393,6 +394,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 320 ? 2 : 1)) fps2_kernel(FpsPa
           }
           if (!done && tid == 0) atomicOr(p.err, ERR_GRID_BARRIER_TIMEOUT);
         }
+      } else if (SYNC == 2 && p.debug_mode == 1) {
+        if (tid == 0) s_idx = static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(v & 0xFFFFFFFFull)) % p.n;
       } else if (SYNC == 2) {
         // all-to-all: this CTA's key goes into column `rank` of EVERY CTA's private row; then poll the own row
         unsigned long long* mat = slots + (size_t(b) * p.m + (i + 1)) * nb * nb;
@@ -497,7 +500,7 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
   // Footprint: the pass time is dominated by the inter-CTA exchange latency, not by the streaming loop, so the default
   // is a LIGHT CTA (<= 320 threads, <= 96 KB shared memory) that leaves room on every SM for the kernels of another
   // frame running on a second stream (see pipeline.py).  UOC_FPS_HEAVY=1 selects the widest configuration instead.
-  bool heavy = false;
+  bool heavy = true;     // measured: the light footprint costs more in the sampling kernel than the overlap returns
   if (const char* e = getenv("UOC_FPS_HEAVY")) heavy = atoi(e) != 0;
   int gpt_t, maxt;
   if (!heavy && chunk <= 640) { gpt_t = 2; maxt = 320; }
@@ -507,7 +510,7 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
   else { gpt_t = 4; maxt = 1024; }
   int threads = ((chunk + gpt_t - 1) / gpt_t + 31) / 32 * 32;
   if (threads < 64) threads = 64;
-  size_t budget = (maxt == 320) ? 96 * 1024 : 200 * 1024;
+  size_t budget = 96 * 1024;     // leaves room for one convolution CTA of another frame on the same SM
   if (const char* e = getenv("UOC_FPS_SMEM_KB")) budget = size_t(atoi(e)) * 1024;
   int rg = int(budget / (16 * size_t(s.d)));
   if (rg > chunk) rg = chunk;
@@ -548,6 +551,8 @@ int launch_select_seeds(const float* X, const ClusterShape& s, const ClusterWork
   if (!p.err) return fail(UOC_ERR_CUDA, "no device error word");
   p.trace = nullptr;
   p.trace_cta = 0;
+  p.debug_mode = 0;
+  if (const char* e = getenv("UOC_FPS_DEBUG_MODE")) p.debug_mode = (atoi(e) == 1) ? 1 : 0;   // measurement knob
   if (const char* e = getenv("UOC_FPS_TRACE")) {
     // debug: the first 3*m int64 of the r[] scratch (unused by the second-generation kernel) receive the time stamps
     p.trace = reinterpret_cast<long long*>(w.r);
