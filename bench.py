@@ -319,7 +319,7 @@ def run_b200(args):
                                       _lib.ptr(ws), ws.numel(), 0, sp), "hill_climb")
         ev[3].record()
         _lib.check(lib.uoc_label_seeds(_lib.ptr(Z), 1, M, D, 0.04, _lib.ptr(sl), _lib.ptr(nu), sp), "label_seeds")
-        _lib.check(lib.uoc_assign_labels(_lib.ptr(feats), D * n, n, 1, n, D, M, _lib.ptr(Z), _lib.ptr(sl), _lib.ptr(nu),
+        _lib.check(lib.uoc_assign_labels(_lib.ptr(feats), D * n, n, _lib.ptr(xb), 1, n, D, M, _lib.ptr(Z), _lib.ptr(sl), _lib.ptr(nu),
                                          _lib.ptr(lab), _lib.ptr(ws), ws.numel(), sp), "assign_labels")
         ev[4].record()
         torch.cuda.synchronize()

@@ -112,9 +112,10 @@ UOC_API int uoc_hill_climb(const float* X, int64_t stride_b, int64_t stride_d, c
 UOC_API int uoc_label_seeds(const float* Z, int batch, int m, int d, float epsilon, int32_t* seed_labels_out,
                             int32_t* num_unique_out, uoc_stream_t stream);
 
-/* nearest-seed assignment + relabel (lib/utils/mean_shift.py:206-227): labels_out [batch,n] int32. */
-UOC_API int uoc_assign_labels(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
-                              const float* Z, const int32_t* seed_labels, const int32_t* num_unique,
+/* nearest-seed assignment + relabel (lib/utils/mean_shift.py:206-227): labels_out [batch,n] int32.
+ * x_bf16 (optional): the bf16 pixel-major copy; when given the tensor-core pass with exactness certificate is used. */
+UOC_API int uoc_assign_labels(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n,
+                              int d, int m, const float* Z, const int32_t* seed_labels, const int32_t* num_unique,
                               int32_t* labels_out, void* workspace, size_t workspace_bytes, uoc_stream_t stream);
 
 /* fp32 planar [batch][d][n] -> bf16 pixel-major [batch][n][d] (the layout the tcgen05 loop streams). */

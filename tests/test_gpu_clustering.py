@@ -93,6 +93,28 @@ def test_assign_bit_exact(H, W, d, m):
     lo2 = C.assign(Xp, Z, sl2, uniq)
     lg2 = MS.assign_labels(X, torch.from_numpy(Z).to(DEV), torch.from_numpy(sl2), uniq)
     assert np.array_equal(lg2.numpy(), lo2)
+    if d in (64, 128):
+        # tensor-core pass with exactness certificate + fp32 fix-up: identical labels
+        lt = MS.assign_labels(X, torch.from_numpy(Z).to(DEV), torch.from_numpy(sl), uniq, use_tensor_cores=True)
+        assert np.array_equal(lt.numpy(), lo)
+        lt2 = MS.assign_labels(X, torch.from_numpy(Z).to(DEV), torch.from_numpy(sl2), uniq, use_tensor_cores=True)
+        assert np.array_equal(lt2.numpy(), lo2)
+
+
+@pytest.mark.parametrize("noise", [0.05, 0.2, 0.5])
+def test_assign_tensor_core_certificate_on_marginless_input(noise):
+    """Every seed its own label + heavy noise: most points sit near a decision border, so the certificate fails
+    often and the fp32 fix-up path does the work; the result must still equal the canonical arg-min."""
+    H, W, d, m = 60, 84, 64, 100
+    feats, _ = _field(H, W, d, 5, noise, seed=int(noise * 100))
+    Xp = feats[0].reshape(d, -1).numpy()
+    _, seeds = C.select_seeds(Xp, m, 3)
+    Z = C.hill_climb(Xp, seeds, 20.0, 2)
+    sl = np.arange(m, dtype=np.int32)                 # all different labels: arg-min ties/borders everywhere
+    lo = C.assign(Xp, Z, sl, m)
+    X = feats.to(DEV)[0].view(d, -1).t()
+    lt = MS.assign_labels(X, torch.from_numpy(Z).to(DEV), torch.from_numpy(sl), m, use_tensor_cores=True)
+    assert np.array_equal(lt.numpy(), lo)
 
 
 FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "cluster_*.npz")))

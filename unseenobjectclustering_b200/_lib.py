@@ -38,7 +38,7 @@ SIGNATURES = {
     "uoc_select_seeds": (_i, [_vp, _i64, _i64, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "uoc_hill_climb": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _f, _i, _vp, _vp, _sz, _i, _vp]),
     "uoc_label_seeds": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp]),
-    "uoc_assign_labels": (_i, [_vp, _i64, _i64, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "uoc_assign_labels": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "uoc_pack_bf16": (_i, [_vp, _i64, _i64, _i, _i64, _i, _vp, _vp]),
     "uoc_backbone_create": (_i, [_c.POINTER(_vp), _c.POINTER(WeightDesc), _i, _i]),
     "uoc_backbone_destroy": (None, [_vp]),

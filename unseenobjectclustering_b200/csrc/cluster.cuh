@@ -50,8 +50,13 @@ int launch_reduce_normalize(const float* partials, int batch, int P, int m, int 
 int launch_label_seeds(const float* Z, int batch, int m, int d, float epsilon, int* seed_labels, int* num_unique,
                        cudaStream_t stream);
 // K5b nearest-seed assignment + histogram + label-0 swap (lib/utils/mean_shift.py:206-227)
-int launch_assign(const float* X, const ClusterShape& s, const float* Z, const int* seed_labels, const int* num_unique,
-                  int* hist, int* labels_tmp, int* labels_out, cudaStream_t stream);
+// xb != nullptr (bf16 pixel-major copy available, d = 64/128): tcgen05 pass with exactness certificate + fp32 fix-up of
+// the uncertified points (assign_tc.cu); otherwise the fp32 SIMT kernel.  Identical labels either way.
+int launch_assign(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w, const float* Z,
+                  const int* seed_labels, const int* num_unique, int* hist, int* labels_tmp, int* labels_out,
+                  cudaStream_t stream);
+int launch_assign_tc(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w, const float* Z,
+                     const int* seed_labels, int* hist, int* labels_tmp, cudaStream_t stream);
 // fp32 planar -> bf16 pixel-major
 int launch_pack_bf16(const float* X, const ClusterShape& s, __nv_bfloat16* xb, cudaStream_t stream);
 

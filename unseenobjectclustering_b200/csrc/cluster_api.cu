@@ -24,7 +24,8 @@ static int upload_first(const int64_t* first_host, int batch, int64_t n, const C
 }
 
 static int hill_climb(const float* X, const void* x_bf16, const ClusterShape& s, const ClusterWorkspace& w, float* Z,
-                      float kappa, int iters, int flags, cudaStream_t st) {
+                      float kappa, int iters, int flags, cudaStream_t st, const __nv_bfloat16** xb_used = nullptr) {
+  if (xb_used) *xb_used = static_cast<const __nv_bfloat16*>(x_bf16);
   if (flags & UOC_FLAG_LOOP_SIMT) return launch_hill_climb_simt(X, s, w, Z, kappa, iters, st);
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x_bf16);
   if (!xb) {
@@ -32,6 +33,7 @@ static int hill_climb(const float* X, const void* x_bf16, const ClusterShape& s,
     if (rc != UOC_OK) return rc;
     xb = w.xb;
   }
+  if (xb_used) *xb_used = xb;
   return launch_hill_climb_tc(xb, s, w, Z, kappa, iters, st);
 }
 
@@ -64,11 +66,12 @@ int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stride_d, co
   if (rc != UOC_OK) return rc;
   rc = launch_select_seeds(X, s, w, selected_out, w.Z, st);
   if (rc != UOC_OK) return rc;
-  rc = hill_climb(X, x_bf16, s, w, w.Z, kappa, iters, flags, st);
+  const __nv_bfloat16* xb = nullptr;
+  rc = hill_climb(X, x_bf16, s, w, w.Z, kappa, iters, flags, st, &xb);
   if (rc != UOC_OK) return rc;
   rc = launch_label_seeds(w.Z, batch, m, d, epsilon, w.seed_labels, w.num_unique, st);
   if (rc != UOC_OK) return rc;
-  rc = launch_assign(X, s, w.Z, w.seed_labels, w.num_unique, w.hist, w.labels_tmp, labels_out, st);
+  rc = launch_assign(X, xb, s, w, w.Z, w.seed_labels, w.num_unique, w.hist, w.labels_tmp, labels_out, st);
   if (rc != UOC_OK) return rc;
   if (seeds_out)
     UOC_CUDA(cudaMemcpyAsync(seeds_out, w.Z, sizeof(float) * size_t(batch) * m * d, cudaMemcpyDeviceToDevice, st));
@@ -127,8 +130,8 @@ int uoc_label_seeds(const float* Z, int batch, int m, int d, float epsilon, int3
   return launch_label_seeds(Z, batch, m, d, epsilon, seed_labels_out, num_unique_out, static_cast<cudaStream_t>(stream));
 }
 
-int uoc_assign_labels(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
-                      const float* Z, const int32_t* seed_labels, const int32_t* num_unique, int32_t* labels_out,
+int uoc_assign_labels(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n, int d,
+                      int m, const float* Z, const int32_t* seed_labels, const int32_t* num_unique, int32_t* labels_out,
                       void* workspace, size_t workspace_bytes, uoc_stream_t stream) {
   int rc = require_sm100();
   if (rc != UOC_OK) return rc;
@@ -139,7 +142,8 @@ int uoc_assign_labels(const float* X, int64_t stride_b, int64_t stride_d, int ba
   rc = carve_cluster_workspace(workspace, workspace_bytes, batch, n, d, m, &w);
   if (rc != UOC_OK) return rc;
   ClusterShape s{batch, n, d, m, stride_b, stride_d};
-  return launch_assign(X, s, Z, seed_labels, num_unique, w.hist, w.labels_tmp, labels_out, static_cast<cudaStream_t>(stream));
+  return launch_assign(X, static_cast<const __nv_bfloat16*>(x_bf16), s, w, Z, seed_labels, num_unique, w.hist, w.labels_tmp,
+                       labels_out, static_cast<cudaStream_t>(stream));
 }
 
 int uoc_pack_bf16(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, void* x_bf16_out,

@@ -899,9 +899,20 @@ __global__ void __launch_bounds__(256) relabel_kernel(const int* __restrict__ la
   }
 }
 
-int launch_assign(const float* X, const ClusterShape& s, const float* Z, const int* seed_labels, const int* num_unique,
-                  int* hist, int* labels_tmp, int* labels_out, cudaStream_t stream) {
+int launch_assign(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w, const float* Z,
+                  const int* seed_labels, const int* num_unique, int* hist, int* labels_tmp, int* labels_out,
+                  cudaStream_t stream) {
   UOC_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * size_t(s.batch) * s.m, stream));
+  bool use_tc = xb != nullptr && (s.d == 64 || s.d == 128);
+  if (const char* e = getenv("UOC_ASSIGN_SIMT")) { if (atoi(e) != 0) use_tc = false; }
+  if (use_tc) {
+    int rc = launch_assign_tc(X, xb, s, w, Z, seed_labels, hist, labels_tmp, stream);
+    if (rc != UOC_OK) return rc;
+    const dim3 grid2(static_cast<unsigned int>((s.n + 255) / 256), s.batch);
+    relabel_kernel<<<grid2, 256, 0, stream>>>(labels_tmp, hist, num_unique, s.n, s.m, labels_out);
+    UOC_CHECK_LAUNCH();
+    return UOC_OK;
+  }
   const size_t smem = sizeof(float) * size_t(s.m) * s.d;
   const dim3 grid(static_cast<unsigned int>((s.n + 127) / 128), s.batch);
   static bool attr_done = false;

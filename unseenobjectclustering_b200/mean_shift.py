@@ -94,7 +94,7 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
                        "uoc_hill_climb")
             _lib.check(lib.uoc_label_seeds(_lib.ptr(seeds), N, num_seeds, C, _epsilon(epsilon), _lib.ptr(seed_labels),
                                            _lib.ptr(nuniq), sp), "uoc_label_seeds")
-            _lib.check(lib.uoc_assign_labels(_lib.ptr(features), sb, sd_, N, n, C, num_seeds, _lib.ptr(seeds),
+            _lib.check(lib.uoc_assign_labels(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, _lib.ptr(seeds),
                                              _lib.ptr(seed_labels), _lib.ptr(nuniq), _lib.ptr(labels), _lib.ptr(ws),
                                              ws.numel(), sp), "uoc_assign_labels")
             if return_seeds:
@@ -199,8 +199,9 @@ def connected_components(Z, epsilon, metric='cosine', return_num_unique=False):
     return labels.to(torch.int64).cpu()
 
 
-def assign_labels(X, Z, seed_labels, num_unique=None):
-    """lib/utils/mean_shift.py:206-227: nearest-seed labels with the label-0 swap. int64 CPU [n]."""
+def assign_labels(X, Z, seed_labels, num_unique=None, use_tensor_cores=False):
+    """lib/utils/mean_shift.py:206-227: nearest-seed labels with the label-0 swap. int64 CPU [n].
+    use_tensor_cores: certified tcgen05 pass + fp32 fix-up instead of the fp32 kernel (identical labels)."""
     n, d = X.shape
     m = Z.shape[0]
     Xp, stride_d = _as_planar(X)
@@ -214,7 +215,10 @@ def assign_labels(X, Z, seed_labels, num_unique=None):
     with torch.cuda.device(dev):
         ws = _workspace(dev, lib.uoc_meanshift_workspace_bytes(1, n, d, m))
         out = torch.empty((n,), dtype=torch.int32, device=dev)
-        st = lib.uoc_assign_labels(_lib.ptr(Xp), d * stride_d, stride_d, 1, n, d, m, _lib.ptr(Zc), _lib.ptr(sl),
+        xb = None
+        if use_tensor_cores:
+            xb = pack_bf16(torch.as_strided(Xp, (1, d, 1, n), (d * stride_d, stride_d, n, 1)).contiguous().view(1, d, 1, n))
+        st = lib.uoc_assign_labels(_lib.ptr(Xp), d * stride_d, stride_d, _lib.ptr(xb), 1, n, d, m, _lib.ptr(Zc), _lib.ptr(sl),
                                    _lib.ptr(nu), _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
         _lib.check(st, "uoc_assign_labels")
     return out.to(torch.int64).cpu()
