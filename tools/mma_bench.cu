@@ -11,7 +11,8 @@ using namespace uoc;
 
 template <int N, bool TS, int NACC = 1>
 __global__ void __launch_bounds__(192, 1) mma_rate_kernel(int iters, int kper, const __grid_constant__ CUtensorMap tmap,
-                                                          int tma_bytes_per_iter, unsigned long long* out, unsigned int* err) {
+                                                          int tma_bytes_per_iter, unsigned long long* out, unsigned int* err,
+                                                          int a_sbo = 1024, int a_off = 0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a = smem;                 // 16 KB: 128 x 64 bf16 (K-major SW128)
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(192, 1) mma_rate_kernel(int iters, int kper, c
         const uint64_t bd = make_smem_desc_sw128(ba + ks * 32, 16, 1024);
         const uint32_t dcol = tm + uint32_t((k % NACC) * N);          // NACC independent accumulators, round-robin
         if (TS) umma_ts_f16(dcol, tm + 256 + ks * 8, bd, idesc, 1u);
-        else { const uint64_t ad = make_smem_desc_sw128(aa + ks * 32, 16, 1024); umma_ss_f16(dcol, ad, bd, idesc, 1u); }
+        else { const uint64_t ad = make_smem_desc_sw128(aa + a_off + ks * 32, 16, a_sbo); umma_ss_f16(dcol, ad, bd, idesc, 1u); }
       }
     }
     umma_commit(done);
@@ -63,14 +64,15 @@ __global__ void __launch_bounds__(192, 1) mma_rate_kernel(int iters, int kper, c
 }
 
 template <int N, bool TS, int NACC = 1>
-void run(const char* name, int grid, int tma_bytes_per_iter, const CUtensorMap& tmap, unsigned long long* dout, unsigned int* derr) {
+void run(const char* name, int grid, int tma_bytes_per_iter, const CUtensorMap& tmap, unsigned long long* dout, unsigned int* derr,
+         int a_sbo = 1024, int a_off = 0) {
   const int iters = 2000, kper = 4;
   const int smem = 1024 + 49152 + 65536 + 256;
   cudaFuncSetAttribute(mma_rate_kernel<N, TS, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  mma_rate_kernel<N, TS, NACC><<<grid, 192, smem>>>(100, kper, tmap, tma_bytes_per_iter, dout, derr);
+  mma_rate_kernel<N, TS, NACC><<<grid, 192, smem>>>(100, kper, tmap, tma_bytes_per_iter, dout, derr, a_sbo, a_off);
   cudaEventRecord(e0);
-  mma_rate_kernel<N, TS, NACC><<<grid, 192, smem>>>(iters, kper, tmap, tma_bytes_per_iter, dout, derr);
+  mma_rate_kernel<N, TS, NACC><<<grid, 192, smem>>>(iters, kper, tmap, tma_bytes_per_iter, dout, derr, a_sbo, a_off);
   cudaEventRecord(e1);
   cudaError_t e = cudaDeviceSynchronize();
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
@@ -163,6 +165,11 @@ int main() {
   run_tma<12>(148, 4, tmap, tmap_s4, dout, derr);
   for (int grid : {148}) {
     run<128, false>("SS 128x128x16", grid, 0, tmap, dout, derr);
+    run<128, false>("SS 128x128x16 A SBO 2048", grid, 0, tmap, dout, derr, 2048, 0);
+    run<128, false>("SS 128x128x16 A SBO 3072", grid, 0, tmap, dout, derr, 3072, 0);
+    run<128, false>("SS 128x128x16 A SBO 3072 off 512", grid, 0, tmap, dout, derr, 3072, 512);
+    run<128, false>("SS 128x128x16 A SBO 1024 off 512", grid, 0, tmap, dout, derr, 1024, 512);
+    run<128, false>("SS 128x128x16 A SBO 2048 off 128", grid, 0, tmap, dout, derr, 2048, 128);
     run<256, false>("SS 128x256x16", grid, 0, tmap, dout, derr);
     run<64, false>("SS 128x64x16", grid, 0, tmap, dout, derr);
     run<128, true>("TS 128x128x16 (A in TMEM)", grid, 0, tmap, dout, derr);

@@ -209,7 +209,7 @@ static int run_conv(const ConvLayer* L[2], const uoc_backbone* bb, const void* x
   }
   p.N = N; p.H = H; p.W = W; p.Cin = L[0]->Cin; p.Cout = L[0]->Cout;
   p.ksize = L[0]->ksize; p.stride = L[0]->stride; p.dilation = L[0]->dil; p.relu = relu; p.out_fp32 = out_fp32;
-  return (flags & UOC_FLAG_CONV_SIMT) ? launch_conv_simt(p, st) : launch_conv_tc(p, st);
+  return (flags & UOC_FLAG_CONV_SIMT) ? launch_conv_simt(p, st) : launch_conv_auto(p, st);
 }
 
 }  // namespace uoc
@@ -352,7 +352,7 @@ int uoc_conv2d_bf16(const void* x, const void* w, const float* bias, const void*
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.stride = stride; p.dilation = dilation;
   p.relu = relu; p.out_fp32 = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = (flags & UOC_FLAG_CONV_SIMT) ? launch_conv_simt(p, st) : launch_conv_tc(p, st);
+  rc = (flags & UOC_FLAG_CONV_SIMT) ? launch_conv_simt(p, st) : launch_conv_auto(p, st);
   if (rc != UOC_OK) return rc;
   if (flags & UOC_FLAG_SYNC_CHECK) return check_device_error(st);
   return UOC_OK;

@@ -714,6 +714,7 @@ int launch_hill_climb_simt(const float* X, const ClusterShape& s, const ClusterW
 // ----------------------------------------------------------------------------------------------
 // K5a: greedy seed labelling, one CTA (512 threads) per field
 // ----------------------------------------------------------------------------------------------
+template <int DREG>   // channels held in registers (0 = generic d)
 __global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restrict__ Z, int m, int d, float eps,
                                                           int* __restrict__ seed_labels, int* __restrict__ num_unique) {
   extern __shared__ float zs[];  // [m][d+1]
@@ -727,17 +728,32 @@ __global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restric
   if (tid < UOC_MAX_SEEDS) { labels[tid] = -1; cnt[tid] = 0; }
   __syncthreads();
   // adjacency: bit j of adj[i] <=> 0.5 * (1 - z_j . z_i) <= eps      (mean_shift.py:62-63)
+  // thread (j, iq): row j held in registers (DREG channels at a time), z_i read as smem broadcasts
   {
     const int j = tid & 127, iq = tid >> 7, w4 = (tid >> 5) & 3;
-    for (int i = iq; i < m; i += 4) {
-      bool in = false;
-      if (j < m) {
+    if (DREG > 0) {
+      float zj[DREG > 0 ? DREG : 1];
+#pragma unroll
+      for (int k = 0; k < DREG; ++k) zj[k] = (j < m) ? zs[j * ld + k] : 0.f;
+      for (int i = iq; i < m; i += 4) {
         float acc = 0.f;
-        for (int k = 0; k < d; ++k) acc = fmaf(zs[j * ld + k], zs[i * ld + k], acc);
-        in = (0.5f * (1.0f - acc)) <= eps;
+#pragma unroll
+        for (int k = 0; k < DREG; ++k) acc = fmaf(zj[k], zs[i * ld + k], acc);
+        const bool in = (j < m) && ((0.5f * (1.0f - acc)) <= eps);
+        const unsigned int bits = __ballot_sync(0xffffffffu, in);
+        if ((tid & 31) == 0) adj[i][w4] = bits;
       }
-      const unsigned int bits = __ballot_sync(0xffffffffu, in);
-      if ((tid & 31) == 0) adj[i][w4] = bits;
+    } else {
+      for (int i = iq; i < m; i += 4) {
+        bool in = false;
+        if (j < m) {
+          float acc = 0.f;
+          for (int k = 0; k < d; ++k) acc = fmaf(zs[j * ld + k], zs[i * ld + k], acc);
+          in = (0.5f * (1.0f - acc)) <= eps;
+        }
+        const unsigned int bits = __ballot_sync(0xffffffffu, in);
+        if ((tid & 31) == 0) adj[i][w4] = bits;
+      }
     }
   }
   __syncthreads();
@@ -799,12 +815,16 @@ __global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restric
 int launch_label_seeds(const float* Z, int batch, int m, int d, float epsilon, int* seed_labels, int* num_unique,
                        cudaStream_t stream) {
   const size_t smem = sizeof(float) * size_t(m) * (d + 1);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    UOC_CUDA(cudaFuncSetAttribute(label_seeds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = smem;
+  static bool configured = false;
+  if (!configured) {
+    UOC_CUDA(cudaFuncSetAttribute(label_seeds_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    UOC_CUDA(cudaFuncSetAttribute(label_seeds_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    UOC_CUDA(cudaFuncSetAttribute(label_seeds_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = true;
   }
-  label_seeds_kernel<<<batch, 512, smem, stream>>>(Z, m, d, epsilon, seed_labels, num_unique);
+  if (d == 64) label_seeds_kernel<64><<<batch, 512, smem, stream>>>(Z, m, d, epsilon, seed_labels, num_unique);
+  else if (d == 128) label_seeds_kernel<128><<<batch, 512, smem, stream>>>(Z, m, d, epsilon, seed_labels, num_unique);
+  else label_seeds_kernel<0><<<batch, 512, smem, stream>>>(Z, m, d, epsilon, seed_labels, num_unique);
   UOC_CHECK_LAUNCH();
   return UOC_OK;
 }

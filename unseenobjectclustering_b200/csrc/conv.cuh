@@ -34,6 +34,11 @@ static inline int conv_out_dim(int in, int ksize, int stride, int dilation) {
 
 // tcgen05 implicit-GEMM convolution (Cin % 64 == 0, Cout % 64 == 0)
 int launch_conv_tc(const ConvProblem& p, cudaStream_t stream);
+// second generation for 3x3 stride-1 convolutions: one halo fetch per 64-channel block serves all nine taps (conv_halo.cu)
+bool conv_halo_supported(const ConvProblem& p);
+int launch_conv_halo(const ConvProblem& p, cudaStream_t stream);
+// picks conv_halo / conv_tc (UOC_CONV_HALO=0 forces the first generation everywhere)
+int launch_conv_auto(const ConvProblem& p, cudaStream_t stream);
 // fp32-accumulate SIMT validation convolution, same interface and data types
 int launch_conv_simt(const ConvProblem& p, cudaStream_t stream);
 

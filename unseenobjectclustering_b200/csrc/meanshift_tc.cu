@@ -61,13 +61,26 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
   const long long tiles_total = (n + kTile - 1) / kTile;
   const int T = (cta < tiles_total) ? int((tiles_total - cta + P - 1) / P) : 0;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_x);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
-    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-    mbar_init(&p_ready[0], 128); mbar_init(&p_ready[1], 128);
-    mbar_init(o_full, 1);
-    fence_mbar_init();
+  int j_pre = 0;                                        // tiles whose TMA loads are issued before the CTA-wide sync
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_x);
+      for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
+      mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+      mbar_init(&p_ready[0], 128); mbar_init(&p_ready[1], 128);
+      mbar_init(o_full, 1);
+      fence_mbar_init();
+      asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: the previous kernel's writes (Z, bf16 field) are visible
+      // the ring is empty: start streaming X right away, the seeds are staged meanwhile
+      for (int j = 0; j < T && j < Cfg::kStages; ++j) {
+        mbar_arrive_expect_tx(&x_full[j], Cfg::kStageBytes);
+        const int row0 = int((cta + (long long)j * P) * kTile);
+#pragma unroll
+        for (int kb = 0; kb < Cfg::kKBlocks; ++kb)
+          tma_load_3d(stages + j * Cfg::kStageBytes + kb * kBoxBytes, &tmap_x, &x_full[j], kb * 64, row0, b);
+      }
+    }
+    j_pre = T < Cfg::kStages ? T : Cfg::kStages;
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -101,7 +114,7 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
 
   if (warp == 0) {
     if (elect_one()) {    // one elected lane: lets the compiler keep descriptors / barriers in uniform registers
-      for (int j = 0; j < T; ++j) {
+      for (int j = j_pre; j < T; ++j) {
         const int s = j % Cfg::kStages;
         const uint32_t ph = (j / Cfg::kStages) & 1;
         if (!mbar_wait(&x_empty[s], ph ^ 1u, err)) break;
