@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_backbone.py -m gpu -q --timeout 300 -p no:cacheprovider -k "conv_matches_torch and (halo_x1 or halo_x0) and not _bo" > gpurun_out/test_conv.log 2>&1; echo "conv tests exit $?"; tail -2 gpurun_out/test_conv.log
+UOC_CONV_HALO=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_halo3.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --depth 1 > gpurun_out/bench_under_ncu.log 2>&1

@@ -37,6 +37,9 @@ struct HaloParams {
   int rows;             // 16 + 2*dil
   int a_bytes;          // bytes of one activation buffer (all boxes)
   int use_base_offset;  // descriptor base-offset field = swizzle phase of the operand start (A/B knob)
+  int a_stride;         // bytes between the two activation buffers (a_bytes rounded up to 1024)
+  int b_stages;         // depth of the weight-tile ring (as many as fit next to the two halo buffers)
+  int part_rows;        // halo rows per TMA slice
   unsigned int* err;
 };
 
@@ -51,12 +54,12 @@ __device__ __forceinline__ uint64_t make_desc_sw128_off(uint32_t smem_addr, uint
   return d;
 }
 
+constexpr int kMaxBStages = 12;
+constexpr int kSmemBudget = 226 * 1024;      // of the 227 KB a CTA may own
+
 template <int BLOCK_N, int SUB, bool XHALO>
 struct HaloCfg {
-  static constexpr int kAMax = XHALO ? (SUB == 2 ? 24 : 16) * 24 * 128 : 3 * (8 * SUB) * 24 * 128;   // bytes, dil <= 4
   static constexpr int kBBytes = BLOCK_N * 128;
-  static constexpr int kBStages = (BLOCK_N >= 256) ? 2 : 4;
-  static constexpr int kSmemBytes = 1024 + 2 * kAMax + kBStages * kBBytes + 256;
   static constexpr uint32_t kTmemCols = (SUB * BLOCK_N <= 128) ? 128 : ((SUB * BLOCK_N <= 256) ? 256 : 512);
 };
 
@@ -66,14 +69,15 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
   using Cfg = HaloCfg<BLOCK_N, SUB, XHALO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* abuf = smem;                                  // 2 x kAMax
-  uint8_t* bbuf = smem + 2 * Cfg::kAMax;                 // kBStages x kBBytes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bbuf + Cfg::kBStages * Cfg::kBBytes);
+  const int NB = p.b_stages;
+  uint8_t* abuf = smem;                                  // 2 x a_stride
+  uint8_t* bbuf = smem + 2 * p.a_stride;                 // NB x kBBytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bbuf + NB * Cfg::kBBytes);
   uint64_t* a_full = bars;                // 2
   uint64_t* a_empty = bars + 2;           // 2
-  uint64_t* b_full = bars + 4;            // kBStages
-  uint64_t* b_empty = b_full + Cfg::kBStages;
-  uint64_t* acc_full = b_empty + Cfg::kBStages;
+  uint64_t* b_full = bars + 4;            // NB
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint64_t* acc_full = b_empty + kMaxBStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,7 +95,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     tma_prefetch_desc(&p.tmap_x[g]);
     tma_prefetch_desc(&p.tmap_w[g]);
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < Cfg::kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -103,27 +107,49 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
 
   if (warp == 0) {
     if (elect_one()) {
-      int bcount = 0;
-      for (int cb = 0; cb < CB; ++cb) {
+      // The halo of block cb+1 is fetched in slices of `p.part_rows` rows, interleaved with the nine weight tiles of
+      // block cb, so that neither stream monopolises the TMA queue.
+      const int nparts = XHALO ? (p.rows + p.part_rows - 1) / p.part_rows : 3;
+      const int part_bytes = XHALO ? p.pitch * p.part_rows * 128 : p.a_bytes / 3;
+      auto issue_part = [&](int cb, int part) {
         const int ab = cb & 1;
-        if (!mbar_wait(&a_empty[ab], ((cb >> 1) & 1) ^ 1u, p.err)) break;
-        mbar_arrive_expect_tx(&a_full[ab], p.a_bytes);
-        uint8_t* adst = abuf + ab * Cfg::kAMax;
-        if (XHALO) {
-          tma_load_4d(adst, &p.tmap_x[g], &a_full[ab], cb * 64, x0 - p.dil, y0 - p.dil, img);
-        } else {
-#pragma unroll
-          for (int s = 0; s < 3; ++s)
-            tma_load_4d(adst + s * (p.a_bytes / 3), &p.tmap_x[g], &a_full[ab], cb * 64, x0 + (s - 1) * p.dil, y0 - p.dil, img);
-        }
-        bool ok = true;
+        uint8_t* adst = abuf + ab * p.a_stride + part * part_bytes;
+        if (XHALO) tma_load_4d(adst, &p.tmap_x[g], &a_full[ab], cb * 64, x0 - p.dil, y0 - p.dil + part * p.part_rows, img);
+        else tma_load_4d(adst, &p.tmap_x[g], &a_full[ab], cb * 64, x0 + (part - 1) * p.dil, y0 - p.dil, img);
+      };
+      // block 0: everything up front
+      mbar_arrive_expect_tx(&a_full[0], p.a_bytes);
+      for (int part = 0; part < nparts; ++part) issue_part(0, part);
+      int bcount = 0;
+      bool ok = true;
+      for (int cb = 0; cb < CB && ok; ++cb) {
+        const bool has_next = cb + 1 < CB;
+        const int nab = (cb + 1) & 1;
+        int next_part = 0;
+        bool next_armed = false;
         for (int tap = 0; tap < 9 && ok; ++tap, ++bcount) {
-          const int s = bcount % Cfg::kBStages;
-          if (!mbar_wait(&b_empty[s], ((bcount / Cfg::kBStages) & 1) ^ 1u, p.err)) { ok = false; break; }
+          const int s = bcount % NB;
+          if (!mbar_wait(&b_empty[s], ((bcount / NB) & 1) ^ 1u, p.err)) { ok = false; break; }
           mbar_arrive_expect_tx(&b_full[s], Cfg::kBBytes);
           tma_load_2d(bbuf + s * Cfg::kBBytes, &p.tmap_w[g], &b_full[s], tap * p.Cin + cb * 64, n0);
+          if (has_next) {
+            if (!next_armed && mbar_try_wait(&a_empty[nab], (((cb + 1) >> 1) & 1) ^ 1u)) {
+              mbar_arrive_expect_tx(&a_full[nab], p.a_bytes);
+              next_armed = true;
+            }
+            if (next_armed) {
+              const int upto = (nparts * (tap + 1) + 8) / 9;           // spread the slices over the nine taps
+              for (; next_part < upto && next_part < nparts; ++next_part) issue_part(cb + 1, next_part);
+            }
+          }
         }
-        if (!ok) break;
+        if (ok && has_next) {
+          if (!next_armed) {
+            if (!mbar_wait(&a_empty[nab], (((cb + 1) >> 1) & 1) ^ 1u, p.err)) { ok = false; break; }
+            mbar_arrive_expect_tx(&a_full[nab], p.a_bytes);
+          }
+          for (; next_part < nparts; ++next_part) issue_part(cb + 1, next_part);
+        }
       }
     }
   } else if (warp == 1) {
@@ -136,10 +162,10 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       for (int cb = 0; cb < CB && ok; ++cb) {
         const int ab = cb & 1;
         if (!mbar_wait(&a_full[ab], (cb >> 1) & 1, p.err)) { ok = false; break; }
-        const uint32_t a_base = a_addr0 + ab * Cfg::kAMax;
+        const uint32_t a_base = a_addr0 + ab * p.a_stride;
         for (int tap = 0; tap < 9; ++tap, ++bcount) {
-          const int s = bcount % Cfg::kBStages;
-          if (!mbar_wait(&b_full[s], (bcount / Cfg::kBStages) & 1, p.err)) { ok = false; break; }
+          const int s = bcount % NB;
+          if (!mbar_wait(&b_full[s], (bcount / NB) & 1, p.err)) { ok = false; break; }
           tc_fence_after();
           const int r = tap / 3, sx = tap - 3 * r;
           const uint32_t b_addr = b_addr0 + s * Cfg::kBBytes;
@@ -229,14 +255,21 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
 }
 
 template <int BLOCK_N, int SUB, bool XHALO>
-int launch(const HaloParams& prm, int ctas, int groups, cudaStream_t stream) {
+int launch(HaloParams prm, int ctas, int groups, cudaStream_t stream) {
   using Cfg = HaloCfg<BLOCK_N, SUB, XHALO>;
   static bool attr = false;
   if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, SUB, XHALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    UOC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, SUB, XHALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr = true;
   }
-  conv_halo_kernel<BLOCK_N, SUB, XHALO><<<dim3(ctas, 1, groups), kThreads, Cfg::kSmemBytes, stream>>>(prm);
+  prm.a_stride = (prm.a_bytes + 1023) / 1024 * 1024;
+  int nb = (kSmemBudget - 1024 - 2 * prm.a_stride - 512) / Cfg::kBBytes;
+  if (nb > kMaxBStages) nb = kMaxBStages;
+  if (const char* e = getenv("UOC_CONV_HALO_BSTAGES")) { int v = atoi(e); if (v >= 2 && v < nb) nb = v; }
+  if (nb < 2) return fail(UOC_ERR_UNSUPPORTED, "conv_halo: tile does not fit in shared memory");
+  prm.b_stages = nb;
+  const int smem_bytes = 1024 + 2 * prm.a_stride + nb * Cfg::kBBytes + 512;
+  conv_halo_kernel<BLOCK_N, SUB, XHALO><<<dim3(ctas, 1, groups), kThreads, smem_bytes, stream>>>(prm);
   UOC_CHECK_LAUNCH();
   return UOC_OK;
 }
@@ -280,6 +313,8 @@ int launch_conv_halo(const ConvProblem& p, cudaStream_t stream) {
   prm.rows = 16 + 2 * p.dilation;
   prm.pitch = xhalo ? (sub == 2 ? 24 : 16) : 8 * sub;
   prm.a_bytes = (xhalo ? 1 : 3) * prm.pitch * prm.rows * 128;
+  prm.part_rows = 2;                              // rows = 18 / 20 / 24 are all even
+  if (const char* e = getenv("UOC_CONV_HALO_PART_ROWS")) { int v = atoi(e); if (v >= 1 && prm.rows % v == 0) prm.part_rows = v; }
   prm.err = device_error_word();
   if (!prm.err) return fail(UOC_ERR_CUDA, "no device error word");
   prm.use_base_offset = 0;
@@ -287,7 +322,7 @@ int launch_conv_halo(const ConvProblem& p, cudaStream_t stream) {
   for (int g = 0; g < p.groups; ++g) {
     const uint64_t xd[4] = {uint64_t(p.Cin), uint64_t(p.W), uint64_t(p.H), uint64_t(p.N)};
     const uint64_t xs[3] = {uint64_t(p.Cin) * 2, uint64_t(p.W) * p.Cin * 2, uint64_t(p.H) * p.W * p.Cin * 2};
-    const uint32_t xb[4] = {64, uint32_t(prm.pitch), uint32_t(prm.rows), 1};
+    const uint32_t xb[4] = {64, uint32_t(prm.pitch), uint32_t(xhalo ? prm.part_rows : prm.rows), 1};
     int rc = make_tmap_bf16(&prm.tmap_x[g], p.g[g].x, 4, xd, xs, xb, nullptr);
     if (rc != UOC_OK) return rc;
     const uint64_t wd[2] = {uint64_t(9) * p.Cin, uint64_t(p.Cout)};

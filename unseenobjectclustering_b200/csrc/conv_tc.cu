@@ -288,15 +288,12 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
 }
 
 int launch_conv_auto(const ConvProblem& p, cudaStream_t stream) {
-  // Measured per layer on B200 (profiles/r01_conv_halo_vs_tc.md): the halo kernel wins where few, weight-light tiles
-  // exist (Cout = 128 at 1/8 resolution); elsewhere its single big CTA per SM loses more to latency / wave
-  // quantisation than it gains in bytes.  UOC_CONV_HALO = 0 / 1 forces first / second generation everywhere.
-  int halo = -1;
+  // Measured per layer on B200 (profiles/r01_conv_halo_vs_tc.md): the halo kernel moves 2.2x fewer bytes per MAC but its
+  // single 200+ KB CTA per SM is latency-bound (tensor pipe 36 % active, 16 B/clk of TMA traffic) and loses to the
+  // first generation's two co-resident CTAs on every layer of this network, so it is opt-in: UOC_CONV_HALO=1.
+  int halo = 0;
   if (const char* e = getenv("UOC_CONV_HALO")) halo = atoi(e);
-  if (conv_halo_supported(p)) {
-    const bool auto_pick = (p.Cout == 128) && ((long long)p.N * p.H * p.W <= 8192);
-    if (halo > 0 || (halo < 0 && auto_pick)) return launch_conv_halo(p, stream);
-  }
+  if (halo > 0 && conv_halo_supported(p)) return launch_conv_halo(p, stream);
   return launch_conv_tc(p, stream);
 }
 
