@@ -46,7 +46,7 @@ def _conv_call(x, w, bias, res, N, H, W, Cin, Cout, k, stride, dil, relu, flags)
     return y
 
 
-@pytest.mark.parametrize("variant", ["tc_cluster1", "halo_x1", "halo_x1_sub1", "halo_x1_bo", "halo_x0", "tc_cluster4", "tc_cluster8", "tc_cluster2_n128", "simt"])
+@pytest.mark.parametrize("variant", ["tc_cluster1", "halo_x1", "halo_x1_sub1", "halo_small_sub1", "halo_x0", "tc_cluster4", "tc_cluster8", "tc_cluster2_n128", "simt"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
 def test_conv_matches_torch(case, variant, monkeypatch):
     """tcgen05 implicit GEMM with every cluster-multicast width (the library reads UOC_CONV_CLUSTER /
@@ -62,7 +62,7 @@ def test_conv_matches_torch(case, variant, monkeypatch):
         monkeypatch.setenv("UOC_CONV_XHALO", "0" if "_x0" in variant else "1")
         if variant.endswith("sub1"):
             monkeypatch.setenv("UOC_CONV_SUB", "1")
-        monkeypatch.setenv("UOC_CONV_BASE_OFFSET", "1" if variant.endswith("_bo") else "0")
+        monkeypatch.setenv("UOC_CONV_HALO_SMALL", "1" if "small" in variant else "0")
     g = torch.Generator().manual_seed(Cin + Cout + k + H)
     x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(torch.bfloat16)
     w = (torch.randn(Cout, k * k, Cin, generator=g) * (1.0 / np.sqrt(k * k * Cin))).to(torch.bfloat16)

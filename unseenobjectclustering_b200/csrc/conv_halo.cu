@@ -40,6 +40,7 @@ struct HaloParams {
   int a_stride;         // bytes between the two activation buffers (a_bytes rounded up to 1024)
   int b_stages;         // depth of the weight-tile ring (as many as fit next to the two halo buffers)
   int part_rows;        // halo rows per TMA slice
+  int a_bufs;           // 2 = double-buffered halo (one big CTA per SM), 1 = single buffer (small CTA, two per SM)
   unsigned int* err;
 };
 
@@ -64,14 +65,14 @@ struct HaloCfg {
 };
 
 template <int BLOCK_N, int SUB, bool XHALO>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_halo_kernel(const __grid_constant__ HaloParams p) {
   using Cfg = HaloCfg<BLOCK_N, SUB, XHALO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int NB = p.b_stages;
   uint8_t* abuf = smem;                                  // 2 x a_stride
-  uint8_t* bbuf = smem + 2 * p.a_stride;                 // NB x kBBytes
+  uint8_t* bbuf = smem + p.a_bufs * p.a_stride;          // NB x kBBytes
   uint64_t* bars = reinterpret_cast<uint64_t*>(bbuf + NB * Cfg::kBBytes);
   uint64_t* a_full = bars;                // 2
   uint64_t* a_empty = bars + 2;           // 2
@@ -111,8 +112,9 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       // block cb, so that neither stream monopolises the TMA queue.
       const int nparts = XHALO ? (p.rows + p.part_rows - 1) / p.part_rows : 3;
       const int part_bytes = XHALO ? p.pitch * p.part_rows * 128 : p.a_bytes / 3;
+      const int AB = p.a_bufs;
       auto issue_part = [&](int cb, int part) {
-        const int ab = cb & 1;
+        const int ab = cb % AB;
         uint8_t* adst = abuf + ab * p.a_stride + part * part_bytes;
         if (XHALO) tma_load_4d(adst, &p.tmap_x[g], &a_full[ab], cb * 64, x0 - p.dil, y0 - p.dil + part * p.part_rows, img);
         else tma_load_4d(adst, &p.tmap_x[g], &a_full[ab], cb * 64, x0 + (part - 1) * p.dil, y0 - p.dil, img);
@@ -124,7 +126,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       bool ok = true;
       for (int cb = 0; cb < CB && ok; ++cb) {
         const bool has_next = cb + 1 < CB;
-        const int nab = (cb + 1) & 1;
+        const int nab = (cb + 1) % AB;
         int next_part = 0;
         bool next_armed = false;
         for (int tap = 0; tap < 9 && ok; ++tap, ++bcount) {
@@ -133,7 +135,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
           mbar_arrive_expect_tx(&b_full[s], Cfg::kBBytes);
           tma_load_2d(bbuf + s * Cfg::kBBytes, &p.tmap_w[g], &b_full[s], tap * p.Cin + cb * 64, n0);
           if (has_next) {
-            if (!next_armed && mbar_try_wait(&a_empty[nab], (((cb + 1) >> 1) & 1) ^ 1u)) {
+            if (!next_armed && mbar_try_wait(&a_empty[nab], ((((cb + 1) / AB)) & 1) ^ 1u)) {
               mbar_arrive_expect_tx(&a_full[nab], p.a_bytes);
               next_armed = true;
             }
@@ -145,7 +147,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
         }
         if (ok && has_next) {
           if (!next_armed) {
-            if (!mbar_wait(&a_empty[nab], (((cb + 1) >> 1) & 1) ^ 1u, p.err)) { ok = false; break; }
+            if (!mbar_wait(&a_empty[nab], ((((cb + 1) / AB)) & 1) ^ 1u, p.err)) { ok = false; break; }
             mbar_arrive_expect_tx(&a_full[nab], p.a_bytes);
           }
           for (; next_part < nparts; ++next_part) issue_part(cb + 1, next_part);
@@ -160,8 +162,8 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       int bcount = 0;
       bool ok = true;
       for (int cb = 0; cb < CB && ok; ++cb) {
-        const int ab = cb & 1;
-        if (!mbar_wait(&a_full[ab], (cb >> 1) & 1, p.err)) { ok = false; break; }
+        const int ab = cb % p.a_bufs;
+        if (!mbar_wait(&a_full[ab], (cb / p.a_bufs) & 1, p.err)) { ok = false; break; }
         const uint32_t a_base = a_addr0 + ab * p.a_stride;
         for (int tap = 0; tap < 9; ++tap, ++bcount) {
           const int s = bcount % NB;
@@ -263,12 +265,17 @@ int launch(HaloParams prm, int ctas, int groups, cudaStream_t stream) {
     attr = true;
   }
   prm.a_stride = (prm.a_bytes + 1023) / 1024 * 1024;
-  int nb = (kSmemBudget - 1024 - 2 * prm.a_stride - 512) / Cfg::kBBytes;
+  int budget = kSmemBudget;
+  prm.a_bufs = 2;
+  if (const char* e = getenv("UOC_CONV_HALO_SMALL")) {
+    if (atoi(e) != 0) { budget = 112 * 1024; prm.a_bufs = 1; }     // two CTAs per SM hide each other's halo-fetch bubble
+  }
+  int nb = (budget - 1024 - prm.a_bufs * prm.a_stride - 512) / Cfg::kBBytes;
   if (nb > kMaxBStages) nb = kMaxBStages;
   if (const char* e = getenv("UOC_CONV_HALO_BSTAGES")) { int v = atoi(e); if (v >= 2 && v < nb) nb = v; }
   if (nb < 2) return fail(UOC_ERR_UNSUPPORTED, "conv_halo: tile does not fit in shared memory");
   prm.b_stages = nb;
-  const int smem_bytes = 1024 + 2 * prm.a_stride + nb * Cfg::kBBytes + 512;
+  const int smem_bytes = 1024 + prm.a_bufs * prm.a_stride + nb * Cfg::kBBytes + 512;
   conv_halo_kernel<BLOCK_N, SUB, XHALO><<<dim3(ctas, 1, groups), kThreads, smem_bytes, stream>>>(prm);
   UOC_CHECK_LAUNCH();
   return UOC_OK;
