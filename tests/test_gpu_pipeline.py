@@ -85,3 +85,48 @@ def test_frame_pipeline_equals_serial_calls():
     for k in range(5):
         want, _ = MS.cluster_fields(fields[k], 100, first_indices=[firsts[k]], flags=_lib.FLAG_SYNC_CHECK)
         assert torch.equal(outs[k].view(-1).to(torch.int32), want[0].cpu())
+
+
+class _FieldNet(torch.nn.Module):
+    """Stand-in network whose output depends on the input: image channel 0 carries a per-pixel cluster id."""
+
+    def __init__(self, d=64, k=8, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.register_buffer("centres", torch.nn.functional.normalize(torch.randn(k, d, generator=g), dim=1))
+        self.register_buffer("noise", 0.05 * torch.randn(d, 96 * 128, generator=g))
+
+    def forward(self, img, label=None, depth=None):
+        ids = img[0, 0].reshape(-1).long()
+        f = self.centres[ids].t() + self.noise + 0.0 * depth[0, 0].reshape(1, -1)
+        return torch.nn.functional.normalize(f, dim=0).reshape(1, -1, img.shape[2], img.shape[3]).contiguous()
+
+
+def test_frame_pipeline_with_cuda_graphs_equals_serial_calls():
+    """After the warm-up every slot replays two captured CUDA graphs per frame; results must not change."""
+    from unseenobjectclustering_b200 import mean_shift as MS
+    from unseenobjectclustering_b200.pipeline import FramePipeline
+    H, W = 96, 128
+    net = _FieldNet().to(DEV)
+    frames = []
+    for k in range(8):
+        _, gt = O.synthetic_clustered_features(H, W, 8, 3 + k % 3, 0.05, seed=90 + k)
+        img = torch.zeros(1, 3, H, W)
+        img[0, 0] = gt.float()
+        frames.append(img)
+    xyz = torch.ones(1, 3, H, W)
+    firsts = [3, 33, 333, 3333, 7, 77, 777, 7777]
+    pipe = FramePipeline(net, H, W, depth=2)
+    outs = []
+    for k in range(8):
+        pipe.submit(frames[k], xyz, firsts[k])
+        if len(pipe.pending) == 2:
+            outs.append(pipe.collect_one()[0].clone())
+    outs.extend(o[0].clone() for o in pipe.drain())
+    assert pipe.graph_error is None, pipe.graph_error
+    assert all(s.graph_a is not None for s in pipe.slots)          # frames 3.. ran from graphs
+    for k in range(8):
+        feats = net(frames[k].to(DEV), None, xyz.to(DEV))
+        want, _ = MS.cluster_fields(feats, 100, first_indices=[firsts[k]], flags=_lib.FLAG_SYNC_CHECK)
+        assert torch.equal(outs[k].view(-1).to(torch.int32), want[0].cpu()), k
+        assert len(torch.unique(want)) >= 3

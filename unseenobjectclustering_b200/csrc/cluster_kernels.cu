@@ -525,7 +525,15 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
   else if (gpt_t == 2) kern = UOC_FPS_PICK(2, 1024, 8);
   else kern = UOC_FPS_PICK(4, 1024, 8);
 #undef UOC_FPS_PICK
-  UOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  {
+    static void* configured_kern = nullptr;
+    static size_t configured_smem = 0;
+    if (configured_kern != kern || smem > configured_smem) {
+      UOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      configured_kern = kern;
+      configured_smem = smem;
+    }
+  }
   if (variant == 0 || variant == 2) {
     UOC_CUDA(cudaMemsetAsync(slots, 0, slot_need + (variant == 0 ? mail_need : 0), stream));
   } else {

@@ -1,60 +1,129 @@
-"""Frame pipeline: several frames in flight on separate CUDA streams.
+"""Frame pipeline: several frames in flight on separate CUDA streams, replayed from CUDA graphs.
 
-One frame is a chain of dependent kernels (backbone -> sampling -> mean-shift loop -> labels) with
+One frame is a chain of ~65 dependent kernels (backbone -> sampling -> mean-shift loop -> labels) with
 latency-bound stretches -- the farthest point sampling spends most of each pass waiting for an
 inter-CTA exchange, tile-quantised convolutions leave SMs idle -- so a second frame on another
-stream fills the gaps.  Each slot owns its stream, pinned host staging buffers, device inputs and
-(through the per-stream workspaces of networks.py / mean_shift.py) its scratch memory.  Sampling
-kernels are cooperative launches; they are chained across slots with events so that two of them never
-compete for residency.
+stream fills the gaps.  Each slot owns its stream, device inputs, outputs and scratch memory.
+
+Enqueueing a frame eagerly costs ~1.7 ms of host time (ctypes calls, ~150 tensor-map encodes,
+~70 launches), which caps the throughput; so after a warm-up every slot captures TWO CUDA graphs:
+  A: backbone forward   (inputs: the slot's device frame buffers; outputs: features + bf16 copy)
+  B: mean-shift loop + seed labelling + pixel labels + D2H of the label map
+The sampling kernel between them stays an eager cooperative launch: it is chained across slots with
+an event so that two cooperative kernels never compete for residency, and its first-seed index is
+a per-frame host value.
 """
+import ctypes
+
 import numpy as np
 import torch
 
+from . import _lib
 from . import mean_shift as _ms
 
 
 class _Slot(object):
     def __init__(self, dev, H, W):
         self.stream = torch.cuda.Stream(device=dev)
-        self.img_pin = torch.empty((1, 3, H, W), dtype=torch.float32).pin_memory()
-        self.xyz_pin = torch.empty((1, 3, H, W), dtype=torch.float32).pin_memory()
         self.img_dev = torch.empty((1, 3, H, W), dtype=torch.float32, device=dev)
         self.xyz_dev = torch.empty((1, 3, H, W), dtype=torch.float32, device=dev)
+        self.img_pin = None
+        self.xyz_pin = None
         self.out_pin = torch.empty((1, H, W), dtype=torch.float32).pin_memory()
         self.done = torch.cuda.Event()
         self.labels = None
         self.busy = False
+        self.graph_a = None
+        self.graph_b = None
+        self.runs = 0
 
 
 class FramePipeline(object):
     """submit() frames, collect float32 CPU label maps (the reference's out_label) in order."""
 
-    def __init__(self, network, H=480, W=640, depth=2, num_seeds=100, kappa=20.0, max_iters=10, device=None):
+    def __init__(self, network, H=480, W=640, depth=2, num_seeds=100, kappa=20.0, max_iters=10, device=None,
+                 use_graphs=True, epsilon=None):
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.network = network
         self.H, self.W = H, W
-        self.num_seeds, self.kappa, self.max_iters = num_seeds, kappa, max_iters
+        self.num_seeds, self.kappa, self.max_iters = num_seeds, float(kappa), int(max_iters)
+        self.eps = _ms._epsilon(epsilon)
         self.slots = [_Slot(self.dev, H, W) for _ in range(depth)]
         self.next = 0
         self.coop_tail = None          # event after the last cooperative sampling kernel
         self.pending = []
+        self.use_graphs = bool(use_graphs) and isinstance(network, torch.nn.Module)
+        self.graph_error = None
 
-    def _run(self, slot, img_dev, xyz_dev, first_index):
-        feats = self.network(img_dev, None, xyz_dev)
+    # -- eager path (also the warm-up of the graph path) ----------------------------------------------
+    def _run_eager(self, slot, first_index):
+        feats = self.network(slot.img_dev, None, slot.xyz_dev)
         if self.coop_tail is not None:
             slot.stream.wait_event(self.coop_tail)          # sampling kernels never overlap each other
+
         def sampled():
             ev = torch.cuda.Event()
             ev.record(slot.stream)          # right after this frame's sampling kernel: the next frame's may start
             self.coop_tail = ev
 
         labels, _ = _ms.cluster_fields(feats, self.num_seeds, self.kappa, self.max_iters, [int(first_index)],
-                                       on_sampling_done=sampled)
+                                       epsilon=self.eps, on_sampling_done=sampled)
         return labels
 
+    # -- graph path -------------------------------------------------------------------------------------
+    def _capture(self, slot):
+        lib = _lib.load()
+        dev, n, m = self.dev, self.H * self.W, self.num_seeds
+        ga = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga, stream=slot.stream):
+            slot.feats = self.network(slot.img_dev, None, slot.xyz_dev)
+        slot.xb = _ms._lookup_bf16(slot.feats)
+        C = slot.feats.shape[1]
+        slot.C = C
+        slot.sel = torch.empty((1, m), dtype=torch.int64, device=dev)
+        slot.Z = torch.empty((1, m, C), dtype=torch.float32, device=dev)
+        slot.sl = torch.empty((1, m), dtype=torch.int32, device=dev)
+        slot.nu = torch.empty((1,), dtype=torch.int32, device=dev)
+        slot.lab = torch.empty((1, n), dtype=torch.int32, device=dev)
+        nbytes = lib.uoc_meanshift_workspace_bytes(1, n, C, m)
+        slot.ws_fps = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=dev)
+        slot.ws_b = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=dev)
+        gb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gb, stream=slot.stream):
+            sp = _lib.stream_ptr(dev)
+            f = slot.feats
+            _lib.check(lib.uoc_hill_climb(_lib.ptr(f), f.stride(0), f.stride(1), _lib.ptr(slot.xb), 1, n, C, m, self.kappa,
+                                          self.max_iters, _lib.ptr(slot.Z), _lib.ptr(slot.ws_b), slot.ws_b.numel(), 0, sp),
+                       "uoc_hill_climb")
+            _lib.check(lib.uoc_label_seeds(_lib.ptr(slot.Z), 1, m, C, self.eps, _lib.ptr(slot.sl), _lib.ptr(slot.nu), sp),
+                       "uoc_label_seeds")
+            _lib.check(lib.uoc_assign_labels(_lib.ptr(f), f.stride(0), f.stride(1), _lib.ptr(slot.xb), 1, n, C, m,
+                                             _lib.ptr(slot.Z), _lib.ptr(slot.sl), _lib.ptr(slot.nu), _lib.ptr(slot.lab),
+                                             _lib.ptr(slot.ws_b), slot.ws_b.numel(), sp), "uoc_assign_labels")
+            slot.out_pin.copy_(slot.lab.view(1, self.H, self.W).to(torch.float32), non_blocking=True)
+        slot.graph_a, slot.graph_b = ga, gb
+
+    def _run_graph(self, slot, first_index):
+        lib = _lib.load()
+        n, m, C = self.H * self.W, self.num_seeds, slot.C
+        slot.graph_a.replay()
+        if self.coop_tail is not None:
+            slot.stream.wait_event(self.coop_tail)
+        first = (ctypes.c_int64 * 1)(int(first_index))
+        f = slot.feats
+        _lib.check(lib.uoc_select_seeds(_lib.ptr(f), f.stride(0), f.stride(1), 1, n, C, m, ctypes.cast(first, ctypes.c_void_p),
+                                        _lib.ptr(slot.sel), _lib.ptr(slot.Z), _lib.ptr(slot.ws_fps), slot.ws_fps.numel(), 0,
+                                        _lib.stream_ptr(self.dev)), "uoc_select_seeds")
+        ev = torch.cuda.Event()
+        ev.record(slot.stream)
+        self.coop_tail = ev
+        slot.graph_b.replay()
+        return slot.lab
+
+    # -- public -----------------------------------------------------------------------------------------
     def submit(self, image, depth, first_index=None, resident=False):
-        """image / depth: [1,3,H,W] float32 CPU tensors (or device tensors with resident=True)."""
+        """image / depth: [1,3,H,W] float32 tensors: pinned or pageable CPU tensors, or device tensors
+        (resident=True).  Returns the slot; collect results with collect_one() / drain() in submission order."""
         slot = self.slots[self.next % len(self.slots)]
         self.next += 1
         if slot.busy:
@@ -63,21 +132,32 @@ class FramePipeline(object):
             first_index = np.random.randint(0, self.H * self.W)     # lib/utils/mean_shift.py:155, drawn in frame order
         with torch.cuda.stream(slot.stream):
             if resident:
-                img_dev, xyz_dev = image, depth
+                slot.img_dev.copy_(image, non_blocking=True)
+                slot.xyz_dev.copy_(depth, non_blocking=True)
             else:
                 src_i, src_d = image, depth
                 if not image.is_pinned():                  # stage through the slot's pinned buffers
+                    if slot.img_pin is None:
+                        slot.img_pin = torch.empty_like(slot.img_dev, device="cpu").pin_memory()
+                        slot.xyz_pin = torch.empty_like(slot.xyz_dev, device="cpu").pin_memory()
                     slot.img_pin.copy_(image)
-                    src_i = slot.img_pin
-                if not depth.is_pinned():
                     slot.xyz_pin.copy_(depth)
-                    src_d = slot.xyz_pin
+                    src_i, src_d = slot.img_pin, slot.xyz_pin
                 slot.img_dev.copy_(src_i, non_blocking=True)
                 slot.xyz_dev.copy_(src_d, non_blocking=True)
-                img_dev, xyz_dev = slot.img_dev, slot.xyz_dev
-            slot.labels = self._run(slot, img_dev, xyz_dev, first_index)
-            if not resident:
+            if self.use_graphs and slot.graph_a is None and slot.runs >= 1 and self.graph_error is None:
+                try:
+                    slot.stream.synchronize()
+                    self._capture(slot)
+                except Exception as e:           # capture is an optimisation of the host side only
+                    self.graph_error = repr(e)
+                    slot.graph_a = slot.graph_b = None
+            if slot.graph_a is not None:
+                slot.labels = self._run_graph(slot, first_index)
+            else:
+                slot.labels = self._run_eager(slot, first_index)
                 slot.out_pin.copy_(slot.labels.view(1, self.H, self.W).to(torch.float32), non_blocking=True)
+            slot.runs += 1
             slot.done.record(slot.stream)
         slot.busy = True
         self.pending.append(slot)
