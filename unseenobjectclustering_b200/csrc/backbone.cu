@@ -23,7 +23,7 @@ struct Block {
 };
 
 struct Branch {
-  size_t stem_w_off = 0, stem_b_off = 0;
+  size_t stem_w_off = 0, stem_b_off = 0, stem_wbf_off = 0;
   std::vector<Block> blocks;
   ConvLayer fc;
 };
@@ -134,6 +134,14 @@ static bool build_branch(const WeightMap& wm, const std::string& prefix, int num
     for (int c = 0; c < 3; ++c)
       for (int t = 0; t < 49; ++t) sw[co * 147 + t * 3 + c] = w[(co * 3 + c) * 49 + t] * scale[co];
     sb[co] = shift[co];
+  }
+  // bf16 copy for the tensor-core stem: [64][192], k = tap*3 + c, zero padded beyond 147
+  br->stem_wbf_off = bb->reserve(64 * 192 * 2);
+  {
+    uint16_t* swb = reinterpret_cast<uint16_t*>(bb->host.data() + br->stem_wbf_off);
+    const float* swf = reinterpret_cast<const float*>(bb->host.data() + br->stem_w_off);
+    for (int co = 0; co < 64; ++co)
+      for (int k = 0; k < 192; ++k) swb[co * 192 + k] = (k < 147) ? f32_to_bf16_rne(swf[co * 147 + k]) : uint16_t(0);
   }
   int inplanes = 64;
   for (int li = 0; li < 4; ++li) {
@@ -283,7 +291,12 @@ int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, i
     sg[g].bias = reinterpret_cast<const float*>(bb->blob + bb->br[g].stem_b_off);
     sg[g].y = ws + wp.stem[g];
   }
-  rc = launch_stem(sg, 2, N, H, W, st);
+  if (flags & UOC_FLAG_CONV_SIMT) {
+    rc = launch_stem(sg, 2, N, H, W, st);
+  } else {
+    const void* wbf[2] = {bb->blob + bb->br[0].stem_wbf_off, bb->blob + bb->br[1].stem_wbf_off};
+    rc = launch_stem_tc(sg, wbf, 2, N, H, W, st);
+  }
   if (rc != UOC_OK) return rc;
   const void* px[2] = {ws + wp.stem[0], ws + wp.stem[1]};
   void* py[2] = {ws + wp.buf[0][0], ws + wp.buf[1][0]};

@@ -314,3 +314,186 @@ int launch_nhwc_to_nchw(const float* in, int N, int h, int w, int d, float* out,
 }
 
 }  // namespace uoc
+
+// ----------------------------------------------------------------------------------------------
+// stem on the tensor cores: the 7x7 stride-2 convolution as an implicit GEMM with K = 7*7*3 = 147 -> 192.
+// A 128-row im2col tile (8 x 16 output pixels) is BUILT in shared memory by the CTA's threads from a staged
+// fp32 input patch (bf16, K-major, 128B-swizzled -- the layout TMA would have produced), the weights
+// [64][192] bf16 sit in shared memory for the CTA's lifetime, 12 tcgen05.mma (M 128, N 64, K 16) per tile
+// accumulate in TMEM, and the same 4 warps run the epilogue (bias, ReLU, bf16 NHWC).  Persistent CTAs,
+// two per SM so that one CTA's tile construction overlaps the other's MMA / epilogue.
+// ----------------------------------------------------------------------------------------------
+namespace uoc {
+
+struct StemTcParams {
+  const float* x[2];
+  const __nv_bfloat16* w[2];     // [64][192] bf16, k = (r*7 + s)*3 + c, zero padded
+  const float* bias[2];
+  __nv_bfloat16* y[2];
+  int N, H, W, Ho, Wo, tiles_x, tiles_y, tiles_per_group;
+  unsigned int* err;
+};
+
+constexpr int kStemK = 192;
+constexpr int kStemPatchH = 8 * 2 + 5;     // 21
+constexpr int kStemPatchW = 16 * 2 + 5;    // 37
+
+__global__ void __launch_bounds__(128, 2) stem_tc_kernel(StemTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_s = smem;                                  // 3 x 16 KB : [kb][128 rows][128 B]
+  uint8_t* w_s = smem + 3 * 16384;                      // 3 x  8 KB : [kb][ 64 rows][128 B]
+  float* patch = reinterpret_cast<float*>(w_s + 3 * 8192);          // [3][21][38]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(patch + 3 * kStemPatchH * 38);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int total_tiles = 2 * p.tiles_per_group;        // both branches
+  int cur_g = -1;
+
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
+  for (int e = tid; e < 3 * 16384 / 16; e += 128) reinterpret_cast<uint4*>(a_s)[e] = make_uint4(0u, 0u, 0u, 0u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t a_addr = smem_u32(a_s), w_addr = smem_u32(w_s);
+  uint32_t phase = 0;
+
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int g = t / p.tiles_per_group;
+    int r = t - g * p.tiles_per_group;
+    const int tx = r % p.tiles_x; r /= p.tiles_x;
+    const int ty = r % p.tiles_y;
+    const int n = r / p.tiles_y;
+    if (g != cur_g) {                                   // (re)load this branch's weights, K-major 128B-swizzled rows
+      const uint4* wg = reinterpret_cast<const uint4*>(p.w[g]);
+      for (int e = tid; e < 64 * 24; e += 128) {
+        const int row = e / 24, j = e - row * 24;
+        const int kb = j >> 3, cc = j & 7;
+        *reinterpret_cast<uint4*>(w_s + kb * 8192 + row * 128 + ((cc ^ (row & 7)) << 4)) = __ldg(wg + e);
+      }
+      cur_g = g;
+    }
+    // stage the fp32 input patch
+    const int iy0 = ty * 16 - 3, ix0 = tx * 32 - 3;
+    const float* xg = p.x[g] + size_t(n) * 3 * p.H * p.W;
+    for (int e = tid; e < 3 * kStemPatchH * kStemPatchW; e += 128) {
+      const int c = e / (kStemPatchH * kStemPatchW);
+      const int rem = e - c * kStemPatchH * kStemPatchW;
+      const int py = rem / kStemPatchW, px = rem - py * kStemPatchW;
+      const int iy = iy0 + py, ix = ix0 + px;
+      float v = 0.f;
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xg + (size_t(c) * p.H + iy) * p.W + ix);
+      patch[(c * kStemPatchH + py) * 38 + px] = v;
+    }
+    __syncthreads();
+    // im2col row of pixel `tid` -> 19 chunks of 8 bf16 (k = 0..151; k >= 147 is zero)
+    {
+      const int ly = tid >> 4, lx = tid & 15;
+      const float* pb = patch + (ly * 2) * 38 + lx * 2;
+      float vals[8];
+#pragma unroll
+      for (int j = 0; j < 19; ++j) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int k = j * 8 + q;                 // compile-time after unrolling: tap / channel offsets fold to constants
+          float v = 0.f;
+          if (k < 147) {
+            const int tap = k / 3, c = k - tap * 3;
+            const int kr = tap / 7, ks = tap - kr * 7;
+            v = pb[(c * kStemPatchH + kr) * 38 + ks];
+          }
+          vals[q] = v;
+        }
+        const uint4 pk = make_uint4(pack_bf16x2(vals[0], vals[1]), pack_bf16x2(vals[2], vals[3]),
+                                    pack_bf16x2(vals[4], vals[5]), pack_bf16x2(vals[6], vals[7]));
+        const int kb = j >> 3, cc = j & 7;
+        *reinterpret_cast<uint4*>(a_s + kb * 16384 + tid * 128 + ((cc ^ (tid & 7)) << 4)) = pk;
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+#pragma unroll
+        for (int kb = 0; kb < 3; ++kb) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = make_smem_desc_sw128(a_addr + kb * 16384 + ks * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(w_addr + kb * 8192 + ks * 32, 16, 1024);
+            umma_ss_f16(tmem, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    if (!mbar_wait(bar, phase, p.err)) break;
+    phase ^= 1u;
+    tc_fence_after();
+    {
+      const int oy = ty * 8 + (tid >> 4), ox = tx * 16 + (tid & 15);
+      const bool inb = (oy < p.Ho) && (ox < p.Wo);
+      const uint32_t ta = tmem + (uint32_t(warp * 32) << 16);
+      const float* bias = p.bias[g];
+      uint4* op = reinterpret_cast<uint4*>(p.y[g] + ((size_t(n) * p.Ho + oy) * p.Wo + ox) * 64);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(ta + c * 32, v);
+        tmem_wait_ld();
+        if (inb) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float f[8];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) f[h] = fmaxf(__uint_as_float(v[8 * e + h]) + __ldg(bias + c * 32 + 8 * e + h), 0.f);
+            op[c * 4 + e] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                       pack_bf16x2(f[6], f[7]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();          // TMEM and the A tile are free again
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+int launch_stem_tc(const StemGroup* g, const void* const* w_bf16, int groups, int N, int H, int W, cudaStream_t stream) {
+  if (groups != 2) return fail(UOC_ERR_INVALID, "stem_tc expects both branches");
+  StemTcParams p;
+  for (int i = 0; i < 2; ++i) {
+    p.x[i] = g[i].x;
+    p.w[i] = static_cast<const __nv_bfloat16*>(w_bf16[i]);
+    p.bias[i] = g[i].bias;
+    p.y[i] = static_cast<__nv_bfloat16*>(g[i].y);
+  }
+  p.N = N; p.H = H; p.W = W;
+  p.Ho = (H + 6 - 7) / 2 + 1;
+  p.Wo = (W + 6 - 7) / 2 + 1;
+  p.tiles_x = (p.Wo + 15) / 16;
+  p.tiles_y = (p.Ho + 7) / 8;
+  p.tiles_per_group = N * p.tiles_y * p.tiles_x;
+  p.err = device_error_word();
+  if (!p.err) return fail(UOC_ERR_CUDA, "no device error word");
+  const int smem = 1024 + 3 * 16384 + 3 * 8192 + 3 * kStemPatchH * 38 * 4 + 64;
+  static bool attr = false;
+  if (!attr) {
+    UOC_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  int grid = 2 * (sm_count() > 0 ? sm_count() : 148);
+  if (grid > 2 * p.tiles_per_group) grid = 2 * p.tiles_per_group;
+  stem_tc_kernel<<<grid, 128, smem, stream>>>(p);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+}  // namespace uoc

@@ -50,6 +50,8 @@ struct StemGroup {
   void* y;                // [N][H/2][W/2][64] bf16
 };
 int launch_stem(const StemGroup* g, int groups, int N, int H, int W, cudaStream_t stream);
+// same on tcgen05 (im2col tile built in shared memory); w_bf16[g]: [64][192] bf16 zero-padded, BN folded
+int launch_stem_tc(const StemGroup* g, const void* const* w_bf16, int groups, int N, int H, int W, cudaStream_t stream);
 // maxpool 3x3 s2 p1 on bf16 NHWC, C = 64
 int launch_maxpool(const void* const* x, void* const* y, int groups, int N, int H, int W, int C, cudaStream_t stream);
 // head: (trunk_rgb + trunk_depth) [N][h][w][d] fp32 -> bilinear x8 (align_corners) -> L2 normalise
