@@ -194,6 +194,18 @@ def test_high_res_128d_30_iters():
     assert O.labels_equal_up_to_permutation(l[0].cpu().numpy(), gt.numpy().ravel())
 
 
+def test_config5_full_size_960x720_128d_30_iters():
+    """BASELINE config 5 at full size (n = 691 200, d = 128, 30 updates): 354 MB field, > L2."""
+    feats, gt = _field(720, 960, 128, 12, 0.04, seed=55)
+    f = feats.to(DEV)
+    l, s = MS.cluster_fields(f, 100, max_iters=30, first_indices=[123456], flags=_lib.FLAG_SYNC_CHECK)
+    assert O.labels_equal_up_to_permutation(l[0].cpu().numpy(), gt.numpy().ravel())
+    sel = s[0].cpu().numpy()
+    assert sel[0] == 123456 and len(set(sel.tolist())) == 100
+    sel_o, _ = C.select_seeds(feats[0].reshape(128, -1).numpy(), 4, 123456)
+    assert np.array_equal(sel[:4], sel_o)
+
+
 def test_bad_arguments_fail_loudly():
     f = torch.zeros(1, 64, 8, 8, device=DEV)
     with pytest.raises(_lib.UocError):
