@@ -48,7 +48,8 @@ enum {
 enum {
   UOC_FLAG_LOOP_SIMT = 1,   /* mean-shift iterations on the fp32 SIMT validation kernel instead of tcgen05 */
   UOC_FLAG_CONV_SIMT = 2,   /* backbone convolutions on the fp32 SIMT validation kernel instead of tcgen05 */
-  UOC_FLAG_SYNC_CHECK = 4   /* synchronise the stream and read back the device error word before returning */
+  UOC_FLAG_SYNC_CHECK = 4,  /* synchronise the stream and read back the device error word before returning */
+  UOC_FLAG_FPS_FP32 = 8     /* seed selection re-reads the fp32 field in every pass (no bf16 screening pass) */
 };
 
 #define UOC_MAX_SEEDS 128   /* num_seeds upper bound: one tcgen05 M=128 accumulator tile */
@@ -97,9 +98,12 @@ UOC_API int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stri
  * tests and by callers that want one stage only). */
 
 /* select_smart_seeds (lib/utils/mean_shift.py:128-189, cosine): selected_out [batch,m] int64,
- * seeds_out [batch,m,d] fp32. */
-UOC_API int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
-                             const int64_t* first_seed_host, int64_t* selected_out, float* seeds_out,
+ * seeds_out [batch,m,d] fp32.
+ * x_bf16 (optional, d = 64/128): the bf16 pixel-major copy of X (round-to-nearest or truncated).  When given, every pass
+ * screens the points with it and evaluates the fp32 distance only where the new seed can lower the running minimum;
+ * the selected indices are bit-identical either way (fps_pruned.cu).  NULL or UOC_FLAG_FPS_FP32: fp32 passes only. */
+UOC_API int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n,
+                             int d, int m, const int64_t* first_seed_host, int64_t* selected_out, float* seeds_out,
                              void* workspace, size_t workspace_bytes, int flags, uoc_stream_t stream);
 
 /* seed_hill_climbing_ball (lib/utils/mean_shift.py:79-109, cosine): Z [batch,m,d] fp32 updated in place. */

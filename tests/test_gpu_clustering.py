@@ -26,16 +26,47 @@ def _field(H, W, d, K, noise, seed):
 
 @pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 100), (30, 44, 128, 100), (24, 24, 64, 40),
                                      (60, 80, 32, 17), (120, 160, 64, 100)])
-def test_select_seeds_bit_exact(H, W, d, m):
+@pytest.mark.parametrize("screen", [True, False], ids=["bf16_screen", "fp32_passes"])
+def test_select_seeds_bit_exact(H, W, d, m, screen, monkeypatch):
+    monkeypatch.setenv("UOC_FPS_PRUNED", "1" if screen else "0")
     feats, _ = _field(H, W, d, 4, 0.05, seed=H * 7 + d)
     Xp = feats[0].reshape(d, -1).numpy()
     first = (H * W) // 3
     sel_o, seeds_o = C.select_seeds(Xp, m, first)
     X = feats.to(DEV)[0].view(d, -1).t()
-    seeds, sel = MS.select_smart_seeds(X, m, return_selected_indices=True, first_index=first)
+    seeds, sel = MS.select_smart_seeds(X, m, return_selected_indices=True, first_index=first, bf16_screen=screen)
     assert np.array_equal(sel.numpy(), sel_o)
     assert np.array_equal(seeds.cpu().numpy(), seeds_o)
     assert sel[0] == first and len(set(sel.tolist())) == m
+
+
+@pytest.mark.parametrize("case", ["isotropic", "scaled", "streamed", "full_frame"])
+def test_select_seeds_bf16_screen_stress(case, monkeypatch):
+    """The bf16 screening pass of the seed selection (fps_pruned.cu) must never change an index:
+    isotropic  - no cluster structure: the screen rejects little, nearly every point takes the fp32 path;
+    scaled     - rows of norm 3 (the error bound of the screen scales with |x| |s|);
+    streamed   - 8 KB of shared memory: almost all rounds are streamed from global memory instead of being resident;
+    full_frame - 480x640: 65 rounds per CTA, 50 resident + 15 streamed, every warp owns several rounds."""
+    monkeypatch.setenv("UOC_FPS_PRUNED", "1")
+    if case == "isotropic":
+        g = torch.Generator().manual_seed(5)
+        feats = torch.nn.functional.normalize(torch.randn(1, 64, 48, 64, generator=g), dim=1)
+    elif case == "scaled":
+        feats = _field(40, 52, 64, 4, 0.1, seed=12)[0] * 3.0
+    elif case == "streamed":
+        monkeypatch.setenv("UOC_FPS_SMEM_KB", "8")
+        feats = _field(120, 160, 64, 5, 0.1, seed=13)[0]
+    else:
+        feats = _field(480, 640, 64, 6, 0.1, seed=14)[0]
+    d = feats.shape[1]
+    m = 100
+    Xp = feats[0].reshape(d, -1).numpy()
+    first = Xp.shape[1] // 5
+    sel_o, seeds_o = C.select_seeds(Xp, m, first)
+    X = feats.to(DEV)[0].view(d, -1).t()
+    seeds, sel = MS.select_smart_seeds(X, m, return_selected_indices=True, first_index=first, bf16_screen=True)
+    assert np.array_equal(sel.numpy(), sel_o)
+    assert np.array_equal(seeds.cpu().numpy(), seeds_o)
 
 
 @pytest.mark.parametrize("flags,tol", [(0, 5e-5), (_lib.FLAG_LOOP_SIMT, 2e-6)])

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_clustering.py -m gpu -q --timeout 300 -p no:cacheprovider -x > gpurun_out/t.log 2>&1; echo "tests exit $?"; tail -2 gpurun_out/t.log
+for pz in ${PZ:-0 1}; do
+  UOC_LOOP_PERSISTENT=$pz timeout 600 python bench.py --steps 30 --warmup 3 --depth 3 --no-cpu-baseline > gpurun_out/bench_persist$pz.json 2> gpurun_out/bench_persist$pz.err; echo "bench persist=$pz exit $?"
+  python -c "
+import json; j=json.load(open('gpurun_out/bench_persist$pz.json')); print(round(j['value'],1), round(j['e2e']['value'],1), 'serial', round(j['serial']['value'],1), j['stages_ms'], j['roofline']['frac'], j['gpu_launches'])"
+done

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libuoc_b200.so")
 FLAG_LOOP_SIMT = 1
 FLAG_CONV_SIMT = 2
 FLAG_SYNC_CHECK = 4
+FLAG_FPS_FP32 = 8
 MAX_SEEDS = 128
 
 
@@ -35,7 +36,7 @@ SIGNATURES = {
     "uoc_meanshift_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "uoc_meanshift_cluster": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                    _i, _vp]),
-    "uoc_select_seeds": (_i, [_vp, _i64, _i64, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "uoc_select_seeds": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "uoc_hill_climb": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _f, _i, _vp, _vp, _sz, _i, _vp]),
     "uoc_label_seeds": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "uoc_assign_labels": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -64,10 +64,16 @@ int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stride_d, co
   ClusterShape s{batch, n, d, m, stride_b, stride_d};
   rc = upload_first(first_seed_host, batch, n, w, st);
   if (rc != UOC_OK) return rc;
-  rc = launch_select_seeds(X, s, w, selected_out, w.Z, st);
+  // the bf16 pixel-major copy serves the screening pass of the seed selection, the tcgen05 loop and the label pass
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x_bf16);
+  if (!xb && !(flags & UOC_FLAG_LOOP_SIMT) && (d == 64 || d == 128)) {
+    rc = launch_pack_bf16(X, s, w.xb, st);
+    if (rc != UOC_OK) return rc;
+    xb = w.xb;
+  }
+  rc = launch_select_seeds(X, (flags & (UOC_FLAG_FPS_FP32 | UOC_FLAG_LOOP_SIMT)) ? nullptr : xb, s, w, selected_out, w.Z, st);
   if (rc != UOC_OK) return rc;
-  const __nv_bfloat16* xb = nullptr;
-  rc = hill_climb(X, x_bf16, s, w, w.Z, kappa, iters, flags, st, &xb);
+  rc = hill_climb(X, xb, s, w, w.Z, kappa, iters, flags, st, &xb);
   if (rc != UOC_OK) return rc;
   rc = launch_label_seeds(w.Z, batch, m, d, epsilon, w.seed_labels, w.num_unique, st);
   if (rc != UOC_OK) return rc;
@@ -81,8 +87,8 @@ int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stride_d, co
   return UOC_OK;
 }
 
-int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
-                     const int64_t* first_seed_host, int64_t* selected_out, float* seeds_out, void* workspace,
+int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n, int d,
+                     int m, const int64_t* first_seed_host, int64_t* selected_out, float* seeds_out, void* workspace,
                      size_t workspace_bytes, int flags, uoc_stream_t stream) {
   int rc = require_sm100();
   if (rc != UOC_OK) return rc;
@@ -96,7 +102,8 @@ int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, int bat
   ClusterShape s{batch, n, d, m, stride_b, stride_d};
   rc = upload_first(first_seed_host, batch, n, w, st);
   if (rc != UOC_OK) return rc;
-  rc = launch_select_seeds(X, s, w, selected_out, seeds_out, st);
+  rc = launch_select_seeds(X, (flags & UOC_FLAG_FPS_FP32) ? nullptr : static_cast<const __nv_bfloat16*>(x_bf16), s, w,
+                           selected_out, seeds_out, st);
   if (rc != UOC_OK) return rc;
   if (flags & UOC_FLAG_SYNC_CHECK) return check_device_error(st);
   return UOC_OK;

@@ -548,8 +548,13 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
   return UOC_OK;
 }
 
-int launch_select_seeds(const float* X, const ClusterShape& s, const ClusterWorkspace& w, int64_t* selected_out,
-                        float* seeds_out, cudaStream_t stream) {
+int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
+                        int64_t* selected_out, float* seeds_out, cudaStream_t stream) {
+  if (xb) {
+    bool used = false;
+    int rc = launch_select_seeds_pruned(X, xb, s, w, selected_out, seeds_out, stream, &used);
+    if (rc != UOC_OK || used) return rc;
+  }
   FpsParams p;
   p.X = X; p.sb = s.stride_b; p.sd = s.stride_d; p.n = s.n; p.d = s.d; p.m = s.m; p.batch = s.batch;
   p.first = w.first; p.r = w.r; p.keys = w.keys; p.barrier = w.barrier;

@@ -16,7 +16,10 @@
 // The factor exp(-kappa) common to all weights cancels in the row normalisation.
 //
 // Algorithmic traffic per update: n*d*2 bytes of bf16 X (fp32-equivalent: n*d*4), see DESIGN.md.
+#include <cstdlib>
 #include <cstring>
+#include <vector>
+#include <cstdio>
 
 #include "cluster.cuh"
 
@@ -36,7 +39,7 @@ struct MsCfg {
   static constexpr int kZBytes = kKBlocks * kBoxBytes;
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kZBytes + kStages * kStageBytes + 256 /*barriers*/;
   static constexpr uint32_t kTmemCols = 512;
-  static constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO = 256;
+  static constexpr uint32_t kColS3 = 128, kColO3 = 384;   // three S/P buffers of 128 columns (tile j -> j % 3), then O
 };
 
 template <int D>
@@ -52,8 +55,8 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
   uint64_t* x_full = bars;
   uint64_t* x_empty = bars + Cfg::kStages;
   uint64_t* s_full = bars + 2 * Cfg::kStages;
-  uint64_t* p_ready = s_full + 2;
-  uint64_t* o_full = p_ready + 2;
+  uint64_t* p_ready = s_full + 3;
+  uint64_t* o_full = p_ready + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -66,8 +69,7 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
     if (elect_one()) {
       tma_prefetch_desc(&tmap_x);
       for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
-      mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-      mbar_init(&p_ready[0], 128); mbar_init(&p_ready[1], 128);
+      for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
       mbar_init(o_full, 1);
       fence_mbar_init();
       asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: the previous kernel's writes (Z, bf16 field) are visible
@@ -132,21 +134,23 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
       const uint32_t zs_addr = smem_u32(zs);
       const uint32_t st_addr = smem_u32(stages);
       bool ok = true;
+      // three S/P buffers (tile j -> buffer j % 3): GEMM1 runs two tiles ahead of the weights, GEMM2(j-2) is issued
+      // after GEMM1(j), so a weight group finds its next S tile ready when it has published P
       auto gemm2 = [&](int i) {
-        const int s = i % Cfg::kStages, buf = i & 1;
-        if (!mbar_wait(&p_ready[buf], (i >> 1) & 1, err)) { ok = false; return; }
+        const int s = i % Cfg::kStages, buf = i % 3;
+        if (!mbar_wait(&p_ready[buf], (i / 3) & 1, err)) { ok = false; return; }
         tc_fence_after();
         const uint32_t xb = st_addr + s * Cfg::kStageBytes;
 #pragma unroll
         for (int ks = 0; ks < kTile / 16; ++ks) {
           const uint64_t bd = make_smem_desc_sw128(xb + ks * 2048, kBoxBytes, 1024);
-          umma_ts_f16(tmem_base + Cfg::kColO, tmem_base + (buf ? Cfg::kColS1 : Cfg::kColS0) + ks * 8, bd, idesc2,
+          umma_ts_f16(tmem_base + Cfg::kColO3, tmem_base + buf * Cfg::kColS3 + ks * 8, bd, idesc2,
                       (i > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(&x_empty[s]);
       };
       for (int j = 0; j < T && ok; ++j) {
-        const int s = j % Cfg::kStages, buf = j & 1;
+        const int s = j % Cfg::kStages, buf = j % 3;
         if (!mbar_wait(&x_full[s], (j / Cfg::kStages) & 1, err)) { ok = false; break; }
         tc_fence_after();
         const uint32_t xb = st_addr + s * Cfg::kStageBytes;
@@ -156,12 +160,13 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t ad = make_smem_desc_sw128(zs_addr + kb * kBoxBytes + ks * 32, 16, 1024);
             const uint64_t bd = make_smem_desc_sw128(xb + kb * kBoxBytes + ks * 32, 16, 1024);
-            umma_ss_f16(tmem_base + (buf ? Cfg::kColS1 : Cfg::kColS0), ad, bd, idesc1, (kb | ks) ? 1u : 0u);
+            umma_ss_f16(tmem_base + buf * Cfg::kColS3, ad, bd, idesc1, (kb | ks) ? 1u : 0u);
           }
         }
         umma_commit(&s_full[buf]);
-        if (j >= 1) gemm2(j - 1);
+        if (j >= 2) gemm2(j - 2);
       }
+      if (ok && T > 1) gemm2(T - 2);
       if (ok && T > 0) gemm2(T - 1);
       if (ok) umma_commit(o_full);
     }
@@ -172,24 +177,38 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
     bool ok = true;
     for (int j = grp; j < T; j += 2) {
-      const int buf = grp;
-      if (!mbar_wait(&s_full[buf], (j >> 1) & 1, err)) { ok = false; break; }
+      const int buf = j % 3;
+      if (!mbar_wait(&s_full[buf], (j / 3) & 1, err)) { ok = false; break; }
       tc_fence_after();
-      const uint32_t sa = lane_addr + (buf ? Cfg::kColS1 : Cfg::kColS0);
-#pragma unroll
-      for (int c = 0; c < kTile / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(sa + c * 32, v);
-        tmem_wait_ld();
+      const uint32_t sa = lane_addr + buf * Cfg::kColS3;
+      // software pipeline over the four 32-column chunks: the TMEM load of chunk c+1 is in flight during the MUFU work of chunk c
+      uint32_t va[32], vb[32];
+      // exp(kappa (s - 1)) * (1 + 2^-9): the factor turns the truncating bf16 pack below into round-to-nearest (within
+      // one ulp) and cancels in the row normalisation
+      const float c0 = 0.0028150156f - c1;
+      auto weights = [&](const uint32_t (&cur)[32], int c) {
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * e]), c1, -c1));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c1, -c1));
-          pk[e] = pack_bf16x2(p0, p1);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(cur[2 * e]), c1, c0));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(cur[2 * e + 1]), c1, c0));
+          pk[e] = pack_bf16x2_trunc(p0, p1);
         }
         tmem_st_32x32b_x16(sa + c * 16, pk);
-      }
+      };
+      static_assert(kTile / 32 == 4, "four chunks per tile");
+      tmem_ld_32x32b_x32(sa, va);
+      tmem_wait_ld();
+      tmem_ld_32x32b_x32(sa + 32, vb);
+      weights(va, 0);
+      tmem_wait_ld();
+      tmem_ld_32x32b_x32(sa + 64, va);
+      weights(vb, 1);
+      tmem_wait_ld();
+      tmem_ld_32x32b_x32(sa + 96, vb);
+      weights(va, 2);
+      tmem_wait_ld();
+      weights(vb, 3);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_ready[buf]);
@@ -200,7 +219,7 @@ meanshift_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __r
 #pragma unroll
       for (int c = grp * (D / 64); c < (grp + 1) * (D / 64); ++c) {   // each group drains half of the columns
         uint32_t v[32];
-        tmem_ld_32x32b_x32(lane_addr + Cfg::kColO + c * 32, v);
+        tmem_ld_32x32b_x32(lane_addr + Cfg::kColO3 + c * 32, v);
         tmem_wait_ld();
         if (row < m) {
 #pragma unroll
@@ -246,6 +265,334 @@ int launch_iter(const CUtensorMap& tmap, const ClusterShape& s, const ClusterWor
   return UOC_OK;
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Persistent variant: ALL updates of the hill climbing in one cooperative launch.
+//   Per update the CTAs exchange through two monotonic counters in global memory instead of kernel boundaries
+//   (one polling thread per CTA; per-CTA flag words polled by every thread turned a few L2 lines into a hot spot):
+//     parts_done[b] += 1  once a CTA has published its partial sums of update u      (reducers wait for (u+1) * P)
+//     rows_done[b]  += 1  once seed row r of Z_{u+1} has been reduced + normalised (by CTA r % P) and stored
+//                         (everybody waits for (u+1) * m before staging Z_{u+1})
+//   Z is updated in place: row r of Z_{u+2} cannot be produced before every CTA has staged Z_{u+1} (its partials of
+//   update u+1 are an input), and the partials of update u+1 are written only after every reducer has finished with
+//   those of update u (all rows of Z_{u+1} are an input of the staging).  The TMA producer is free running over
+//   iters x T tiles (X does not change), so the next update's first tiles arrive during the exchange.
+//   Warps 2..9 double as the 8 reduce warps; warp 1 joins them on named barrier 1 once per update ("Z staged, O drained").
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool poll_flag(const unsigned int* p, unsigned int target, unsigned int* err) {
+  for (unsigned int it = 0; it < (1u << 24); ++it)
+    if (ld_acquire_u32(p) >= target) return true;
+  atomicOr(err, ERR_GRID_BARRIER_TIMEOUT);
+  return false;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1)
+meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float* Z, float* partials,
+                               unsigned int* done, unsigned int* rowflag, int m, long long n, float c1, int P,
+                               int iters, unsigned int* err, long long* trace) {
+  using Cfg = MsCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_part[8][D];
+  __shared__ float s_sq[8];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* zs = smem;
+  uint8_t* stages = smem + Cfg::kZBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = bars + Cfg::kStages;
+  uint64_t* s_full = bars + 2 * Cfg::kStages;
+  uint64_t* p_ready = s_full + 3;
+  uint64_t* o_full = p_ready + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x, b = blockIdx.y;
+  const long long tiles_total = (n + kTile - 1) / kTile;
+  const int T = (cta < tiles_total) ? int((tiles_total - cta + P - 1) / P) : 0;
+  const long long TT = (long long)T * iters;           // tiles this CTA streams over the whole hill climbing
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (long long jj = 0; jj < TT; ++jj) {
+        const int s = int(jj % Cfg::kStages);
+        const uint32_t ph = uint32_t(jj / Cfg::kStages) & 1u;
+        if (jj >= Cfg::kStages && !mbar_wait(&x_empty[s], ph ^ 1u, err)) break;
+        mbar_arrive_expect_tx(&x_full[s], Cfg::kStageBytes);
+        const int j = int(jj % T);
+        const int row0 = int((cta + (long long)j * P) * kTile);
+#pragma unroll
+        for (int kb = 0; kb < Cfg::kKBlocks; ++kb)
+          tma_load_3d(stages + s * Cfg::kStageBytes + kb * kBoxBytes, &tmap_x, &x_full[s], kb * 64, row0, b);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc1 = make_idesc_bf16(128, kTile, 0, 0);
+    constexpr uint32_t idesc2 = make_idesc_bf16(128, D, 0, 1);
+    const uint32_t zs_addr = smem_u32(zs);
+    const uint32_t st_addr = smem_u32(stages);
+    bool ok = true;
+    for (int u = 0; u < iters; ++u) {
+      named_bar_sync(1, 288);              // seeds of this update staged, O of the previous one drained
+      tc_fence_after();
+      if (elect_one()) {
+        const long long base = (long long)u * T;
+        // three S/P buffers (global tile jj -> buffer jj % 3): GEMM1 runs two tiles ahead of the weights
+        auto gemm2 = [&](int j) {
+          const long long jj = base + j;
+          const int s = int(jj % Cfg::kStages), buf = int(jj % 3);
+          if (!mbar_wait(&p_ready[buf], uint32_t(jj / 3) & 1u, err)) { ok = false; return; }
+          tc_fence_after();
+          const uint32_t xb = st_addr + s * Cfg::kStageBytes;
+#pragma unroll
+          for (int ks = 0; ks < kTile / 16; ++ks) {
+            const uint64_t bd = make_smem_desc_sw128(xb + ks * 2048, kBoxBytes, 1024);
+            umma_ts_f16(tmem_base + Cfg::kColO3, tmem_base + buf * Cfg::kColS3 + ks * 8, bd, idesc2,
+                        (j > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&x_empty[s]);
+        };
+        for (int j = 0; j < T && ok; ++j) {
+          const long long jj = base + j;
+          const int s = int(jj % Cfg::kStages), buf = int(jj % 3);
+          if (!mbar_wait(&x_full[s], uint32_t(jj / Cfg::kStages) & 1u, err)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t xb = st_addr + s * Cfg::kStageBytes;
+#pragma unroll
+          for (int kb = 0; kb < Cfg::kKBlocks; ++kb) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ad = make_smem_desc_sw128(zs_addr + kb * kBoxBytes + ks * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc_sw128(xb + kb * kBoxBytes + ks * 32, 16, 1024);
+              umma_ss_f16(tmem_base + buf * Cfg::kColS3, ad, bd, idesc1, (kb | ks) ? 1u : 0u);
+            }
+          }
+          umma_commit(&s_full[buf]);
+          if (j >= 2) gemm2(j - 2);
+        }
+        if (ok && T > 1) gemm2(T - 2);
+        if (ok && T > 0) gemm2(T - 1);
+        if (ok) umma_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int grp = (warp - 2) >> 2;        // weight group
+    const int row = q * 32 + lane;          // seed index
+    const int w8 = warp - 2;                // reduce warp 0..7
+    const int t256 = threadIdx.x - 64;      // 0..255
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+    unsigned int* parts_done = done + size_t(b) * 64;       // counters on separate 128-byte lines per batch item
+    unsigned int* rows_done = parts_done + 32;
+    bool ok = true;
+    // debug trace (UOC_LOOP_TRACE): CTA 0 (a reducer) and CTA P-1 stamp 6 phases per update
+    long long* tr = (trace && t256 == 0 && b == 0 && (cta == 0 || cta == P - 1)) ? trace + (cta == 0 ? 0 : iters * 8) : nullptr;
+    auto stamp = [&](int u, int k) {
+      if (tr) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[u * 8 + k] = t; }
+    };
+    for (int u = 0; u < iters; ++u) {
+      stamp(u, 0);
+      // ---- stage the seeds Z_u: fp32 [m][D] -> bf16, K-major 128B-swizzled rows
+      {
+        const int r = t256 & 127;
+        const int half = t256 >> 7;
+        if (u > 0) {      // all m rows of Z_u are stored: one polling thread per CTA, the named barrier releases the rest
+          if (t256 == 0) ok = poll_flag(rows_done, (unsigned int)(u * m), err) && ok;
+          named_bar_sync(2, 256);
+        }
+        const float* zr = Z + (size_t(b) * m + (r < m ? r : 0)) * D;
+#pragma unroll
+        for (int c = half * (D / 16); c < (half + 1) * (D / 16); ++c) {
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (r < m) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(zr + c * 8));
+            const float4 bb = __ldcg(reinterpret_cast<const float4*>(zr + c * 8 + 4));
+            v.x = pack_bf16x2(a.x, a.y); v.y = pack_bf16x2(a.z, a.w);
+            v.z = pack_bf16x2(bb.x, bb.y); v.w = pack_bf16x2(bb.z, bb.w);
+          }
+          const int kb = c >> 3, cc = c & 7;
+          *reinterpret_cast<uint4*>(zs + kb * kBoxBytes + r * 128 + ((cc ^ (r & 7)) << 4)) = v;
+        }
+        fence_proxy_async();
+      }
+      tc_fence_before();
+      named_bar_sync(1, 288);
+      tc_fence_after();
+      stamp(u, 1);
+      // ---- weights: this group's tiles are those with global parity == grp
+      const long long base = (long long)u * T;
+      const float c0 = 0.0028150156f - c1;   // * (1 + 2^-9): makes the truncating bf16 pack round to nearest, cancels in the normalisation
+      for (int j = int((grp - base) & 1); j < T; j += 2) {
+        const long long jj = base + j;
+        const int buf = int(jj % 3);
+        const long long tw0 = tr ? clock64() : 0;
+        if (!mbar_wait(&s_full[buf], uint32_t(jj / 3) & 1u, err)) { ok = false; break; }
+        tc_fence_after();
+        const long long tw1 = tr ? clock64() : 0;
+        const uint32_t sa = lane_addr + buf * Cfg::kColS3;
+        uint32_t va[32], vb[32];
+        auto weights = [&](const uint32_t (&cur)[32], int c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(cur[2 * e]), c1, c0));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(cur[2 * e + 1]), c1, c0));
+            pk[e] = pack_bf16x2_trunc(p0, p1);
+          }
+          tmem_st_32x32b_x16(sa + c * 16, pk);
+        };
+        tmem_ld_32x32b_x32(sa, va);
+        tmem_wait_ld();
+        tmem_ld_32x32b_x32(sa + 32, vb);
+        weights(va, 0);
+        tmem_wait_ld();
+        tmem_ld_32x32b_x32(sa + 64, va);
+        weights(vb, 1);
+        tmem_wait_ld();
+        tmem_ld_32x32b_x32(sa + 96, vb);
+        weights(va, 2);
+        tmem_wait_ld();
+        weights(vb, 3);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_ready[buf]);
+        if (tr) { tr[u * 8 + 6] += tw1 - tw0; tr[u * 8 + 7] += clock64() - tw1; }
+      }
+      // ---- epilogue: O -> this CTA's partial sums
+      stamp(u, 2);
+      if (ok && T > 0 && mbar_wait(o_full, uint32_t(u) & 1u, err)) {
+        tc_fence_after();
+        stamp(u, 3);
+        float* dst = partials + ((size_t(b) * P + cta) * 128 + row) * D;
+#pragma unroll
+        for (int c = grp * (D / 64); c < (grp + 1) * (D / 64); ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(lane_addr + Cfg::kColO3 + c * 32, v);
+          tmem_wait_ld();
+          if (row < m) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              __stcg(reinterpret_cast<uint4*>(dst + c * 32 + e * 4), make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]));
+          }
+        }
+      }
+      named_bar_sync(2, 256);
+      if (t256 == 0) { __threadfence(); atomicAdd(parts_done, 1u); }
+      stamp(u, 4);
+      // ---- reduce + normalise the rows this CTA owns
+      if (cta < m) {
+        if (t256 == 0) ok = poll_flag(parts_done, (unsigned int)((u + 1) * P), err) && ok;
+        named_bar_sync(2, 256);
+      }
+      for (int r = cta; r < m; r += P) {
+        float acc[D / 32];
+#pragma unroll
+        for (int qq = 0; qq < D / 32; ++qq) acc[qq] = 0.f;
+#pragma unroll 4
+        for (int part = w8; part < P; part += 8) {
+          const float* src = partials + ((size_t(b) * P + part) * 128 + r) * D;
+#pragma unroll
+          for (int qq = 0; qq < D / 32; ++qq) acc[qq] += __ldcg(src + lane + 32 * qq);
+        }
+#pragma unroll
+        for (int qq = 0; qq < D / 32; ++qq) s_part[w8][lane + 32 * qq] = acc[qq];
+        named_bar_sync(2, 256);
+        float tot = 0.f;
+        if (t256 < D) {
+#pragma unroll
+          for (int w = 0; w < 8; ++w) tot += s_part[w][t256];
+        }
+        float sq = tot * tot;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) s_sq[w8] = sq;
+        named_bar_sync(2, 256);
+        float all = 0.f;
+#pragma unroll
+        for (int w = 0; w < D / 32; ++w) all += s_sq[w];
+        const float denom = fmaxf(sqrtf(all), 1e-12f);  // F.normalize eps (lib/utils/mean_shift.py:107)
+        if (t256 < D) __stcg(Z + (size_t(b) * m + r) * D + t256, tot / denom);
+        named_bar_sync(2, 256);
+        if (t256 == 0) { __threadfence(); atomicAdd(rows_done, 1u); }
+      }
+      stamp(u, 5);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int D>
+int launch_persistent(const CUtensorMap& tmap, const ClusterShape& s, const ClusterWorkspace& w, float* Z, int P,
+                      float kappa, int iters, cudaStream_t stream) {
+  using Cfg = MsCfg<D>;
+  static bool attr = false;
+  if (!attr) {
+    UOC_CUDA(cudaFuncSetAttribute(meanshift_tc_persistent_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
+    attr = true;
+  }
+  unsigned int* done = reinterpret_cast<unsigned int*>(w.slots);   // two counters per batch item, 128 bytes apart
+  unsigned int* rowflag = nullptr;
+  UOC_CUDA(cudaMemsetAsync(done, 0, 256 * size_t(s.batch), stream));
+  float c1 = kappa * 1.4426950408889634f;
+  CUtensorMap tm = tmap;
+  float* partials = w.partials;
+  int m = s.m;
+  long long n = s.n;
+  unsigned int* err = device_error_word();
+  long long* trace = nullptr;
+  const bool want_trace = getenv("UOC_LOOP_TRACE") != nullptr;     // debug: per-phase timeline on stderr (synchronises)
+  if (want_trace) {
+    UOC_CUDA(cudaMalloc(&trace, sizeof(long long) * 16 * iters));
+    UOC_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * 16 * iters, stream));
+  }
+  void* args[] = {&tm, &Z, &partials, &done, &rowflag, &m, &n, &c1, &P, &iters, &err, &trace};
+  UOC_CUDA(cudaLaunchCooperativeKernel(meanshift_tc_persistent_kernel<D>, dim3(P, s.batch), dim3(kThreads), args,
+                                       Cfg::kSmemBytes, stream));
+  count_launch();
+  if (want_trace) {
+    std::vector<long long> h(size_t(16) * iters);
+    UOC_CUDA(cudaStreamSynchronize(stream));
+    UOC_CUDA(cudaMemcpy(h.data(), trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    cudaFree(trace);
+    const long long t0 = h[0];
+    for (int c = 0; c < 2; ++c)
+      for (int u = 0; u < iters; ++u) {
+        const long long* q = h.data() + (size_t(c) * iters + u) * 8;
+        fprintf(stderr, "[loop trace] cta %s update %d: start %lld staged %lld weights_done %lld o_full %lld published %lld reduced %lld (ns); group-0 warp: s_full wait %lld clk, weights %lld clk\n",
+                c == 0 ? "0" : "P-1", u, q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0, q[4] - t0, q[5] - t0, q[6], q[7]);
+      }
+  }
+  return UOC_OK;
+}
+
 }  // namespace
 
 int launch_hill_climb_tc(const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w, float* Z,
@@ -263,6 +610,21 @@ int launch_hill_climb_tc(const __nv_bfloat16* xb, const ClusterShape& s, const C
   const long long tiles = (s.n + kTile - 1) / kTile;
   int P = w.max_partials;
   if (P > tiles) P = int(tiles);
+  // persistent single-launch variant (default): needs every CTA resident (cooperative launch) and cannot be captured
+  // into a CUDA graph; UOC_LOOP_PERSISTENT=0 or an ongoing stream capture select the launch-per-update form
+  {
+    bool persistent = true;
+    if (const char* e = getenv("UOC_LOOP_PERSISTENT")) persistent = atoi(e) != 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (persistent && cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) persistent = false;
+    const int sms = sm_count();
+    int Pp = P;
+    if (sms > 0 && (long long)Pp * s.batch > sms) Pp = sms / s.batch;
+    if (Pp < 1 || iters < 1 || w.slot_bytes < 256 * size_t(s.batch)) persistent = false;
+    if (persistent)
+      return (s.d == 64) ? launch_persistent<64>(tmap, s, w, Z, Pp, kappa, iters, stream)
+                         : launch_persistent<128>(tmap, s, w, Z, Pp, kappa, iters, stream);
+  }
   for (int it = 0; it < iters; ++it) {
     rc = (s.d == 64) ? launch_iter<64>(tmap, s, w, Z, P, kappa, stream) : launch_iter<128>(tmap, s, w, Z, P, kappa, stream);
     if (rc != UOC_OK) return rc;

@@ -86,8 +86,9 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
             seed_labels = torch.empty((N, num_seeds), dtype=torch.int32, device=dev)
             nuniq = torch.empty((N,), dtype=torch.int32, device=dev)
             sb, sd_ = features.stride(0), features.stride(1)
-            _lib.check(lib.uoc_select_seeds(_lib.ptr(features), sb, sd_, N, n, C, num_seeds, fptr, _lib.ptr(selected),
-                                            _lib.ptr(seeds), _lib.ptr(ws), ws.numel(), 0, sp), "uoc_select_seeds")
+            _lib.check(lib.uoc_select_seeds(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, fptr,
+                                            _lib.ptr(selected), _lib.ptr(seeds), _lib.ptr(ws), ws.numel(),
+                                            int(flags) & _lib.FLAG_FPS_FP32, sp), "uoc_select_seeds")
             on_sampling_done()
             _lib.check(lib.uoc_hill_climb(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, float(kappa),
                                           int(max_iters), _lib.ptr(seeds), _lib.ptr(ws), ws.numel(), int(flags), sp),
@@ -137,8 +138,9 @@ def mean_shift_smart_init(X, kappa, num_seeds=100, max_iters=10, metric='cosine'
 
 
 def select_smart_seeds(X, num_seeds, return_selected_indices=False, init_seeds=None, num_init_seeds=None,
-                       metric='cosine', first_index=None):
-    """lib/utils/mean_shift.py:128-189 (fresh start only: init_seeds is not supported)."""
+                       metric='cosine', first_index=None, bf16_screen=True):
+    """lib/utils/mean_shift.py:128-189 (fresh start only: init_seeds is not supported).
+    bf16_screen: screen every pass with a bf16 copy of X (d = 64/128; same indices, see fps_pruned.cu)."""
     if metric != 'cosine' or init_seeds is not None:
         raise NotImplementedError("cosine metric without init_seeds only")
     n, d = X.shape
@@ -152,7 +154,12 @@ def select_smart_seeds(X, num_seeds, return_selected_indices=False, init_seeds=N
         ws = _workspace(dev, lib.uoc_meanshift_workspace_bytes(1, n, d, num_seeds))
         selected = torch.empty((num_seeds,), dtype=torch.int64, device=dev)
         seeds = torch.empty((num_seeds, d), dtype=torch.float32, device=dev)
-        st = lib.uoc_select_seeds(_lib.ptr(Xp), d * stride_d, stride_d, 1, n, d, num_seeds,
+        xb = None
+        if bf16_screen and d in (64, 128):
+            xb = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.uoc_pack_bf16(_lib.ptr(Xp), d * stride_d, stride_d, 1, n, d, _lib.ptr(xb), _lib.stream_ptr(dev)),
+                       "uoc_pack_bf16")
+        st = lib.uoc_select_seeds(_lib.ptr(Xp), d * stride_d, stride_d, _lib.ptr(xb), 1, n, d, num_seeds,
                                   ctypes.cast(first, ctypes.c_void_p), _lib.ptr(selected), _lib.ptr(seeds), _lib.ptr(ws),
                                   ws.numel(), _lib.FLAG_SYNC_CHECK, _lib.stream_ptr(dev))
         _lib.check(st, "uoc_select_seeds")

@@ -8,10 +8,10 @@ stream fills the gaps.  Each slot owns its stream, device inputs, outputs and sc
 Enqueueing a frame eagerly costs ~1.7 ms of host time (ctypes calls, ~150 tensor-map encodes,
 ~70 launches), which caps the throughput; so after a warm-up every slot captures TWO CUDA graphs:
   A: backbone forward   (inputs: the slot's device frame buffers; outputs: features + bf16 copy)
-  B: mean-shift loop + seed labelling + pixel labels + D2H of the label map
-The sampling kernel between them stays an eager cooperative launch: it is chained across slots with
-an event so that two cooperative kernels never compete for residency, and its first-seed index is
-a per-frame host value.
+  B: seed labelling + pixel labels + D2H of the label map
+The sampling kernel and the persistent mean-shift loop kernel between them stay eager cooperative
+launches (2 launches): they are chained across slots with an event so that cooperative kernels of
+different frames never compete for residency; the first-seed index is a per-frame host value.
 """
 import ctypes
 
@@ -92,9 +92,6 @@ class FramePipeline(object):
         with torch.cuda.graph(gb, stream=slot.stream):
             sp = _lib.stream_ptr(dev)
             f = slot.feats
-            _lib.check(lib.uoc_hill_climb(_lib.ptr(f), f.stride(0), f.stride(1), _lib.ptr(slot.xb), 1, n, C, m, self.kappa,
-                                          self.max_iters, _lib.ptr(slot.Z), _lib.ptr(slot.ws_b), slot.ws_b.numel(), 0, sp),
-                       "uoc_hill_climb")
             _lib.check(lib.uoc_label_seeds(_lib.ptr(slot.Z), 1, m, C, self.eps, _lib.ptr(slot.sl), _lib.ptr(slot.nu), sp),
                        "uoc_label_seeds")
             _lib.check(lib.uoc_assign_labels(_lib.ptr(f), f.stride(0), f.stride(1), _lib.ptr(slot.xb), 1, n, C, m,
@@ -111,9 +108,14 @@ class FramePipeline(object):
             slot.stream.wait_event(self.coop_tail)
         first = (ctypes.c_int64 * 1)(int(first_index))
         f = slot.feats
-        _lib.check(lib.uoc_select_seeds(_lib.ptr(f), f.stride(0), f.stride(1), 1, n, C, m, ctypes.cast(first, ctypes.c_void_p),
+        _lib.check(lib.uoc_select_seeds(_lib.ptr(f), f.stride(0), f.stride(1), _lib.ptr(slot.xb), 1, n, C, m,
+                                        ctypes.cast(first, ctypes.c_void_p),
                                         _lib.ptr(slot.sel), _lib.ptr(slot.Z), _lib.ptr(slot.ws_fps), slot.ws_fps.numel(), 0,
                                         _lib.stream_ptr(self.dev)), "uoc_select_seeds")
+        # the mean-shift loop is ONE persistent cooperative kernel (all updates): eager as well
+        _lib.check(lib.uoc_hill_climb(_lib.ptr(f), f.stride(0), f.stride(1), _lib.ptr(slot.xb), 1, n, C, m, self.kappa,
+                                      self.max_iters, _lib.ptr(slot.Z), _lib.ptr(slot.ws_b), slot.ws_b.numel(), 0,
+                                      _lib.stream_ptr(self.dev)), "uoc_hill_climb")
         ev = torch.cuda.Event()
         ev.record(slot.stream)
         self.coop_tail = ev
