@@ -101,7 +101,7 @@ UOC_API int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stri
  * seeds_out [batch,m,d] fp32.
  * x_bf16 (optional, d = 64/128): the bf16 pixel-major copy of X (round-to-nearest or truncated).  When given, every pass
  * screens the points with it and evaluates the fp32 distance only where the new seed can lower the running minimum;
- * the selected indices are bit-identical either way (fps_pruned.cu).  NULL or UOC_FLAG_FPS_FP32: fp32 passes only. */
+ * the selected indices are bit-identical either way (fps_tc.cu).  NULL or UOC_FLAG_FPS_FP32: fp32 passes only. */
 UOC_API int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n,
                              int d, int m, const int64_t* first_seed_host, int64_t* selected_out, float* seeds_out,
                              void* workspace, size_t workspace_bytes, int flags, uoc_stream_t stream);

@@ -26,9 +26,20 @@ def _field(H, W, d, K, noise, seed):
 
 @pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 100), (30, 44, 128, 100), (24, 24, 64, 40),
                                      (60, 80, 32, 17), (120, 160, 64, 100)])
-@pytest.mark.parametrize("screen", [True, False], ids=["bf16_screen", "fp32_passes"])
-def test_select_seeds_bit_exact(H, W, d, m, screen, monkeypatch):
-    monkeypatch.setenv("UOC_FPS_PRUNED", "1" if screen else "0")
+def _fps_mode(monkeypatch, mode):
+    """tc: tcgen05 screen (fps_tc.cu, default: tiles in tensor memory first); tc_smem: same with every tile in shared memory;
+    fp32: no screen (fps2_kernel).  Returns bf16_screen."""
+    monkeypatch.setenv("UOC_FPS_TC", "1" if mode in ("tc", "tc_smem") else "0")
+    if mode == "tc_smem":
+        monkeypatch.setenv("UOC_FPS_TC_TMEM_TILES", "0")
+    return mode != "fp32"
+
+
+@pytest.mark.parametrize("mode", ["tc", "tc_smem", "fp32"])
+@pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 100), (30, 44, 128, 100), (24, 24, 64, 40),
+                                     (60, 80, 32, 17), (120, 160, 64, 100)])
+def test_select_seeds_bit_exact(H, W, d, m, mode, monkeypatch):
+    screen = _fps_mode(monkeypatch, mode)
     feats, _ = _field(H, W, d, 4, 0.05, seed=H * 7 + d)
     Xp = feats[0].reshape(d, -1).numpy()
     first = (H * W) // 3
@@ -40,24 +51,27 @@ def test_select_seeds_bit_exact(H, W, d, m, screen, monkeypatch):
     assert sel[0] == first and len(set(sel.tolist())) == m
 
 
-@pytest.mark.parametrize("case", ["isotropic", "scaled", "streamed", "full_frame"])
+@pytest.mark.parametrize("case", ["isotropic", "scaled", "two_homes", "full_frame", "full_frame_128"])
 def test_select_seeds_bf16_screen_stress(case, monkeypatch):
-    """The bf16 screening pass of the seed selection (fps_pruned.cu) must never change an index:
+    """The bf16 screening pass of the seed selection (fps_tc.cu) must never change an index:
     isotropic  - no cluster structure: the screen rejects little, nearly every point takes the fp32 path;
     scaled     - rows of norm 3 (the error bound of the screen scales with |x| |s|);
-    streamed   - 8 KB of shared memory: almost all rounds are streamed from global memory instead of being resident;
-    full_frame - 480x640: 65 rounds per CTA, 50 resident + 15 streamed, every warp owns several rounds."""
-    monkeypatch.setenv("UOC_FPS_PRUNED", "1")
+    two_homes  - one tile in tensor memory, the second in shared memory (small field, both operand homes);
+    full_frame - 480x640x64: 17 tiles per CTA (7 in tensor memory + 10 in shared memory for fps_tc);
+    full_frame_128 - 240x320x128: the two-block (d = 128) operand layouts at several tiles per CTA."""
+    _fps_mode(monkeypatch, "tc")
     if case == "isotropic":
         g = torch.Generator().manual_seed(5)
         feats = torch.nn.functional.normalize(torch.randn(1, 64, 48, 64, generator=g), dim=1)
     elif case == "scaled":
         feats = _field(40, 52, 64, 4, 0.1, seed=12)[0] * 3.0
-    elif case == "streamed":
-        monkeypatch.setenv("UOC_FPS_SMEM_KB", "8")
+    elif case == "two_homes":
+        monkeypatch.setenv("UOC_FPS_TC_TMEM_TILES", "1")
         feats = _field(120, 160, 64, 5, 0.1, seed=13)[0]
-    else:
+    elif case == "full_frame":
         feats = _field(480, 640, 64, 6, 0.1, seed=14)[0]
+    else:
+        feats = _field(240, 320, 128, 6, 0.1, seed=15)[0]
     d = feats.shape[1]
     m = 100
     Xp = feats[0].reshape(d, -1).numpy()

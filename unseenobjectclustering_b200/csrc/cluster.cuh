@@ -35,11 +35,11 @@ size_t cluster_workspace_bytes(int batch, int64_t n, int d, int m);
 int carve_cluster_workspace(void* ws, size_t ws_bytes, int batch, int64_t n, int d, int m, ClusterWorkspace* out);
 
 // K3  farthest point sampling (lib/utils/mean_shift.py:128-189)
-// xb != nullptr (d = 64/128): third-generation kernel with the bf16 screening pass (fps_pruned.cu), same indices
+// xb != nullptr (d = 64/128): kernel with the bf16 screening pass on tcgen05 (fps_tc.cu), same indices
 int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
                         int64_t* selected_out, float* seeds_out, cudaStream_t stream);
-int launch_select_seeds_pruned(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
-                               int64_t* selected_out, float* seeds_out, cudaStream_t stream, bool* used);
+int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
+                           int64_t* selected_out, float* seeds_out, cudaStream_t stream, bool* used);
 // K4  mean-shift iterations (lib/utils/mean_shift.py:79-109): fp32 SIMT validation kernel ...
 int launch_hill_climb_simt(const float* X, const ClusterShape& s, const ClusterWorkspace& w, float* Z, float kappa,
                            int iters, cudaStream_t stream);

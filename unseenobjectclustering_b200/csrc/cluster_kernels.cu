@@ -552,7 +552,7 @@ int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterSh
                         int64_t* selected_out, float* seeds_out, cudaStream_t stream) {
   if (xb) {
     bool used = false;
-    int rc = launch_select_seeds_pruned(X, xb, s, w, selected_out, seeds_out, stream, &used);
+    int rc = launch_select_seeds_tc(X, xb, s, w, selected_out, seeds_out, stream, &used);
     if (rc != UOC_OK || used) return rc;
   }
   FpsParams p;

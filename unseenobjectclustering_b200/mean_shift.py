@@ -140,7 +140,7 @@ def mean_shift_smart_init(X, kappa, num_seeds=100, max_iters=10, metric='cosine'
 def select_smart_seeds(X, num_seeds, return_selected_indices=False, init_seeds=None, num_init_seeds=None,
                        metric='cosine', first_index=None, bf16_screen=True):
     """lib/utils/mean_shift.py:128-189 (fresh start only: init_seeds is not supported).
-    bf16_screen: screen every pass with a bf16 copy of X (d = 64/128; same indices, see fps_pruned.cu)."""
+    bf16_screen: screen every pass with a bf16 copy of X (d = 64/128; same indices, see fps_tc.cu)."""
     if metric != 'cosine' or init_seeds is not None:
         raise NotImplementedError("cosine metric without init_seeds only")
     n, d = X.shape
