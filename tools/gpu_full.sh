@@ -8,4 +8,4 @@ done
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 900 python bench.py --steps 50 --warmup 3 --depth 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench exit $?"
 python -c "
-import json; j=json.load(open('gpurun_out/bench_final.json')); print(round(j['value'],1), round(j['e2e']['value'],1), 'serial', round(j['serial']['value'],1), j['stages_ms'], 'host', j['host_enqueue_ms_per_step'], j['clocks'], j['cpu_baseline'], j['gpu_launches'])"
+import json; j=json.load(open('gpurun_out/bench_final.json')); print(round(j['value'],1), round(j['e2e']['value'],1), 'serial', round(j['serial']['value'],1), j['stages_ms'], 'host', j.get('host_loop_ms_per_step'), j['clocks'], j['cpu_baseline'], j['gpu_launches'])"
