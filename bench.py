@@ -190,7 +190,7 @@ def run_b200(args):
     frames = [synthetic.rgbd_frame(H, W, seed=100 * rank + i) for i in range(nframes)]
     dev_frames = [(a.to(dev), b.to(dev)) for a, b in frames]
     pin_frames = [(a.pin_memory(), b.pin_memory()) for a, b in frames]
-    firsts = UD.draw_first_indices(warmup + 3 * steps + 16, n, seed=3 + rank)
+    firsts = UD.draw_first_indices(warmup + 4 * steps + 16, n, seed=3 + rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gathered = torch.empty((world, n), dtype=torch.int32, device=dev) if world > 1 else None
     out_pin = torch.empty((1, H, W), dtype=torch.float32).pin_memory()
@@ -254,7 +254,14 @@ def run_b200(args):
 
     host_ms = [0.0]
 
-    def timed_pipe(resident, count, base):
+    # raw frames (uint8 BGR + uint16 depth as cv2.imread returns them), inputs built on the device (input_prep.py)
+    import numpy as np
+    rng = np.random.RandomState(7 + rank)
+    raw_frames = [(torch.from_numpy(rng.randint(0, 256, (H, W, 3)).astype(np.uint8)).pin_memory(),
+                   torch.from_numpy(rng.randint(300, 1500, (H, W)).astype(np.int16)).pin_memory()) for _ in range(nframes)]
+    camera = {"fx": 612.937, "fy": 613.173, "x_offset": 322.549, "y_offset": 248.158}   # data/demo/camera_params.json
+
+    def timed_pipe(resident, count, base, raw=False):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -270,8 +277,12 @@ def run_b200(args):
                 pipe.collect_one()
             with torch.cuda.stream(sl.stream):
                 flush.zero_()                               # L2 flush before every frame, INSIDE the timed region
-            a, b = (dev_frames if resident else pin_frames)[(base + i) % nframes]
-            pipe.submit(a, b, firsts[base + i], resident=resident)
+            if raw:
+                a, b = raw_frames[(base + i) % nframes]
+                pipe.submit_raw(a, b, camera, firsts[base + i])
+            else:
+                a, b = (dev_frames if resident else pin_frames)[(base + i) % nframes]
+                pipe.submit(a, b, firsts[base + i], resident=resident)
             if world > 1:
                 with torch.cuda.stream(sl.stream):
                     dist.all_gather_into_tensor(gathered, sl.labels.view(-1))
@@ -292,11 +303,13 @@ def run_b200(args):
     for i in range(warmup):
         timed_pipe(True, 2, i)
         timed_pipe(False, 2, i)
+        timed_pipe(False, 2, i, raw=True)
     l0 = lib.uoc_launch_count()
     ms_pipe_dev = timed_pipe(True, steps, warmup)
     host_enqueue_ms = host_ms[0]
     launches_pipe = int(lib.uoc_launch_count() - l0)
     ms_pipe_e2e = timed_pipe(False, steps, warmup + steps)
+    ms_pipe_raw = timed_pipe(False, steps, warmup + 2 * steps, raw=True)
 
     # ---- stage split (same kernels through the stage entry points), rank-local, for the roofline ----
     import ctypes
@@ -372,6 +385,9 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": world * steps / (ms_pipe_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 3 * H * W * 4,
                 "d2h_bytes_per_step": H * W * 4, "ms_per_step": ms_pipe_e2e / steps},
+        # same, from RAW host frames (uint8 BGR + uint16 depth): the reference's read_sample arithmetic runs on the device
+        "e2e_raw_inputs": {"value": world * steps / (ms_pipe_raw * 1e-3), "unit": UNIT, "h2d_bytes_per_step": H * W * 5,
+                           "d2h_bytes_per_step": H * W * 4, "ms_per_step": ms_pipe_raw / steps},
         "serial": {"value": world * steps / (ms_dev * 1e-3), "ms_per_step": ms_dev / steps, "e2e_value": world * steps / (ms_e2e * 1e-3),
                    "e2e_ms_per_step": ms_e2e / steps, "note": "one frame at a time, L2 flushed (untimed) between frames"},
         # the pipelined region replays CUDA graphs (not visible to the library's launch counter): the same kernels as the

@@ -170,6 +170,24 @@ UOC_API int uoc_conv2d_bf16(const void* x, const void* w, const float* bias, con
                             int H, int W, int Cin, int Cout, int ksize, int stride, int dilation, int relu, int flags,
                             uoc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Input preparation (the step before the path): replaces read_sample's tensor arithmetic
+ * and compute_xyz (tools/test_images.py:96-135; ros/test_images_segmentation.py:38-44,146-159).
+ * All pointers are device pointers.  Outputs are bit-identical to the reference's numpy / torch fp32 arithmetic.
+ * ------------------------------------------------------------------------------------------ */
+
+/* bgr [N,H,W,3] uint8 (cv2.imread order) -> image_out [N,3,H,W] fp32 = bgr/255 - pixel_means_over_255[c]
+ *   (pixel_means_over_255 = float32(cfg.PIXEL_MEANS / 255.0), 3 HOST floats);
+ * depth_raw [N,H,W] uint16 -> xyz_out [N,3,H,W] fp32: z = raw / depth_divisor (1000), x = (col - px) z / fx,
+ *   y = (row - py) z / fy.   Either input may be NULL (COLOR / DEPTH only). */
+UOC_API int uoc_prepare_inputs(const uint8_t* bgr, const uint16_t* depth_raw, int N, int H, int W, float fx, float fy,
+                               float px, float py, const float* pixel_means_over_255, float depth_divisor,
+                               float* image_out, float* xyz_out, uoc_stream_t stream);
+
+/* compute_xyz (tools/test_images.py:96-102): metric depth [N,H,W] fp32 -> xyz_out [N,3,H,W] fp32. */
+UOC_API int uoc_compute_xyz(const float* depth_m, int N, int H, int W, float fx, float fy, float px, float py,
+                            float* xyz_out, uoc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,9 +100,46 @@ def gen_backbone(ref):
         print(name, ta.shape, float(ta.abs().mean()), float(tb.abs().mean()))
 
 
+def gen_input_prep(ref):
+    """The reference's own read_sample (tools/test_images.py:105-135) on windows of its demo frames (data/demo):
+    the windows are written as PNG files so that the unmodified function -- cv2.imread included -- produces the
+    expected tensors.  compute_xyz uses absolute pixel indices, so a window is a small frame of its own."""
+    import json
+    import tempfile
+    import cv2
+    tool = rh.load_tool("test_images")
+    demo = os.path.join(rh.REF_ROOT, "data", "demo")
+    cam = json.load(open(os.path.join(demo, "camera_params.json")))
+    cases = [("000000", 150, 200, 40, 56), ("000003", 0, 0, 33, 47), ("000006", 300, 420, 48, 64)]
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for k, (stem, y0, x0, h, w) in enumerate(cases):
+            im = cv2.imread(os.path.join(demo, stem + "-color.png"))[y0:y0 + h, x0:x0 + w].copy()
+            dp = cv2.imread(os.path.join(demo, stem + "-depth.png"), cv2.IMREAD_ANYDEPTH)[y0:y0 + h, x0:x0 + w].copy()
+            if k == 1:
+                dp[5:9, 7:20] = 0                     # a hole: invalid depth stays exactly 0 in all three channels
+            fc, fd = os.path.join(tmp, "c%d.png" % k), os.path.join(tmp, "d%d.png" % k)
+            cv2.imwrite(fc, im)
+            cv2.imwrite(fd, dp)
+            sample = tool.read_sample(fc, fd, cam)
+            out["im%d" % k] = im
+            out["depth%d" % k] = dp
+            out["image_color%d" % k] = sample["image_color"].numpy()
+            out["xyz%d" % k] = sample["depth"].numpy()
+            print("input_prep", k, im.shape, dp.dtype, float(sample["depth"].abs().mean()))
+    np.savez_compressed(os.path.join(OUT, "input_prep.npz"), cases=len(cases), fx=cam["fx"], fy=cam["fy"],
+                        x_offset=cam["x_offset"], y_offset=cam["y_offset"], **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = rh.load()
-    gen_cluster(ref)
-    gen_two_stage(ref)
-    gen_backbone(ref)
+    only = sys.argv[1:]
+    if not only or "cluster" in only:
+        gen_cluster(ref)
+    if not only or "two_stage" in only:
+        gen_two_stage(ref)
+    if not only or "backbone" in only:
+        gen_backbone(ref)
+    if not only or "input_prep" in only:
+        gen_input_prep(ref)

@@ -123,3 +123,23 @@ def build_network(num_units=64, state_dict=None, seed=0, name="seg_resnet34_8s_e
     with contextlib.redirect_stdout(io.StringIO()):
         net = ref.networks.__dict__[name](2, num_units, state_dict)
     return net.eval()
+
+
+def load_tool(name="test_images"):
+    """Import an UNMODIFIED script of the reference's tools/ directory as a module (its __main__ block does not run):
+    gives access to read_sample / compute_xyz of tools/test_images.py:96-135."""
+    import importlib.util
+    load()
+    tools = os.path.join(REF_ROOT, "tools")
+    if tools not in sys.path:
+        sys.path.insert(0, tools)          # for `import _init_paths`
+    key = "uoc_ref_tool_" + name
+    if key in sys.modules:
+        return sys.modules[key]
+    spec = importlib.util.spec_from_file_location(key, os.path.join(tools, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    with contextlib.redirect_stdout(io.StringIO()):
+        spec.loader.exec_module(mod)
+    sys.modules[key] = mod
+    return mod
+

@@ -401,3 +401,30 @@ def labels_equal_up_to_permutation(a, b):
         if fwd.setdefault(int(x), int(y)) != int(y) or bwd.setdefault(int(y), int(x)) != int(x):
             return False
     return True
+
+
+# ---------------------------------------------------------------------------------------------
+# input preparation (the step before the path)
+# ---------------------------------------------------------------------------------------------
+PIXEL_MEANS = np.array([[[102.9801, 115.9465, 122.7717]]])        # fcn/config.py:376
+
+
+def compute_xyz(depth_img, fx, fy, px, py, height, width):
+    """tools/test_images.py:96-102 (utils/mask.py:41-46 for the index grid): [H,W] fp32 metres -> [H,W,3] fp32."""
+    indices = np.indices((height, width), dtype=np.float32).transpose(1, 2, 0)
+    z_e = depth_img
+    x_e = (indices[..., 1] - px) * z_e / fx
+    y_e = (indices[..., 0] - py) * z_e / fy
+    return np.stack([x_e, y_e, z_e], axis=-1)
+
+
+def read_sample_arrays(im_bgr_u8, depth_u16, camera_params, pixel_means=PIXEL_MEANS):
+    """tools/test_images.py:105-135 after the two cv2.imread calls: (image_color [1,3,H,W], depth [1,3,H,W]) fp32 CPU."""
+    depth = depth_u16.astype(np.float32) / 1000.0
+    h, w = depth.shape
+    xyz = compute_xyz(depth, camera_params['fx'], camera_params['fy'], camera_params['x_offset'],
+                      camera_params['y_offset'], h, w)
+    im_tensor = torch.from_numpy(im_bgr_u8) / 255.0
+    im_tensor -= torch.tensor(pixel_means / 255.0).float()
+    return im_tensor.permute(2, 0, 1).unsqueeze(0), torch.from_numpy(xyz).permute(2, 0, 1).unsqueeze(0)
+

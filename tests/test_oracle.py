@@ -161,3 +161,26 @@ def test_state_dict_keys_match_the_reference_module():
     assert [k for k, _ in ours] == list(ref_sd.keys())
     for k, shape in ours:
         assert tuple(ref_sd[k].shape) == tuple(shape), k
+
+
+def test_input_prep_oracle_matches_reference_golden():
+    """oracle read_sample_arrays / compute_xyz == the reference's own read_sample on windows of its demo frames (bit-exact)."""
+    g = np.load(os.path.join(GOLDEN, "input_prep.npz"))
+    cam = {"fx": float(g["fx"]), "fy": float(g["fy"]), "x_offset": float(g["x_offset"]), "y_offset": float(g["y_offset"])}
+    for k in range(int(g["cases"])):
+        image, xyz = O.read_sample_arrays(g["im%d" % k], g["depth%d" % k], cam)
+        assert image.dtype == torch.float32 and xyz.dtype == torch.float32
+        assert np.array_equal(image.numpy(), g["image_color%d" % k])
+        assert np.array_equal(xyz.numpy(), g["xyz%d" % k])
+    assert np.all(g["xyz1"][0, :, 5:9, 7:20] == 0)                     # invalid depth -> exact zeros in x, y and z
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not present (GPU box)")
+def test_input_prep_oracle_matches_the_live_reference_tool():
+    tool = rh.load_tool("test_images")
+    rng = np.random.RandomState(0)
+    depth = (rng.randint(0, 3000, (20, 30)).astype(np.float32)) / 1000.0
+    want = tool.compute_xyz(depth, 612.937, 613.173, 322.549, 248.158, 20, 30)
+    got = O.compute_xyz(depth, 612.937, 613.173, 322.549, 248.158, 20, 30)
+    assert want.dtype == got.dtype == np.float32 and np.array_equal(want, got)
+

@@ -2,7 +2,7 @@
 # full GPU validation: every -m gpu test file in its own process, smoke, bench (N=1)
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
-for f in test_gpu_clustering test_gpu_backbone test_gpu_pipeline; do
+for f in test_gpu_clustering test_gpu_backbone test_gpu_pipeline test_gpu_input_prep; do
   timeout 900 python -m pytest tests/$f.py -m gpu -q --timeout 300 -p no:cacheprovider > gpurun_out/$f.log 2>&1; echo "$f exit $?"; tail -2 gpurun_out/$f.log
 done
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

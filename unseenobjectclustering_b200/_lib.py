@@ -47,6 +47,8 @@ SIGNATURES = {
     "uoc_backbone_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "uoc_backbone_read_trunk": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "uoc_conv2d_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "uoc_prepare_inputs": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _f, _vp, _vp, _vp]),
+    "uoc_compute_xyz": (_i, [_vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp]),
 }
 
 _lib = None

@@ -29,6 +29,8 @@ class _Slot(object):
         self.xyz_dev = torch.empty((1, 3, H, W), dtype=torch.float32, device=dev)
         self.img_pin = None
         self.xyz_pin = None
+        self.raw_im = None
+        self.raw_dp = None
         self.out_pin = torch.empty((1, H, W), dtype=torch.float32).pin_memory()
         self.done = torch.cuda.Event()
         self.labels = None
@@ -123,7 +125,14 @@ class FramePipeline(object):
         return slot.lab
 
     # -- public -----------------------------------------------------------------------------------------
-    def submit(self, image, depth, first_index=None, resident=False):
+    def submit_raw(self, im_bgr, depth_raw, camera_params, first_index=None):
+        """Raw frame: im_bgr [H,W,3] uint8 and depth_raw [H,W] uint16 (int16 storage) CPU tensors -- pinned for an
+        asynchronous upload -- as cv2.imread returns them; the network inputs are built on the device by
+        input_prep.prepare_inputs (tools/test_images.py:105-135 arithmetic, bit-identical): 1.5 MB instead of 7.4 MB
+        over PCIe per frame."""
+        return self.submit(None, None, first_index=first_index, raw=(im_bgr, depth_raw, camera_params))
+
+    def submit(self, image, depth, first_index=None, resident=False, raw=None):
         """image / depth: [1,3,H,W] float32 tensors: pinned or pageable CPU tensors, or device tensors
         (resident=True).  Returns the slot; collect results with collect_one() / drain() in submission order."""
         slot = self.slots[self.next % len(self.slots)]
@@ -133,7 +142,16 @@ class FramePipeline(object):
         if first_index is None:
             first_index = np.random.randint(0, self.H * self.W)     # lib/utils/mean_shift.py:155, drawn in frame order
         with torch.cuda.stream(slot.stream):
-            if resident:
+            if raw is not None:
+                from . import input_prep
+                im_bgr, depth_raw, cam = raw
+                if slot.raw_im is None:
+                    slot.raw_im = torch.empty((1, self.H, self.W, 3), dtype=torch.uint8, device=self.dev)
+                    slot.raw_dp = torch.empty((1, self.H, self.W), dtype=torch.int16, device=self.dev)
+                slot.raw_im.copy_(im_bgr.view(1, self.H, self.W, 3), non_blocking=True)
+                slot.raw_dp.copy_(depth_raw.view(1, self.H, self.W), non_blocking=True)
+                input_prep.prepare_inputs(slot.raw_im, slot.raw_dp, cam, device=self.dev, out=(slot.img_dev, slot.xyz_dev))
+            elif resident:
                 slot.img_dev.copy_(image, non_blocking=True)
                 slot.xyz_dev.copy_(depth, non_blocking=True)
             else:
