@@ -145,13 +145,31 @@ typedef struct {
 /* Folds eval-mode BatchNorm (eps 1e-5) into the convolutions, converts to bf16, re-packs to the
  * K-major [Cout][tap][Cin] layout the implicit-GEMM kernel reads, uploads.  Blocking. */
 UOC_API int uoc_backbone_create(uoc_backbone** out, const uoc_weight_desc* tensors, int n_tensors, int num_units);
+
+/* The other input / fusion variants behind the same reference factory (lib/networks/SEG.py:36-37,:69-71,:97-114;
+ * SURVEY section 8(f) rank 2), selected by what the reference reads from cfg.INPUT / cfg.TRAIN.FUSION_TYPE /
+ * cfg.TRAIN.EMBEDDING_NORMALIZATION:
+ *   input_type  UOC_INPUT_RGBD | UOC_INPUT_COLOR (features = fcn(img)) | UOC_INPUT_DEPTH (features = fcn(depth))
+ *   fusion_type (RGBD only) UOC_FUSION_ADD (fcn(img) + fcn_depth(depth)) | UOC_FUSION_CAT (channel concatenation,
+ *               2 * num_units channels, num_units = 64 only) | UOC_FUSION_EARLY (one trunk on cat(img, depth), 6-channel
+ *               stem: seg_resnet34_8s_embedding_early, SEG.py:178-181)
+ *   normalize   0 skips the F.normalize of SEG.py:113-114
+ * State-dict keys: 'fcn.resnet34_8s.*' always; 'fcn_depth.resnet34_8s.*' for RGBD add / cat.
+ * uoc_backbone_create(...) == uoc_backbone_create_ex(..., UOC_INPUT_RGBD, UOC_FUSION_ADD, 1). */
+enum { UOC_INPUT_RGBD = 0, UOC_INPUT_COLOR = 1, UOC_INPUT_DEPTH = 2 };
+enum { UOC_FUSION_ADD = 0, UOC_FUSION_CAT = 1, UOC_FUSION_EARLY = 2 };
+UOC_API int uoc_backbone_create_ex(uoc_backbone** out, const uoc_weight_desc* tensors, int n_tensors, int num_units,
+                                   int input_type, int fusion_type, int normalize);
+/* channels of the field uoc_backbone_forward writes: num_units, or 2 * num_units for cat fusion */
+UOC_API int uoc_backbone_feature_dim(const uoc_backbone* bb);
 UOC_API void uoc_backbone_destroy(uoc_backbone* bb);
 UOC_API size_t uoc_backbone_workspace_bytes(const uoc_backbone* bb, int N, int H, int W);
 
 /*
  * rgb, xyz: [N,3,H,W] fp32 NCHW (image_color / depth of the reference sample dict,
- * lib/fcn/test_dataset.py:235-239).  features_out: [N,num_units,H,W] fp32 NCHW, unit L2 norm over
- * channels.  features_bf16_out (optional, may be NULL): [N,H*W,num_units] bf16 copy for
+ * lib/fcn/test_dataset.py:235-239); rgb may be NULL for UOC_INPUT_DEPTH, xyz for UOC_INPUT_COLOR.
+ * features_out: [N,C,H,W] fp32 NCHW, C = uoc_backbone_feature_dim(), unit L2 norm over channels (unless
+ * normalize == 0).  features_bf16_out (optional, may be NULL): [N,H*W,C] bf16 copy for
  * uoc_meanshift_cluster.  H and W must be multiples of 8.
  */
 UOC_API int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, int N, int H, int W,

@@ -100,6 +100,35 @@ def gen_backbone(ref):
         print(name, ta.shape, float(ta.abs().mean()), float(tb.abs().mean()))
 
 
+VARIANT_CASES = [
+    # name, factory, input_type, fusion_type, normalize, in_channels, H, W, weight seed, frame seed
+    ("variant_color", "seg_resnet34_8s_embedding", "COLOR", "add", True, 3, 48, 64, 21, 22),
+    ("variant_depth", "seg_resnet34_8s_embedding", "DEPTH", "add", True, 3, 48, 64, 23, 24),
+    ("variant_early", "seg_resnet34_8s_embedding_early", "RGBD", "early", True, 6, 48, 64, 25, 26),
+    ("variant_cat", "seg_resnet34_8s_embedding", "RGBD", "cat", True, 3, 48, 64, 27, 28),
+    ("variant_add_nonorm", "seg_resnet34_8s_embedding", "RGBD", "add", False, 3, 48, 64, 29, 30),
+]
+
+
+def gen_variants(ref):
+    """The reference's other input / fusion variants (SEG.py:97-114), built through its own
+    factories with cfg.INPUT / cfg.TRAIN.FUSION_TYPE / cfg.TRAIN.EMBEDDING_NORMALIZATION set."""
+    from unseenobjectclustering_b200.networks import random_state_dict
+    for name, factory, it, ft, norm, cin, H, W, wseed, fseed in VARIANT_CASES:
+        sd = O.randomise_bn_(random_state_dict(64, seed=wseed, input_type=it, fusion_type=ft, in_channels=cin), wseed + 1000)
+        net = rh.build_network(64, state_dict=sd, name=factory, input_type=it, fusion_type=ft, normalize=norm)
+        have = net.state_dict()
+        assert sorted(have.keys()) == sorted(sd.keys()), (name, set(have) ^ set(sd))
+        assert all(torch.equal(have[k], sd[k]) for k in sd), name
+        img, xyz = O.synthetic_rgbd_frame(H, W, seed=fseed)
+        with torch.no_grad():
+            feats = net(img, None, xyz)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), H=H, W=W, weight_seed=wseed, frame_seed=fseed,
+                            input_type=it, fusion_type=ft, normalize=norm, in_channels=cin, factory=factory,
+                            features_sub=feats[:, :, ::2, ::2].numpy(), features_sum=feats.double().sum().item())
+        print(name, tuple(feats.shape), float(feats.abs().mean()))
+
+
 def gen_input_prep(ref):
     """The reference's own read_sample (tools/test_images.py:105-135) on windows of its demo frames (data/demo):
     the windows are written as PNG files so that the unmodified function -- cv2.imread included -- produces the
@@ -143,3 +172,5 @@ if __name__ == "__main__":
         gen_backbone(ref)
     if not only or "input_prep" in only:
         gen_input_prep(ref)
+    if not only or "variants" in only:
+        gen_variants(ref)

@@ -115,13 +115,21 @@ def cpu_cuda_identity():
         torch.Tensor.cuda = orig
 
 
-def build_network(num_units=64, state_dict=None, seed=0, name="seg_resnet34_8s_embedding"):
-    """Construct the reference network quietly (update_model prints ~900 lines), eval mode."""
+def build_network(num_units=64, state_dict=None, seed=0, name="seg_resnet34_8s_embedding", input_type="RGBD",
+                  fusion_type="add", normalize=True):
+    """Construct the reference network quietly (update_model prints ~900 lines), eval mode.  The variant is set
+    the way the reference's tools do it -- through the global cfg SEGNET.__init__ reads (SEG.py:34-38) -- and
+    restored afterwards."""
     import torch
     ref = load()
     torch.manual_seed(seed)
-    with contextlib.redirect_stdout(io.StringIO()):
-        net = ref.networks.__dict__[name](2, num_units, state_dict)
+    saved = (ref.cfg.INPUT, ref.cfg.TRAIN.FUSION_TYPE, ref.cfg.TRAIN.EMBEDDING_NORMALIZATION)
+    ref.cfg.INPUT, ref.cfg.TRAIN.FUSION_TYPE, ref.cfg.TRAIN.EMBEDDING_NORMALIZATION = input_type, fusion_type, normalize
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = ref.networks.__dict__[name](2, num_units, state_dict)
+    finally:
+        ref.cfg.INPUT, ref.cfg.TRAIN.FUSION_TYPE, ref.cfg.TRAIN.EMBEDDING_NORMALIZATION = saved
     return net.eval()
 
 

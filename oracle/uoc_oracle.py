@@ -323,15 +323,38 @@ def normalize_state_dict(data):
     return out
 
 
+def segnet_forward(sd, img, depth, input_type="RGBD", fusion_type="add", normalize=True):
+    """lib/networks/SEG.py:88-119 in eval mode for every input / fusion variant of the ResNet34-8s network:
+    DEPTH -> fcn(depth) (:97-98); COLOR -> fcn(img) (:99-100); RGBD early -> fcn(cat(img, depth)) (:101-103);
+    RGBD add / cat -> fcn(img) (+ | cat) fcn_depth(depth) (:105-110); F.normalize iff EMBEDDING_NORMALIZATION (:113-114)."""
+    def branch(x, prefix):
+        return F.interpolate(resnet34_8s_trunk(x, sd, prefix), size=x.shape[2:], mode="bilinear", align_corners=True)
+
+    if input_type == "DEPTH":
+        f = branch(depth, "fcn.resnet34_8s.")
+    elif input_type == "COLOR":
+        f = branch(img, "fcn.resnet34_8s.")
+    elif input_type == "RGBD" and fusion_type == "early":
+        f = branch(torch.cat((img, depth), 1), "fcn.resnet34_8s.")
+    else:
+        a = branch(img, "fcn.resnet34_8s.")
+        b = branch(depth, "fcn_depth.resnet34_8s.")
+        f = a + b if fusion_type == "add" else torch.cat((a, b), 1)
+    return F.normalize(f, p=2, dim=1) if normalize else f
+
+
 class OracleSegNet:
     """Callable with the reference's network signature net(img, label, depth) -> features."""
 
-    def __init__(self, state_dict):
+    def __init__(self, state_dict, input_type="RGBD", fusion_type="add", normalize=True):
         self.sd = {k: v.detach().float() for k, v in normalize_state_dict(state_dict).items()}
+        self.variant = (input_type, fusion_type, normalize)
 
     def __call__(self, img, label=None, depth=None):
         with torch.no_grad():
-            return segnet_rgbd_add_forward(self.sd, img, depth)
+            if self.variant == ("RGBD", "add", True):
+                return segnet_rgbd_add_forward(self.sd, img, depth)
+            return segnet_forward(self.sd, img, depth, *self.variant)
 
 
 # --------------------------------------------------------------------------------------------

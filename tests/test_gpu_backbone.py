@@ -143,3 +143,52 @@ def test_module_drop_in_behaviour():
     assert f.shape == (1, 64, 64, 96)
     assert (f.norm(dim=1) - 1).abs().max() < 1e-4
     _ = f[0, 0::3]      # the indexing the reference's visualisation does
+
+
+VARIANTS = ["variant_color", "variant_depth", "variant_early", "variant_cat", "variant_add_nonorm"]
+
+
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_CONV_SIMT], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("name", VARIANTS)
+def test_network_variants_match_reference_golden(name, flags):
+    """COLOR / DEPTH single trunk, early fusion (6-channel stem), cat fusion (128-channel field),
+    EMBEDDING_NORMALIZATION off -- against fixtures written by the unmodified reference factories."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    it, ft, norm, cin = str(g["input_type"]), str(g["fusion_type"]), bool(g["normalize"]), int(g["in_channels"])
+    H, W = int(g["H"]), int(g["W"])
+    sd = O.randomise_bn_(NW.random_state_dict(64, seed=int(g["weight_seed"]), input_type=it, fusion_type=ft, in_channels=cin),
+                         int(g["weight_seed"]) + 1000)
+    factory = getattr(NW, str(g["factory"]))
+    net = factory(2, 64, sd, input_type=it, fusion_type=ft, normalize=norm).to(DEV)
+    net.flags = flags | _lib.FLAG_SYNC_CHECK
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed=int(g["frame_seed"]))
+    f = net(img.to(DEV) if it != "DEPTH" else None, None, xyz.to(DEV) if it != "COLOR" else None)
+    C = 128 if (it == "RGBD" and ft == "cat") else 64
+    assert f.shape == (1, C, H, W) and f.dtype == torch.float32 and f.is_cuda
+    sub = f.cpu()[:, :, ::2, ::2].numpy()
+    want = g["features_sub"]
+    cosd = 1.0 - (sub * want).sum(1) / np.maximum(np.linalg.norm(sub, axis=1) * np.linalg.norm(want, axis=1), 1e-12)
+    assert np.abs(cosd).max() < 1e-3, np.abs(cosd).max()          # BASELINE.json tolerance
+    if norm:
+        assert (f.norm(dim=1) - 1).abs().max() < 1e-4
+    else:                                                          # un-normalised field: magnitudes must agree too
+        rel = np.abs(sub - want).max() / np.abs(want).max()
+        assert rel < 0.03, rel
+    # the field feeds the clustering like the default variant's does (bf16 copy registered, d = C)
+    from unseenobjectclustering_b200 import mean_shift as MS
+    xb = MS._lookup_bf16(f)
+    assert xb is not None and xb.shape == (1, H * W, C)
+
+
+def test_variant_argument_errors():
+    with pytest.raises(ValueError):
+        NW.seg_resnet34_8s_embedding(2, 64, None, input_type="RGBD", fusion_type="early")     # needs the _early factory
+    with pytest.raises(ValueError):
+        NW.SEGNET_B200(64, None, input_type="LIDAR")
+    net = NW.seg_resnet34_8s_embedding(2, 128, None, input_type="RGBD", fusion_type="cat").to(DEV)
+    img, xyz = O.synthetic_rgbd_frame(32, 32, seed=0)
+    with pytest.raises(_lib.UocError):                               # cat fusion is built for num_units = 64 only
+        net(img.to(DEV), None, xyz.to(DEV))
+    net = NW.seg_resnet34_8s_embedding(2, 64, None, input_type="COLOR").to(DEV)
+    with pytest.raises(_lib.UocError):
+        net(None, None, xyz.to(DEV))

@@ -134,6 +134,43 @@ def test_assign_histogram_quirk_with_label_gaps():
     assert np.array_equal(t, c)
 
 
+VARIANTS = ["variant_color", "variant_depth", "variant_early", "variant_cat", "variant_add_nonorm"]
+
+
+def _variant_setup(g):
+    from unseenobjectclustering_b200.networks import random_state_dict
+    it, ft, norm, cin = str(g["input_type"]), str(g["fusion_type"]), bool(g["normalize"]), int(g["in_channels"])
+    sd = O.randomise_bn_(random_state_dict(64, seed=int(g["weight_seed"]), input_type=it, fusion_type=ft, in_channels=cin),
+                         int(g["weight_seed"]) + 1000)
+    img, xyz = O.synthetic_rgbd_frame(int(g["H"]), int(g["W"]), seed=int(g["frame_seed"]))
+    return sd, img, xyz, it, ft, norm, cin
+
+
+@pytest.mark.parametrize("name", VARIANTS)
+def test_network_variant_oracle_matches_reference_golden(name):
+    """COLOR / DEPTH / early / cat / un-normalised variants (SEG.py:97-114) against fixtures written by the
+    unmodified reference factories (oracle/make_golden.py gen_variants)."""
+    g = _load(os.path.join(GOLDEN, name + ".npz"))
+    sd, img, xyz, it, ft, norm, _ = _variant_setup(g)
+    f = O.OracleSegNet(sd, it, ft, norm)(img, None, xyz)
+    assert f.shape[1] == (128 if ft == "cat" and it == "RGBD" else 64)
+    assert np.allclose(f[:, :, ::2, ::2].numpy(), g["features_sub"], atol=1e-5, rtol=1e-5)
+    assert abs(f.double().sum().item() - float(g["features_sum"])) < 1e-2 * max(1.0, abs(float(g["features_sum"])) * 1e-3)
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not present (GPU box)")
+def test_variant_state_dict_keys_match_the_reference_factories():
+    from unseenobjectclustering_b200.networks import reference_state_dict_keys
+    for factory, it, ft, cin in (("seg_resnet34_8s_embedding", "COLOR", "add", 3),
+                                 ("seg_resnet34_8s_embedding_early", "RGBD", "early", 6),
+                                 ("seg_resnet34_8s_embedding", "RGBD", "cat", 3)):
+        ref_sd = rh.build_network(64, name=factory, input_type=it, fusion_type=ft).state_dict()
+        ours = reference_state_dict_keys(64, it, ft, cin)
+        assert [k for k, _ in ours] == list(ref_sd.keys()), factory
+        for k, shape in ours:
+            assert tuple(ref_sd[k].shape) == tuple(shape), k
+
+
 @pytest.mark.skipif(not rh.available(), reason="reference tree not present (GPU box)")
 def test_torch_oracle_is_bit_identical_to_the_live_reference():
     ref = rh.load()

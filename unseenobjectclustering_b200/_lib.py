@@ -42,6 +42,8 @@ SIGNATURES = {
     "uoc_assign_labels": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "uoc_pack_bf16": (_i, [_vp, _i64, _i64, _i, _i64, _i, _vp, _vp]),
     "uoc_backbone_create": (_i, [_c.POINTER(_vp), _c.POINTER(WeightDesc), _i, _i]),
+    "uoc_backbone_create_ex": (_i, [_c.POINTER(_vp), _c.POINTER(WeightDesc), _i, _i, _i, _i, _i]),
+    "uoc_backbone_feature_dim": (_i, [_vp]),
     "uoc_backbone_destroy": (None, [_vp]),
     "uoc_backbone_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "uoc_backbone_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),

@@ -32,6 +32,10 @@ struct Branch {
 
 struct uoc_backbone {
   int num_units = 64;
+  int input_type = UOC_INPUT_RGBD, fusion = UOC_FUSION_ADD, normalize = 1;
+  int groups = 2;         // trunks evaluated side by side: 2 for RGBD add / cat, 1 for COLOR / DEPTH / early fusion
+  int cin = 3;            // stem input channels: 6 for early fusion (SEG.py:101-103, :178-181)
+  int feat_dim = 64;      // channels of the returned field: 2 * num_units for cat fusion (SEG.py:110)
   int device = -1;
   uoc::Branch br[2];
   char* blob = nullptr;   // device
@@ -119,29 +123,30 @@ static const int kBlocks[4] = {3, 4, 6, 3};
 static const int kStride[4] = {1, 2, 1, 1};   // after the output_stride = 8 conversion (resnet.py:203-214)
 static const int kDil[4] = {1, 1, 2, 4};
 
-static bool build_branch(const WeightMap& wm, const std::string& prefix, int num_units, Branch* br, BlobBuilder* bb,
-                         std::string* err) {
-  // stem: [64][3][7][7] -> fp32 [64][(r*7+s)*3 + c], BN folded
-  const float* w = find(wm, prefix + "conv1.weight", 64 * 3 * 49, err);
+static bool build_branch(const WeightMap& wm, const std::string& prefix, int num_units, int cin, Branch* br,
+                         BlobBuilder* bb, std::string* err) {
+  // stem: [64][cin][7][7] -> fp32 [64][(r*7+s)*cin + c], BN folded
+  const int K = 49 * cin, Kpad = (K + 63) / 64 * 64;
+  const float* w = find(wm, prefix + "conv1.weight", int64_t(64) * cin * 49, err);
   if (!w) return false;
   std::vector<float> scale, shift;
   if (!bn_fold(wm, prefix + "bn1", 64, &scale, &shift, err)) return false;
-  br->stem_w_off = bb->reserve(64 * 147 * 4);
+  br->stem_w_off = bb->reserve(size_t(64) * K * 4);
   br->stem_b_off = bb->reserve(64 * 4);
   float* sw = reinterpret_cast<float*>(bb->host.data() + br->stem_w_off);
   float* sb = reinterpret_cast<float*>(bb->host.data() + br->stem_b_off);
   for (int co = 0; co < 64; ++co) {
-    for (int c = 0; c < 3; ++c)
-      for (int t = 0; t < 49; ++t) sw[co * 147 + t * 3 + c] = w[(co * 3 + c) * 49 + t] * scale[co];
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < 49; ++t) sw[co * K + t * cin + c] = w[(co * cin + c) * 49 + t] * scale[co];
     sb[co] = shift[co];
   }
-  // bf16 copy for the tensor-core stem: [64][192], k = tap*3 + c, zero padded beyond 147
-  br->stem_wbf_off = bb->reserve(64 * 192 * 2);
+  // bf16 copy for the tensor-core stem: [64][Kpad], k = tap*cin + c, zero padded beyond K
+  br->stem_wbf_off = bb->reserve(size_t(64) * Kpad * 2);
   {
     uint16_t* swb = reinterpret_cast<uint16_t*>(bb->host.data() + br->stem_wbf_off);
     const float* swf = reinterpret_cast<const float*>(bb->host.data() + br->stem_w_off);
     for (int co = 0; co < 64; ++co)
-      for (int k = 0; k < 192; ++k) swb[co * 192 + k] = (k < 147) ? f32_to_bf16_rne(swf[co * 147 + k]) : uint16_t(0);
+      for (int k = 0; k < Kpad; ++k) swb[co * Kpad + k] = (k < K) ? f32_to_bf16_rne(swf[co * K + k]) : uint16_t(0);
   }
   int inplanes = 64;
   for (int li = 0; li < 4; ++li) {
@@ -207,8 +212,8 @@ static int run_conv(const ConvLayer* L[2], const uoc_backbone* bb, const void* x
                     int H, int W, int relu, int out_fp32, int flags, cudaStream_t st) {
   ConvProblem p;
   memset(&p, 0, sizeof(p));
-  p.groups = 2;
-  for (int g = 0; g < 2; ++g) {
+  p.groups = bb->groups;
+  for (int g = 0; g < bb->groups; ++g) {
     p.g[g].x = x[g];
     p.g[g].w = bb->blob + L[g]->w_off;
     p.g[g].bias = reinterpret_cast<const float*>(bb->blob + L[g]->b_off);
@@ -227,11 +232,23 @@ using namespace uoc;
 extern "C" {
 
 int uoc_backbone_create(uoc_backbone** out, const uoc_weight_desc* tensors, int n_tensors, int num_units) {
+  return uoc_backbone_create_ex(out, tensors, n_tensors, num_units, UOC_INPUT_RGBD, UOC_FUSION_ADD, 1);
+}
+
+int uoc_backbone_feature_dim(const uoc_backbone* bb) { return bb ? bb->feat_dim : 0; }
+
+int uoc_backbone_create_ex(uoc_backbone** out, const uoc_weight_desc* tensors, int n_tensors, int num_units, int input_type,
+                           int fusion_type, int normalize) {
   if (!out || !tensors || n_tensors < 1) return fail(UOC_ERR_INVALID, "null argument");
   *out = nullptr;
   int rc = require_sm100();
   if (rc != UOC_OK) return rc;
   if (num_units != 64 && num_units != 128) return fail(UOC_ERR_UNSUPPORTED, "num_units must be 64 or 128");
+  if (input_type < UOC_INPUT_RGBD || input_type > UOC_INPUT_DEPTH) return fail(UOC_ERR_INVALID, "bad input_type");
+  if (fusion_type < UOC_FUSION_ADD || fusion_type > UOC_FUSION_EARLY) return fail(UOC_ERR_INVALID, "bad fusion_type");
+  const bool rgbd = input_type == UOC_INPUT_RGBD;
+  if (rgbd && fusion_type == UOC_FUSION_CAT && num_units != 64)
+    return fail(UOC_ERR_UNSUPPORTED, "cat fusion is supported for num_units = 64 (128-channel field)");
   WeightMap wm;
   for (int i = 0; i < n_tensors; ++i) {
     if (!tensors[i].name || !tensors[i].data_host) return fail(UOC_ERR_INVALID, "weight descriptor with null name / data");
@@ -241,10 +258,17 @@ int uoc_backbone_create(uoc_backbone** out, const uoc_weight_desc* tensors, int 
   }
   uoc_backbone* bb = new uoc_backbone();
   bb->num_units = num_units;
+  bb->input_type = input_type;
+  bb->fusion = rgbd ? fusion_type : UOC_FUSION_ADD;
+  bb->normalize = normalize ? 1 : 0;
+  // SEG.py:69-71: the depth trunk exists only for INPUT == 'RGBD' with a late fusion
+  bb->groups = (rgbd && fusion_type != UOC_FUSION_EARLY) ? 2 : 1;
+  bb->cin = (rgbd && fusion_type == UOC_FUSION_EARLY) ? 6 : 3;
+  bb->feat_dim = (rgbd && fusion_type == UOC_FUSION_CAT) ? 2 * num_units : num_units;
   BlobBuilder builder;
   std::string err;
-  if (!build_branch(wm, "fcn.resnet34_8s.", num_units, &bb->br[0], &builder, &err) ||
-      !build_branch(wm, "fcn_depth.resnet34_8s.", num_units, &bb->br[1], &builder, &err)) {
+  if (!build_branch(wm, "fcn.resnet34_8s.", num_units, bb->cin, &bb->br[0], &builder, &err) ||
+      (bb->groups == 2 && !build_branch(wm, "fcn_depth.resnet34_8s.", num_units, 3, &bb->br[1], &builder, &err))) {
     delete bb;
     return fail(UOC_ERR_INVALID, err);
   }
@@ -274,7 +298,9 @@ int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, i
                          uoc_stream_t stream) {
   int rc = require_sm100();
   if (rc != UOC_OK) return rc;
-  if (!bb || !rgb || !xyz || !features_out || !workspace) return fail(UOC_ERR_INVALID, "null argument");
+  if (!bb || !features_out || !workspace) return fail(UOC_ERR_INVALID, "null argument");
+  if (bb->input_type != UOC_INPUT_DEPTH && !rgb) return fail(UOC_ERR_INVALID, "rgb is required for this input type");
+  if (bb->input_type != UOC_INPUT_COLOR && !xyz) return fail(UOC_ERR_INVALID, "xyz is required for this input type");
   if (N < 1 || H < 16 || W < 16) return fail(UOC_ERR_INVALID, "bad N / H / W");
   if (reinterpret_cast<uintptr_t>(workspace) % 1024 != 0) return fail(UOC_ERR_INVALID, "workspace must be 1024-byte aligned");
   const WsPlan wp = plan_ws(bb->num_units, N, H, W);
@@ -282,31 +308,35 @@ int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
   const Dims d = trunk_dims(H, W);
+  const int G = bb->groups;
 
+  // SEG.py:97-108: DEPTH -> fcn(depth); COLOR -> fcn(img); early -> fcn(cat(img, depth)); else fcn(img), fcn_depth(depth)
   StemGroup sg[2];
-  const float* inputs[2] = {rgb, xyz};
+  const float* inputs[2] = {bb->input_type == UOC_INPUT_DEPTH ? xyz : rgb, xyz};
   for (int g = 0; g < 2; ++g) {
-    sg[g].x = inputs[g];
-    sg[g].w = reinterpret_cast<const float*>(bb->blob + bb->br[g].stem_w_off);
-    sg[g].bias = reinterpret_cast<const float*>(bb->blob + bb->br[g].stem_b_off);
-    sg[g].y = ws + wp.stem[g];
+    const int b = g < G ? g : 0;
+    sg[g].x = inputs[b];
+    sg[g].x2 = xyz;
+    sg[g].w = reinterpret_cast<const float*>(bb->blob + bb->br[b].stem_w_off);
+    sg[g].bias = reinterpret_cast<const float*>(bb->blob + bb->br[b].stem_b_off);
+    sg[g].y = ws + wp.stem[b];
   }
   if (flags & UOC_FLAG_CONV_SIMT) {
-    rc = launch_stem(sg, 2, N, H, W, st);
+    rc = launch_stem(sg, G, bb->cin, N, H, W, st);
   } else {
-    const void* wbf[2] = {bb->blob + bb->br[0].stem_wbf_off, bb->blob + bb->br[1].stem_wbf_off};
-    rc = launch_stem_tc(sg, wbf, 2, N, H, W, st);
+    const void* wbf[2] = {bb->blob + bb->br[0].stem_wbf_off, bb->blob + bb->br[G - 1].stem_wbf_off};
+    rc = launch_stem_tc(sg, wbf, G, bb->cin, N, H, W, st);
   }
   if (rc != UOC_OK) return rc;
   const void* px[2] = {ws + wp.stem[0], ws + wp.stem[1]};
   void* py[2] = {ws + wp.buf[0][0], ws + wp.buf[1][0]};
-  rc = launch_maxpool(px, py, 2, N, d.H1, d.W1, 64, st);
+  rc = launch_maxpool(px, py, G, N, d.H1, d.W1, 64, st);
   if (rc != UOC_OK) return rc;
 
   int cur = 0, curH = d.H2, curW = d.W2;
   for (size_t bi = 0; bi < bb->br[0].blocks.size(); ++bi) {
     const Block& b0 = bb->br[0].blocks[bi];
-    const Block& b1 = bb->br[1].blocks[bi];
+    const Block& b1 = bb->br[G - 1].blocks[bi];
     const int t = (cur + 1) & 3, r = (cur + 2) & 3, y = (cur + 3) & 3;
     const void* xin[2] = {ws + wp.buf[0][cur], ws + wp.buf[1][cur]};
     void* tout[2] = {ws + wp.buf[0][t], ws + wp.buf[1][t]};
@@ -333,12 +363,13 @@ int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, i
   {
     const void* xin[2] = {ws + wp.buf[0][cur], ws + wp.buf[1][cur]};
     void* tr[2] = {ws + wp.trunk[0], ws + wp.trunk[1]};
-    const ConvLayer* LF[2] = {&bb->br[0].fc, &bb->br[1].fc};
+    const ConvLayer* LF[2] = {&bb->br[0].fc, &bb->br[G - 1].fc};
     rc = run_conv(LF, bb, xin, nullptr, tr, N, curH, curW, 0, 1, flags, st);
     if (rc != UOC_OK) return rc;
   }
-  rc = launch_head(reinterpret_cast<const float*>(ws + wp.trunk[0]), reinterpret_cast<const float*>(ws + wp.trunk[1]), N,
-                   curH, curW, bb->num_units, H, W, features_out, features_bf16_out, st);
+  const int mode = (G == 1) ? HEAD_SINGLE : (bb->fusion == UOC_FUSION_CAT ? HEAD_CAT : HEAD_ADD);
+  rc = launch_head(reinterpret_cast<const float*>(ws + wp.trunk[0]), reinterpret_cast<const float*>(ws + wp.trunk[1]), mode,
+                   bb->normalize, N, curH, curW, bb->feat_dim, H, W, features_out, features_bf16_out, st);
   if (rc != UOC_OK) return rc;
   if (flags & UOC_FLAG_SYNC_CHECK) return check_device_error(st);
   return UOC_OK;
@@ -346,7 +377,7 @@ int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, i
 
 int uoc_backbone_read_trunk(uoc_backbone* bb, int branch, int N, int H, int W, const void* workspace, float* out,
                             uoc_stream_t stream) {
-  if (!bb || !workspace || !out || branch < 0 || branch > 1) return fail(UOC_ERR_INVALID, "bad argument");
+  if (!bb || !workspace || !out || branch < 0 || branch >= bb->groups) return fail(UOC_ERR_INVALID, "bad argument");
   const WsPlan wp = plan_ws(bb->num_units, N, H, W);
   const Dims d = trunk_dims(H, W);
   return launch_nhwc_to_nchw(reinterpret_cast<const float*>(static_cast<const char*>(workspace) + wp.trunk[branch]), N, d.H3,

@@ -89,27 +89,29 @@ struct StemParams {
 
 constexpr int kStemPatch = 16 * 2 + 5;  // 37 input rows / cols per 16 output rows / cols
 
+template <int CIN>
 __global__ void __launch_bounds__(256) stem_kernel(StemParams p) {
+  constexpr int K = 49 * CIN;
   extern __shared__ float sm[];
-  float* wsm = sm;                               // [147][64]  (k-major so that 4 channels = one float4)
-  float* patch = sm + 147 * 64;                  // [3][37][38]
+  float* wsm = sm;                               // [K][64]  (k-major so that 4 channels = one float4)
+  float* patch = sm + K * 64;                    // [CIN][37][38]
   const int g = blockIdx.z / p.N, n = blockIdx.z % p.N;
   const int tid = threadIdx.x;
   const float* wg = p.g[g].w;
-  for (int e = tid; e < 147 * 64; e += 256) {
+  for (int e = tid; e < K * 64; e += 256) {
     const int k = e >> 6, co = e & 63;
-    wsm[e] = __ldg(wg + co * 147 + k);
+    wsm[e] = __ldg(wg + co * K + k);
   }
   const int oy0 = blockIdx.y * 16, ox0 = blockIdx.x * 16;
   const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
-  const float* xg = p.g[g].x + size_t(n) * 3 * p.H * p.W;
-  for (int e = tid; e < 3 * kStemPatch * kStemPatch; e += 256) {
+  for (int e = tid; e < CIN * kStemPatch * kStemPatch; e += 256) {
     const int c = e / (kStemPatch * kStemPatch);
     const int rem = e - c * kStemPatch * kStemPatch;
     const int py = rem / kStemPatch, px = rem - py * kStemPatch;
     const int iy = iy0 + py, ix = ix0 + px;
+    const float* xg = (c < 3 ? p.g[g].x : p.g[g].x2) + size_t(n) * 3 * p.H * p.W;
     float v = 0.f;
-    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xg + (size_t(c) * p.H + iy) * p.W + ix);
+    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xg + (size_t(c < 3 ? c : c - 3) * p.H + iy) * p.W + ix);
     patch[(c * kStemPatch + py) * 38 + px] = v;
   }
   __syncthreads();
@@ -120,9 +122,9 @@ __global__ void __launch_bounds__(256) stem_kernel(StemParams p) {
   for (int r = 0; r < 7; ++r) {
     for (int s = 0; s < 7; ++s) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+      for (int c = 0; c < CIN; ++c) {
         const float xv = patch[(c * kStemPatch + ly * 2 + r) * 38 + lx * 2 + s];
-        const float4* wk = reinterpret_cast<const float4*>(wsm + ((r * 7 + s) * 3 + c) * 64);
+        const float4* wk = reinterpret_cast<const float4*>(wsm + ((r * 7 + s) * CIN + c) * 64);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           const float4 wv = wk[q];
@@ -148,21 +150,27 @@ __global__ void __launch_bounds__(256) stem_kernel(StemParams p) {
   }
 }
 
-int launch_stem(const StemGroup* g, int groups, int N, int H, int W, cudaStream_t stream) {
+template <int CIN>
+static int launch_stem_t(const StemParams& p, int groups, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * (49 * CIN * 64 + CIN * kStemPatch * 38);
+  static bool attr = false;
+  if (!attr) {
+    UOC_CUDA(cudaFuncSetAttribute(stem_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr = true;
+  }
+  stem_kernel<CIN><<<dim3((p.Wo + 15) / 16, (p.Ho + 15) / 16, groups * p.N), 256, smem, stream>>>(p);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+int launch_stem(const StemGroup* g, int groups, int cin, int N, int H, int W, cudaStream_t stream) {
+  if (cin != 3 && cin != 6) return fail(UOC_ERR_UNSUPPORTED, "stem supports 3 or 6 input channels");
   StemParams p;
   for (int i = 0; i < 2; ++i) p.g[i] = g[i < groups ? i : 0];
   p.N = N; p.H = H; p.W = W;
   p.Ho = (H + 6 - 7) / 2 + 1;
   p.Wo = (W + 6 - 7) / 2 + 1;
-  const size_t smem = sizeof(float) * (147 * 64 + 3 * kStemPatch * 38);
-  static bool attr = false;
-  if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr = true;
-  }
-  stem_kernel<<<dim3((p.Wo + 15) / 16, (p.Ho + 15) / 16, groups * N), 256, smem, stream>>>(p);
-  UOC_CHECK_LAUNCH();
-  return UOC_OK;
+  return cin == 3 ? launch_stem_t<3>(p, groups, stream) : launch_stem_t<6>(p, groups, stream);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -228,10 +236,12 @@ int launch_maxpool(const void* const* x, void* const* y, int groups, int N, int 
 // reference's "upsample each, then add" by rounding only.
 // One thread per output pixel, channels in registers.
 // ----------------------------------------------------------------------------------------------
-template <int D>
+// D = channels of the output field; MODE: HEAD_ADD (a + b), HEAD_SINGLE (a), HEAD_CAT (a | b, D/2 channels each)
+template <int D, int MODE>
 __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w,
-                                                   int H, int W, float sy, float sx, float* __restrict__ out_nchw,
-                                                   __nv_bfloat16* __restrict__ out_bf16) {
+                                                   int H, int W, float sy, float sx, int normalize,
+                                                   float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_bf16) {
+  constexpr int DU = (MODE == HEAD_CAT) ? D / 2 : D;     // channels of one trunk output
   const int n = blockIdx.z;
   const int oy = blockIdx.y;
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,24 +252,24 @@ __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ a, 
   const float ly1 = fy - float(y0), lx1 = fx - float(x0);
   const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
   const size_t base = size_t(n) * h * w;
-  const float4* a00 = reinterpret_cast<const float4*>(a + (base + size_t(y0) * w + x0) * D);
-  const float4* a01 = reinterpret_cast<const float4*>(a + (base + size_t(y0) * w + x1) * D);
-  const float4* a10 = reinterpret_cast<const float4*>(a + (base + size_t(y1) * w + x0) * D);
-  const float4* a11 = reinterpret_cast<const float4*>(a + (base + size_t(y1) * w + x1) * D);
-  const float4* b00 = reinterpret_cast<const float4*>(b + (base + size_t(y0) * w + x0) * D);
-  const float4* b01 = reinterpret_cast<const float4*>(b + (base + size_t(y0) * w + x1) * D);
-  const float4* b10 = reinterpret_cast<const float4*>(b + (base + size_t(y1) * w + x0) * D);
-  const float4* b11 = reinterpret_cast<const float4*>(b + (base + size_t(y1) * w + x1) * D);
+  const size_t o00 = (base + size_t(y0) * w + x0) * DU, o01 = (base + size_t(y0) * w + x1) * DU;
+  const size_t o10 = (base + size_t(y1) * w + x0) * DU, o11 = (base + size_t(y1) * w + x1) * DU;
   float f[D];
   float ss = 0.f;
 #pragma unroll
   for (int k4 = 0; k4 < D / 4; ++k4) {
-    float4 v00 = __ldg(a00 + k4), v01 = __ldg(a01 + k4), v10 = __ldg(a10 + k4), v11 = __ldg(a11 + k4);
-    const float4 u00 = __ldg(b00 + k4), u01 = __ldg(b01 + k4), u10 = __ldg(b10 + k4), u11 = __ldg(b11 + k4);
-    v00.x += u00.x; v00.y += u00.y; v00.z += u00.z; v00.w += u00.w;
-    v01.x += u01.x; v01.y += u01.y; v01.z += u01.z; v01.w += u01.w;
-    v10.x += u10.x; v10.y += u10.y; v10.z += u10.z; v10.w += u10.w;
-    v11.x += u11.x; v11.y += u11.y; v11.z += u11.z; v11.w += u11.w;
+    const float* src = (MODE == HEAD_CAT && k4 >= DU / 4) ? b : a;
+    const int kk = (MODE == HEAD_CAT && k4 >= DU / 4) ? k4 - DU / 4 : k4;
+    float4 v00 = __ldg(reinterpret_cast<const float4*>(src + o00) + kk), v01 = __ldg(reinterpret_cast<const float4*>(src + o01) + kk);
+    float4 v10 = __ldg(reinterpret_cast<const float4*>(src + o10) + kk), v11 = __ldg(reinterpret_cast<const float4*>(src + o11) + kk);
+    if (MODE == HEAD_ADD) {
+      const float4 u00 = __ldg(reinterpret_cast<const float4*>(b + o00) + kk), u01 = __ldg(reinterpret_cast<const float4*>(b + o01) + kk);
+      const float4 u10 = __ldg(reinterpret_cast<const float4*>(b + o10) + kk), u11 = __ldg(reinterpret_cast<const float4*>(b + o11) + kk);
+      v00.x += u00.x; v00.y += u00.y; v00.z += u00.z; v00.w += u00.w;
+      v01.x += u01.x; v01.y += u01.y; v01.z += u01.z; v01.w += u01.w;
+      v10.x += u10.x; v10.y += u10.y; v10.z += u10.z; v10.w += u10.w;
+      v11.x += u11.x; v11.y += u11.y; v11.z += u11.z; v11.w += u11.w;
+    }
     f[4 * k4 + 0] = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
     f[4 * k4 + 1] = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
     f[4 * k4 + 2] = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ a, 
     ss = fmaf(f[4 * k4 + 0], f[4 * k4 + 0], ss); ss = fmaf(f[4 * k4 + 1], f[4 * k4 + 1], ss);
     ss = fmaf(f[4 * k4 + 2], f[4 * k4 + 2], ss); ss = fmaf(f[4 * k4 + 3], f[4 * k4 + 3], ss);
   }
-  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  const float inv = normalize ? 1.0f / fmaxf(sqrtf(ss), 1e-12f) : 1.0f;   // cfg.TRAIN.EMBEDDING_NORMALIZATION (SEG.py:113-114)
   const size_t HW = size_t(H) * W;
   const size_t pix = size_t(oy) * W + ox;
   float* o = out_nchw + size_t(n) * D * HW + pix;
@@ -285,15 +295,20 @@ __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ a, 
   }
 }
 
-int launch_head(const float* a, const float* b, int N, int h, int w, int d, int H, int W, float* out_nchw, void* out_bf16,
-                cudaStream_t stream) {
+int launch_head(const float* a, const float* b, int mode, int normalize, int N, int h, int w, int d, int H, int W,
+                float* out_nchw, void* out_bf16, cudaStream_t stream) {
   const float sy = (H > 1) ? float(h - 1) / float(H - 1) : 0.f;
   const float sx = (W > 1) ? float(w - 1) / float(W - 1) : 0.f;
   const dim3 grid((W + 127) / 128, H, N);
   __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
-  if (d == 64) head_kernel<64><<<grid, 128, 0, stream>>>(a, b, h, w, H, W, sy, sx, out_nchw, ob);
-  else if (d == 128) head_kernel<128><<<grid, 128, 0, stream>>>(a, b, h, w, H, W, sy, sx, out_nchw, ob);
-  else return fail(UOC_ERR_UNSUPPORTED, "head supports num_units = 64 or 128");
+#define UOC_HEAD(DD, MM) head_kernel<DD, MM><<<grid, 128, 0, stream>>>(a, b, h, w, H, W, sy, sx, normalize, out_nchw, ob)
+  if (mode == HEAD_ADD && d == 64) UOC_HEAD(64, HEAD_ADD);
+  else if (mode == HEAD_ADD && d == 128) UOC_HEAD(128, HEAD_ADD);
+  else if (mode == HEAD_SINGLE && d == 64) UOC_HEAD(64, HEAD_SINGLE);
+  else if (mode == HEAD_SINGLE && d == 128) UOC_HEAD(128, HEAD_SINGLE);
+  else if (mode == HEAD_CAT && d == 128) UOC_HEAD(128, HEAD_CAT);
+  else return fail(UOC_ERR_UNSUPPORTED, "head supports 64 or 128 output channels (cat fusion: 2 x 64)");
+#undef UOC_HEAD
   UOC_CHECK_LAUNCH();
   return UOC_OK;
 }
@@ -327,32 +342,43 @@ namespace uoc {
 
 struct StemTcParams {
   const float* x[2];
-  const __nv_bfloat16* w[2];     // [64][192] bf16, k = (r*7 + s)*3 + c, zero padded
+  const float* x2[2];            // channels 3..5 (early fusion), else unused
+  const __nv_bfloat16* w[2];     // [64][KB*64] bf16, k = (r*7 + s)*CIN + c, zero padded
   const float* bias[2];
   __nv_bfloat16* y[2];
-  int N, H, W, Ho, Wo, tiles_x, tiles_y, tiles_per_group;
+  int N, H, W, Ho, Wo, tiles_x, tiles_y, tiles_per_group, groups;
   unsigned int* err;
 };
 
-constexpr int kStemK = 192;
 constexpr int kStemPatchH = 8 * 2 + 5;     // 21
 constexpr int kStemPatchW = 16 * 2 + 5;    // 37
 
-__global__ void __launch_bounds__(128, 2) stem_tc_kernel(StemTcParams p) {
+template <int CIN>
+struct StemTcCfg {
+  static constexpr int K = 49 * CIN;                 // 147 | 294
+  static constexpr int KB = (K + 63) / 64;           // 3 | 5 K-blocks of 64
+  static constexpr int NCH = (K + 7) / 8;            // 19 | 37 16-byte chunks per im2col row that hold data
+  static constexpr int kSmem = 1024 + KB * 16384 + KB * 8192 + CIN * kStemPatchH * 38 * 4 + 64;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(StemTcParams p) {
+  using Cfg = StemTcCfg<CIN>;
+  constexpr int KB = Cfg::KB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_s = smem;                                  // 3 x 16 KB : [kb][128 rows][128 B]
-  uint8_t* w_s = smem + 3 * 16384;                      // 3 x  8 KB : [kb][ 64 rows][128 B]
-  float* patch = reinterpret_cast<float*>(w_s + 3 * 8192);          // [3][21][38]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(patch + 3 * kStemPatchH * 38);
+  uint8_t* a_s = smem;                                  // KB x 16 KB : [kb][128 rows][128 B]
+  uint8_t* w_s = smem + KB * 16384;                     // KB x  8 KB : [kb][ 64 rows][128 B]
+  float* patch = reinterpret_cast<float*>(w_s + KB * 8192);         // [CIN][21][38]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(patch + CIN * kStemPatchH * 38);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int total_tiles = 2 * p.tiles_per_group;        // both branches
+  const int total_tiles = p.groups * p.tiles_per_group;
   int cur_g = -1;
 
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   if (warp == 0) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
-  for (int e = tid; e < 3 * 16384 / 16; e += 128) reinterpret_cast<uint4*>(a_s)[e] = make_uint4(0u, 0u, 0u, 0u);
+  for (int e = tid; e < KB * 16384 / 16; e += 128) reinterpret_cast<uint4*>(a_s)[e] = make_uint4(0u, 0u, 0u, 0u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -368,8 +394,8 @@ __global__ void __launch_bounds__(128, 2) stem_tc_kernel(StemTcParams p) {
     const int n = r / p.tiles_y;
     if (g != cur_g) {                                   // (re)load this branch's weights, K-major 128B-swizzled rows
       const uint4* wg = reinterpret_cast<const uint4*>(p.w[g]);
-      for (int e = tid; e < 64 * 24; e += 128) {
-        const int row = e / 24, j = e - row * 24;
+      for (int e = tid; e < 64 * KB * 8; e += 128) {
+        const int row = e / (KB * 8), j = e - row * (KB * 8);
         const int kb = j >> 3, cc = j & 7;
         *reinterpret_cast<uint4*>(w_s + kb * 8192 + row * 128 + ((cc ^ (row & 7)) << 4)) = __ldg(wg + e);
       }
@@ -377,30 +403,30 @@ __global__ void __launch_bounds__(128, 2) stem_tc_kernel(StemTcParams p) {
     }
     // stage the fp32 input patch
     const int iy0 = ty * 16 - 3, ix0 = tx * 32 - 3;
-    const float* xg = p.x[g] + size_t(n) * 3 * p.H * p.W;
-    for (int e = tid; e < 3 * kStemPatchH * kStemPatchW; e += 128) {
+    for (int e = tid; e < CIN * kStemPatchH * kStemPatchW; e += 128) {
       const int c = e / (kStemPatchH * kStemPatchW);
       const int rem = e - c * kStemPatchH * kStemPatchW;
       const int py = rem / kStemPatchW, px = rem - py * kStemPatchW;
       const int iy = iy0 + py, ix = ix0 + px;
+      const float* xg = (c < 3 ? p.x[g] : p.x2[g]) + size_t(n) * 3 * p.H * p.W;
       float v = 0.f;
-      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xg + (size_t(c) * p.H + iy) * p.W + ix);
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xg + (size_t(c < 3 ? c : c - 3) * p.H + iy) * p.W + ix);
       patch[(c * kStemPatchH + py) * 38 + px] = v;
     }
     __syncthreads();
-    // im2col row of pixel `tid` -> 19 chunks of 8 bf16 (k = 0..151; k >= 147 is zero)
+    // im2col row of pixel `tid` -> NCH chunks of 8 bf16 (k >= K is zero)
     {
       const int ly = tid >> 4, lx = tid & 15;
       const float* pb = patch + (ly * 2) * 38 + lx * 2;
       float vals[8];
 #pragma unroll
-      for (int j = 0; j < 19; ++j) {
+      for (int j = 0; j < Cfg::NCH; ++j) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int k = j * 8 + q;                 // compile-time after unrolling: tap / channel offsets fold to constants
           float v = 0.f;
-          if (k < 147) {
-            const int tap = k / 3, c = k - tap * 3;
+          if (k < Cfg::K) {
+            const int tap = k / CIN, c = k - tap * CIN;
             const int kr = tap / 7, ks = tap - kr * 7;
             v = pb[(c * kStemPatchH + kr) * 38 + ks];
           }
@@ -419,7 +445,7 @@ __global__ void __launch_bounds__(128, 2) stem_tc_kernel(StemTcParams p) {
         tc_fence_after();
         constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
 #pragma unroll
-        for (int kb = 0; kb < 3; ++kb) {
+        for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t ad = make_smem_desc_sw128(a_addr + kb * 16384 + ks * 32, 16, 1024);
@@ -466,14 +492,33 @@ __global__ void __launch_bounds__(128, 2) stem_tc_kernel(StemTcParams p) {
   if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
-int launch_stem_tc(const StemGroup* g, const void* const* w_bf16, int groups, int N, int H, int W, cudaStream_t stream) {
-  if (groups != 2) return fail(UOC_ERR_INVALID, "stem_tc expects both branches");
+template <int CIN>
+static int launch_stem_tc_t(const StemTcParams& p, cudaStream_t stream) {
+  using Cfg = StemTcCfg<CIN>;
+  static bool attr = false;
+  if (!attr) {
+    UOC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr = true;
+  }
+  const int per_sm = (CIN == 3) ? 2 : 1;
+  int grid = per_sm * (sm_count() > 0 ? sm_count() : 148);
+  if (grid > p.groups * p.tiles_per_group) grid = p.groups * p.tiles_per_group;
+  stem_tc_kernel<CIN><<<grid, 128, Cfg::kSmem, stream>>>(p);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
+int launch_stem_tc(const StemGroup* g, const void* const* w_bf16, int groups, int cin, int N, int H, int W, cudaStream_t stream) {
+  if (groups < 1 || groups > 2) return fail(UOC_ERR_INVALID, "stem_tc: 1 or 2 branches");
+  if (cin != 3 && cin != 6) return fail(UOC_ERR_UNSUPPORTED, "stem supports 3 or 6 input channels");
   StemTcParams p;
   for (int i = 0; i < 2; ++i) {
-    p.x[i] = g[i].x;
-    p.w[i] = static_cast<const __nv_bfloat16*>(w_bf16[i]);
-    p.bias[i] = g[i].bias;
-    p.y[i] = static_cast<__nv_bfloat16*>(g[i].y);
+    const int j = i < groups ? i : 0;
+    p.x[i] = g[j].x;
+    p.x2[i] = g[j].x2;
+    p.w[i] = static_cast<const __nv_bfloat16*>(w_bf16[j]);
+    p.bias[i] = g[j].bias;
+    p.y[i] = static_cast<__nv_bfloat16*>(g[j].y);
   }
   p.N = N; p.H = H; p.W = W;
   p.Ho = (H + 6 - 7) / 2 + 1;
@@ -481,19 +526,10 @@ int launch_stem_tc(const StemGroup* g, const void* const* w_bf16, int groups, in
   p.tiles_x = (p.Wo + 15) / 16;
   p.tiles_y = (p.Ho + 7) / 8;
   p.tiles_per_group = N * p.tiles_y * p.tiles_x;
+  p.groups = groups;
   p.err = device_error_word();
   if (!p.err) return fail(UOC_ERR_CUDA, "no device error word");
-  const int smem = 1024 + 3 * 16384 + 3 * 8192 + 3 * kStemPatchH * 38 * 4 + 64;
-  static bool attr = false;
-  if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
-  int grid = 2 * (sm_count() > 0 ? sm_count() : 148);
-  if (grid > 2 * p.tiles_per_group) grid = 2 * p.tiles_per_group;
-  stem_tc_kernel<<<grid, 128, smem, stream>>>(p);
-  UOC_CHECK_LAUNCH();
-  return UOC_OK;
+  return cin == 3 ? launch_stem_tc_t<3>(p, stream) : launch_stem_tc_t<6>(p, stream);
 }
 
 }  // namespace uoc

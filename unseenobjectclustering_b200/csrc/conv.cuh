@@ -42,22 +42,26 @@ int launch_conv_auto(const ConvProblem& p, cudaStream_t stream);
 // fp32-accumulate SIMT validation convolution, same interface and data types
 int launch_conv_simt(const ConvProblem& p, cudaStream_t stream);
 
-// stem: conv 7x7 s2 p3 (Cin = 3, fp32 NCHW input) + folded BN + ReLU -> bf16 NHWC [N][H/2][W/2][64]
+// stem: conv 7x7 s2 p3 (Cin = 3, or 6 for early fusion; fp32 NCHW input) + folded BN + ReLU -> bf16 NHWC [N][H/2][W/2][64]
 struct StemGroup {
-  const float* x;         // [N][3][H][W] fp32
-  const float* w;         // [64][7*7*3] fp32, k = (r*7 + s)*3 + c, BN folded
+  const float* x;         // [N][3][H][W] fp32 (channels 0..2)
+  const float* x2;        // [N][3][H][W] fp32 (channels 3..5 when cin == 6: torch.cat((img, depth), 1), SEG.py:101-103), else unused
+  const float* w;         // [64][7*7*cin] fp32, k = (r*7 + s)*cin + c, BN folded
   const float* bias;      // [64]
   void* y;                // [N][H/2][W/2][64] bf16
 };
-int launch_stem(const StemGroup* g, int groups, int N, int H, int W, cudaStream_t stream);
-// same on tcgen05 (im2col tile built in shared memory); w_bf16[g]: [64][192] bf16 zero-padded, BN folded
-int launch_stem_tc(const StemGroup* g, const void* const* w_bf16, int groups, int N, int H, int W, cudaStream_t stream);
+int launch_stem(const StemGroup* g, int groups, int cin, int N, int H, int W, cudaStream_t stream);
+// same on tcgen05 (im2col tile built in shared memory); w_bf16[g]: [64][192 (cin 3) | 320 (cin 6)] bf16 zero-padded, BN folded
+int launch_stem_tc(const StemGroup* g, const void* const* w_bf16, int groups, int cin, int N, int H, int W, cudaStream_t stream);
 // maxpool 3x3 s2 p1 on bf16 NHWC, C = 64
 int launch_maxpool(const void* const* x, void* const* y, int groups, int N, int H, int W, int C, cudaStream_t stream);
-// head: (trunk_rgb + trunk_depth) [N][h][w][d] fp32 -> bilinear x8 (align_corners) -> L2 normalise
+// head: trunk outputs [N][h][w][du] fp32 -> bilinear x8 (align_corners) -> (optional) L2 normalise
 //       -> fp32 NCHW [N][d][H][W]  and (optional) bf16 pixel-major [N][H*W][d]
-int launch_head(const float* a, const float* b, int N, int h, int w, int d, int H, int W, float* out_nchw,
-                void* out_bf16, cudaStream_t stream);
+//   mode HEAD_ADD: f = a + b (d = du; SEG.py:108)   HEAD_SINGLE: f = a (COLOR / DEPTH / early fusion; b unused)
+//   mode HEAD_CAT: f = cat(a, b) over channels (d = 2 du; SEG.py:110)
+enum { HEAD_ADD = 0, HEAD_SINGLE = 1, HEAD_CAT = 2 };
+int launch_head(const float* a, const float* b, int mode, int normalize, int N, int h, int w, int d, int H, int W,
+                float* out_nchw, void* out_bf16, cudaStream_t stream);
 // [N][h][w][d] fp32 NHWC -> [N][d][h][w] fp32 NCHW (debug / test hook)
 int launch_nhwc_to_nchw(const float* in, int N, int h, int w, int d, float* out, cudaStream_t stream);
 

@@ -30,6 +30,7 @@ namespace {
 constexpr int kTile = 128;          // points per tile
 constexpr int kThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-5 weight group 0 (even tiles), warps 6-9 group 1 (odd tiles)
 constexpr int kBoxBytes = 128 * 128;  // one [128 x 64ch] bf16 box, 16 KiB
+constexpr int kDefaultPoly = 0;       // weights per 32-column chunk evaluated on the FMA pipe (UOC_LOOP_POLY overrides: 0 / 8 / 12)
 
 template <int D>
 struct MsCfg {
@@ -294,7 +295,9 @@ __device__ __forceinline__ bool poll_flag(const unsigned int* p, unsigned int ta
   return false;
 }
 
-template <int D>
+// POLY: of the 32 weights a thread computes per 32-column chunk, POLY are evaluated with ex2_poly on the FMA pipe and
+// the rest with MUFU.EX2, interleaved (the two pipes run concurrently; UOC_LOOP_POLY selects the split).
+template <int D, int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float* Z, float* partials,
                                unsigned int* done, unsigned int* rowflag, int m, long long n, float c1, int P,
@@ -460,8 +463,13 @@ meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float
           uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(cur[2 * e]), c1, c0));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(cur[2 * e + 1]), c1, c0));
+            const float x0 = fmaf(__uint_as_float(cur[2 * e]), c1, c0);
+            const float x1 = fmaf(__uint_as_float(cur[2 * e + 1]), c1, c0);
+            // spread the polynomial evaluations evenly over the chunk so that both pipes stay busy
+            const bool poly0 = ((2 * e) * POLY) / 32 != ((2 * e + 1) * POLY) / 32;
+            const bool poly1 = ((2 * e + 1) * POLY) / 32 != ((2 * e + 2) * POLY) / 32;
+            const float p0 = poly0 ? ex2_poly(x0) : ex2_approx(x0);
+            const float p1 = poly1 ? ex2_poly(x1) : ex2_approx(x1);
             pk[e] = pack_bf16x2_trunc(p0, p1);
           }
           tmem_st_32x32b_x16(sa + c * 16, pk);
@@ -513,11 +521,22 @@ meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float
         float acc[D / 32];
 #pragma unroll
         for (int qq = 0; qq < D / 32; ++qq) acc[qq] = 0.f;
-#pragma unroll 4
-        for (int part = w8; part < P; part += 8) {
-          const float* src = partials + ((size_t(b) * P + part) * 128 + r) * D;
+        // batches of kRedBatch independent loads per thread: the whole row costs ~2 L2 round trips instead of one per
+        // 4 partials (fixed summation order -> deterministic)
+        constexpr int kRedBatch = (D == 64) ? 10 : 5;
+        for (int part0 = w8; part0 < P; part0 += 8 * kRedBatch) {
+          float v[kRedBatch][D / 32];
 #pragma unroll
-          for (int qq = 0; qq < D / 32; ++qq) acc[qq] += __ldcg(src + lane + 32 * qq);
+          for (int i = 0; i < kRedBatch; ++i) {
+            const int part = part0 + 8 * i;
+            const float* src = partials + ((size_t(b) * P + (part < P ? part : w8)) * 128 + r) * D;
+#pragma unroll
+            for (int qq = 0; qq < D / 32; ++qq) v[i][qq] = (part < P) ? __ldcg(src + lane + 32 * qq) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < kRedBatch; ++i)
+#pragma unroll
+            for (int qq = 0; qq < D / 32; ++qq) acc[qq] += v[i][qq];
         }
 #pragma unroll
         for (int qq = 0; qq < D / 32; ++qq) s_part[w8][lane + 32 * qq] = acc[qq];
@@ -548,13 +567,13 @@ meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-template <int D>
+template <int D, int POLY>
 int launch_persistent(const CUtensorMap& tmap, const ClusterShape& s, const ClusterWorkspace& w, float* Z, int P,
                       float kappa, int iters, cudaStream_t stream) {
   using Cfg = MsCfg<D>;
   static bool attr = false;
   if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(meanshift_tc_persistent_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UOC_CUDA(cudaFuncSetAttribute(meanshift_tc_persistent_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr = true;
   }
@@ -574,7 +593,7 @@ int launch_persistent(const CUtensorMap& tmap, const ClusterShape& s, const Clus
     UOC_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * 16 * iters, stream));
   }
   void* args[] = {&tm, &Z, &partials, &done, &rowflag, &m, &n, &c1, &P, &iters, &err, &trace};
-  UOC_CUDA(cudaLaunchCooperativeKernel(meanshift_tc_persistent_kernel<D>, dim3(P, s.batch), dim3(kThreads), args,
+  UOC_CUDA(cudaLaunchCooperativeKernel(meanshift_tc_persistent_kernel<D, POLY>, dim3(P, s.batch), dim3(kThreads), args,
                                        Cfg::kSmemBytes, stream));
   count_launch();
   if (want_trace) {
@@ -621,9 +640,18 @@ int launch_hill_climb_tc(const __nv_bfloat16* xb, const ClusterShape& s, const C
     int Pp = P;
     if (sms > 0 && (long long)Pp * s.batch > sms) Pp = sms / s.batch;
     if (Pp < 1 || iters < 1 || w.slot_bytes < 256 * size_t(s.batch)) persistent = false;
-    if (persistent)
-      return (s.d == 64) ? launch_persistent<64>(tmap, s, w, Z, Pp, kappa, iters, stream)
-                         : launch_persistent<128>(tmap, s, w, Z, Pp, kappa, iters, stream);
+    if (persistent) {
+      int poly = kDefaultPoly;
+      if (const char* e = getenv("UOC_LOOP_POLY")) poly = atoi(e);
+      if (s.d == 64) {
+        if (poly >= 12) return launch_persistent<64, 12>(tmap, s, w, Z, Pp, kappa, iters, stream);
+        if (poly >= 8) return launch_persistent<64, 8>(tmap, s, w, Z, Pp, kappa, iters, stream);
+        return launch_persistent<64, 0>(tmap, s, w, Z, Pp, kappa, iters, stream);
+      }
+      if (poly >= 12) return launch_persistent<128, 12>(tmap, s, w, Z, Pp, kappa, iters, stream);
+      if (poly >= 8) return launch_persistent<128, 8>(tmap, s, w, Z, Pp, kappa, iters, stream);
+      return launch_persistent<128, 0>(tmap, s, w, Z, Pp, kappa, iters, stream);
+    }
   }
   for (int it = 0; it < iters; ++it) {
     rc = (s.d == 64) ? launch_iter<64>(tmap, s, w, Z, P, kappa, stream) : launch_iter<128>(tmap, s, w, Z, P, kappa, stream);

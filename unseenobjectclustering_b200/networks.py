@@ -1,5 +1,11 @@
-"""Host-side mirror of the reference's network factory for the RGB-D add-fusion ResNet34-8s
-(lib/networks/SEG.py:173-176 `seg_resnet34_8s_embedding`, class SEGNET :26-119).
+"""Host-side mirror of the reference's network factories for the ResNet34-8s embedding network
+(lib/networks/SEG.py:173-181 `seg_resnet34_8s_embedding`, `seg_resnet34_8s_embedding_early`, class SEGNET :26-119).
+
+The reference SEGNET reads cfg.INPUT / cfg.TRAIN.FUSION_TYPE / cfg.TRAIN.EMBEDDING_NORMALIZATION at
+construction (SEG.py:34-38); the factories here read the same three settings from the module-level
+CONFIG dict (defaults = the shipped rgbd_add configs; `configure(cfg)` copies them from a reference
+cfg object), or take them as keyword arguments.  Variants: INPUT 'RGBD' | 'COLOR' | 'DEPTH';
+FUSION_TYPE 'add' | 'cat' | 'early' (SEG.py:97-110).
 
 The module keeps the weights as a reference-format state_dict (same keys, so reference
 checkpoints load unchanged and .state_dict()/.cuda()/DataParallel behave), and runs the forward
@@ -15,12 +21,32 @@ import torch.nn as nn
 from . import _lib
 from . import mean_shift as _ms
 
-__all__ = ["seg_resnet34_8s_embedding", "SEGNET_B200", "reference_state_dict_keys", "random_state_dict"]
+__all__ = ["seg_resnet34_8s_embedding", "seg_resnet34_8s_embedding_early", "SEGNET_B200", "reference_state_dict_keys",
+           "random_state_dict", "CONFIG", "configure"]
 
 _LAYERS = ((64, 3), (128, 4), (256, 6), (512, 3))
 
+# what SEGNET.__init__ reads from the reference's global cfg (SEG.py:34-38); defaults = experiments/cfgs/*rgbd_add*.yml
+CONFIG = {"INPUT": "RGBD", "FUSION_TYPE": "add", "EMBEDDING_NORMALIZATION": True}
 
-def reference_state_dict_keys(num_units=64):
+_INPUT_IDS = {"RGBD": 0, "COLOR": 1, "DEPTH": 2}
+_FUSION_IDS = {"add": 0, "cat": 1, "early": 2}
+
+
+def configure(cfg):
+    """Copy INPUT / TRAIN.FUSION_TYPE / TRAIN.EMBEDDING_NORMALIZATION from a reference cfg (lib/fcn/config.py)."""
+    CONFIG["INPUT"] = str(cfg.INPUT)
+    CONFIG["FUSION_TYPE"] = str(cfg.TRAIN.FUSION_TYPE)
+    CONFIG["EMBEDDING_NORMALIZATION"] = bool(cfg.TRAIN.EMBEDDING_NORMALIZATION)
+
+
+def _branches(input_type, fusion_type, in_channels):
+    """[(state-dict prefix, stem input channels)] of the trunks SEGNET builds (SEG.py:69-71)."""
+    two = input_type == "RGBD" and fusion_type != "early"
+    return [("fcn", in_channels)] + ([("fcn_depth", in_channels)] if two else [])
+
+
+def reference_state_dict_keys(num_units=64, input_type="RGBD", fusion_type="add", in_channels=3):
     """(key, shape) for every tensor of the reference module's state_dict, in its order
     (lib/networks/resnet.py:141-186: conv1, bn1, layer1..4, fc; num_batches_tracked included)."""
     out = []
@@ -29,9 +55,9 @@ def reference_state_dict_keys(num_units=64):
         out.extend([(p + ".weight", (c,)), (p + ".bias", (c,)), (p + ".running_mean", (c,)),
                     (p + ".running_var", (c,)), (p + ".num_batches_tracked", ())])
 
-    for top in ("fcn", "fcn_depth"):
+    for top, cin in _branches(input_type, fusion_type, in_channels):
         p = top + ".resnet34_8s."
-        out.append((p + "conv1.weight", (64, 3, 7, 7)))
+        out.append((p + "conv1.weight", (64, cin, 7, 7)))
         bn(p + "bn1", 64)
         inplanes = 64
         for li, (planes, blocks) in enumerate(_LAYERS, start=1):
@@ -50,7 +76,7 @@ def reference_state_dict_keys(num_units=64):
     return out
 
 
-def random_state_dict(num_units=64, seed=None):
+def random_state_dict(num_units=64, seed=None, input_type="RGBD", fusion_type="add", in_channels=3):
     """Random initialisation in the spirit of SEGNET._initialize_weights (SEG.py:77-85): xavier-normal
     convolutions, zero biases, BN weight 1 / bias 0 / running stats (0, 1)."""
     gen = torch.Generator()
@@ -59,7 +85,7 @@ def random_state_dict(num_units=64, seed=None):
     else:
         gen.seed()
     sd = {}
-    for k, shape in reference_state_dict_keys(num_units):
+    for k, shape in reference_state_dict_keys(num_units, input_type, fusion_type, in_channels):
         if k.endswith("num_batches_tracked"):
             sd[k] = torch.zeros((), dtype=torch.long)
         elif len(shape) == 4:
@@ -85,15 +111,27 @@ def _normalize_keys(data):
 
 
 class SEGNET_B200(nn.Module):
-    """Drop-in for the reference SEGNET built by seg_resnet34_8s_embedding (INPUT='RGBD',
-    FUSION_TYPE='add', cosine metric, EMBEDDING_NORMALIZATION=True).  forward(img, label, depth)
-    returns unit-norm features [N, num_units, H, W] float32 on the input's device."""
+    """Drop-in for the reference SEGNET built by seg_resnet34_8s_embedding[_early].  forward(img, label, depth)
+    returns features [N, C, H, W] float32 on the input's device (C = num_units, or 2 * num_units for cat
+    fusion; unit L2 norm over C when `normalize`)."""
 
-    def __init__(self, num_units=64, data=None, flags=0):
+    def __init__(self, num_units=64, data=None, flags=0, input_type=None, fusion_type=None, normalize=None,
+                 in_channels=3):
         super().__init__()
         self.num_units = int(num_units)
         self.flags = int(flags)
-        sd = random_state_dict(num_units)
+        self.input_type = str(CONFIG["INPUT"] if input_type is None else input_type)
+        self.fusion_type = str(CONFIG["FUSION_TYPE"] if fusion_type is None else fusion_type)
+        self.normalize = bool(CONFIG["EMBEDDING_NORMALIZATION"] if normalize is None else normalize)
+        self.in_channels = int(in_channels)
+        if self.input_type not in _INPUT_IDS or self.fusion_type not in _FUSION_IDS:
+            raise ValueError("INPUT must be RGBD / COLOR / DEPTH and FUSION_TYPE add / cat / early")
+        early = self.input_type == "RGBD" and self.fusion_type == "early"
+        if self.in_channels != (6 if early else 3):
+            raise ValueError("in_channels must be 6 for early fusion (seg_resnet34_8s_embedding_early) and 3 otherwise")
+        cat = self.input_type == "RGBD" and self.fusion_type == "cat"
+        self.feature_dim = 2 * self.num_units if cat else self.num_units
+        sd = random_state_dict(num_units, None, self.input_type, self.fusion_type, self.in_channels)
         if data is not None:
             given = _normalize_keys(data)
             for k, v in given.items():          # same filter as SEG.py:152: name and shape must match
@@ -160,21 +198,27 @@ class SEGNET_B200(nn.Module):
         arr = (_lib.WeightDesc * len(descs))(*descs)
         h = ctypes.c_void_p()
         with torch.cuda.device(device):
-            _lib.check(lib.uoc_backbone_create(ctypes.byref(h), arr, len(descs), self.num_units), "uoc_backbone_create")
+            _lib.check(lib.uoc_backbone_create_ex(ctypes.byref(h), arr, len(descs), self.num_units,
+                                                  _INPUT_IDS[self.input_type], _FUSION_IDS[self.fusion_type],
+                                                  int(self.normalize)), "uoc_backbone_create_ex")
         self._handle = h
         self._handle_dev = device
 
     def forward(self, img, label=None, depth=None):
-        if depth is None:
-            raise _lib.UocError("this module implements INPUT='RGBD' (image + depth); depth is required")
-        if not img.is_cuda:
+        need_img, need_depth = self.input_type != "DEPTH", self.input_type != "COLOR"
+        if need_depth and depth is None:
+            raise _lib.UocError("INPUT=%r needs the depth (XYZ) tensor" % self.input_type)
+        if need_img and img is None:
+            raise _lib.UocError("INPUT=%r needs the image tensor" % self.input_type)
+        lead = img if need_img else depth
+        if not lead.is_cuda:
             raise _lib.UocError("inputs must be CUDA tensors: there is no CPU path in this package")
-        dev = img.device
+        dev = lead.device
         self._ensure_handle(dev)
         lib = _lib.load()
-        img = img.detach().to(torch.float32).contiguous()
-        depth = depth.detach().to(device=dev, dtype=torch.float32).contiguous()
-        N, _, H, W = img.shape
+        img = img.detach().to(device=dev, dtype=torch.float32).contiguous() if need_img else None
+        depth = depth.detach().to(device=dev, dtype=torch.float32).contiguous() if need_depth else None
+        N, _, H, W = lead.shape
         with torch.cuda.device(dev):
             nbytes = lib.uoc_backbone_workspace_bytes(self._handle, N, H, W)
             sid = torch.cuda.current_stream(dev).cuda_stream       # one activation workspace per stream in flight
@@ -184,8 +228,8 @@ class SEGNET_B200(nn.Module):
                 self._ws_by_stream[sid] = self._ws
             off = (-self._ws.data_ptr()) % 1024
             ws_ptr = ctypes.c_void_p(self._ws.data_ptr() + off)
-            out = torch.empty((N, self.num_units, H, W), dtype=torch.float32, device=dev)
-            xb = torch.empty((N, H * W, self.num_units), dtype=torch.bfloat16, device=dev) if self.keep_bf16 else None
+            out = torch.empty((N, self.feature_dim, H, W), dtype=torch.float32, device=dev)
+            xb = torch.empty((N, H * W, self.feature_dim), dtype=torch.bfloat16, device=dev) if self.keep_bf16 else None
             st = lib.uoc_backbone_forward(self._handle, _lib.ptr(img), _lib.ptr(depth), N, H, W, _lib.ptr(out),
                                           _lib.ptr(xb), ws_ptr, self._ws.numel() - off, self.flags,
                                           _lib.stream_ptr(dev))
@@ -209,6 +253,16 @@ class SEGNET_B200(nn.Module):
         return out
 
 
-def seg_resnet34_8s_embedding(num_classes=2, num_units=64, data=None):
-    """Same signature as lib/networks/SEG.py:173-176."""
-    return SEGNET_B200(num_units=num_units, data=data)
+def seg_resnet34_8s_embedding(num_classes=2, num_units=64, data=None, **variant):
+    """Same signature as lib/networks/SEG.py:173-176 (in_channels=3).  The variant (INPUT, FUSION_TYPE,
+    EMBEDDING_NORMALIZATION) comes from CONFIG like the reference's from cfg, or from the keyword arguments
+    input_type= / fusion_type= / normalize=."""
+    return SEGNET_B200(num_units=num_units, data=data, in_channels=3, **variant)
+
+
+def seg_resnet34_8s_embedding_early(num_classes=2, num_units=64, data=None, **variant):
+    """Same signature as lib/networks/SEG.py:178-181: one trunk with a 6-channel stem on cat(img, depth)
+    (meaningful with INPUT='RGBD', FUSION_TYPE='early', which is the default here)."""
+    variant.setdefault("input_type", "RGBD")
+    variant.setdefault("fusion_type", "early")
+    return SEGNET_B200(num_units=num_units, data=data, in_channels=6, **variant)
