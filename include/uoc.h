@@ -49,7 +49,11 @@ enum {
   UOC_FLAG_LOOP_SIMT = 1,   /* mean-shift iterations on the fp32 SIMT validation kernel instead of tcgen05 */
   UOC_FLAG_CONV_SIMT = 2,   /* backbone convolutions on the fp32 SIMT validation kernel instead of tcgen05 */
   UOC_FLAG_SYNC_CHECK = 4,  /* synchronise the stream and read back the device error word before returning */
-  UOC_FLAG_FPS_FP32 = 8     /* seed selection re-reads the fp32 field in every pass (no bf16 screening pass) */
+  UOC_FLAG_FPS_FP32 = 8,    /* seed selection re-reads the fp32 field in every pass (no bf16 screening pass) */
+  UOC_FLAG_EUCLIDEAN = 16   /* metric='euclidean' (cfg.TRAIN.EMBEDDING_METRIC, lib/fcn/config.py:261; the euclidean branches
+                               of lib/utils/mean_shift.py:21-24,58-60,101-105,159-160,207-209): distances ||x - z||, weights
+                               exp(-kappa ||x - z||^2), update divided by max(sum of weights, 1).  X need not be unit norm.
+                               fp32 SIMT kernels (no tensor-core path); SURVEY section 8(f) rank 3. */
 };
 
 #define UOC_MAX_SEEDS 128   /* num_seeds upper bound: one tcgen05 M=128 accumulator tile */
@@ -115,12 +119,19 @@ UOC_API int uoc_hill_climb(const float* X, int64_t stride_b, int64_t stride_d, c
  * num_unique_out [batch] int32 = len(unique(seed labels)) (mean_shift.py:218). */
 UOC_API int uoc_label_seeds(const float* Z, int batch, int m, int d, float epsilon, int32_t* seed_labels_out,
                             int32_t* num_unique_out, uoc_stream_t stream);
+/* same with flags (UOC_FLAG_EUCLIDEAN: ||z_j - z_i|| <= epsilon, mean_shift.py:58-60) */
+UOC_API int uoc_label_seeds_ex(const float* Z, int batch, int m, int d, float epsilon, int flags, int32_t* seed_labels_out,
+                               int32_t* num_unique_out, uoc_stream_t stream);
 
 /* nearest-seed assignment + relabel (lib/utils/mean_shift.py:206-227): labels_out [batch,n] int32.
  * x_bf16 (optional): the bf16 pixel-major copy; when given the tensor-core pass with exactness certificate is used. */
 UOC_API int uoc_assign_labels(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n,
                               int d, int m, const float* Z, const int32_t* seed_labels, const int32_t* num_unique,
                               int32_t* labels_out, void* workspace, size_t workspace_bytes, uoc_stream_t stream);
+/* same with flags (UOC_FLAG_EUCLIDEAN: arg-min of ||x - z_j||, mean_shift.py:207-209; x_bf16 is ignored) */
+UOC_API int uoc_assign_labels_ex(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n,
+                                 int d, int m, const float* Z, const int32_t* seed_labels, const int32_t* num_unique,
+                                 int32_t* labels_out, void* workspace, size_t workspace_bytes, int flags, uoc_stream_t stream);
 
 /* fp32 planar [batch][d][n] -> bf16 pixel-major [batch][n][d] (the layout the tcgen05 loop streams). */
 UOC_API int uoc_pack_bf16(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d,

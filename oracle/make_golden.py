@@ -52,6 +52,36 @@ def gen_cluster(ref):
         print(name, "labels", np.unique(labels.numpy()).tolist())
 
 
+EUCLID_CASES = [
+    # name, H, W, d, objects, noise, seed, num_seeds, np_seed, scale (features are multiplied by it: not unit norm)
+    ("euclid_a", 32, 48, 64, 4, 0.02, 41, 100, 3, 1.0),
+    ("euclid_b", 30, 40, 64, 3, 0.03, 42, 60, 5, 1.5),
+    ("euclid_c", 24, 32, 128, 2, 0.02, 43, 100, 7, 1.0),
+]
+
+
+def gen_euclid(ref):
+    """metric='euclidean' (cfg.TRAIN.EMBEDDING_METRIC default, lib/fcn/config.py:261) through the
+    reference's own mean_shift functions."""
+    for name, H, W, d, K, noise, seed, m, npseed, scale in EUCLID_CASES:
+        feats, gt = O.synthetic_clustered_features(H, W, d, K, noise, seed)
+        feats = feats * scale
+        X = feats[0].view(d, -1).t()
+        np.random.seed(npseed)
+        first = np.random.randint(0, H * W)
+        np.random.seed(npseed)
+        labels, selected = ref.mean_shift.mean_shift_smart_init(X, kappa=20, num_seeds=m, max_iters=10, metric='euclidean')
+        np.random.seed(npseed)
+        seeds, sel2 = ref.mean_shift.select_smart_seeds(X, m, return_selected_indices=True, metric='euclidean')
+        assert torch.equal(sel2, selected)
+        seed_labels, Z = ref.mean_shift.mean_shift_with_seeds(X, seeds, 20, max_iters=10, metric='euclidean')
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), H=H, W=W, d=d, objects=K, noise=noise, seed=seed, scale=scale,
+                            num_seeds=m, first_index=first, features=feats.numpy(), gt=gt.numpy(),
+                            labels=labels.numpy(), selected=selected.numpy(), Z=Z.numpy(),
+                            seed_labels=seed_labels.numpy())
+        print(name, "labels", np.unique(labels.numpy()).tolist(), "seed labels", len(np.unique(seed_labels.numpy())))
+
+
 def gen_two_stage(ref):
     H, W = 96, 128
     feats, gt = O.synthetic_clustered_features(H, W, 64, 4, 0.05, seed=21)
@@ -174,3 +204,5 @@ if __name__ == "__main__":
         gen_input_prep(ref)
     if not only or "variants" in only:
         gen_variants(ref)
+    if not only or "euclid" in only:
+        gen_euclid(ref)

@@ -44,8 +44,24 @@ def label_mode(values):
     return int(vals[np.argmax(counts)])
 
 
-def label_seeds(Z, epsilon):
-    """lib/utils/mean_shift.py:41-76 (cosine branch).  Greedy, order dependent labelling of the
+def ball_kernel(Z, X, kappa, metric="cosine"):
+    """lib/utils/mean_shift.py:11-27, both branches: euclidean W = exp(-kappa * ||z - x||^2) with the norm taken
+    first and squared afterwards (:22-24, materialises [m, n, d]); cosine W = exp(kappa * Z X^T) (:26)."""
+    if metric == "euclidean":
+        distance = torch.norm(Z.unsqueeze(1) - X.unsqueeze(0), dim=2)
+        return torch.exp(-kappa * torch.pow(distance, 2))
+    return cosine_kernel(Z, X, kappa)
+
+
+def _seed_distances(Zall, z, metric):
+    """distance of every row of Zall to the single row z ([1,d]): mean_shift.py:58-62 / :159-162 / :180-184."""
+    if metric == "euclidean":
+        return torch.norm(Zall.unsqueeze(1) - z.unsqueeze(0), dim=2)[:, 0]
+    return 0.5 * (1 - torch.mm(Zall, z.t()))[:, 0]
+
+
+def label_seeds(Z, epsilon, metric="cosine"):
+    """lib/utils/mean_shift.py:41-76.  Greedy, order dependent labelling of the
     converged seeds: every still-unlabelled seed i claims all seeds within cosine distance epsilon
     (fp32 `<=`); the claimed set takes the mode of its existing labels if any member is already
     labelled, else a fresh label; the WHOLE claimed set is overwritten."""
@@ -55,7 +71,7 @@ def label_seeds(Z, epsilon):
     for i in range(m):
         if labels[i] != -1:
             continue
-        dist = 0.5 * (1 - torch.mm(Z, Z[i:i + 1].t()))[:, 0]
+        dist = _seed_distances(Z, Z[i:i + 1], metric)
         comp = dist <= epsilon
         current = labels[comp]
         if torch.unique(current).shape[0] > 1:
@@ -68,17 +84,20 @@ def label_seeds(Z, epsilon):
     return labels
 
 
-def hill_climb(X, Z, kappa, max_iters):
-    """lib/utils/mean_shift.py:79-109 (cosine branch).  max_iters fixed-count mean-shift updates
-    Z <- normalize_rows(exp(kappa Z X^T) X); no convergence test."""
+def hill_climb(X, Z, kappa, max_iters, metric="cosine"):
+    """lib/utils/mean_shift.py:79-109.  max_iters fixed-count mean-shift updates, no convergence test:
+    cosine Z <- normalize_rows(exp(kappa Z X^T) X) (:107); euclidean Z <- (W X) / clamp(W.sum(1), min=1) (:101-105)."""
     for _ in range(max_iters):
-        W = cosine_kernel(Z, X, kappa)
-        Z = F.normalize(torch.mm(W, X), p=2, dim=1)
+        W = ball_kernel(Z, X, kappa, metric)
+        if metric == "euclidean":
+            Z = torch.mm(W, X) / torch.clamp(W.sum(dim=1).unsqueeze(1), min=1.0)
+        else:
+            Z = F.normalize(torch.mm(W, X), p=2, dim=1)
     return Z
 
 
-def select_seeds(X, num_seeds, first_index):
-    """lib/utils/mean_shift.py:128-189 (cosine branch).  Farthest point sampling.  `first_index`
+def select_seeds(X, num_seeds, first_index, metric="cosine"):
+    """lib/utils/mean_shift.py:128-189.  Farthest point sampling (euclidean: ||X - seed||, :159-160,:181-182).  `first_index`
     is the value the reference draws with np.random.randint(0, n) (:155).  Returns
     (seeds [m,d], selected_indices [m] int64)."""
     n, d = X.shape
@@ -87,21 +106,29 @@ def select_seeds(X, num_seeds, first_index):
     distances = torch.empty((n, num_seeds))
     selected[0] = int(first_index)
     seeds[0] = X[int(first_index)]
-    distances[:, 0] = 0.5 * (1 - torch.mm(X, seeds[0].unsqueeze(1))[:, 0])
+    def column(seed):
+        if metric == "euclidean":
+            return torch.norm(X - seed.unsqueeze(0), dim=1)
+        return 0.5 * (1 - torch.mm(X, seed.unsqueeze(1))[:, 0])
+
+    distances[:, 0] = column(seeds[0])
     for i in range(1, num_seeds):
         nearest = torch.min(distances[:, :i], dim=1)[0]
         idx = torch.argmax(nearest)
         selected[i] = idx
         seeds[i] = X[idx]
-        distances[:, i] = 0.5 * (1 - torch.mm(X, seeds[i].unsqueeze(1))[:, 0])
+        distances[:, i] = column(seeds[i])
     return seeds, selected
 
 
-def assign_and_relabel(X, Z, seed_labels):
+def assign_and_relabel(X, Z, seed_labels, metric="cosine"):
     """lib/utils/mean_shift.py:206-227.  Nearest-seed assignment (argmin of 0.5(1 - x.z), first
     minimum), then swap label 0 with the most populated label.  Reproduces the histogram quirk:
     counts exist only for labels in range(len(unique(seed_labels)))."""
-    dist = 0.5 * (1 - torch.mm(X, Z.t()))
+    if metric == "euclidean":                                   # mean_shift.py:207-209
+        dist = torch.norm(X.unsqueeze(1) - Z.unsqueeze(0), dim=2)
+    else:
+        dist = 0.5 * (1 - torch.mm(X, Z.t()))
     closest = torch.argmin(dist, dim=1)
     labels = seed_labels[closest]
     num = len(torch.unique(seed_labels))
@@ -118,31 +145,31 @@ def assign_and_relabel(X, Z, seed_labels):
 
 
 def mean_shift_smart_init(X, kappa=KAPPA, num_seeds=NUM_SEEDS, max_iters=MAX_ITERS, first_index=None,
-                          return_all=False):
+                          return_all=False, metric="cosine"):
     """lib/utils/mean_shift.py:192-229.  X: [n,d] unit rows (any strides).  `first_index` None ->
     draw it from numpy's global RNG exactly like the reference (:155)."""
     n = X.shape[0]
     if first_index is None:
         first_index = np.random.randint(0, n)
-    seeds, selected = select_seeds(X, num_seeds, first_index)
-    Z = hill_climb(X, seeds, kappa, max_iters)
-    seed_labels = label_seeds(Z, 2 * EMBEDDING_ALPHA)          # mean_shift.py:123
-    labels = assign_and_relabel(X, Z, seed_labels)
+    seeds, selected = select_seeds(X, num_seeds, first_index, metric)
+    Z = hill_climb(X, seeds, kappa, max_iters, metric)
+    seed_labels = label_seeds(Z, 2 * EMBEDDING_ALPHA, metric)  # mean_shift.py:123
+    labels = assign_and_relabel(X, Z, seed_labels, metric)
     if return_all:
         return labels, selected, seeds, Z, seed_labels
     return labels, selected
 
 
-def clustering_features(features, num_seeds=NUM_SEEDS, first_indices=None):
+def clustering_features(features, num_seeds=NUM_SEEDS, first_indices=None, metric="cosine"):
     """lib/fcn/test_dataset.py:44-59.  features [N,C,H,W] -> (labels float32 [N,H,W] CPU,
-    list of N int64 [num_seeds] tensors)."""
+    list of N int64 [num_seeds] tensors).  metric = cfg.TRAIN.EMBEDDING_METRIC (:45)."""
     N, C, H, W = features.shape
     out = torch.zeros((N, H, W))
     picked = []
     for j in range(N):
         X = features[j].reshape(C, -1).t()
         fi = None if first_indices is None else int(first_indices[j])
-        labels, sel = mean_shift_smart_init(X, KAPPA, num_seeds, MAX_ITERS, fi)
+        labels, sel = mean_shift_smart_init(X, KAPPA, num_seeds, MAX_ITERS, fi, metric=metric)
         out[j] = labels.view(H, W)
         picked.append(sel)
     return out, picked

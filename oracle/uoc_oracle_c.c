@@ -30,9 +30,21 @@ static float dot_chain(const float* a, int64_t sa, const float* b, int64_t sb, i
   return acc;
 }
 
+/* metric 0 = cosine: 0.5f * (1 - dot chain);  metric 1 = euclidean (the 'euclidean' branches of mean_shift.py:21-24,
+ * 58-60,159-160,207-209): sqrtf of the chain acc = fmaf(t, t, acc), t = a_k - b_k. */
+static float distance(const float* a, int64_t sa, const float* b, int64_t sb, int d, int metric) {
+  if (metric == 0) return 0.5f * (1.0f - dot_chain(a, sa, b, sb, d));
+  float acc = 0.0f;
+  for (int k = 0; k < d; ++k) {
+    const float t = a[k * sa] - b[k * sb];
+    acc = fmaf(t, t, acc);
+  }
+  return sqrtf(acc);
+}
+
 /* mean_shift.py:128-189.  selected[m], seeds[m*d]. */
-int uoc_oracle_select_seeds(const float* X, int64_t n, int d, int64_t stride_d, int m, int64_t first,
-                            int64_t* selected, float* seeds) {
+int uoc_oracle_select_seeds_metric(const float* X, int64_t n, int d, int64_t stride_d, int m, int64_t first,
+                                   int64_t* selected, float* seeds, int metric) {
   if (first < 0 || first >= n) return 1;
   float* r = (float*)malloc(sizeof(float) * (size_t)n);
   float* s = (float*)malloc(sizeof(float) * (size_t)d);
@@ -44,7 +56,7 @@ int uoc_oracle_select_seeds(const float* X, int64_t n, int d, int64_t stride_d, 
     if (i + 1 == m) break;
 #pragma omp parallel for schedule(static)
     for (int64_t p = 0; p < n; ++p) {
-      const float dist = 0.5f * (1.0f - dot_chain(X + p, stride_d, s, 1, d));
+      const float dist = distance(X + p, stride_d, s, 1, d, metric);
       r[p] = (i == 0) ? dist : (dist < r[p] ? dist : r[p]);       /* running min == min over columns [:i+1] (:174) */
     }
     float best = r[0];
@@ -58,8 +70,13 @@ int uoc_oracle_select_seeds(const float* X, int64_t n, int d, int64_t stride_d, 
   return 0;
 }
 
+int uoc_oracle_select_seeds(const float* X, int64_t n, int d, int64_t stride_d, int m, int64_t first,
+                            int64_t* selected, float* seeds) {
+  return uoc_oracle_select_seeds_metric(X, n, d, stride_d, m, first, selected, seeds, 0);
+}
+
 /* mean_shift.py:41-76 + :30-38.  Z [m][d] row-major.  labels[m]; returns len(unique(labels)). */
-int uoc_oracle_label_seeds(const float* Z, int m, int d, float eps, int32_t* labels) {
+int uoc_oracle_label_seeds_metric(const float* Z, int m, int d, float eps, int32_t* labels, int metric) {
   unsigned char* comp = (unsigned char*)malloc((size_t)m);
   int* cnt = (int*)malloc(sizeof(int) * (size_t)(m + 1));
   for (int j = 0; j < m; ++j) labels[j] = -1;
@@ -69,7 +86,7 @@ int uoc_oracle_label_seeds(const float* Z, int m, int d, float eps, int32_t* lab
     int any = 0;
     for (int l = 0; l < K; ++l) cnt[l] = 0;
     for (int j = 0; j < m; ++j) {
-      const float dist = 0.5f * (1.0f - dot_chain(Z + (size_t)j * d, 1, Z + (size_t)i * d, 1, d));
+      const float dist = distance(Z + (size_t)j * d, 1, Z + (size_t)i * d, 1, d, metric);
       comp[j] = dist <= eps;
       if (comp[j] && labels[j] != -1) { cnt[labels[j]] += 1; any = 1; }
     }
@@ -93,15 +110,19 @@ int uoc_oracle_label_seeds(const float* Z, int m, int d, float eps, int32_t* lab
   return uniq;
 }
 
+int uoc_oracle_label_seeds(const float* Z, int m, int d, float eps, int32_t* labels) {
+  return uoc_oracle_label_seeds_metric(Z, m, d, eps, labels, 0);
+}
+
 /* mean_shift.py:206-227.  labels_out[n]. */
-int uoc_oracle_assign(const float* X, int64_t n, int d, int64_t stride_d, const float* Z, int m,
-                      const int32_t* seed_labels, int num_unique, int32_t* labels_out) {
+int uoc_oracle_assign_metric(const float* X, int64_t n, int d, int64_t stride_d, const float* Z, int m,
+                             const int32_t* seed_labels, int num_unique, int32_t* labels_out, int metric) {
 #pragma omp parallel for schedule(static)
   for (int64_t p = 0; p < n; ++p) {
     float best = 0.f;
     int bj = 0;
     for (int j = 0; j < m; ++j) {
-      const float dist = 0.5f * (1.0f - dot_chain(X + p, stride_d, Z + (size_t)j * d, 1, d));
+      const float dist = distance(X + p, stride_d, Z + (size_t)j * d, 1, d, metric);
       if (j == 0 || dist < best) { best = dist; bj = j; }
     }
     labels_out[p] = seed_labels[bj];
@@ -122,30 +143,58 @@ int uoc_oracle_assign(const float* X, int64_t n, int d, int64_t stride_d, const 
   return 0;
 }
 
-/* mean_shift.py:79-109 in double precision (tolerance oracle for the tensor-core loop). Z [m][d] in/out. */
-int uoc_oracle_hill_climb(const float* X, int64_t n, int d, int64_t stride_d, float* Z, int m, float kappa, int iters) {
+int uoc_oracle_assign(const float* X, int64_t n, int d, int64_t stride_d, const float* Z, int m,
+                      const int32_t* seed_labels, int num_unique, int32_t* labels_out) {
+  return uoc_oracle_assign_metric(X, n, d, stride_d, Z, m, seed_labels, num_unique, labels_out, 0);
+}
+
+/* mean_shift.py:79-109 in double precision (tolerance oracle for the tensor-core loop). Z [m][d] in/out.
+ * metric 1: weights exp(-kappa ||x - z||^2), rows divided by max(sum of weights, 1) (:21-24, :101-105). */
+int uoc_oracle_hill_climb_metric(const float* X, int64_t n, int d, int64_t stride_d, float* Z, int m, float kappa, int iters,
+                                 int metric) {
   double* acc = (double*)malloc(sizeof(double) * (size_t)m * d);
-  if (!acc) return 2;
+  double* wsum = (double*)malloc(sizeof(double) * (size_t)m);
+  if (!acc || !wsum) return 2;
   for (int it = 0; it < iters; ++it) {
 #pragma omp parallel for schedule(static)
     for (int j = 0; j < m; ++j) {
       double* a = acc + (size_t)j * d;
       for (int k = 0; k < d; ++k) a[k] = 0.0;
+      double ws = 0.0;
       for (int64_t p = 0; p < n; ++p) {
         double s = 0.0;
-        for (int k = 0; k < d; ++k) s += (double)X[k * stride_d + p] * (double)Z[(size_t)j * d + k];
+        if (metric == 0) {
+          for (int k = 0; k < d; ++k) s += (double)X[k * stride_d + p] * (double)Z[(size_t)j * d + k];
+        } else {
+          for (int k = 0; k < d; ++k) {
+            const double t = (double)X[k * stride_d + p] - (double)Z[(size_t)j * d + k];
+            s -= t * t;
+          }
+        }
         const double w = exp((double)kappa * s);
+        ws += w;
         for (int k = 0; k < d; ++k) a[k] += w * (double)X[k * stride_d + p];
       }
+      wsum[j] = ws;
     }
     for (int j = 0; j < m; ++j) {
-      double ss = 0.0;
-      for (int k = 0; k < d; ++k) ss += acc[(size_t)j * d + k] * acc[(size_t)j * d + k];
-      double nrm = sqrt(ss);
-      if (nrm < 1e-12) nrm = 1e-12;
+      double nrm;
+      if (metric == 0) {
+        double ss = 0.0;
+        for (int k = 0; k < d; ++k) ss += acc[(size_t)j * d + k] * acc[(size_t)j * d + k];
+        nrm = sqrt(ss);
+        if (nrm < 1e-12) nrm = 1e-12;
+      } else {
+        nrm = wsum[j] < 1.0 ? 1.0 : wsum[j];
+      }
       for (int k = 0; k < d; ++k) Z[(size_t)j * d + k] = (float)(acc[(size_t)j * d + k] / nrm);
     }
   }
   free(acc);
+  free(wsum);
   return 0;
+}
+
+int uoc_oracle_hill_climb(const float* X, int64_t n, int d, int64_t stride_d, float* Z, int m, float kappa, int iters) {
+  return uoc_oracle_hill_climb_metric(X, n, d, stride_d, Z, m, kappa, iters, 0);
 }

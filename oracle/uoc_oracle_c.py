@@ -29,52 +29,57 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def select_seeds(X_planar, m, first):
+METRICS = {"cosine": 0, "euclidean": 1}
+
+
+def select_seeds(X_planar, m, first, metric="cosine"):
     """X_planar: [d, n] float32 (row k = channel k).  Returns (selected int64 [m], seeds float32 [m, d])."""
     X = _f32(X_planar)
     d, n = X.shape
     sel = np.empty(m, dtype=np.int64)
     seeds = np.empty((m, d), dtype=np.float32)
-    rc = load().uoc_oracle_select_seeds(_p(X), ctypes.c_int64(n), d, ctypes.c_int64(n), m, ctypes.c_int64(int(first)),
-                                        _p(sel), _p(seeds))
+    rc = load().uoc_oracle_select_seeds_metric(_p(X), ctypes.c_int64(n), d, ctypes.c_int64(n), m, ctypes.c_int64(int(first)),
+                                               _p(sel), _p(seeds), METRICS[metric])
     assert rc == 0, rc
     return sel, seeds
 
 
-def label_seeds(Z, eps):
+def label_seeds(Z, eps, metric="cosine"):
     Z = _f32(Z)
     m, d = Z.shape
     labels = np.empty(m, dtype=np.int32)
-    uniq = load().uoc_oracle_label_seeds(_p(Z), m, d, ctypes.c_float(eps), _p(labels))
+    uniq = load().uoc_oracle_label_seeds_metric(_p(Z), m, d, ctypes.c_float(eps), _p(labels), METRICS[metric])
     return labels, int(uniq)
 
 
-def assign(X_planar, Z, seed_labels, num_unique):
+def assign(X_planar, Z, seed_labels, num_unique, metric="cosine"):
     X = _f32(X_planar)
     Z = _f32(Z)
     d, n = X.shape
     m = Z.shape[0]
     sl = np.ascontiguousarray(seed_labels, dtype=np.int32)
     out = np.empty(n, dtype=np.int32)
-    rc = load().uoc_oracle_assign(_p(X), ctypes.c_int64(n), d, ctypes.c_int64(n), _p(Z), m, _p(sl), int(num_unique), _p(out))
+    rc = load().uoc_oracle_assign_metric(_p(X), ctypes.c_int64(n), d, ctypes.c_int64(n), _p(Z), m, _p(sl), int(num_unique),
+                                         _p(out), METRICS[metric])
     assert rc == 0, rc
     return out
 
 
-def hill_climb(X_planar, Z, kappa, iters):
+def hill_climb(X_planar, Z, kappa, iters, metric="cosine"):
     X = _f32(X_planar)
     Zc = _f32(Z).copy()
     d, n = X.shape
     m = Zc.shape[0]
-    rc = load().uoc_oracle_hill_climb(_p(X), ctypes.c_int64(n), d, ctypes.c_int64(n), _p(Zc), m, ctypes.c_float(kappa), int(iters))
+    rc = load().uoc_oracle_hill_climb_metric(_p(X), ctypes.c_int64(n), d, ctypes.c_int64(n), _p(Zc), m, ctypes.c_float(kappa),
+                                             int(iters), METRICS[metric])
     assert rc == 0, rc
     return Zc
 
 
-def cluster(X_planar, m, first, kappa=20.0, iters=10, eps=0.04):
+def cluster(X_planar, m, first, kappa=20.0, iters=10, eps=0.04, metric="cosine"):
     """Whole pipeline in canonical arithmetic: returns dict(selected, seeds, Z, seed_labels, num_unique, labels)."""
-    sel, seeds = select_seeds(X_planar, m, first)
-    Z = hill_climb(X_planar, seeds, kappa, iters)
-    sl, uniq = label_seeds(Z, eps)
-    labels = assign(X_planar, Z, sl, uniq)
+    sel, seeds = select_seeds(X_planar, m, first, metric)
+    Z = hill_climb(X_planar, seeds, kappa, iters, metric)
+    sl, uniq = label_seeds(Z, eps, metric)
+    labels = assign(X_planar, Z, sl, uniq, metric)
     return dict(selected=sel, seeds=seeds, Z=Z, seed_labels=sl, num_unique=uniq, labels=labels)

@@ -24,8 +24,6 @@ def _field(H, W, d, K, noise, seed):
     return feats, gt
 
 
-@pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 100), (30, 44, 128, 100), (24, 24, 64, 40),
-                                     (60, 80, 32, 17), (120, 160, 64, 100)])
 def _fps_mode(monkeypatch, mode):
     """tc: tcgen05 screen (fps_tc.cu, default: tiles in tensor memory first); tc_smem: same with every tile in shared memory;
     fp32: no screen (fps2_kernel).  Returns bf16_screen."""
@@ -259,3 +257,80 @@ def test_bad_arguments_fail_loudly():
         MS.cluster_fields(f, 10, first_indices=[64])   # first seed out of range
     with pytest.raises(_lib.UocError):
         MS.cluster_fields(f.cpu(), 10)
+
+
+# ----------------------------------------------------------------------------------------------
+# metric='euclidean' (lib/utils/mean_shift.py:21-24,58-60,101-105,159-160,207-209)
+# ----------------------------------------------------------------------------------------------
+EUCLID_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "euclid_*.npz")))
+
+
+@pytest.mark.parametrize("path", EUCLID_FIXTURES, ids=[os.path.basename(p) for p in EUCLID_FIXTURES])
+def test_euclidean_matches_reference_golden(path):
+    """Whole euclidean clustering against fixtures written by the unmodified reference (euclid_b is not unit norm):
+    selected indices, seed labels and pixel labels identical, converged seeds within 2e-5."""
+    g = np.load(path)
+    d, m = int(g["d"]), int(g["num_seeds"])
+    feats = torch.from_numpy(g["features"]).to(DEV)
+    labels, sel, Z, sl = MS.cluster_fields(feats, m, 20.0, 10, [int(g["first_index"])], flags=_lib.FLAG_SYNC_CHECK,
+                                           return_seeds=True, metric="euclidean")
+    assert np.array_equal(sel[0].cpu().numpy(), g["selected"])
+    assert np.abs(Z[0].cpu().numpy() - g["Z"]).max() < 2e-5
+    assert np.array_equal(sl[0].cpu().numpy(), g["seed_labels"])
+    assert np.array_equal(labels[0].cpu().numpy(), g["labels"])
+    # the reference-named entry point returns the reference's types
+    X = feats[0].view(d, -1).t()
+    l2, s2 = MS.mean_shift_smart_init(X, 20.0, m, 10, metric="euclidean", first_index=int(g["first_index"]))
+    assert l2.dtype == torch.int64 and not l2.is_cuda and np.array_equal(l2.numpy(), g["labels"])
+    assert np.array_equal(s2.numpy(), g["selected"])
+
+
+@pytest.mark.parametrize("H,W,d,m,scale", [(32, 48, 64, 100, 1.0), (37, 41, 64, 50, 2.0), (30, 44, 128, 100, 1.0),
+                                           (60, 80, 32, 17, 0.7), (33, 35, 20, 9, 1.0)])
+def test_euclidean_stages_bit_exact_vs_c_oracle(H, W, d, m, scale):
+    """Every discrete decision of the euclidean path against the canonical-order C oracle (bit-exact), stage by stage;
+    the fp32 loop against the double-precision oracle (<= 1e-5 absolute)."""
+    feats, _ = _field(H, W, d, 4, 0.03, seed=H + d)
+    feats = feats * scale
+    Xp = feats[0].reshape(d, -1).numpy()
+    first = (H * W) // 3
+    sel_o, seeds_o = C.select_seeds(Xp, m, first, metric="euclidean")
+    X = feats.to(DEV)[0].view(d, -1).t()
+    seeds, sel = MS.select_smart_seeds(X, m, return_selected_indices=True, first_index=first, metric="euclidean")
+    assert np.array_equal(sel.numpy(), sel_o)
+    assert np.array_equal(seeds.cpu().numpy(), seeds_o)
+    Zo = C.hill_climb(Xp, seeds_o, 20.0, 10, metric="euclidean")
+    Z = MS.seed_hill_climbing_ball(X, seeds, 20.0, 10, metric="euclidean").cpu().numpy()
+    assert np.isfinite(Z).all() and np.abs(Z - Zo).max() < 1e-5 * max(1.0, scale), np.abs(Z - Zo).max()
+    lo, uo = C.label_seeds(Z, 0.04, metric="euclidean")
+    lg, ug = MS.connected_components(torch.from_numpy(Z).to(DEV), 0.04, metric="euclidean", return_num_unique=True)
+    assert np.array_equal(lg.numpy(), lo) and ug == uo
+    want = C.assign(Xp, Z, lo, uo, metric="euclidean")
+    got = MS.assign_labels(X, torch.from_numpy(Z).to(DEV), torch.from_numpy(lo), uo, metric="euclidean")
+    assert np.array_equal(got.numpy(), want)
+
+
+def test_euclidean_weight_sum_clamp():
+    """Isolated seeds (sum of weights < 1) are divided by 1, not by the sum (mean_shift.py:103-104)."""
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(64, 2000, generator=g) * 2.0                 # far-apart points: every weight but the self-weight ~ 0
+    Xp = X.numpy()
+    seeds = (X[:, :10].t().contiguous() + 0.05)                   # one neighbour at distance 0.4: sum of weights ~ 0.04 < 1
+    Zo = C.hill_climb(Xp, seeds.numpy(), 20.0, 1, metric="euclidean")
+    Z = MS.seed_hill_climbing_ball(X.t().to(DEV), seeds.to(DEV), 20.0, 1, metric="euclidean").cpu().numpy()
+    assert 1e-3 < np.abs(Zo).max() < 1.0 and np.abs(Z - Zo).max() < 1e-6
+
+
+def test_euclidean_clustering_features_and_batch():
+    """clustering_features(metric='euclidean') on a batch equals the per-item calls and the torch oracle."""
+    fa, _ = _field(32, 40, 64, 3, 0.02, seed=5)
+    fb, _ = _field(32, 40, 64, 4, 0.02, seed=6)
+    feats = torch.cat([fa, fb * 1.3], 0)
+    out, sel = TD.clustering_features(feats.to(DEV), 60, [11, 700], metric="euclidean")
+    want, wsel = O.clustering_features(feats, 60, [11, 700], metric="euclidean")
+    assert out.dtype == torch.float32 and not out.is_cuda
+    for j in range(2):
+        assert torch.equal(sel[j], wsel[j])
+        assert O.labels_equal_up_to_permutation(out[j].numpy().ravel(), want[j].numpy().ravel())
+    with pytest.raises(ValueError):
+        TD.clustering_features(feats.to(DEV), 60, [11, 700], metric="manhattan")

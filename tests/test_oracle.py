@@ -52,6 +52,43 @@ def test_c_oracle_matches_golden_clustering(path):
     assert np.array_equal(res["labels"], g["labels"])
 
 
+EUCLID_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "euclid_*.npz")))
+
+
+@pytest.mark.parametrize("path", EUCLID_FIXTURES, ids=[os.path.basename(p) for p in EUCLID_FIXTURES])
+def test_euclidean_oracles_match_reference_golden(path):
+    """metric='euclidean' (lib/utils/mean_shift.py:21-24,58-60,101-105,159-160,207-209): torch oracle bit-identical to
+    the fixtures written by the unmodified reference, C oracle (canonical fp32 chain + sqrtf) identical in every
+    discrete decision; euclid_b is not unit norm."""
+    g = _load(path)
+    d, m = int(g["d"]), int(g["num_seeds"])
+    feats = torch.from_numpy(g["features"])
+    X = feats[0].view(d, -1).t()
+    labels, sel, seeds, Z, sl = O.mean_shift_smart_init(X, num_seeds=m, first_index=int(g["first_index"]), return_all=True,
+                                                        metric="euclidean")
+    assert np.array_equal(sel.numpy(), g["selected"])
+    assert np.array_equal(labels.numpy(), g["labels"])
+    assert np.array_equal(sl.numpy(), g["seed_labels"])
+    assert np.allclose(Z.numpy(), g["Z"], atol=1e-6)
+    res = C.cluster(g["features"][0].reshape(d, -1), m, int(g["first_index"]), metric="euclidean")
+    assert np.array_equal(res["selected"], g["selected"])
+    assert np.abs(res["Z"] - g["Z"]).max() < 2e-5
+    assert np.array_equal(res["seed_labels"], g["seed_labels"])
+    assert np.array_equal(res["labels"], g["labels"])
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not present (GPU box)")
+def test_euclidean_torch_oracle_is_bit_identical_to_the_live_reference():
+    ref = rh.load()
+    feats, _ = O.synthetic_clustered_features(28, 36, 64, 3, 0.02, seed=77)
+    X = (feats[0] * 1.25).view(64, -1).t()
+    np.random.seed(11)
+    lr, sr = ref.mean_shift.mean_shift_smart_init(X, kappa=20, num_seeds=50, max_iters=10, metric='euclidean')
+    np.random.seed(11)
+    lo, so = O.mean_shift_smart_init(X, num_seeds=50, metric="euclidean")
+    assert torch.equal(lr, lo) and torch.equal(sr, so)
+
+
 def test_two_stage_oracle_matches_golden():
     g = _load(os.path.join(GOLDEN, "two_stage.npz"))
     H, W = int(g["H"]), int(g["W"])

@@ -13,6 +13,7 @@ FLAG_LOOP_SIMT = 1
 FLAG_CONV_SIMT = 2
 FLAG_SYNC_CHECK = 4
 FLAG_FPS_FP32 = 8
+FLAG_EUCLIDEAN = 16
 MAX_SEEDS = 128
 
 
@@ -40,6 +41,8 @@ SIGNATURES = {
     "uoc_hill_climb": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _f, _i, _vp, _vp, _sz, _i, _vp]),
     "uoc_label_seeds": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "uoc_assign_labels": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "uoc_label_seeds_ex": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "uoc_assign_labels_ex": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "uoc_pack_bf16": (_i, [_vp, _i64, _i64, _i, _i64, _i, _vp, _vp]),
     "uoc_backbone_create": (_i, [_c.POINTER(_vp), _c.POINTER(WeightDesc), _i, _i]),
     "uoc_backbone_create_ex": (_i, [_c.POINTER(_vp), _c.POINTER(WeightDesc), _i, _i, _i, _i, _i]),

@@ -9,7 +9,8 @@
 // Canonical fp32 arithmetic (mirrored bit for bit by oracle/uoc_oracle_c.c): every dot product that
 // feeds a discrete decision (arg-max of the sampling, epsilon threshold of the labelling, arg-min
 // of the assignment) is one sequential fused-multiply-add chain over the channels k = 0..d-1
-// starting from +0, and the cosine distance is 0.5f * (1.0f - dot).
+// starting from +0, and the cosine distance is 0.5f * (1.0f - dot).  Euclidean metric (METRIC_EUCLIDEAN): the chain is
+// acc = fmaf(t, t, acc) with t = x_k - z_k, and the distance is sqrtf(acc) (IEEE round-to-nearest).
 #include <cooperative_groups.h>
 
 #include <cstdlib>
@@ -36,7 +37,7 @@ static size_t carve(size_t& off, size_t bytes) {
 }
 
 struct WsLayout {
-  size_t r, keys, slots, barrier, first, Z, partials, seed_labels, num_unique, hist, labels_tmp, xb, total;
+  size_t r, keys, slots, barrier, first, Z, partials, seed_labels, num_unique, hist, labels_tmp, xb, wsum, total;
   size_t slot_bytes;
   int P;
 };
@@ -65,6 +66,7 @@ static WsLayout ws_layout(int batch, int64_t n, int d, int m) {
   L.hist = carve(off, sizeof(int) * size_t(batch) * m);
   L.labels_tmp = carve(off, sizeof(int) * size_t(batch) * n);
   L.xb = carve(off, sizeof(__nv_bfloat16) * size_t(batch) * n * d);
+  L.wsum = carve(off, sizeof(float) * size_t(batch) * L.P * 128);
   L.total = off;
   return L;
 }
@@ -94,6 +96,7 @@ int carve_cluster_workspace(void* ws, size_t ws_bytes, int batch, int64_t n, int
   out->hist = reinterpret_cast<int*>(base + L.hist);
   out->labels_tmp = reinterpret_cast<int*>(base + L.labels_tmp);
   out->xb = reinterpret_cast<__nv_bfloat16*>(base + L.xb);
+  out->wsum = reinterpret_cast<float*>(base + L.wsum);
   out->max_partials = L.P;
   return UOC_OK;
 }
@@ -146,7 +149,7 @@ __device__ __forceinline__ bool grid_barrier(unsigned int* counter, unsigned int
   return s_ok != 0;
 }
 
-template <int VEC>
+template <int VEC, int METRIC>
 __global__ void __launch_bounds__(256) fps_kernel(FpsParams p) {
   extern __shared__ float s_seed[];  // d floats
   __shared__ unsigned long long s_red[8];
@@ -188,19 +191,32 @@ __global__ void __launch_bounds__(256) fps_kernel(FpsParams p) {
           for (int k = 0; k < p.d; ++k) {
             const float sk = s_seed[k];
             if (VEC == 4) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(xp + k * p.sd));
-              acc[0] = fmaf(v.x, sk, acc[0]);
-              acc[1 % VEC] = fmaf(v.y, sk, acc[1 % VEC]);
-              acc[2 % VEC] = fmaf(v.z, sk, acc[2 % VEC]);
-              acc[3 % VEC] = fmaf(v.w, sk, acc[3 % VEC]);
+              float4 v = __ldg(reinterpret_cast<const float4*>(xp + k * p.sd));
+              if (METRIC == METRIC_EUCLIDEAN) {
+                v.x -= sk; v.y -= sk; v.z -= sk; v.w -= sk;
+                acc[0] = fmaf(v.x, v.x, acc[0]);
+                acc[1 % VEC] = fmaf(v.y, v.y, acc[1 % VEC]);
+                acc[2 % VEC] = fmaf(v.z, v.z, acc[2 % VEC]);
+                acc[3 % VEC] = fmaf(v.w, v.w, acc[3 % VEC]);
+              } else {
+                acc[0] = fmaf(v.x, sk, acc[0]);
+                acc[1 % VEC] = fmaf(v.y, sk, acc[1 % VEC]);
+                acc[2 % VEC] = fmaf(v.z, sk, acc[2 % VEC]);
+                acc[3 % VEC] = fmaf(v.w, sk, acc[3 % VEC]);
+              }
+            } else if (METRIC == METRIC_EUCLIDEAN) {
+              const float t = __ldg(xp + k * p.sd) - sk;
+              acc[0] = fmaf(t, t, acc[0]);
             } else {
               acc[0] = fmaf(__ldg(xp + k * p.sd), sk, acc[0]);
             }
           }
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[j] = (METRIC == METRIC_EUCLIDEAN) ? sqrtf(acc[j]) : 0.5f * (1.0f - acc[j]);
           float rn[VEC];
           if (i == 0) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) rn[j] = 0.5f * (1.0f - acc[j]);
+            for (int j = 0; j < VEC; ++j) rn[j] = acc[j];
           } else {
             float ro[VEC];
             if (VEC == 4) {
@@ -211,7 +227,7 @@ __global__ void __launch_bounds__(256) fps_kernel(FpsParams p) {
             }
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-              const float dj = 0.5f * (1.0f - acc[j]);
+              const float dj = acc[j];
               rn[j] = dj < ro[j] ? dj : ro[j];
             }
           }
@@ -549,8 +565,8 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
 }
 
 int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
-                        int64_t* selected_out, float* seeds_out, cudaStream_t stream) {
-  if (xb) {
+                        int64_t* selected_out, float* seeds_out, cudaStream_t stream, int metric) {
+  if (xb && metric == METRIC_COSINE) {
     bool used = false;
     int rc = launch_select_seeds_tc(X, xb, s, w, selected_out, seeds_out, stream, &used);
     if (rc != UOC_OK || used) return rc;
@@ -575,12 +591,14 @@ int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterSh
   UOC_CUDA(cudaMemsetAsync(w.barrier, 0, sizeof(unsigned int), stream));
   const bool vec4 = (s.n % 4 == 0) && (s.stride_d % 4 == 0) && (s.stride_b % 4 == 0) &&
                     (reinterpret_cast<uintptr_t>(X) % 16 == 0);
-  if (vec4) {
+  if (vec4 && metric == METRIC_COSINE) {
     bool used = false;
     int rc = launch_select_seeds_v2(p, s, w.slots, w.slot_bytes, stream, &used);
     if (rc != UOC_OK || used) return rc;
   }
-  void* kern = vec4 ? reinterpret_cast<void*>(&fps_kernel<4>) : reinterpret_cast<void*>(&fps_kernel<1>);
+  void* kern = vec4 ? reinterpret_cast<void*>(&fps_kernel<4, METRIC_COSINE>) : reinterpret_cast<void*>(&fps_kernel<1, METRIC_COSINE>);
+  if (metric == METRIC_EUCLIDEAN)
+    kern = vec4 ? reinterpret_cast<void*>(&fps_kernel<4, METRIC_EUCLIDEAN>) : reinterpret_cast<void*>(&fps_kernel<1, METRIC_EUCLIDEAN>);
   const int threads = 256;
   const size_t smem = sizeof(float) * size_t(s.d);
   int per_sm = 0;
@@ -605,9 +623,12 @@ int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterSh
 // K4': fp32 SIMT mean-shift iteration (validation path)
 // ----------------------------------------------------------------------------------------------
 // grid (P, m, batch); each block accumulates sum_p exp(kappa * x_p.z_j) * x_p over its point slice.
+// METRIC_EUCLIDEAN: weights exp(-kappa ||x_p - z_j||^2) (mean_shift.py:21-24), their sum goes to wsum[b][part][j].
+template <int METRIC>
 __global__ void __launch_bounds__(256) meanshift_simt_kernel(const float* __restrict__ X, long long sb, long long sd,
                                                              long long n, int d, int m, const float* __restrict__ Z,
-                                                             float kappa, float* __restrict__ partials, int P) {
+                                                             float kappa, float* __restrict__ partials, int P,
+                                                             float* __restrict__ wsum) {
   extern __shared__ float sm[];  // z[d] + red[8][32]
   float* z = sm;
   float* red = sm + d;
@@ -622,15 +643,35 @@ __global__ void __launch_bounds__(256) meanshift_simt_kernel(const float* __rest
   float* out = partials + ((size_t(b) * P + part) * 128 + j) * d;
   for (int kc = 0; kc < d; kc += 32) {
     float acc[32];
+    float wtot = 0.f;
 #pragma unroll
     for (int q = 0; q < 32; ++q) acc[q] = 0.f;
     for (long long pnt = p0 + tid; pnt < p1; pnt += blockDim.x) {
       float s = 0.f;
-      for (int k = 0; k < d; ++k) s = fmaf(__ldg(Xb + k * sd + pnt), z[k], s);
-      const float wgt = expf(kappa * s);
+      float wgt;
+      if (METRIC == METRIC_EUCLIDEAN) {
+        for (int k = 0; k < d; ++k) { const float t = __ldg(Xb + k * sd + pnt) - z[k]; s = fmaf(t, t, s); }
+        wgt = expf(-kappa * s);
+        wtot += wgt;
+      } else {
+        for (int k = 0; k < d; ++k) s = fmaf(__ldg(Xb + k * sd + pnt), z[k], s);
+        wgt = expf(kappa * s);
+      }
 #pragma unroll
       for (int q = 0; q < 32; ++q)
         if (kc + q < d) acc[q] = fmaf(wgt, __ldg(Xb + (kc + q) * sd + pnt), acc[q]);
+    }
+    if (METRIC == METRIC_EUCLIDEAN && kc == 0) {      // block sum of the weights, fixed order
+      __shared__ float s_w[8];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wtot += __shfl_xor_sync(0xffffffffu, wtot, o);
+      if ((tid & 31) == 0) s_w[tid >> 5] = wtot;
+      __syncthreads();
+      if (tid == 0) {
+        float v = 0.f;
+        for (int wq = 0; wq < int(blockDim.x >> 5); ++wq) v += s_w[wq];
+        wsum[(size_t(b) * P + part) * 128 + j] = v;
+      }
     }
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
@@ -653,7 +694,8 @@ __global__ void __launch_bounds__(256) meanshift_simt_kernel(const float* __rest
 // Warp w adds parts w, w+8, w+16, ... (each a coalesced row read), the 8 warp sums are combined in a
 // fixed order -> deterministic.  Lane l owns channels l, l+32, ... (d <= 256).
 __global__ void __launch_bounds__(256) reduce_normalize_kernel(const float* __restrict__ partials, int P, int m, int d,
-                                                               int row_stride, float* __restrict__ Z) {
+                                                               int row_stride, float* __restrict__ Z,
+                                                               const float* __restrict__ wsum) {
   __shared__ float s_part[8][256];
   __shared__ float s_sq[8];
   asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: partials are complete
@@ -684,12 +726,17 @@ __global__ void __launch_bounds__(256) reduce_normalize_kernel(const float* __re
   float all = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) all += s_sq[w];
-  const float denom = fmaxf(sqrtf(all), 1e-12f);  // F.normalize eps (lib/utils/mean_shift.py:107)
+  float denom = fmaxf(sqrtf(all), 1e-12f);  // F.normalize eps (lib/utils/mean_shift.py:107)
+  if (wsum) {                                // euclidean: Z = new_Z / clamp(sum of weights, min=1)  (mean_shift.py:101-105)
+    float sw = 0.f;
+    for (int part = 0; part < P; ++part) sw += __ldcg(wsum + (size_t(b) * P + part) * row_stride + j);
+    denom = fmaxf(sw, 1.0f);
+  }
   if (tid < d) Z[(size_t(b) * m + j) * d + tid] = tot / denom;
 }
 
 int launch_reduce_normalize(const float* partials, int batch, int P, int m, int d, int row_stride, float* Z,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const float* wsum) {
   if (d > 256) return fail(UOC_ERR_UNSUPPORTED, "d > 256 is not supported");
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -701,13 +748,13 @@ int launch_reduce_normalize(const float* partials, int batch, int P, int m, int 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  UOC_CUDA(cudaLaunchKernelEx(&cfg, reduce_normalize_kernel, partials, P, m, d, row_stride, Z));
+  UOC_CUDA(cudaLaunchKernelEx(&cfg, reduce_normalize_kernel, partials, P, m, d, row_stride, Z, wsum));
   count_launch();
   return UOC_OK;
 }
 
 int launch_hill_climb_simt(const float* X, const ClusterShape& s, const ClusterWorkspace& w, float* Z, float kappa,
-                           int iters, cudaStream_t stream) {
+                           int iters, cudaStream_t stream, int metric) {
   int P = w.max_partials;
   const long long min_pts = 2048;
   long long maxP = (s.n + min_pts - 1) / min_pts;
@@ -715,10 +762,15 @@ int launch_hill_climb_simt(const float* X, const ClusterShape& s, const ClusterW
   if (P < 1) P = 1;
   const size_t smem = sizeof(float) * (size_t(s.d) + 8 * 32);
   for (int it = 0; it < iters; ++it) {
-    meanshift_simt_kernel<<<dim3(P, s.m, s.batch), 256, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, Z,
-                                                                       kappa, w.partials, P);
+    if (metric == METRIC_EUCLIDEAN)
+      meanshift_simt_kernel<METRIC_EUCLIDEAN><<<dim3(P, s.m, s.batch), 256, smem, stream>>>(
+          X, s.stride_b, s.stride_d, s.n, s.d, s.m, Z, kappa, w.partials, P, w.wsum);
+    else
+      meanshift_simt_kernel<METRIC_COSINE><<<dim3(P, s.m, s.batch), 256, smem, stream>>>(
+          X, s.stride_b, s.stride_d, s.n, s.d, s.m, Z, kappa, w.partials, P, nullptr);
     UOC_CHECK_LAUNCH();
-    int rc = launch_reduce_normalize(w.partials, s.batch, P, s.m, s.d, 128, Z, stream);
+    int rc = launch_reduce_normalize(w.partials, s.batch, P, s.m, s.d, 128, Z, stream,
+                                     metric == METRIC_EUCLIDEAN ? w.wsum : nullptr);
     if (rc != UOC_OK) return rc;
   }
   return UOC_OK;
@@ -728,7 +780,7 @@ int launch_hill_climb_simt(const float* X, const ClusterShape& s, const ClusterW
 // K5a: greedy seed labelling, one CTA (512 threads) per field
 // ----------------------------------------------------------------------------------------------
 template <int DREG>   // channels held in registers (0 = generic d)
-__global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restrict__ Z, int m, int d, float eps,
+__global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restrict__ Z, int m, int d, float eps, int metric,
                                                           int* __restrict__ seed_labels, int* __restrict__ num_unique) {
   extern __shared__ float zs[];  // [m][d+1]
   __shared__ unsigned int adj[UOC_MAX_SEEDS][4];
@@ -750,9 +802,14 @@ __global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restric
       for (int k = 0; k < DREG; ++k) zj[k] = (j < m) ? zs[j * ld + k] : 0.f;
       for (int i = iq; i < m; i += 4) {
         float acc = 0.f;
+        if (metric == METRIC_EUCLIDEAN) {      // ||z_j - z_i|| <= eps  (mean_shift.py:58-60)
 #pragma unroll
-        for (int k = 0; k < DREG; ++k) acc = fmaf(zj[k], zs[i * ld + k], acc);
-        const bool in = (j < m) && ((0.5f * (1.0f - acc)) <= eps);
+          for (int k = 0; k < DREG; ++k) { const float t = zj[k] - zs[i * ld + k]; acc = fmaf(t, t, acc); }
+        } else {
+#pragma unroll
+          for (int k = 0; k < DREG; ++k) acc = fmaf(zj[k], zs[i * ld + k], acc);
+        }
+        const bool in = (j < m) && ((metric == METRIC_EUCLIDEAN ? sqrtf(acc) : 0.5f * (1.0f - acc)) <= eps);
         const unsigned int bits = __ballot_sync(0xffffffffu, in);
         if ((tid & 31) == 0) adj[i][w4] = bits;
       }
@@ -761,8 +818,13 @@ __global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restric
         bool in = false;
         if (j < m) {
           float acc = 0.f;
-          for (int k = 0; k < d; ++k) acc = fmaf(zs[j * ld + k], zs[i * ld + k], acc);
-          in = (0.5f * (1.0f - acc)) <= eps;
+          if (metric == METRIC_EUCLIDEAN) {
+            for (int k = 0; k < d; ++k) { const float t = zs[j * ld + k] - zs[i * ld + k]; acc = fmaf(t, t, acc); }
+            in = sqrtf(acc) <= eps;
+          } else {
+            for (int k = 0; k < d; ++k) acc = fmaf(zs[j * ld + k], zs[i * ld + k], acc);
+            in = (0.5f * (1.0f - acc)) <= eps;
+          }
         }
         const unsigned int bits = __ballot_sync(0xffffffffu, in);
         if ((tid & 31) == 0) adj[i][w4] = bits;
@@ -826,7 +888,7 @@ __global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restric
 }
 
 int launch_label_seeds(const float* Z, int batch, int m, int d, float epsilon, int* seed_labels, int* num_unique,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int metric) {
   const size_t smem = sizeof(float) * size_t(m) * (d + 1);
   static bool configured = false;
   if (!configured) {
@@ -835,9 +897,9 @@ int launch_label_seeds(const float* Z, int batch, int m, int d, float epsilon, i
     UOC_CUDA(cudaFuncSetAttribute(label_seeds_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured = true;
   }
-  if (d == 64) label_seeds_kernel<64><<<batch, 512, smem, stream>>>(Z, m, d, epsilon, seed_labels, num_unique);
-  else if (d == 128) label_seeds_kernel<128><<<batch, 512, smem, stream>>>(Z, m, d, epsilon, seed_labels, num_unique);
-  else label_seeds_kernel<0><<<batch, 512, smem, stream>>>(Z, m, d, epsilon, seed_labels, num_unique);
+  if (d == 64) label_seeds_kernel<64><<<batch, 512, smem, stream>>>(Z, m, d, epsilon, metric, seed_labels, num_unique);
+  else if (d == 128) label_seeds_kernel<128><<<batch, 512, smem, stream>>>(Z, m, d, epsilon, metric, seed_labels, num_unique);
+  else label_seeds_kernel<0><<<batch, 512, smem, stream>>>(Z, m, d, epsilon, metric, seed_labels, num_unique);
   UOC_CHECK_LAUNCH();
   return UOC_OK;
 }
@@ -847,7 +909,7 @@ int launch_label_seeds(const float* Z, int batch, int m, int d, float epsilon, i
 // ----------------------------------------------------------------------------------------------
 template <int D>  // D > 0: channels held in registers; D == 0: generic (re-reads x through L1)
 __global__ void __launch_bounds__(128) assign_kernel(const float* __restrict__ X, long long sb, long long sd, long long n,
-                                                     int d, int m, const float* __restrict__ Z,
+                                                     int d, int m, int metric, const float* __restrict__ Z,
                                                      const int* __restrict__ seed_labels, int* __restrict__ hist,
                                                      int* __restrict__ labels_tmp) {
   extern __shared__ float zs[];  // [m][d]
@@ -871,22 +933,38 @@ __global__ void __launch_bounds__(128) assign_kernel(const float* __restrict__ X
       for (int j = 0; j < m; ++j) {
         const float4* zj = reinterpret_cast<const float4*>(zs + j * D);
         float acc = 0.f;
+        if (metric == METRIC_EUCLIDEAN) {      // ||x - z_j||  (mean_shift.py:207-209)
 #pragma unroll
-        for (int k4 = 0; k4 < D / 4; ++k4) {
-          const float4 zv = zj[k4];
-          acc = fmaf(x[4 * k4 + 0], zv.x, acc);
-          acc = fmaf(x[4 * k4 + 1], zv.y, acc);
-          acc = fmaf(x[4 * k4 + 2], zv.z, acc);
-          acc = fmaf(x[4 * k4 + 3], zv.w, acc);
+          for (int k4 = 0; k4 < D / 4; ++k4) {
+            const float4 zv = zj[k4];
+            const float t0 = x[4 * k4 + 0] - zv.x, t1 = x[4 * k4 + 1] - zv.y, t2 = x[4 * k4 + 2] - zv.z, t3 = x[4 * k4 + 3] - zv.w;
+            acc = fmaf(t0, t0, acc);
+            acc = fmaf(t1, t1, acc);
+            acc = fmaf(t2, t2, acc);
+            acc = fmaf(t3, t3, acc);
+          }
+        } else {
+#pragma unroll
+          for (int k4 = 0; k4 < D / 4; ++k4) {
+            const float4 zv = zj[k4];
+            acc = fmaf(x[4 * k4 + 0], zv.x, acc);
+            acc = fmaf(x[4 * k4 + 1], zv.y, acc);
+            acc = fmaf(x[4 * k4 + 2], zv.z, acc);
+            acc = fmaf(x[4 * k4 + 3], zv.w, acc);
+          }
         }
-        const float dist = 0.5f * (1.0f - acc);
+        const float dist = (metric == METRIC_EUCLIDEAN) ? sqrtf(acc) : 0.5f * (1.0f - acc);
         if (j == 0 || dist < best) { best = dist; bj = j; }   // first minimum (torch.argmin)
       }
     } else {
       for (int j = 0; j < m; ++j) {
         float acc = 0.f;
-        for (int k = 0; k < d; ++k) acc = fmaf(__ldg(Xb + k * sd + pnt), zs[j * d + k], acc);
-        const float dist = 0.5f * (1.0f - acc);
+        if (metric == METRIC_EUCLIDEAN) {
+          for (int k = 0; k < d; ++k) { const float t = __ldg(Xb + k * sd + pnt) - zs[j * d + k]; acc = fmaf(t, t, acc); }
+        } else {
+          for (int k = 0; k < d; ++k) acc = fmaf(__ldg(Xb + k * sd + pnt), zs[j * d + k], acc);
+        }
+        const float dist = (metric == METRIC_EUCLIDEAN) ? sqrtf(acc) : 0.5f * (1.0f - acc);
         if (j == 0 || dist < best) { best = dist; bj = j; }
       }
     }
@@ -934,9 +1012,9 @@ __global__ void __launch_bounds__(256) relabel_kernel(const int* __restrict__ la
 
 int launch_assign(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w, const float* Z,
                   const int* seed_labels, const int* num_unique, int* hist, int* labels_tmp, int* labels_out,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, int metric) {
   UOC_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * size_t(s.batch) * s.m, stream));
-  bool use_tc = xb != nullptr && (s.d == 64 || s.d == 128);
+  bool use_tc = xb != nullptr && (s.d == 64 || s.d == 128) && metric == METRIC_COSINE;
   if (const char* e = getenv("UOC_ASSIGN_SIMT")) { if (atoi(e) != 0) use_tc = false; }
   if (use_tc) {
     int rc = launch_assign_tc(X, xb, s, w, Z, seed_labels, hist, labels_tmp, stream);
@@ -956,11 +1034,11 @@ int launch_assign(const float* X, const __nv_bfloat16* xb, const ClusterShape& s
     attr_done = true;
   }
   if (s.d == 64)
-    assign_kernel<64><<<grid, 128, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, Z, seed_labels, hist, labels_tmp);
+    assign_kernel<64><<<grid, 128, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, metric, Z, seed_labels, hist, labels_tmp);
   else if (s.d == 128)
-    assign_kernel<128><<<grid, 128, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, Z, seed_labels, hist, labels_tmp);
+    assign_kernel<128><<<grid, 128, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, metric, Z, seed_labels, hist, labels_tmp);
   else
-    assign_kernel<0><<<grid, 128, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, Z, seed_labels, hist, labels_tmp);
+    assign_kernel<0><<<grid, 128, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, metric, Z, seed_labels, hist, labels_tmp);
   UOC_CHECK_LAUNCH();
   const dim3 grid2(static_cast<unsigned int>((s.n + 255) / 256), s.batch);
   relabel_kernel<<<grid2, 256, 0, stream>>>(labels_tmp, hist, num_unique, s.n, s.m, labels_out);

@@ -95,6 +95,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   tc_fence_after();
   if (CLUSTER > 1) cluster_sync_all();     // every CTA's barriers are initialised before any remote arrive / multicast
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the
+  // previous layer's tail; its activations are complete and visible after the wait.  The next layer may start its own
+  // prologue as soon as every CTA of this grid has got here (it waits for this grid's completion before touching memory).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     if (elect_one()) {    // one elected lane: lets the compiler keep descriptors / barriers in uniform registers
@@ -214,13 +219,20 @@ int launch(const ConvTcParams& prm, int m_tiles, int groups, cudaStream_t stream
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute lattr[1];
+  cudaLaunchAttribute lattr[2];
   lattr[0].id = cudaLaunchAttributeClusterDimension;
   lattr[0].val.clusterDim.x = CLUSTER;
   lattr[0].val.clusterDim.y = 1;
   lattr[0].val.clusterDim.z = 1;
+  lattr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the previous layer's tail
+  lattr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = lattr;
   cfg.numAttrs = 1;
+  {
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("UOC_CONV_PDL"); pdl = (e && atoi(e) == 0) ? 0 : 1; }
+    if (pdl) cfg.numAttrs = 2;
+  }
   UOC_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, CLUSTER>, prm));
   count_launch();
   return UOC_OK;

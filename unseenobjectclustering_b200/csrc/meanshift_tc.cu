@@ -359,16 +359,21 @@ meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float
     const uint32_t zs_addr = smem_u32(zs);
     const uint32_t st_addr = smem_u32(stages);
     bool ok = true;
+    long long* tr2 = (trace && b == 0 && cta == 0) ? trace + 16 * iters : nullptr;   // debug: the issuing thread's waits
     for (int u = 0; u < iters; ++u) {
       named_bar_sync(1, 288);              // seeds of this update staged, O of the previous one drained
       tc_fence_after();
       if (elect_one()) {
         const long long base = (long long)u * T;
+        long long w_x = 0, w_p = 0;
+        const long long t_begin = tr2 ? clock64() : 0;
         // three S/P buffers (global tile jj -> buffer jj % 3): GEMM1 runs two tiles ahead of the weights
         auto gemm2 = [&](int j) {
           const long long jj = base + j;
           const int s = int(jj % Cfg::kStages), buf = int(jj % 3);
+          const long long tw = tr2 ? clock64() : 0;
           if (!mbar_wait(&p_ready[buf], uint32_t(jj / 3) & 1u, err)) { ok = false; return; }
+          if (tr2) w_p += clock64() - tw;
           tc_fence_after();
           const uint32_t xb = st_addr + s * Cfg::kStageBytes;
 #pragma unroll
@@ -382,7 +387,9 @@ meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float
         for (int j = 0; j < T && ok; ++j) {
           const long long jj = base + j;
           const int s = int(jj % Cfg::kStages), buf = int(jj % 3);
+          const long long tw = tr2 ? clock64() : 0;
           if (!mbar_wait(&x_full[s], uint32_t(jj / Cfg::kStages) & 1u, err)) { ok = false; break; }
+          if (tr2) w_x += clock64() - tw;
           tc_fence_after();
           const uint32_t xb = st_addr + s * Cfg::kStageBytes;
 #pragma unroll
@@ -400,6 +407,7 @@ meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float
         if (ok && T > 1) gemm2(T - 2);
         if (ok && T > 0) gemm2(T - 1);
         if (ok) umma_commit(o_full);
+        if (tr2) { tr2[u * 4 + 0] = w_x; tr2[u * 4 + 1] = w_p; tr2[u * 4 + 2] = clock64() - t_begin; tr2[u * 4 + 3] = T; }
       }
       __syncwarp();
     }
@@ -589,15 +597,15 @@ int launch_persistent(const CUtensorMap& tmap, const ClusterShape& s, const Clus
   long long* trace = nullptr;
   const bool want_trace = getenv("UOC_LOOP_TRACE") != nullptr;     // debug: per-phase timeline on stderr (synchronises)
   if (want_trace) {
-    UOC_CUDA(cudaMalloc(&trace, sizeof(long long) * 16 * iters));
-    UOC_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * 16 * iters, stream));
+    UOC_CUDA(cudaMalloc(&trace, sizeof(long long) * 20 * iters));
+    UOC_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * 20 * iters, stream));
   }
   void* args[] = {&tm, &Z, &partials, &done, &rowflag, &m, &n, &c1, &P, &iters, &err, &trace};
   UOC_CUDA(cudaLaunchCooperativeKernel(meanshift_tc_persistent_kernel<D, POLY>, dim3(P, s.batch), dim3(kThreads), args,
                                        Cfg::kSmemBytes, stream));
   count_launch();
   if (want_trace) {
-    std::vector<long long> h(size_t(16) * iters);
+    std::vector<long long> h(size_t(20) * iters);
     UOC_CUDA(cudaStreamSynchronize(stream));
     UOC_CUDA(cudaMemcpy(h.data(), trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
     cudaFree(trace);
@@ -608,6 +616,11 @@ int launch_persistent(const CUtensorMap& tmap, const ClusterShape& s, const Clus
         fprintf(stderr, "[loop trace] cta %s update %d: start %lld staged %lld weights_done %lld o_full %lld published %lld reduced %lld (ns); group-0 warp: s_full wait %lld clk, weights %lld clk\n",
                 c == 0 ? "0" : "P-1", u, q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0, q[4] - t0, q[5] - t0, q[6], q[7]);
       }
+    for (int u = 0; u < iters; ++u) {
+      const long long* q = h.data() + size_t(16) * iters + size_t(u) * 4;
+      fprintf(stderr, "[loop trace] cta 0 update %d, issuing thread: %lld tiles, waited %lld clk for X tiles (TMA), %lld clk for P tiles (weights), %lld clk in total\n",
+              u, q[3], q[0], q[1], q[2]);
+    }
   }
   return UOC_OK;
 }

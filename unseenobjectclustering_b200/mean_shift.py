@@ -1,9 +1,10 @@
 """Host-side mirror of the reference's lib/utils/mean_shift.py on top of the CUDA C ABI.
 
-Same function names, argument meaning and return types as the reference (cosine metric, which is
-what every shipped config uses -- experiments/cfgs/*.yml `EMBEDDING_METRIC: cosine`); the arithmetic
-runs in libuoc_b200.so (farthest point sampling, tcgen05 mean-shift loop, greedy seed labelling,
-nearest-seed assignment).  PyTorch is used for device memory and streams only.
+Same function names, argument meaning and return types as the reference; the arithmetic runs in
+libuoc_b200.so (farthest point sampling, tcgen05 mean-shift loop, greedy seed labelling, nearest-seed
+assignment).  metric='cosine' (every shipped config: experiments/cfgs/*.yml `EMBEDDING_METRIC: cosine`)
+takes the tensor-core kernels; metric='euclidean' (the cfg default, lib/fcn/config.py:261) runs the same
+stages on the fp32 SIMT kernels.  PyTorch is used for device memory and streams only.
 """
 import ctypes
 
@@ -48,8 +49,16 @@ def _epsilon(epsilon=None):
     return float(2 * EMBEDDING_ALPHA) if epsilon is None else float(epsilon)   # mean_shift.py:123
 
 
+def _metric_flag(metric):
+    if metric == 'cosine':
+        return 0
+    if metric == 'euclidean':
+        return _lib.FLAG_EUCLIDEAN
+    raise ValueError("metric must be 'cosine' or 'euclidean' (cfg.TRAIN.EMBEDDING_METRIC)")
+
+
 def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indices=None, epsilon=None, flags=0,
-                   return_seeds=False, on_sampling_done=None):
+                   return_seeds=False, on_sampling_done=None, metric='cosine'):
     """Cluster a batch of embedding fields in ONE library call.
 
     features: [N, C, H, W] float32 CUDA tensor, unit norm over C (any batch stride; each item must
@@ -71,7 +80,8 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
     if first_indices is None:
         first_indices = [np.random.randint(0, n) for _ in range(N)]
     first = (ctypes.c_int64 * N)(*[int(v) for v in first_indices])
-    xb = _lookup_bf16(features)
+    flags = int(flags) | _metric_flag(metric)
+    xb = _lookup_bf16(features) if metric == 'cosine' else None
     with torch.cuda.device(dev):
         nbytes = lib.uoc_meanshift_workspace_bytes(N, n, C, num_seeds)
         ws = _workspace(dev, nbytes)
@@ -88,16 +98,16 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
             sb, sd_ = features.stride(0), features.stride(1)
             _lib.check(lib.uoc_select_seeds(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, fptr,
                                             _lib.ptr(selected), _lib.ptr(seeds), _lib.ptr(ws), ws.numel(),
-                                            int(flags) & _lib.FLAG_FPS_FP32, sp), "uoc_select_seeds")
+                                            int(flags) & (_lib.FLAG_FPS_FP32 | _lib.FLAG_EUCLIDEAN), sp), "uoc_select_seeds")
             on_sampling_done()
             _lib.check(lib.uoc_hill_climb(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, float(kappa),
                                           int(max_iters), _lib.ptr(seeds), _lib.ptr(ws), ws.numel(), int(flags), sp),
                        "uoc_hill_climb")
-            _lib.check(lib.uoc_label_seeds(_lib.ptr(seeds), N, num_seeds, C, _epsilon(epsilon), _lib.ptr(seed_labels),
-                                           _lib.ptr(nuniq), sp), "uoc_label_seeds")
-            _lib.check(lib.uoc_assign_labels(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, _lib.ptr(seeds),
-                                             _lib.ptr(seed_labels), _lib.ptr(nuniq), _lib.ptr(labels), _lib.ptr(ws),
-                                             ws.numel(), sp), "uoc_assign_labels")
+            _lib.check(lib.uoc_label_seeds_ex(_lib.ptr(seeds), N, num_seeds, C, _epsilon(epsilon), int(flags),
+                                              _lib.ptr(seed_labels), _lib.ptr(nuniq), sp), "uoc_label_seeds")
+            _lib.check(lib.uoc_assign_labels_ex(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, _lib.ptr(seeds),
+                                                _lib.ptr(seed_labels), _lib.ptr(nuniq), _lib.ptr(labels), _lib.ptr(ws),
+                                                ws.numel(), int(flags), sp), "uoc_assign_labels")
             if return_seeds:
                 return labels, selected, seeds, seed_labels
             return labels, selected
@@ -127,13 +137,11 @@ def mean_shift_smart_init(X, kappa, num_seeds=100, max_iters=10, metric='cosine'
     """lib/utils/mean_shift.py:192-229.  X: [n, d] CUDA float32 unit rows.  Returns
     (cluster_labels int64 [n] on the CPU, selected_indices int64 [num_seeds] on the CPU), like the
     reference."""
-    if metric != 'cosine':
-        raise NotImplementedError("only the cosine metric is implemented (all shipped configs use it)")
     n, d = X.shape
     Xp, stride_d = _as_planar(X)
     feats = torch.as_strided(Xp, (1, d, 1, n), (d * stride_d, stride_d, n, 1))
     fi = None if first_index is None else [first_index]
-    labels, selected = cluster_fields(feats, num_seeds, kappa, max_iters, fi, flags=flags)
+    labels, selected = cluster_fields(feats, num_seeds, kappa, max_iters, fi, flags=flags, metric=metric)
     return labels[0].to(torch.int64).cpu(), selected[0].cpu()
 
 
@@ -141,8 +149,9 @@ def select_smart_seeds(X, num_seeds, return_selected_indices=False, init_seeds=N
                        metric='cosine', first_index=None, bf16_screen=True):
     """lib/utils/mean_shift.py:128-189 (fresh start only: init_seeds is not supported).
     bf16_screen: screen every pass with a bf16 copy of X (d = 64/128; same indices, see fps_tc.cu)."""
-    if metric != 'cosine' or init_seeds is not None:
-        raise NotImplementedError("cosine metric without init_seeds only")
+    if init_seeds is not None:
+        raise NotImplementedError("fresh start only: init_seeds is not supported")
+    mflag = _metric_flag(metric)
     n, d = X.shape
     Xp, stride_d = _as_planar(X)
     lib = _lib.load()
@@ -155,13 +164,13 @@ def select_smart_seeds(X, num_seeds, return_selected_indices=False, init_seeds=N
         selected = torch.empty((num_seeds,), dtype=torch.int64, device=dev)
         seeds = torch.empty((num_seeds, d), dtype=torch.float32, device=dev)
         xb = None
-        if bf16_screen and d in (64, 128):
+        if bf16_screen and d in (64, 128) and not mflag:
             xb = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
             _lib.check(lib.uoc_pack_bf16(_lib.ptr(Xp), d * stride_d, stride_d, 1, n, d, _lib.ptr(xb), _lib.stream_ptr(dev)),
                        "uoc_pack_bf16")
         st = lib.uoc_select_seeds(_lib.ptr(Xp), d * stride_d, stride_d, _lib.ptr(xb), 1, n, d, num_seeds,
                                   ctypes.cast(first, ctypes.c_void_p), _lib.ptr(selected), _lib.ptr(seeds), _lib.ptr(ws),
-                                  ws.numel(), _lib.FLAG_SYNC_CHECK, _lib.stream_ptr(dev))
+                                  ws.numel(), _lib.FLAG_SYNC_CHECK | mflag, _lib.stream_ptr(dev))
         _lib.check(st, "uoc_select_seeds")
     if return_selected_indices:
         return seeds, selected.cpu()
@@ -170,8 +179,7 @@ def select_smart_seeds(X, num_seeds, return_selected_indices=False, init_seeds=N
 
 def seed_hill_climbing_ball(X, Z, kappa, max_iters=10, metric='cosine', flags=0):
     """lib/utils/mean_shift.py:79-109.  Returns the updated seeds (new tensor)."""
-    if metric != 'cosine':
-        raise NotImplementedError("cosine metric only")
+    flags = int(flags) | _metric_flag(metric)
     n, d = X.shape
     m = Z.shape[0]
     Xp, stride_d = _as_planar(X)
@@ -189,8 +197,7 @@ def seed_hill_climbing_ball(X, Z, kappa, max_iters=10, metric='cosine', flags=0)
 
 def connected_components(Z, epsilon, metric='cosine', return_num_unique=False):
     """lib/utils/mean_shift.py:41-76.  Z: [m, d] CUDA float32.  Returns int64 labels on the CPU."""
-    if metric != 'cosine':
-        raise NotImplementedError("cosine metric only")
+    mflag = _metric_flag(metric)
     m, d = Z.shape
     lib = _lib.load()
     dev = Z.device
@@ -198,15 +205,15 @@ def connected_components(Z, epsilon, metric='cosine', return_num_unique=False):
     with torch.cuda.device(dev):
         labels = torch.empty((m,), dtype=torch.int32, device=dev)
         num = torch.empty((1,), dtype=torch.int32, device=dev)
-        st = lib.uoc_label_seeds(_lib.ptr(Zc), 1, m, d, float(epsilon), _lib.ptr(labels), _lib.ptr(num),
-                                 _lib.stream_ptr(dev))
+        st = lib.uoc_label_seeds_ex(_lib.ptr(Zc), 1, m, d, float(epsilon), mflag, _lib.ptr(labels), _lib.ptr(num),
+                                    _lib.stream_ptr(dev))
         _lib.check(st, "uoc_label_seeds")
     if return_num_unique:
         return labels.to(torch.int64).cpu(), int(num.item())
     return labels.to(torch.int64).cpu()
 
 
-def assign_labels(X, Z, seed_labels, num_unique=None, use_tensor_cores=False):
+def assign_labels(X, Z, seed_labels, num_unique=None, use_tensor_cores=False, metric='cosine'):
     """lib/utils/mean_shift.py:206-227: nearest-seed labels with the label-0 swap. int64 CPU [n].
     use_tensor_cores: certified tcgen05 pass + fp32 fix-up instead of the fp32 kernel (identical labels)."""
     n, d = X.shape
@@ -223,10 +230,11 @@ def assign_labels(X, Z, seed_labels, num_unique=None, use_tensor_cores=False):
         ws = _workspace(dev, lib.uoc_meanshift_workspace_bytes(1, n, d, m))
         out = torch.empty((n,), dtype=torch.int32, device=dev)
         xb = None
-        if use_tensor_cores:
+        mflag = _metric_flag(metric)
+        if use_tensor_cores and not mflag:
             xb = pack_bf16(torch.as_strided(Xp, (1, d, 1, n), (d * stride_d, stride_d, n, 1)).contiguous().view(1, d, 1, n))
-        st = lib.uoc_assign_labels(_lib.ptr(Xp), d * stride_d, stride_d, _lib.ptr(xb), 1, n, d, m, _lib.ptr(Zc), _lib.ptr(sl),
-                                   _lib.ptr(nu), _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+        st = lib.uoc_assign_labels_ex(_lib.ptr(Xp), d * stride_d, stride_d, _lib.ptr(xb), 1, n, d, m, _lib.ptr(Zc), _lib.ptr(sl),
+                                      _lib.ptr(nu), _lib.ptr(out), _lib.ptr(ws), ws.numel(), mflag, _lib.stream_ptr(dev))
         _lib.check(st, "uoc_assign_labels")
     return out.to(torch.int64).cpu()
 

@@ -33,11 +33,25 @@ _INPUT_IDS = {"RGBD": 0, "COLOR": 1, "DEPTH": 2}
 _FUSION_IDS = {"add": 0, "cat": 1, "early": 2}
 
 
-def configure(cfg):
-    """Copy INPUT / TRAIN.FUSION_TYPE / TRAIN.EMBEDDING_NORMALIZATION from a reference cfg (lib/fcn/config.py)."""
+_LIVE_CFG = [None]      # a reference cfg object to read at construction time (set by shim.install)
+
+
+def configure(cfg, live=False):
+    """Copy INPUT / TRAIN.FUSION_TYPE / TRAIN.EMBEDDING_NORMALIZATION from a reference cfg (lib/fcn/config.py).
+    live=True keeps the object instead and reads it whenever a network is constructed, like the reference's
+    SEGNET.__init__ does (the tools call cfg_from_file() after importing the modules)."""
+    if live:
+        _LIVE_CFG[0] = cfg
+        return
     CONFIG["INPUT"] = str(cfg.INPUT)
     CONFIG["FUSION_TYPE"] = str(cfg.TRAIN.FUSION_TYPE)
     CONFIG["EMBEDDING_NORMALIZATION"] = bool(cfg.TRAIN.EMBEDDING_NORMALIZATION)
+
+
+def current_config():
+    if _LIVE_CFG[0] is not None:
+        configure(_LIVE_CFG[0])
+    return CONFIG
 
 
 def _branches(input_type, fusion_type, in_channels):
@@ -120,9 +134,10 @@ class SEGNET_B200(nn.Module):
         super().__init__()
         self.num_units = int(num_units)
         self.flags = int(flags)
-        self.input_type = str(CONFIG["INPUT"] if input_type is None else input_type)
-        self.fusion_type = str(CONFIG["FUSION_TYPE"] if fusion_type is None else fusion_type)
-        self.normalize = bool(CONFIG["EMBEDDING_NORMALIZATION"] if normalize is None else normalize)
+        conf = current_config()
+        self.input_type = str(conf["INPUT"] if input_type is None else input_type)
+        self.fusion_type = str(conf["FUSION_TYPE"] if fusion_type is None else fusion_type)
+        self.normalize = bool(conf["EMBEDDING_NORMALIZATION"] if normalize is None else normalize)
         self.in_channels = int(in_channels)
         if self.input_type not in _INPUT_IDS or self.fusion_type not in _FUSION_IDS:
             raise ValueError("INPUT must be RGBD / COLOR / DEPTH and FUSION_TYPE add / cat / early")

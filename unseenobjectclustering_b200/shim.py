@@ -23,10 +23,18 @@ from . import mean_shift as _ms
 def install(verbose=False):
     """Patch every already-imported reference module. Returns the list of patched attributes."""
     patched = []
+    ref_cfg_mod = sys.modules.get("fcn.config")
+    if ref_cfg_mod is not None and hasattr(ref_cfg_mod, "cfg"):
+        # what the reference's SEGNET.__init__ / clustering_features read from the global cfg (SEG.py:34-38,
+        # test_dataset.py:45) is read from the same object at the same moments (the tools call cfg_from_file() later)
+        _networks.configure(ref_cfg_mod.cfg, live=True)
+        _td._LIVE_CFG[0] = ref_cfg_mod.cfg
+        patched.append("cfg (INPUT, TRAIN.FUSION_TYPE, TRAIN.EMBEDDING_NORMALIZATION, TRAIN.EMBEDDING_METRIC read live)")
     ref_networks = sys.modules.get("networks")
     if ref_networks is not None and hasattr(ref_networks, "__dict__"):
-        ref_networks.__dict__["seg_resnet34_8s_embedding"] = _networks.seg_resnet34_8s_embedding
-        patched.append("networks.seg_resnet34_8s_embedding")
+        for name in ("seg_resnet34_8s_embedding", "seg_resnet34_8s_embedding_early"):
+            ref_networks.__dict__[name] = getattr(_networks, name)
+            patched.append("networks." + name)
     ref_td = sys.modules.get("fcn.test_dataset")
     if ref_td is not None:
         for name in ("clustering_features", "crop_rois", "match_label_crop", "filter_labels_depth", "test_sample"):

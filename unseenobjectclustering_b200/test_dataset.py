@@ -11,23 +11,35 @@ from . import mean_shift as _ms
 
 CROP_SIZE = 224           # cfg.TRAIN.SYN_CROP_SIZE, lib/fcn/config.py:129
 PADDING_PERCENTAGE = 0.25  # lib/fcn/test_dataset.py:66
+METRIC = 'cosine'         # cfg.TRAIN.EMBEDDING_METRIC as read by clustering_features (lib/fcn/test_dataset.py:45);
+                          # every shipped yml says cosine
+_LIVE_CFG = [None]        # a reference cfg object read at call time instead (set by shim.install)
 
 
-def clustering_features(features, num_seeds=100, first_indices=None, flags=0):
+def _metric(metric=None):
+    if metric is not None:
+        return metric
+    if _LIVE_CFG[0] is not None:
+        return str(_LIVE_CFG[0].TRAIN.EMBEDDING_METRIC)
+    return METRIC
+
+
+
+def clustering_features(features, num_seeds=100, first_indices=None, flags=0, metric=None):
     """lib/fcn/test_dataset.py:44-59.  Returns (out_label float32 CPU [N,H,W], list of N int64 CPU
     [num_seeds] tensors).  One np.random.randint(0, n) is consumed per item, in order, exactly like
-    the reference (lib/utils/mean_shift.py:155)."""
-    labels, selected = clustering_features_device(features, num_seeds, first_indices, flags)
+    the reference (lib/utils/mean_shift.py:155).  metric None -> the module-level METRIC."""
+    labels, selected = clustering_features_device(features, num_seeds, first_indices, flags, metric)
     N, _, H, W = features.shape
     out_label = labels.view(N, H, W).to(torch.float32).cpu()
     sel = selected.cpu()
     return out_label, [sel[j] for j in range(N)]
 
 
-def clustering_features_device(features, num_seeds=100, first_indices=None, flags=0):
+def clustering_features_device(features, num_seeds=100, first_indices=None, flags=0, metric=None):
     """Same, but results stay on the device: (int32 [N, H*W], int64 [N, num_seeds])."""
     return _ms.cluster_fields(features, num_seeds=num_seeds, kappa=20.0, max_iters=10, first_indices=first_indices,
-                              flags=flags)
+                              flags=flags, metric=_metric(metric))
 
 
 # --------------------------------------------------------------------------------------------
