@@ -190,9 +190,11 @@ def run_b200(args):
     frames = [synthetic.rgbd_frame(H, W, seed=100 * rank + i) for i in range(nframes)]
     dev_frames = [(a.to(dev), b.to(dev)) for a, b in frames]
     pin_frames = [(a.pin_memory(), b.pin_memory()) for a, b in frames]
-    firsts = UD.draw_first_indices(warmup + 4 * steps + 16, n, seed=3 + rank)
+    firsts = UD.draw_first_indices(4 * (warmup + 4 * steps + 16) * max(1, args.batch), n, seed=3 + rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    B = max(1, args.batch)                                 # frames per GPU per step (one slot launch of the pipeline)
     gathered = torch.empty((world, n), dtype=torch.int32, device=dev) if world > 1 else None
+    gathered_b = torch.empty((world, B * n), dtype=torch.int32, device=dev) if world > 1 else None
     out_pin = torch.empty((1, H, W), dtype=torch.float32).pin_memory()
 
     def step_device(i):
@@ -250,7 +252,8 @@ def run_b200(args):
 
     # ---- pipelined throughput: --depth frames in flight on separate streams --------------------------------
     from unseenobjectclustering_b200.pipeline import FramePipeline
-    pipe = FramePipeline(net, H, W, depth=max(1, args.depth), num_seeds=M, kappa=KAPPA, max_iters=ITERS, device=dev)
+    pipe = FramePipeline(net, H, W, depth=max(1, args.depth), num_seeds=M, kappa=KAPPA, max_iters=ITERS, device=dev,
+                         frames_per_slot=B)
 
     host_ms = [0.0]
 
@@ -271,25 +274,28 @@ def run_b200(args):
             sl.stream.wait_event(start)
         ends = []
         host_t0 = time.perf_counter()
-        for i in range(count):
+        for i in range(count * B):                          # count steps of B frames
             sl = pipe.slots[pipe.next % len(pipe.slots)]
-            if sl.busy:
-                pipe.collect_one()
-            with torch.cuda.stream(sl.stream):
-                flush.zero_()                               # L2 flush before every frame, INSIDE the timed region
+            if sl.fill == 0:
+                if sl.busy:
+                    pipe.collect_one()
+                with torch.cuda.stream(sl.stream):
+                    flush.zero_()                           # L2 flush before every step, INSIDE the timed region
             if raw:
                 a, b = raw_frames[(base + i) % nframes]
                 pipe.submit_raw(a, b, camera, firsts[base + i])
             else:
                 a, b = (dev_frames if resident else pin_frames)[(base + i) % nframes]
                 pipe.submit(a, b, firsts[base + i], resident=resident)
+            if sl.fill != 0:
+                continue                                    # the slot's batch is not complete yet
             if world > 1:
                 with torch.cuda.stream(sl.stream):
-                    dist.all_gather_into_tensor(gathered, sl.labels.view(-1))
+                    dist.all_gather_into_tensor(gathered_b, sl.labels.view(-1))
             e = torch.cuda.Event(enable_timing=True)
             e.record(sl.stream)
             ends.append(e)
-        host_ms[0] = (time.perf_counter() - host_t0) * 1e3 / max(count, 1)     # host time to enqueue one frame
+        host_ms[0] = (time.perf_counter() - host_t0) * 1e3 / max(count, 1)     # host time to enqueue one step
         pipe.drain()
         torch.cuda.synchronize()
         if world > 1:
@@ -375,19 +381,19 @@ def run_b200(args):
         kname = "meanshift_tc_kernel<64> (+reduce_normalize_kernel), per mean-shift update"
     achieved = bytes_actual / t_launch_s / 1e9 if t_launch_s > 0 else 0.0
     line = {
-        "metric": METRIC, "value": world * steps / (ms_pipe_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+        "metric": METRIC, "value": world * B * steps / (ms_pipe_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms_pipe_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": 1, "frames_in_flight": max(1, args.depth),
-                   "l2": "flushed before every frame (256 MiB memset on the frame's stream, inside the timed region)",
+        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "steps_in_flight": max(1, args.depth),
+                   "l2": "flushed before every step (256 MiB memset on the step's stream, inside the timed region)",
                    "timing": "CUDA events on the launching streams (start -> last frame done), max over ranks",
                    "multi_gpu": "frames sharded, one NCCL all-gather of label maps per step" if world > 1 else "single GPU"},
         "clocks": clocks,
-        "e2e": {"value": world * steps / (ms_pipe_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * 3 * H * W * 4,
-                "d2h_bytes_per_step": H * W * 4, "ms_per_step": ms_pipe_e2e / steps},
+        "e2e": {"value": world * B * steps / (ms_pipe_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 2 * 3 * H * W * 4,
+                "d2h_bytes_per_step": B * H * W * 4, "ms_per_step": ms_pipe_e2e / steps},
         # same, from RAW host frames (uint8 BGR + uint16 depth): the reference's read_sample arithmetic runs on the device
-        "e2e_raw_inputs": {"value": world * steps / (ms_pipe_raw * 1e-3), "unit": UNIT, "h2d_bytes_per_step": H * W * 5,
-                           "d2h_bytes_per_step": H * W * 4, "ms_per_step": ms_pipe_raw / steps},
+        "e2e_raw_inputs": {"value": world * B * steps / (ms_pipe_raw * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * H * W * 5,
+                           "d2h_bytes_per_step": B * H * W * 4, "ms_per_step": ms_pipe_raw / steps},
         "serial": {"value": world * steps / (ms_dev * 1e-3), "ms_per_step": ms_dev / steps, "e2e_value": world * steps / (ms_e2e * 1e-3),
                    "e2e_ms_per_step": ms_e2e / steps, "note": "one frame at a time, L2 flushed (untimed) between frames"},
         # the pipelined region replays CUDA graphs (not visible to the library's launch counter): the same kernels as the
@@ -420,7 +426,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=2, help="frames in flight per GPU (1 = strictly serial)")
+    ap.add_argument("--depth", type=int, default=2, help="steps in flight per GPU (1 = strictly serial)")
+    ap.add_argument("--batch", type=int, default=1, help="frames per GPU per step: they go through every kernel together")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

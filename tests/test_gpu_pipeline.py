@@ -162,3 +162,72 @@ def test_frame_pipeline_raw_frames_equal_prepared_frames():
         io, xo = O.read_sample_arrays(raws[k][0], raws[k][1], cam)
         slot = pipe_b.slots[k % 2]
         assert torch.equal(slot.img_dev.cpu(), io) and torch.equal(slot.xyz_dev.cpu(), xo)
+
+
+class _BatchFieldNet(torch.nn.Module):
+    """Batch-capable stand-in network: image channel 0 carries a per-pixel cluster id."""
+
+    def __init__(self, d=64, k=8, hw=96 * 128, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.register_buffer("centres", torch.nn.functional.normalize(torch.randn(k, d, generator=g), dim=1))
+        self.register_buffer("noise", 0.05 * torch.randn(d, hw, generator=g))
+
+    def forward(self, img, label=None, depth=None):
+        N, _, H, W = img.shape
+        ids = img[:, 0].reshape(N, -1).long()
+        f = self.centres[ids].permute(0, 2, 1) + self.noise.unsqueeze(0) + 0.0 * depth[:, 0].reshape(N, 1, -1)
+        return torch.nn.functional.normalize(f, dim=1).reshape(N, -1, H, W).contiguous()
+
+
+@pytest.mark.parametrize("B,depth", [(2, 2), (3, 1)])
+def test_frame_pipeline_frames_per_slot_equals_serial_calls(B, depth):
+    """frames_per_slot = B: B frames go through every kernel together (eager warm-up, then CUDA graphs); an
+    incomplete last batch is flushed by drain().  Every frame's labels equal the one-at-a-time call's."""
+    from unseenobjectclustering_b200 import mean_shift as MS
+    from unseenobjectclustering_b200.pipeline import FramePipeline
+    H, W = 96, 128
+    net = _BatchFieldNet().to(DEV)
+    nframes = 4 * B * depth + 1                          # the last slot launch is incomplete
+    frames = []
+    for k in range(nframes):
+        _, gt = O.synthetic_clustered_features(H, W, 8, 3 + k % 3, 0.05, seed=190 + k)
+        img = torch.zeros(1, 3, H, W)
+        img[0, 0] = gt.float()
+        frames.append(img)
+    xyz = torch.ones(1, 3, H, W)
+    firsts = [(37 * k + 5) % (H * W) for k in range(nframes)]
+    pipe = FramePipeline(net, H, W, depth=depth, frames_per_slot=B)
+    outs = []
+    for k in range(nframes):
+        pipe.submit(frames[k], xyz, firsts[k])
+        while len(pipe.pending) >= depth:
+            outs.extend(o.clone() for o in pipe.collect_one()[0])
+    for res in pipe.drain():
+        outs.extend(o.clone() for o in res[0])
+    assert pipe.graph_error is None, pipe.graph_error
+    assert all(s.graph_a is not None for s in pipe.slots)
+    assert len(outs) >= nframes
+    for k in range(nframes):
+        feats = net(frames[k].to(DEV), None, xyz.to(DEV))
+        want, _ = MS.cluster_fields(feats, 100, first_indices=[firsts[k]], flags=_lib.FLAG_SYNC_CHECK)
+        assert torch.equal(outs[k].view(-1).to(torch.int32), want[0].cpu()), k
+
+
+def test_batch_of_full_frames_equals_single_calls():
+    """Two 640x480 fields in one library call: they do not fit the resident-slice sampler together, so the fields take
+    turns there (same kernel, same indices); loop and label kernels run at batch 2.  Everything equals the single calls."""
+    from unseenobjectclustering_b200 import mean_shift as MS
+    fa, _ = O.synthetic_clustered_features(480, 640, 64, 6, 0.05, seed=301)
+    fb, _ = O.synthetic_clustered_features(480, 640, 64, 4, 0.05, seed=302)
+    both = torch.cat([fa, fb], 0).to(DEV)
+    MS.register_bf16_copy(both, MS.pack_bf16(both))
+    lab, sel, Z, sl = MS.cluster_fields(both, 100, first_indices=[1234, 99999], flags=_lib.FLAG_SYNC_CHECK, return_seeds=True)
+    for j, (f, first) in enumerate(((fa, 1234), (fb, 99999))):
+        one = f.to(DEV)
+        MS.register_bf16_copy(one, MS.pack_bf16(one))
+        l1, s1, Z1, sl1 = MS.cluster_fields(one, 100, first_indices=[first], flags=_lib.FLAG_SYNC_CHECK, return_seeds=True)
+        assert torch.equal(sel[j], s1[0])
+        assert torch.equal(sl[j], sl1[0])
+        assert torch.equal(lab[j], l1[0])
+        assert (1 - (Z[j] * Z1[0]).sum(-1)).abs().max().item() < 1e-6

@@ -22,6 +22,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t a, const uint32_t (&v)[16]) {
 
 // MODE 0: loads only (wait after every load)   1: loads, two in flight   2: load + store (mean-shift pattern)
 // MODE 3: load + 32 MUFU.EX2 + store           4: 32 MUFU.EX2 only per iteration
+// MODE 5: load + 24 MUFU.EX2 + 8 polynomial ex2 (FMA pipe) + store      6: load + 20 MUFU + 12 polynomial + store
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.f);
+  const float r = x + 12582912.f;
+  const float f = x - (r - 12582912.f);
+  const float p = fmaf(fmaf(fmaf(0.055268917f, f, 0.24221092f), f, 0.6932298f), f, 1.0f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
+}
 template <int MODE>
 __global__ void k(float* out, long long* clk, int iters) {
   __shared__ uint32_t slot;
@@ -52,6 +60,21 @@ __global__ void k(float* out, long long* clk, int iters) {
       tmem_ld32(a ^ 64, vb);
       asm volatile("tcgen05.wait::ld.sync.aligned;");
       acc += __uint_as_float(va[it & 31]) + __uint_as_float(vb[it & 31]);
+    } else if (MODE == 5 || MODE == 6) {
+      constexpr int POLY = (MODE == 5) ? 8 : 12;
+      tmem_ld32(a, va);
+      asm volatile("tcgen05.wait::ld.sync.aligned;");
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float p0 = fmaf(__uint_as_float(va[2 * e]), 1e-30f, -0.5f), p1 = fmaf(__uint_as_float(va[2 * e + 1]), 1e-30f, -0.5f);
+        const bool poly0 = ((2 * e) * POLY) / 32 != ((2 * e + 1) * POLY) / 32;
+        const bool poly1 = ((2 * e + 1) * POLY) / 32 != ((2 * e + 2) * POLY) / 32;
+        if (poly0) p0 = ex2_poly(p0); else asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(p0));
+        if (poly1) p1 = ex2_poly(p1); else asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(p1));
+        asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(pk[e]) : "r"(__float_as_uint(p0)), "r"(__float_as_uint(p1)));
+      }
+      tmem_st16(base + (it & 7) * 16, pk);
+      if ((it & 3) == 3) asm volatile("tcgen05.wait::st.sync.aligned;");
     } else if (MODE == 2 || MODE == 3) {
       tmem_ld32(a, va);
       asm volatile("tcgen05.wait::ld.sync.aligned;");
@@ -106,6 +129,8 @@ int main() {
     run<2>("ld + pack + st.x16 (no MUFU)", w, 1);
     run<3>("ld + 32 ex2 + pack + st.x16 (mean-shift)", w, 1);
     run<4>("32 ex2 only", w, 0);
+    run<5>("ld + 24 ex2 + 8 poly + pack + st.x16", w, 1);
+    run<6>("ld + 20 ex2 + 12 poly + pack + st.x16", w, 1);
   }
   return 0;
 }

@@ -55,6 +55,9 @@ static WsLayout ws_layout(int batch, int64_t n, int d, int m) {
     size_t per_pass = size_t(nb) * 128;                               // leader protocol: one line per CTA
     if (size_t(nb) * nb * 8 > per_pass) per_pass = size_t(nb) * nb * 8;   // all-to-all protocol: nb x nb key matrix
     L.slot_bytes = size_t(batch) * m * per_pass + size_t(batch) * m * d * 8;   // key slots + seed mailboxes
+    // a batch whose fields do not fit on chip together is sampled one field at a time at full width (nb = all SMs)
+    const size_t single = size_t(m) * size_t(sms) * sms * 8 + size_t(m) * d * 8;
+    if (batch > 1 && single > L.slot_bytes) L.slot_bytes = single;
     L.slots = carve(off, L.slot_bytes);
   }
   L.barrier = carve(off, 256);
@@ -570,6 +573,22 @@ int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterSh
     bool used = false;
     int rc = launch_select_seeds_tc(X, xb, s, w, selected_out, seeds_out, stream, &used);
     if (rc != UOC_OK || used) return rc;
+    if (s.batch > 1) {
+      // The resident-slice sampler keeps a whole field on chip (tensor + shared memory of all SMs); a batch of large
+      // fields does not fit at once, so the fields take turns, each at full width (same kernel, same indices).
+      ClusterShape s1 = s;
+      s1.batch = 1;
+      int done = 0;
+      for (int b = 0; b < s.batch; ++b, ++done) {
+        ClusterWorkspace w1 = w;
+        w1.first = w.first + b;
+        rc = launch_select_seeds_tc(X + b * s.stride_b, xb + size_t(b) * s.n * s.d, s1, w1, selected_out + size_t(b) * s.m,
+                                    seeds_out + size_t(b) * s.m * s.d, stream, &used);
+        if (rc != UOC_OK) return rc;
+        if (!used) break;
+      }
+      if (done == s.batch) return UOC_OK;
+    }
   }
   FpsParams p;
   p.X = X; p.sb = s.stride_b; p.sd = s.stride_d; p.n = s.n; p.d = s.d; p.m = s.m; p.batch = s.batch;

@@ -29,6 +29,9 @@ namespace {
 
 constexpr int kTile = 128;          // points per tile
 constexpr int kThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-5 weight group 0 (even tiles), warps 6-9 group 1 (odd tiles)
+constexpr int kThreadsP = 352;      // persistent kernel: + warp 10, the GEMM2 issuer
+constexpr int kIssue2Warp = 10;
+constexpr int kIssueBar = 320;      // named barrier 1: the two issuing warps + the eight weight warps
 constexpr int kBoxBytes = 128 * 128;  // one [128 x 64ch] bf16 box, 16 KiB
 constexpr int kDefaultPoly = 0;       // weights per 32-column chunk evaluated on the FMA pipe (UOC_LOOP_POLY overrides: 0 / 8 / 12)
 
@@ -298,7 +301,7 @@ __device__ __forceinline__ bool poll_flag(const unsigned int* p, unsigned int ta
 // POLY: of the 32 weights a thread computes per 32-column chunk, POLY are evaluated with ex2_poly on the FMA pipe and
 // the rest with MUFU.EX2, interleaved (the two pipes run concurrently; UOC_LOOP_POLY selects the split).
 template <int D, int POLY>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsP, 1)
 meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float* Z, float* partials,
                                unsigned int* done, unsigned int* rowflag, int m, long long n, float c1, int P,
                                int iters, unsigned int* err, long long* trace) {
@@ -315,7 +318,8 @@ meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float
   uint64_t* s_full = bars + 2 * Cfg::kStages;
   uint64_t* p_ready = s_full + 3;
   uint64_t* o_full = p_ready + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* s_free = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, b = blockIdx.y;
@@ -326,7 +330,7 @@ meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
-    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&s_free[i], 1); }
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -354,42 +358,31 @@ meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float
       }
     }
   } else if (warp == 1) {
+    // ---- GEMM1 issuer: S(tile) = Zs . X^T as soon as the X tile has landed and the S/P buffer is free again.
+    // GEMM1 and GEMM2 have their OWN issuing threads (warps 1 and 10): with a single in-order issuer every wait for a
+    // P tile also held back the next S tile, and tcgen05.mma issue blocks while the queue is full (measured: the
+    // single issuer spent 10.8k of 23k clk per update inside issue and 9.3k waiting for P).
     constexpr uint32_t idesc1 = make_idesc_bf16(128, kTile, 0, 0);
-    constexpr uint32_t idesc2 = make_idesc_bf16(128, D, 0, 1);
     const uint32_t zs_addr = smem_u32(zs);
     const uint32_t st_addr = smem_u32(stages);
     bool ok = true;
     long long* tr2 = (trace && b == 0 && cta == 0) ? trace + 16 * iters : nullptr;   // debug: the issuing thread's waits
     for (int u = 0; u < iters; ++u) {
-      named_bar_sync(1, 288);              // seeds of this update staged, O of the previous one drained
+      named_bar_sync(1, kIssueBar);        // seeds of this update staged, O of the previous one drained
       tc_fence_after();
       if (elect_one()) {
         const long long base = (long long)u * T;
-        long long w_x = 0, w_p = 0;
+        long long w_x = 0, w_f = 0;
         const long long t_begin = tr2 ? clock64() : 0;
-        // three S/P buffers (global tile jj -> buffer jj % 3): GEMM1 runs two tiles ahead of the weights
-        auto gemm2 = [&](int j) {
-          const long long jj = base + j;
-          const int s = int(jj % Cfg::kStages), buf = int(jj % 3);
-          const long long tw = tr2 ? clock64() : 0;
-          if (!mbar_wait(&p_ready[buf], uint32_t(jj / 3) & 1u, err)) { ok = false; return; }
-          if (tr2) w_p += clock64() - tw;
-          tc_fence_after();
-          const uint32_t xb = st_addr + s * Cfg::kStageBytes;
-#pragma unroll
-          for (int ks = 0; ks < kTile / 16; ++ks) {
-            const uint64_t bd = make_smem_desc_sw128(xb + ks * 2048, kBoxBytes, 1024);
-            umma_ts_f16(tmem_base + Cfg::kColO3, tmem_base + buf * Cfg::kColS3 + ks * 8, bd, idesc2,
-                        (j > 0 || ks > 0) ? 1u : 0u);
-          }
-          umma_commit(&x_empty[s]);
-        };
         for (int j = 0; j < T && ok; ++j) {
           const long long jj = base + j;
           const int s = int(jj % Cfg::kStages), buf = int(jj % 3);
-          const long long tw = tr2 ? clock64() : 0;
+          long long tw = tr2 ? clock64() : 0;
           if (!mbar_wait(&x_full[s], uint32_t(jj / Cfg::kStages) & 1u, err)) { ok = false; break; }
-          if (tr2) w_x += clock64() - tw;
+          if (tr2) { const long long t = clock64(); w_x += t - tw; tw = t; }
+          // the S/P buffer of tile jj was last used by tile jj - 3: its GEMM2 must have consumed P
+          if (jj >= 3 && !mbar_wait(&s_free[buf], (uint32_t(jj / 3) + 1u) & 1u, err)) { ok = false; break; }
+          if (tr2) w_f += clock64() - tw;
           tc_fence_after();
           const uint32_t xb = st_addr + s * Cfg::kStageBytes;
 #pragma unroll
@@ -402,12 +395,37 @@ meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float
             }
           }
           umma_commit(&s_full[buf]);
-          if (j >= 2) gemm2(j - 2);
         }
-        if (ok && T > 1) gemm2(T - 2);
-        if (ok && T > 0) gemm2(T - 1);
+        if (tr2) { tr2[u * 4 + 0] = w_x; tr2[u * 4 + 1] = w_f; tr2[u * 4 + 2] = clock64() - t_begin; tr2[u * 4 + 3] = T; }
+      }
+      __syncwarp();
+    }
+  } else if (warp == kIssue2Warp) {
+    // ---- GEMM2 issuer: O += P(tile) . X(tile) as soon as a weight group has published P
+    constexpr uint32_t idesc2 = make_idesc_bf16(128, D, 0, 1);
+    const uint32_t st_addr = smem_u32(stages);
+    bool ok = true;
+    for (int u = 0; u < iters; ++u) {
+      named_bar_sync(1, kIssueBar);
+      tc_fence_after();
+      if (elect_one()) {
+        const long long base = (long long)u * T;
+        for (int j = 0; j < T && ok; ++j) {
+          const long long jj = base + j;
+          const int s = int(jj % Cfg::kStages), buf = int(jj % 3);
+          if (!mbar_wait(&p_ready[buf], uint32_t(jj / 3) & 1u, err)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t xb = st_addr + s * Cfg::kStageBytes;
+#pragma unroll
+          for (int ks = 0; ks < kTile / 16; ++ks) {
+            const uint64_t bd = make_smem_desc_sw128(xb + ks * 2048, kBoxBytes, 1024);
+            umma_ts_f16(tmem_base + Cfg::kColO3, tmem_base + buf * Cfg::kColS3 + ks * 8, bd, idesc2,
+                        (j > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&x_empty[s]);      // GEMM1 of this tile completed before its P existed: the X stage is free
+          umma_commit(&s_free[buf]);     // ... and so is the S/P buffer
+        }
         if (ok) umma_commit(o_full);
-        if (tr2) { tr2[u * 4 + 0] = w_x; tr2[u * 4 + 1] = w_p; tr2[u * 4 + 2] = clock64() - t_begin; tr2[u * 4 + 3] = T; }
       }
       __syncwarp();
     }
@@ -452,7 +470,7 @@ meanshift_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x, float
         fence_proxy_async();
       }
       tc_fence_before();
-      named_bar_sync(1, 288);
+      named_bar_sync(1, kIssueBar);
       tc_fence_after();
       stamp(u, 1);
       // ---- weights: this group's tiles are those with global parity == grp
@@ -601,7 +619,7 @@ int launch_persistent(const CUtensorMap& tmap, const ClusterShape& s, const Clus
     UOC_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * 20 * iters, stream));
   }
   void* args[] = {&tm, &Z, &partials, &done, &rowflag, &m, &n, &c1, &P, &iters, &err, &trace};
-  UOC_CUDA(cudaLaunchCooperativeKernel(meanshift_tc_persistent_kernel<D, POLY>, dim3(P, s.batch), dim3(kThreads), args,
+  UOC_CUDA(cudaLaunchCooperativeKernel(meanshift_tc_persistent_kernel<D, POLY>, dim3(P, s.batch), dim3(kThreadsP), args,
                                        Cfg::kSmemBytes, stream));
   count_launch();
   if (want_trace) {
@@ -618,7 +636,7 @@ int launch_persistent(const CUtensorMap& tmap, const ClusterShape& s, const Clus
       }
     for (int u = 0; u < iters; ++u) {
       const long long* q = h.data() + size_t(16) * iters + size_t(u) * 4;
-      fprintf(stderr, "[loop trace] cta 0 update %d, issuing thread: %lld tiles, waited %lld clk for X tiles (TMA), %lld clk for P tiles (weights), %lld clk in total\n",
+      fprintf(stderr, "[loop trace] cta 0 update %d, GEMM1 issuing thread: %lld tiles, waited %lld clk for X tiles (TMA), %lld clk for free S/P buffers, %lld clk in total\n",
               u, q[3], q[0], q[1], q[2]);
     }
   }
