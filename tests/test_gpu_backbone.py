@@ -46,13 +46,14 @@ def _conv_call(x, w, bias, res, N, H, W, Cin, Cout, k, stride, dil, relu, flags)
     return y
 
 
-@pytest.mark.parametrize("variant", ["tc_cluster1", "halo_x1", "halo_x1_sub1", "halo_small_sub1", "halo_x0", "tc_cluster4", "tc_cluster8", "tc_cluster2_n128", "simt"])
+@pytest.mark.parametrize("variant", ["tc_cluster1", "pair", "halo_x1", "halo_x1_sub1", "halo_small_sub1", "halo_x0", "tc_cluster4", "tc_cluster8", "tc_cluster2_n128", "simt"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
 def test_conv_matches_torch(case, variant, monkeypatch):
     """tcgen05 implicit GEMM with every cluster-multicast width (the library reads UOC_CONV_CLUSTER /
     UOC_CONV_MAX_BLOCK_N at each launch) and the SIMT validation kernel, against torch's convolution."""
     Cin, Cout, k, stride, dil, H, W, N = case
     flags = _lib.FLAG_CONV_SIMT if variant == "simt" else 0
+    monkeypatch.setenv("UOC_CONV_2SM", "1" if variant == "pair" else "0")     # CTA pairs (cta_group::2), Cout % 128 == 0
     if variant.startswith("tc_cluster"):
         monkeypatch.setenv("UOC_CONV_CLUSTER", variant[len("tc_cluster")])
     if variant.endswith("_n128"):

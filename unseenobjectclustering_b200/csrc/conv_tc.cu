@@ -248,6 +248,198 @@ int launch_n(const ConvTcParams& prm, int cluster, int m_tiles, int groups, cuda
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): the kernel above is bound by the ~48 B/clk an SM can ingest from L2 (a 128x128 tile
+// needs 32 KB per 256 MMA-clk), and multicast does not help because the bytes still enter every SM.  Here two CTAs on
+// the two SMs of a TPC execute ONE tcgen05.mma of M = 256: each stages its own 128 pixels of A and only HALF of the
+// weight rows (BLOCK_N / 2); the tensor core reads the other half from the peer's shared memory.  BLOCK_N = 256:
+// 32 KB per CTA and K block for a 128 x 256 output slab -- half the bytes per MAC of the single-CTA tile.
+//   both CTAs : warp 0 = TMA producer (loads signal the LEADER's full barrier), warps 2-5 = epilogue of the own 128 rows
+//   leader    : warp 1 = MMA issuer; tcgen05.commit multicasts onto both CTAs' empty / accumulator barriers
+// ----------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct Conv2Cfg {
+  static constexpr int kBBytes = (BLOCK_N / 2) * 128;       // this CTA's half of the weight tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+  static constexpr uint32_t kTmemCols = BLOCK_N;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
+  using Cfg = Conv2Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* acc_full = bars + 2 * Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.z;
+  const int rank = int(cluster_ctarank());               // 0 = leader
+  const int pair = int(blockIdx.x) >> 1;
+  const int n_tile = pair % p.n_tiles;
+  int m_tile = (pair / p.n_tiles) * 2 + rank;            // may exceed the real tile count (padding CTA): zero A, no stores
+  const int tx = m_tile % p.tiles_x; m_tile /= p.tiles_x;
+  const int ty = m_tile % p.tiles_y;
+  const int img = m_tile / p.tiles_y;
+  const int n0 = n_tile * BLOCK_N;
+  const int cblocks = p.Cin >> 6;
+  const int KB = p.ksize * p.ksize * cblocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_x[g]);
+    tma_prefetch_desc(&p.tmap_w[g]);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // both CTAs' barriers are initialised and both allocations done before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const int x_base = tx * 16 * p.stride - p.pad;
+      const int y_base = ty * 8 * p.stride - p.pad;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % Cfg::kStages;
+        if (!mbar_wait(&empty[s], ((kb / Cfg::kStages) & 1) ^ 1u, p.err)) break;
+        const int tap = kb / cblocks, cb = kb - tap * cblocks;
+        const int r = tap / p.ksize, sx = tap - r * p.ksize;
+        uint8_t* st = smem + s * Cfg::kStageBytes;
+        if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);     // the bytes of BOTH CTAs
+        const uint32_t lbar = leader_bar_addr(&full[s]);
+        tma_load_4d_2sm(st, &p.tmap_x[g], lbar, cb * 64, x_base + sx * p.dil, y_base + r * p.dil, img);
+        tma_load_2d_2sm(st + kABytes, &p.tmap_w[g], lbar, kb * 64, n0 + rank * (BLOCK_N / 2));
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 0, 0);
+      bool ok = true;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % Cfg::kStages;
+        if (!mbar_wait(&full[s], (kb / Cfg::kStages) & 1, p.err)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ad = make_smem_desc_sw128(a_addr + ks * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc_sw128(b_addr + ks * 32, 16, 1024);
+          umma_ss_f16_2sm(tmem_base, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+        }
+        umma_commit_2sm(&empty[s], 3);
+      }
+      if (ok) umma_commit_2sm(acc_full, 3);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int oy = ty * 8 + (row >> 4), ox = tx * 16 + (row & 15);
+    const bool inb = (oy < p.Ho) && (ox < p.Wo) && (img < p.N);
+    const size_t pix = (size_t(img) * p.Ho + oy) * p.Wo + ox;
+    const float* bias = p.bias[g] + n0;
+    if (mbar_wait(acc_full, 0, p.err)) {
+      tc_fence_after();
+      const uint32_t ta = tmem_base + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(ta + c * 32, v);
+        tmem_wait_ld();
+        if (inb) {
+          float f[32];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + e * 4));
+            f[4 * e + 0] = __uint_as_float(v[4 * e + 0]) + bv.x;
+            f[4 * e + 1] = __uint_as_float(v[4 * e + 1]) + bv.y;
+            f[4 * e + 2] = __uint_as_float(v[4 * e + 2]) + bv.z;
+            f[4 * e + 3] = __uint_as_float(v[4 * e + 3]) + bv.w;
+          }
+          if (p.residual[g]) {
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual[g]) +
+                                                             pix * p.Cout + n0 + c * 32);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint4 rv = __ldg(rp + e);
+              const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                f[8 * e + 2 * h + 0] += __uint_as_float(w4[h] << 16);
+                f[8 * e + 2 * h + 1] += __uint_as_float(w4[h] & 0xFFFF0000u);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = fmaxf(f[e], 0.f);
+          }
+          if (p.out_fp32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.y[g]) + pix * p.Cout + n0 + c * 32);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) op[e] = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y[g]) + pix * p.Cout + n0 + c * 32);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              op[e] = make_uint4(pack_bf16x2(f[8 * e + 0], f[8 * e + 1]), pack_bf16x2(f[8 * e + 2], f[8 * e + 3]),
+                                 pack_bf16x2(f[8 * e + 4], f[8 * e + 5]), pack_bf16x2(f[8 * e + 6], f[8 * e + 7]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // the peer may still be reading this CTA's weight half / arriving on its barriers
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+}
+
+template <int BLOCK_N>
+int launch_pair(const ConvTcParams& prm, int m_tiles, int groups, cudaStream_t stream) {
+  using Cfg = Conv2Cfg<BLOCK_N>;
+  static bool attr = false;
+  if (!attr) {
+    UOC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr = true;
+  }
+  const int m_pairs = (m_tiles + 1) / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(m_pairs * prm.n_tiles * 2, 1, groups);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute lattr[2];
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = 2;
+  lattr[0].val.clusterDim.y = 1;
+  lattr[0].val.clusterDim.z = 1;
+  lattr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  lattr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = lattr;
+  cfg.numAttrs = 2;
+  UOC_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BLOCK_N>, prm));
+  count_launch();
+  return UOC_OK;
+}
+
 }  // namespace
 
 int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
@@ -265,7 +457,12 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
   prm.tiles_y = (prm.Ho + 7) / 8;
   // Measured on B200 (profiles/r01_conv_notes.md): the kernel is bound by the ~48 B/clk/SM TMA ingest rate, which
   // multicast does not relieve (the bytes still enter every SM), so the defaults are the plain 128-wide tiles, 2 CTAs/SM.
+  // CTA pairs (cta_group::2) for the wide layers: UOC_CONV_2SM=0 keeps the single-CTA tiles everywhere
+  int pair = 0;
+  if (const char* e = getenv("UOC_CONV_2SM")) pair = atoi(e);
+  if (p.Cout % 128 != 0) pair = 0;
   int block_n = (p.Cout % 128 == 0) ? 128 : 64;
+  if (pair) block_n = (p.Cout % 256 == 0) ? 256 : 128;
   if (const char* e = getenv("UOC_CONV_BLOCK_N")) { if (atoi(e) == 256 && p.Cout % 256 == 0) block_n = 256; }
   int cluster = 1;
   if (const char* e = getenv("UOC_CONV_CLUSTER")) cluster = atoi(e);
@@ -286,7 +483,7 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
     if (rc != UOC_OK) return rc;
     const uint64_t wd[2] = {uint64_t(taps) * p.Cin, uint64_t(p.Cout)};
     const uint64_t wsb[1] = {uint64_t(taps) * p.Cin * 2};
-    const uint32_t wb[2] = {64, uint32_t(block_n / cluster)};   // each CTA of a cluster fetches (and multicasts) one slice
+    const uint32_t wb[2] = {64, uint32_t(pair ? block_n / 2 : block_n / cluster)};   // each CTA of a cluster / pair fetches one slice
     rc = make_tmap_bf16(&prm.tmap_w[g], p.g[g].w, 2, wd, wsb, wb, nullptr);
     if (rc != UOC_OK) return rc;
     prm.bias[g] = p.g[g].bias;
@@ -294,6 +491,7 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
     prm.y[g] = p.g[g].y;
   }
   const int m_tiles = p.N * prm.tiles_y * prm.tiles_x;
+  if (pair) return (block_n == 256) ? launch_pair<256>(prm, m_tiles, p.groups, stream) : launch_pair<128>(prm, m_tiles, p.groups, stream);
   if (block_n == 256) return launch_n<256>(prm, cluster, m_tiles, p.groups, stream);
   if (block_n == 128) return launch_n<128>(prm, cluster, m_tiles, p.groups, stream);
   return launch_n<64>(prm, cluster, m_tiles, p.groups, stream);
