@@ -13,9 +13,10 @@ Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; 
 through the public API with pinned HOST buffers (H2D of the frame + D2H of the labels inside the
 timed region); `roofline` = the mean-shift loop kernel (the kernel BASELINE.json's metric names)
 against the measured HBM peak; `cpu_baseline` = the oracle port on the host cores (N=1 only).
-Timing: CUDA events on the launching streams, max over ranks.  Default mode keeps --depth frames in
-flight on separate CUDA streams (pipeline.py) and flushes L2 with a 256 MiB memset before EVERY frame,
-inside the timed region; `serial` in the JSON line is the one-frame-at-a-time latency (flush untimed).
+Timing: CUDA events on the launching streams, max over ranks.  A step = --batch frames per GPU that go
+through every kernel together (pipeline.py, frames_per_slot); --depth steps are in flight on separate CUDA
+streams; L2 is flushed with a 256 MiB memset before EVERY step, inside the timed region; `serial` in the
+JSON line is the one-frame-at-a-time latency (flush untimed).
 """
 import argparse
 import json
@@ -332,7 +333,7 @@ def run_b200(args):
         flush.zero_()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         a, b = dev_frames[rep % nframes]
-        torch.cuda._sleep(3_000_000)      # ~1.5 ms of GPU spin: the host enqueues the backbone's ~45 launches meanwhile (else host-bound)
+        torch.cuda._sleep(8_000_000)      # ~4 ms of GPU spin: the host enqueues the backbone's ~45 launches meanwhile (else host-bound)
         ev[0].record()
         feats = net(a, None, b)
         xb = MS._lookup_bf16(feats)
@@ -426,8 +427,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=2, help="steps in flight per GPU (1 = strictly serial)")
-    ap.add_argument("--batch", type=int, default=1, help="frames per GPU per step: they go through every kernel together")
+    ap.add_argument("--depth", type=int, default=3, help="steps in flight per GPU (1 = strictly serial)")
+    ap.add_argument("--batch", type=int, default=4, help="frames per GPU per step: they go through every kernel together")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

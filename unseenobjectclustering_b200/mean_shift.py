@@ -79,7 +79,9 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
     dev = features.device
     if first_indices is None:
         first_indices = [np.random.randint(0, n) for _ in range(N)]
-    first = (ctypes.c_int64 * N)(*[int(v) for v in first_indices])
+    if len(first_indices) < N:
+        raise ValueError("first_indices has %d entries for %d fields" % (len(first_indices), N))
+    first = (ctypes.c_int64 * N)(*[int(v) for v in list(first_indices)[:N]])     # extra entries are left unused
     flags = int(flags) | _metric_flag(metric)
     xb = _lookup_bf16(features) if metric == 'cosine' else None
     with torch.cuda.device(dev):
