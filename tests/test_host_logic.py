@@ -93,3 +93,44 @@ def test_inputs_must_be_cuda():
     net = N.seg_resnet34_8s_embedding(2, 64, None)
     with pytest.raises(_lib.UocError):
         net(torch.zeros(1, 3, 32, 32), None, torch.zeros(1, 3, 32, 32))
+
+
+def test_variant_configuration_and_factories():
+    """The factories take INPUT / FUSION_TYPE / EMBEDDING_NORMALIZATION like the reference's SEGNET.__init__ takes them
+    from cfg (SEG.py:34-38): module-level CONFIG, configure(cfg), keyword arguments; construction needs no GPU."""
+    net = N.seg_resnet34_8s_embedding(2, 64, None)
+    assert (net.input_type, net.fusion_type, net.normalize, net.feature_dim) == ("RGBD", "add", True, 64)
+    assert len(net.state_dict()) == 436                      # SURVEY section 3C: 436 tensors for rgbd_add
+    cat = N.seg_resnet34_8s_embedding(2, 64, None, fusion_type="cat")
+    assert cat.feature_dim == 128
+    color = N.seg_resnet34_8s_embedding(2, 64, None, input_type="COLOR")
+    assert len(color.state_dict()) == 218 and all(k.startswith("fcn.") for k in color.state_dict())
+    early = N.seg_resnet34_8s_embedding_early(2, 64, None)
+    assert early.state_dict()["fcn.resnet34_8s.conv1.weight"].shape == (64, 6, 7, 7)
+
+    class _T(object):
+        FUSION_TYPE, EMBEDDING_NORMALIZATION, EMBEDDING_METRIC = "cat", False, "euclidean"
+
+    class _Cfg(object):
+        INPUT, TRAIN = "RGBD", _T
+
+    saved = dict(N.CONFIG)
+    try:
+        N.configure(_Cfg)
+        net = N.seg_resnet34_8s_embedding(2, 64, None)
+        assert (net.fusion_type, net.normalize, net.feature_dim) == ("cat", False, 128)
+        N.configure(_Cfg, live=True)                             # what shim.install() does: read at construction time
+        _T.FUSION_TYPE = "add"
+        assert N.seg_resnet34_8s_embedding(2, 64, None).fusion_type == "add"
+        TD._LIVE_CFG[0] = _Cfg
+        assert TD._metric() == "euclidean" and TD._metric("cosine") == "cosine"
+    finally:
+        N.CONFIG.update(saved)
+        N._LIVE_CFG[0] = None
+        TD._LIVE_CFG[0] = None
+    assert TD._metric() == "cosine"
+    # a checkpoint of another variant is filtered by name and shape like SEG.py:152 (nothing matches -> random init kept)
+    sd = N.random_state_dict(64, seed=1, input_type="RGBD", fusion_type="early", in_channels=6)
+    net = N.seg_resnet34_8s_embedding(2, 64, {"module." + k: v for k, v in sd.items()})
+    assert not torch.equal(net.state_dict()["fcn.resnet34_8s.conv1.weight"][:, :3], sd["fcn.resnet34_8s.conv1.weight"][:, :3])
+    assert torch.equal(net.state_dict()["fcn.resnet34_8s.layer1.0.conv1.weight"], sd["fcn.resnet34_8s.layer1.0.conv1.weight"])
