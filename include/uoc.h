@@ -217,6 +217,39 @@ UOC_API int uoc_prepare_inputs(const uint8_t* bgr, const uint16_t* depth_raw, in
 UOC_API int uoc_compute_xyz(const float* depth_m, int N, int H, int W, float fx, float fy, float px, float py,
                             float* xyz_out, uoc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Two-stage plumbing (lib/fcn/test_dataset.py:62-198) on the device.  Label ids < 256.
+ * ------------------------------------------------------------------------------------------ */
+
+/* bytes of workspace for the functions below (N label maps, K crops) */
+UOC_API size_t uoc_refine_workspace_bytes(int N, int K);
+
+/* filter_labels_depth (test_dataset.py:183-198): labels [N,n] int32; depth_z = channel 2 (Z) of the XYZ tensor, item b at
+ * depth_z + b * z_stride_b; a non-zero id whose share of pixels with Z > 0 is < threshold becomes 0.  labels_out may alias. */
+UOC_API int uoc_filter_labels_depth(const int32_t* labels, const float* depth_z, int64_t z_stride_b, int N, int64_t n,
+                                    float threshold, int32_t* labels_out, void* workspace, size_t workspace_bytes,
+                                    uoc_stream_t stream);
+
+/* first half of crop_rois (test_dataset.py:68-94 + utils/mask.py:180-195): the non-zero ids of labels [H,W] in ascending
+ * order, their tight boxes padded by round(padding_percentage * extent) (half to even) and clamped.
+ * count_ids_out [1 + 256] int32: K, then the K ids;  rois_out [256,4] float: x_min, y_min, x_max, y_max (inclusive). */
+UOC_API int uoc_crop_boxes(const int32_t* labels, int H, int W, float padding_percentage, int32_t* count_ids_out,
+                           float* rois_out, void* workspace, size_t workspace_bytes, uoc_stream_t stream);
+
+/* second half of crop_rois (:96-110): rgb / depth [3,H,W] (depth may be NULL) cropped to the K rois and resized to SxS
+ * (bilinear, align_corners); mask_crops = (labels == id) resized with the legacy nearest rule. */
+UOC_API int uoc_crop_resize(const float* rgb, const float* depth, const int32_t* labels, int H, int W, const int32_t* ids,
+                            const float* rois, int K, int S, float* rgb_crops, float* mask_crops, float* depth_crops,
+                            uoc_stream_t stream);
+
+/* match_label_crop (:116-179): labels_crop [K,S,S] int32, mask_crops [K,S,S] (0/1), rois [K,4], depth_crops [K,3,S,S] or
+ * NULL.  Clusters overlapping the stage-1 mask by < 50 % of their area become -1 (labels_crop_out); crops are ordered far
+ * to near by the mean Z of their kept pixels (roi area without depth), kept clusters renumbered 1, 2, .. in that order and
+ * pasted back (legacy nearest) into refined_out [H,W] float, nearer crops overwriting farther ones. */
+UOC_API int uoc_match_label_crop(const int32_t* labels_crop, const float* mask_crops, const float* rois,
+                                 const float* depth_crops, int K, int S, int H, int W, float* refined_out,
+                                 int32_t* labels_crop_out, void* workspace, size_t workspace_bytes, uoc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

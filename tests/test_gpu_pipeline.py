@@ -231,3 +231,61 @@ def test_batch_of_full_frames_equals_single_calls():
         assert torch.equal(sl[j], sl1[0])
         assert torch.equal(lab[j], l1[0])
         assert (1 - (Z[j] * Z1[0]).sum(-1)).abs().max().item() < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------
+# two-stage plumbing kernels (csrc/refine.cu) against the oracle (= the reference's torch code)
+# ----------------------------------------------------------------------------------------------
+def _gt_labels(H, W, K, seed):
+    _, gt = O.synthetic_clustered_features(H, W, 8, K, 0.05, seed)
+    return gt
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_filter_labels_depth_kernel_matches_oracle(seed):
+    H, W = 60, 80
+    lab = torch.stack([_gt_labels(H, W, 5, seed).float(), _gt_labels(H, W, 3, seed + 10).float()])
+    xyz = torch.cat([O.synthetic_rgbd_frame(H, W, seed)[1], O.synthetic_rgbd_frame(H, W, seed + 1)[1]])
+    g = torch.Generator().manual_seed(seed)
+    xyz[:, 2][torch.rand(2, H, W, generator=g) < 0.3] = 0
+    xyz[0, 2, : H // 2, : W // 2] = 0
+    for thr in (0.5, 0.8):
+        want = O.filter_labels_depth(lab, xyz, thr)
+        got = TD.filter_labels_depth(lab.to(DEV), xyz.to(DEV), thr)
+        assert got.is_cuda and got.dtype == lab.dtype and torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("seed,H,W", [(0, 96, 128), (1, 96, 128), (2, 75, 101), (3, 480, 640)])
+def test_crop_rois_kernel_matches_oracle(seed, H, W):
+    lab = _gt_labels(H, W, 5, seed).float()[None]
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed)
+    ra, ma, roa, da = O.crop_rois(img, lab.clone(), xyz)
+    rb, mb, rob, db = TD.crop_rois(img.to(DEV), lab.to(DEV), xyz.to(DEV))
+    assert rb.is_cuda and torch.equal(roa, rob.cpu())                     # ids order, boxes, half-to-even padding, clamping
+    assert torch.equal(ma, mb.cpu())                                      # legacy nearest rule
+    assert torch.allclose(ra, rb.cpu(), atol=2e-6, rtol=1e-6) and torch.allclose(da, db.cpu(), atol=2e-6, rtol=1e-6)
+    rb, mb, rob, db = TD.crop_rois(img.to(DEV), lab.to(DEV), None)
+    assert db is None and torch.equal(roa, rob.cpu())
+    r0, m0, rois0, d0 = TD.crop_rois(img.to(DEV), torch.zeros(1, H, W, device=DEV), xyz.to(DEV))
+    assert r0.shape[0] == 0 and rois0.shape == (0, 4)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("with_depth", [True, False])
+def test_match_label_crop_kernel_matches_oracle(seed, with_depth):
+    H, W = 96, 128
+    lab = _gt_labels(H, W, 4, seed).float()[None]
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed)
+    if seed == 1:
+        xyz[:, 2, :, : W // 3] = 0                                        # crops with holes in the depth
+    rgb_c, mask_c, rois, depth_c = O.crop_rois(img, lab.clone(), xyz)
+    K = rgb_c.shape[0]
+    # crop label maps: some clusters agree with the mask crop (kept), some do not (dropped)
+    crops = torch.stack([torch.where(mask_c[k] > 0, _gt_labels(224, 224, 2, 50 + seed * 10 + k).float() + 1,
+                                     (_gt_labels(224, 224, 3, 80 + seed * 10 + k).float() + 4) * float(k % 2)) for k in range(K)])
+    want_ref, want_lc = O.match_label_crop(lab.clone(), crops.clone(), mask_c, rois, depth_c if with_depth else None)
+    got_ref, got_lc = TD.match_label_crop(lab.clone(), crops.to(DEV), mask_c.to(DEV), rois.to(DEV),
+                                          depth_c.to(DEV) if with_depth else None)
+    assert not got_ref.is_cuda and torch.equal(got_ref, want_ref)
+    assert torch.equal(got_lc.cpu(), want_lc)
+    assert len(torch.unique(want_ref)) > 2

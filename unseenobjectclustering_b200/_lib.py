@@ -52,6 +52,11 @@ SIGNATURES = {
     "uoc_backbone_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "uoc_backbone_read_trunk": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "uoc_conv2d_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "uoc_refine_workspace_bytes": (_sz, [_i, _i]),
+    "uoc_filter_labels_depth": (_i, [_vp, _vp, _i64, _i, _i64, _f, _vp, _vp, _sz, _vp]),
+    "uoc_crop_boxes": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "uoc_crop_resize": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "uoc_match_label_crop": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "uoc_prepare_inputs": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _f, _vp, _vp, _vp]),
     "uoc_compute_xyz": (_i, [_vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp]),
 }

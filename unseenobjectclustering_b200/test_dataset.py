@@ -1,13 +1,32 @@
 """Host-side mirror of the reference's inference driver lib/fcn/test_dataset.py (same function
 names, argument meaning and return types/devices), with everything kept on the GPU until the
 API boundary.  clustering_features -> one batched uoc_meanshift_cluster call; the two-stage
-plumbing (filter_labels_depth, crop_rois, match_label_crop) is vectorised tensor plumbing.
+plumbing (filter_labels_depth, crop_rois, match_label_crop) runs in csrc/refine.cu for CUDA tensors
+(a few launches per frame for all objects, one host round trip for the number of boxes); for CPU
+tensors the same functions are plain torch tensor plumbing (host logic tests).
 """
+import ctypes
+
 import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import _lib
 from . import mean_shift as _ms
+
+_refine_ws = {}
+
+
+def _refine_workspace(dev, N, K):
+    lib = _lib.load()
+    nbytes = int(lib.uoc_refine_workspace_bytes(int(N), int(K)))
+    sid = torch.cuda.current_stream(dev).cuda_stream
+    key = (dev.index, sid)
+    ws = _refine_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        _refine_ws[key] = ws
+    return ws
 
 CROP_SIZE = 224           # cfg.TRAIN.SYN_CROP_SIZE, lib/fcn/config.py:129
 PADDING_PERCENTAGE = 0.25  # lib/fcn/test_dataset.py:66
@@ -48,6 +67,19 @@ def clustering_features_device(features, num_seeds=100, first_indices=None, flag
 def _filter_labels_depth_device(labels, depth, threshold, max_label=256):
     """labels int [N,H,W] (device), depth [N,3,H,W].  Zero ids whose valid-depth fraction < threshold."""
     N = labels.shape[0]
+    if labels.is_cuda:
+        lib = _lib.load()
+        dev = labels.device
+        H, W = labels.shape[1], labels.shape[2]
+        lab = labels.to(torch.int32).contiguous()
+        dep = depth.to(device=dev, dtype=torch.float32).contiguous()
+        out = torch.empty_like(lab)
+        with torch.cuda.device(dev):
+            ws = _refine_workspace(dev, N, 1)
+            zptr = ctypes.c_void_p(dep.data_ptr() + 2 * H * W * 4)
+            _lib.check(lib.uoc_filter_labels_depth(_lib.ptr(lab), zptr, 3 * H * W, N, H * W, float(threshold), _lib.ptr(out),
+                                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "uoc_filter_labels_depth")
+        return out.to(labels.dtype)
     lab = labels.reshape(N, -1).to(torch.int64)
     valid = (depth[:, 2].reshape(N, -1) > 0).to(torch.float32)
     tot = torch.zeros((N, max_label), dtype=torch.float32, device=lab.device).scatter_add_(1, lab, torch.ones_like(valid))
@@ -101,6 +133,29 @@ def crop_rois(rgb, initial_masks, depth, crop_size=CROP_SIZE):
     Returns (rgb_crops [K,3,S,S], mask_crops [K,S,S], rois [K,4] float, depth_crops | None) on
     rgb's device."""
     dev = rgb.device
+    if rgb.is_cuda:
+        lib = _lib.load()
+        H, W = int(initial_masks.shape[1]), int(initial_masks.shape[2])
+        lab0 = initial_masks[0].to(device=dev, dtype=torch.int32).contiguous()
+        rgb0 = rgb[0].to(torch.float32).contiguous()
+        dep0 = depth[0].to(device=dev, dtype=torch.float32).contiguous() if depth is not None else None
+        with torch.cuda.device(dev):
+            ws = _refine_workspace(dev, 1, 1)
+            count_ids = torch.empty((257,), dtype=torch.int32, device=dev)
+            rois_all = torch.empty((256, 4), dtype=torch.float32, device=dev)
+            sp = _lib.stream_ptr(dev)
+            _lib.check(lib.uoc_crop_boxes(_lib.ptr(lab0), H, W, float(PADDING_PERCENTAGE), _lib.ptr(count_ids),
+                                          _lib.ptr(rois_all), _lib.ptr(ws), ws.numel(), sp), "uoc_crop_boxes")
+            K = int(count_ids[0].item())                    # the one host round trip: the output shapes depend on it
+            rgb_crops = torch.empty((K, 3, crop_size, crop_size), dtype=torch.float32, device=dev)
+            mask_crops = torch.empty((K, crop_size, crop_size), dtype=torch.float32, device=dev)
+            depth_crops = torch.empty((K, 3, crop_size, crop_size), dtype=torch.float32, device=dev) if dep0 is not None else None
+            if K > 0:
+                ids_ptr = ctypes.c_void_p(count_ids.data_ptr() + 4)
+                _lib.check(lib.uoc_crop_resize(_lib.ptr(rgb0), _lib.ptr(dep0), _lib.ptr(lab0), H, W, ids_ptr, _lib.ptr(rois_all), K,
+                                               int(crop_size), _lib.ptr(rgb_crops), _lib.ptr(mask_crops), _lib.ptr(depth_crops), sp),
+                           "uoc_crop_resize")
+        return rgb_crops, mask_crops, rois_all[:K].clone(), depth_crops
     masks0 = initial_masks[0].to(dev).to(torch.int64)
     ids, rois_l = _rois_from_labels(masks0)
     K = len(ids)
@@ -126,6 +181,23 @@ def match_label_crop(initial_masks, labels_crop, out_label_crop, rois, depth_cro
     """Returns (refined_masks float32 [N,H,W] on the CPU like the reference's `refined_masks`,
     labels_crop with dropped clusters set to -1)."""
     dev = out_label_crop.device
+    if out_label_crop.is_cuda:
+        lib = _lib.load()
+        K, S = int(labels_crop.shape[0]), int(labels_crop.shape[1])
+        H, W = int(initial_masks.shape[-2]), int(initial_masks.shape[-1])
+        lc32 = labels_crop.to(device=dev, dtype=torch.int32).contiguous()
+        mc = out_label_crop.to(torch.float32).contiguous()
+        ro = rois.to(device=dev, dtype=torch.float32).contiguous()
+        dc = depth_crop.to(torch.float32).contiguous() if depth_crop is not None else None
+        refined = torch.zeros(tuple(initial_masks.shape), dtype=torch.float32, device=dev)
+        lc_out = torch.empty_like(lc32)
+        with torch.cuda.device(dev):
+            ws = _refine_workspace(dev, 1, max(K, 1))
+            # only batch item 0 is refined, like the reference (test_dataset.py:177)
+            _lib.check(lib.uoc_match_label_crop(_lib.ptr(lc32), _lib.ptr(mc), _lib.ptr(ro), _lib.ptr(dc), K, S, H, W,
+                                                _lib.ptr(refined), _lib.ptr(lc_out), _lib.ptr(ws), ws.numel(),
+                                                _lib.stream_ptr(dev)), "uoc_match_label_crop")
+        return refined.cpu(), lc_out.to(labels_crop.dtype)
     lc = labels_crop.to(dev).to(torch.int64)
     K = lc.shape[0]
     flat = lc.view(K, -1)
