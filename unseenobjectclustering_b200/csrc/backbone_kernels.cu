@@ -403,14 +403,16 @@ __global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(StemTc
     }
     // stage the fp32 input patch
     const int iy0 = ty * 16 - 3, ix0 = tx * 32 - 3;
+    const float* xa = p.x[g] + size_t(n) * 3 * p.H * p.W;                     // channels 0..2
+    const float* xb = (CIN == 6) ? p.x2[g] + size_t(n) * 3 * p.H * p.W : xa;  // channels 3..5 (early fusion)
     for (int e = tid; e < CIN * kStemPatchH * kStemPatchW; e += 128) {
       const int c = e / (kStemPatchH * kStemPatchW);
       const int rem = e - c * kStemPatchH * kStemPatchW;
       const int py = rem / kStemPatchW, px = rem - py * kStemPatchW;
       const int iy = iy0 + py, ix = ix0 + px;
-      const float* xg = (c < 3 ? p.x[g] : p.x2[g]) + size_t(n) * 3 * p.H * p.W;
+      const float* xg = (CIN == 6 && c >= 3) ? xb + size_t(c - 3) * p.H * p.W : xa + size_t(c) * p.H * p.W;
       float v = 0.f;
-      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xg + (size_t(c < 3 ? c : c - 3) * p.H + iy) * p.W + ix);
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xg + size_t(iy) * p.W + ix);
       patch[(c * kStemPatchH + py) * 38 + px] = v;
     }
     __syncthreads();
