@@ -26,14 +26,16 @@ def _field(H, W, d, K, noise, seed):
 
 def _fps_mode(monkeypatch, mode):
     """tc: tcgen05 screen (fps_tc.cu, default: tiles in tensor memory first); tc_smem: same with every tile in shared memory;
+    stream: the streaming bf16 screen for fields that do not fit on chip (fps5_kernel), forced on small fields;
     fp32: no screen (fps2_kernel).  Returns bf16_screen."""
-    monkeypatch.setenv("UOC_FPS_TC", "1" if mode in ("tc", "tc_smem") else "0")
+    monkeypatch.setenv("UOC_FPS_TC", "1" if mode in ("tc", "tc_smem", "stream") else "0")
+    monkeypatch.setenv("UOC_FPS_STREAM", "1" if mode == "stream" else "0")
     if mode == "tc_smem":
         monkeypatch.setenv("UOC_FPS_TC_TMEM_TILES", "0")
     return mode != "fp32"
 
 
-@pytest.mark.parametrize("mode", ["tc", "tc_smem", "fp32"])
+@pytest.mark.parametrize("mode", ["tc", "tc_smem", "stream", "fp32"])
 @pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 100), (30, 44, 128, 100), (24, 24, 64, 40),
                                      (60, 80, 32, 17), (120, 160, 64, 100)])
 def test_select_seeds_bit_exact(H, W, d, m, mode, monkeypatch):
@@ -49,15 +51,17 @@ def test_select_seeds_bit_exact(H, W, d, m, mode, monkeypatch):
     assert sel[0] == first and len(set(sel.tolist())) == m
 
 
+@pytest.mark.parametrize("mode", ["tc", "stream"])
 @pytest.mark.parametrize("case", ["isotropic", "scaled", "two_homes", "full_frame", "full_frame_128"])
-def test_select_seeds_bf16_screen_stress(case, monkeypatch):
+def test_select_seeds_bf16_screen_stress(case, mode, monkeypatch):
     """The bf16 screening pass of the seed selection (fps_tc.cu) must never change an index:
     isotropic  - no cluster structure: the screen rejects little, nearly every point takes the fp32 path;
     scaled     - rows of norm 3 (the error bound of the screen scales with |x| |s|);
     two_homes  - one tile in tensor memory, the second in shared memory (small field, both operand homes);
     full_frame - 480x640x64: 17 tiles per CTA (7 in tensor memory + 10 in shared memory for fps_tc);
-    full_frame_128 - 240x320x128: the two-block (d = 128) operand layouts at several tiles per CTA."""
-    _fps_mode(monkeypatch, "tc")
+    full_frame_128 - 240x320x128: the two-block (d = 128) operand layouts at several tiles per CTA.
+    mode stream: the same inputs through the streaming screen (fps5_kernel)."""
+    _fps_mode(monkeypatch, mode)
     if case == "isotropic":
         g = torch.Generator().manual_seed(5)
         feats = torch.nn.functional.normalize(torch.randn(1, 64, 48, 64, generator=g), dim=1)
@@ -245,8 +249,9 @@ def test_config5_full_size_960x720_128d_30_iters():
     assert O.labels_equal_up_to_permutation(l[0].cpu().numpy(), gt.numpy().ravel())
     sel = s[0].cpu().numpy()
     assert sel[0] == 123456 and len(set(sel.tolist())) == 100
-    sel_o, _ = C.select_seeds(feats[0].reshape(128, -1).numpy(), 4, 123456)
-    assert np.array_equal(sel[:4], sel_o)
+    # the field does not fit on chip: the streaming bf16 screen (fps5_kernel) picks the seeds; same indices as the oracle
+    sel_o, _ = C.select_seeds(feats[0].reshape(128, -1).numpy(), 24, 123456)
+    assert np.array_equal(sel[:24], sel_o)
 
 
 def test_bad_arguments_fail_loudly():

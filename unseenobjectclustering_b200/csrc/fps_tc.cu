@@ -334,10 +334,215 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Streaming variant for fields that do NOT fit on chip (BASELINE config 5: 960x720x128, bf16 copy 177 MB): the same
+// screen-then-exact scheme, but every pass STREAMS the bf16 pixel-major copy (n*d*2 bytes instead of the n*d*4 of the fp32
+// passes of fps2_kernel) and screens on the CUDA cores: each lane reads its own point's row with 16-byte loads (a warp's 32
+// rows are contiguous; a shared-memory staged variant with cp.async measured the same: 6.0 vs 6.2 ms at config 5) and
+// accumulates bf16(x_p) . s with the fp32 seed.  Config 5: 9.1 ms (fp32 passes) -> 6.1 ms; the rest is the exact chain of
+// the new seed's own cluster (bf16 cannot resolve within-cluster distances) reading fp32 rows from HBM.  |d~ - d| <= 2^-8 |x_p||s| + rounding (the seed is exact here, so no
+// two-term split is needed); everything the screen cannot prove unchanged runs the canonical fp32 chain -> bit-identical
+// indices.  32-point tiles are dealt round-robin to all warps of the item, running minima live in registers.
+// ----------------------------------------------------------------------------------------------
+constexpr int kMaxSlots5 = 12;             // 32-point tiles per warp: n <= 148 * 16 * 32 * 12 = 909k points
+
+// canonical fp32 chain over the channels of point xp (planar field, channel stride sd): out of line so that the twelve
+// unrolled slots of fps5_kernel do not each carry their own 32-register load batch
+template <int D>
+__device__ __noinline__ float exact_chain5(const float* __restrict__ xp, long long sd, const float* s_seed, bool want_sq,
+                                           float* sq_out) {
+  float acc = 0.f, sq = 0.f;
+  constexpr int XB = 32;
+#pragma unroll 1
+  for (int k0 = 0; k0 < D; k0 += XB) {
+    float x[XB];
+#pragma unroll
+    for (int k = 0; k < XB; ++k) x[k] = __ldg(xp + (k0 + k) * sd);
+#pragma unroll
+    for (int k = 0; k < XB; ++k) {
+      acc = fmaf(x[k], s_seed[k0 + k], acc);
+      if (want_sq) sq = fmaf(x[k], x[k], sq);
+    }
+  }
+  *sq_out = sq;
+  return acc;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads4, 1) fps5_kernel(Fps4Params p) {
+  constexpr int NL = D / 8;                  // 16-byte units per point
+  __shared__ float s_seed[D];
+  __shared__ float s_ns;
+  __shared__ unsigned long long s_red[kWarps4];
+  __shared__ int s_fail;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nb = p.nb;
+  const int b = blockIdx.x / nb, rank = blockIdx.x % nb;
+  const int NW = nb * kWarps4;               // warps of the item
+  const int gw = rank * kWarps4 + warp;      // this warp among them
+  const long long tiles = (p.n + 31) >> 5;
+  const float* Xb = p.X + b * p.sb;
+  const uint4* xbb = p.xb + size_t(b) * p.n * NL;
+
+  if (tid == 0) s_fail = 0;
+  unsigned long long mybest = 1ull;
+  float r[kMaxSlots5], nx[kMaxSlots5];
+#pragma unroll
+  for (int s = 0; s < kMaxSlots5; ++s) { r[s] = 0.f; nx[s] = 0.f; }
+
+  auto stage_seed = [&](long long idx, int i) {       // warp 0: fetch seed `idx` (fp32) and its norm
+    float sq = 0.f;
+#pragma unroll
+    for (int h = 0; h < D / 64; ++h) {
+      const int c0 = h * 64 + 2 * lane;
+      const float v0 = __ldg(Xb + c0 * p.sd + idx), v1 = __ldg(Xb + (c0 + 1) * p.sd + idx);
+      s_seed[c0] = v0; s_seed[c0 + 1] = v1;
+      sq = fmaf(v0, v0, fmaf(v1, v1, sq));
+      if (rank == 0) {
+        float* so = p.seeds_out + (size_t(b) * p.m + i) * D;
+        so[c0] = v0; so[c0 + 1] = v1;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) {
+      s_ns = sqrtf(sq) * 1.000001f;
+      if (rank == 0) p.selected_out[size_t(b) * p.m + i] = idx;
+    }
+  };
+  if (warp == 0) stage_seed(p.first[b], 0);
+  __syncthreads();
+
+  for (int i = 0; i + 1 < p.m; ++i) {
+    const float ns = s_ns;
+    bool changed = (i == 0);
+#pragma unroll
+    for (int s = 0; s < kMaxSlots5; ++s) {
+      const long long t = (long long)s * NW + gw;
+      if (t < tiles) {                          // warp-uniform
+        const long long base = t << 5;
+        const long long gp = base + lane;
+        const bool valid = gp < p.n;
+        bool need = valid;
+        if (i > 0) {
+          // ---- every lane streams its own point's bf16 row: 8 x 16-byte loads in flight per lane; the warp's 32 rows are
+          // 32 * D * 2 contiguous bytes and the consecutive loads of a lane hit the L1 lines its first load brought in
+          float acc0 = 0.f, acc1 = 0.f;
+          if (valid) {
+            const uint4* row = xbb + gp * NL;
+#pragma unroll
+            for (int u0 = 0; u0 < NL; u0 += 8) {
+              uint4 v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] = __ldg(row + u0 + u);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const float* sk = s_seed + (u0 + u) * 8;
+                acc0 = fmaf(__uint_as_float(v[u].x << 16), sk[0], acc0); acc1 = fmaf(__uint_as_float(v[u].x & 0xFFFF0000u), sk[1], acc1);
+                acc0 = fmaf(__uint_as_float(v[u].y << 16), sk[2], acc0); acc1 = fmaf(__uint_as_float(v[u].y & 0xFFFF0000u), sk[3], acc1);
+                acc0 = fmaf(__uint_as_float(v[u].z << 16), sk[4], acc0); acc1 = fmaf(__uint_as_float(v[u].z & 0xFFFF0000u), sk[5], acc1);
+                acc0 = fmaf(__uint_as_float(v[u].w << 16), sk[6], acc0); acc1 = fmaf(__uint_as_float(v[u].w & 0xFFFF0000u), sk[7], acc1);
+              }
+            }
+          }
+          const float dapprox = 0.5f * (1.0f - (acc0 + acc1));
+          need = valid && !((dapprox - fmaf(kRelMargin4 * nx[s], ns, kAbsMargin4)) >= r[s]);
+        }
+        if (__any_sync(0xffffffffu, need)) {
+          if (need) {
+            // canonical fp32 chain (bit-identical to fps_kernel / fps2_kernel / fps4_kernel / the oracle)
+            float sq;
+            const float acc = exact_chain5<D>(Xb + gp, p.sd, s_seed, i == 0, &sq);
+            const float dist = 0.5f * (1.0f - acc);
+            if (i == 0) {
+              r[s] = dist;
+              nx[s] = sqrtf(sq) * 1.000001f;
+            } else {
+              changed = changed || dist < r[s];
+              r[s] = dist < r[s] ? dist : r[s];
+            }
+          }
+        }
+      }
+    }
+    if (changed) {
+      mybest = 1ull;
+#pragma unroll
+      for (int s = 0; s < kMaxSlots5; ++s) {
+        const long long t = (long long)s * NW + gw;
+        const long long gp = (t << 5) + lane;
+        if (t < tiles && gp < p.n) {
+          const unsigned long long key = pack_key4(r[s], static_cast<unsigned int>(gp));
+          mybest = key > mybest ? key : mybest;
+        }
+      }
+    }
+    unsigned long long best = mybest;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == 0) s_red[warp] = best;
+    __syncthreads();                          // everybody is done with s_seed / s_ns of this pass
+    if (warp == 0) {
+      unsigned long long v = (lane < kWarps4) ? s_red[lane] : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+      }
+      // all-to-all: this CTA's key goes into column `rank` of EVERY CTA's private row; then poll the own row
+      unsigned long long* mat = p.slots + (size_t(b) * p.m + (i + 1)) * nb * nb;
+#pragma unroll
+      for (int c5 = 0; c5 < 5; ++c5) {
+        const int c = lane + 32 * c5;
+        if (c < nb) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mat + size_t(c) * nb + rank), "l"(v) : "memory");
+      }
+      const unsigned long long* row = mat + size_t(rank) * nb;
+      unsigned long long gmax = 0ull;
+      bool done = false;
+      for (unsigned int it = 0; it < (1u << 22) && !done; ++it) {
+        unsigned long long kv[5];
+#pragma unroll
+        for (int c5 = 0; c5 < 5; ++c5) {
+          const int c = lane + 32 * c5;
+          kv[c5] = 1ull;
+          if (c < nb) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(kv[c5]) : "l"(row + c));
+        }
+        bool all = true;
+        gmax = 0ull;
+#pragma unroll
+        for (int c5 = 0; c5 < 5; ++c5) {
+          all = all && (kv[c5] != 0ull);
+          gmax = kv[c5] > gmax ? kv[c5] : gmax;
+        }
+        done = __all_sync(0xffffffffu, all);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, gmax, o);
+        gmax = other > gmax ? other : gmax;
+      }
+      if (done) {
+        stage_seed(static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(gmax & 0xFFFFFFFFull)), i + 1);
+      } else if (lane == 0) {
+        s_fail = 1;
+        atomicOr(p.err, ERR_GRID_BARRIER_TIMEOUT);
+      }
+    }
+    __syncthreads();
+    if (s_fail) break;
+  }
+}
+
 }  // namespace
 
 int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
-                           int64_t* selected_out, float* seeds_out, cudaStream_t stream, bool* used) {
+                           int64_t* selected_out, float* seeds_out, cudaStream_t stream_, bool* used) {
+  cudaStream_t stream = stream_;
   *used = false;
   if (!xb || (s.d != 64 && s.d != 128)) return UOC_OK;
   if (reinterpret_cast<uintptr_t>(xb) % 16 != 0) return UOC_OK;
@@ -348,7 +553,42 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   if (nb > 160) return UOC_OK;                      // the poll loop reads at most 5 keys per lane
   const long long total_tiles = (s.n + 127) / 128;
   const long long T = (total_tiles + nb - 1) / nb;  // tiles of the busiest CTA
-  if (T > 4 * kMaxSlots) return UOC_OK;             // larger fields: earlier generations
+  bool streaming = false;                           // the field does not fit on chip: stream the bf16 copy in every pass
+  if (const char* e = getenv("UOC_FPS_STREAM")) streaming = atoi(e) != 0;   // test knob: force the streaming variant
+  if (T > 4 * kMaxSlots) streaming = true;
+  {
+    const int acols0 = s.d / 2, kb0 = s.d / 64;
+    int TA0 = int((512 - 16 * T) / acols0);
+    if (TA0 > T) TA0 = int(T);
+    if (TA0 < 0) TA0 = 0;
+    if (1024 + size_t(kb0) * 2048 + size_t(T - TA0) * kb0 * 16384 > 225 * 1024) streaming = true;
+  }
+  if (streaming) {
+    const long long tiles32 = (s.n + 31) / 32;
+    if ((tiles32 + (long long)nb * kWarps4 - 1) / ((long long)nb * kWarps4) > kMaxSlots5) return UOC_OK;   // larger still: fp32 passes
+    const size_t slot_need5 = size_t(s.batch) * s.m * nb * nb * 8;
+    if (slot_need5 > w.slot_bytes) return UOC_OK;
+    unsigned int* err5 = device_error_word();
+    if (!err5) return fail(UOC_ERR_CUDA, "no device error word");
+    void* kern5 = s.d == 64 ? reinterpret_cast<void*>(&fps5_kernel<64>) : reinterpret_cast<void*>(&fps5_kernel<128>);
+    const size_t smem5 = 0;
+    Fps4Params p5;
+    p5.X = X; p5.xb = reinterpret_cast<const uint4*>(xb);
+    p5.sb = s.stride_b; p5.sd = s.stride_d; p5.n = s.n; p5.d = s.d; p5.m = s.m; p5.batch = s.batch;
+    p5.first = w.first;
+    p5.selected_out = reinterpret_cast<long long*>(selected_out);
+    p5.seeds_out = seeds_out;
+    p5.err = err5;
+    p5.slots = w.slots;
+    p5.nb = nb; p5.T = 0; p5.TA = 0;
+    p5.trace = nullptr; p5.trace_cta = 0;
+    UOC_CUDA(cudaMemsetAsync(w.slots, 0, slot_need5, stream_));
+    void* args5[] = {&p5};
+    UOC_CUDA(cudaLaunchCooperativeKernel(kern5, dim3(nb * s.batch), dim3(kThreads4), args5, smem5, stream_));
+    count_launch();
+    *used = true;
+    return UOC_OK;
+  }
   const int acols = s.d / 2, kb = s.d / 64;
   // accumulators: 16 columns per tile; tensor memory takes as many A tiles as fit next to them, shared memory the rest
   int TA = int((512 - 16 * T) / acols);
