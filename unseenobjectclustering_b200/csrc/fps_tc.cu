@@ -57,6 +57,7 @@ struct Fps4Params {
   int nb;                   // CTAs per batch item
   int T;                    // tiles of the busiest CTA (accumulator columns: 16 * T)
   int TA;                   // tiles kept in tensor memory (the rest in shared memory)
+  float rel_margin;         // screening margin per unit |x||s| (kRelMargin4, or half of it for round-to-nearest copies)
   long long* trace;         // debug (UOC_FPS_TC_TRACE=<cta>): per pass {start, screened, local arg-max, exchanged+seed, fp32 rounds}
   int trace_cta;
 };
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
         bool need = valid;
         if (i > 0 && ok) {
           const float dapprox = 0.5f * (1.0f - (__uint_as_float(c0[s]) + __uint_as_float(c1[s])));
-          need = valid && !((dapprox - fmaf(kRelMargin4 * nx[s], ns, kAbsMargin4)) >= r[s]);
+          need = valid && !((dapprox - fmaf(p.rel_margin * nx[s], ns, kAbsMargin4)) >= r[s]);
         }
         if (__any_sync(0xffffffffu, need)) {
           ++n_exact;
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps5_kernel(Fps4Params p) {
             }
           }
           const float dapprox = 0.5f * (1.0f - (acc0 + acc1));
-          need = valid && !((dapprox - fmaf(kRelMargin4 * nx[s], ns, kAbsMargin4)) >= r[s]);
+          need = valid && !((dapprox - fmaf(p.rel_margin * nx[s], ns, kAbsMargin4)) >= r[s]);
         }
         if (__any_sync(0xffffffffu, need)) {
           if (need) {
@@ -551,6 +552,8 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   if (sms <= 0 || s.batch > sms) return UOC_OK;
   const int nb = sms / s.batch;
   if (nb > 160) return UOC_OK;                      // the poll loop reads at most 5 keys per lane
+  float rel_margin = kRelMargin4;
+  if (const char* e = getenv("UOC_FPS_RN_MARGIN")) { if (atoi(e) != 0) rel_margin = 0.00205f; }   // A/B: copy known to be round-to-nearest
   const long long total_tiles = (s.n + 127) / 128;
   const long long T = (total_tiles + nb - 1) / nb;  // tiles of the busiest CTA
   bool streaming = false;                           // the field does not fit on chip: stream the bf16 copy in every pass
@@ -581,6 +584,7 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
     p5.err = err5;
     p5.slots = w.slots;
     p5.nb = nb; p5.T = 0; p5.TA = 0;
+    p5.rel_margin = rel_margin;
     p5.trace = nullptr; p5.trace_cta = 0;
     UOC_CUDA(cudaMemsetAsync(w.slots, 0, slot_need5, stream_));
     void* args5[] = {&p5};
@@ -614,6 +618,7 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   p.err = err;
   p.slots = w.slots;
   p.nb = nb; p.T = int(T); p.TA = TA;
+  p.rel_margin = rel_margin;
   p.trace = nullptr;
   p.trace_cta = 0;
   if (const char* e = getenv("UOC_FPS_TC_TRACE")) {
