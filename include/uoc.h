@@ -250,6 +250,22 @@ UOC_API int uoc_match_label_crop(const int32_t* labels_crop, const float* mask_c
                                  const float* depth_crops, int K, int S, int H, int W, float* refined_out,
                                  int32_t* labels_crop_out, void* workspace, size_t workspace_bytes, uoc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Evaluation tail: the pixel work of utils.evaluation.multilabel_metrics
+ * (lib/utils/evaluation.py:109-257, called per frame by fcn.test_dataset.test_segnet :307-330).  prediction, gt: [H,W]
+ * int32 label maps on the device, ids in [0, 254], 0 = background.  All outputs are [256,256] int32 indexed
+ * [gt label][predicted label]:
+ *   tp_out                 pixels carrying both labels (:186-188)
+ *   boundary_prec_tp_out   boundary pixels of the predicted label inside the disk(bound_pix)-dilated boundary of the
+ *                          ground-truth label, boundary_rec_tp_out the other way round (seg2bmap :15-70, boundary_overlap :73-106)
+ *   boundary_denoms_out    [2] uint64: boundary pixels summed over the predicted / the ground-truth object labels (:206-213)
+ * The Hungarian matching and the ratios are host work (evaluation.py of the Python mirror). */
+UOC_API size_t uoc_metrics_workspace_bytes(int H, int W);
+UOC_API int uoc_multilabel_counts(const int32_t* prediction, const int32_t* gt, int H, int W, int bound_pix, int32_t* tp_out,
+                                  int32_t* boundary_prec_tp_out, int32_t* boundary_rec_tp_out,
+                                  unsigned long long* boundary_denoms_out, void* workspace, size_t workspace_bytes,
+                                  uoc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

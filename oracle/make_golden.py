@@ -82,6 +82,31 @@ def gen_euclid(ref):
         print(name, "labels", np.unique(labels.numpy()).tolist(), "seed labels", len(np.unique(seed_labels.numpy())))
 
 
+METRIC_CASES = [(96, 128, 4, 0), (96, 128, 5, 1), (75, 101, 4, 2), (120, 160, 6, 3), (480, 640, 6, 4), (64, 64, 3, 5)]
+METRIC_KEYS = ['Objects F-measure', 'Objects Precision', 'Objects Recall', 'Boundary F-measure', 'Boundary Precision',
+               'Boundary Recall', 'obj_detected', 'obj_detected_075', 'obj_gt', 'obj_detected_075_percentage']
+
+
+def gen_metrics(ref):
+    """utils.evaluation.multilabel_metrics of the unmodified reference (lib/utils/evaluation.py:109-257; skimage's disk
+    supplied by ref_harness) on synthetic (prediction, gt) pairs; plus its three degenerate cases."""
+    out = {"cases": len(METRIC_CASES)}
+    for k, (H, W, K, seed) in enumerate(METRIC_CASES):
+        _, gt = O.synthetic_clustered_features(H, W, 8, K, 0.05, 200 + seed)
+        gt = gt.numpy().astype(np.float32)
+        pred = O.synthetic_prediction(gt.astype(np.int64), seed).astype(np.float32)
+        m = ref.evaluation.multilabel_metrics(pred, gt)
+        out["meta%d" % k] = np.array([H, W, K, seed])
+        out["values%d" % k] = np.array([float(m[key]) for key in METRIC_KEYS])
+        print("metrics", k, {key: round(float(m[key]), 4) for key in METRIC_KEYS[:6]})
+    z = np.zeros((40, 48), dtype=np.float32)
+    one = z.copy(); one[5:20, 6:30] = 3
+    for name, (p, g) in (("none_pred", (z, one)), ("none_gt", (one, z)), ("none_both", (z, z))):
+        m = ref.evaluation.multilabel_metrics(p, g)
+        out[name] = np.array([float(m[key]) for key in METRIC_KEYS])
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
+
+
 def gen_two_stage(ref):
     H, W = 96, 128
     feats, gt = O.synthetic_clustered_features(H, W, 64, 4, 0.05, seed=21)
@@ -206,3 +231,5 @@ if __name__ == "__main__":
         gen_variants(ref)
     if not only or "euclid" in only:
         gen_euclid(ref)
+    if not only or "metrics" in only:
+        gen_metrics(ref)

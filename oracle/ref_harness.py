@@ -79,6 +79,25 @@ def load(device="cpu"):
     for fn in ("mat2euler", "euler2mat", "euler2quat", "quat2euler"):
         if not hasattr(e, fn):
             setattr(e, fn, lambda *a, **k: None)
+    if "skimage" not in sys.modules:
+        # lib/utils/evaluation.py:94 imports skimage.morphology.disk inside boundary_overlap; skimage is not installed here:
+        # provide the one function with skimage's own definition (footprint of the pixels with x^2 + y^2 <= r^2)
+        try:
+            import skimage.morphology  # noqa: F401
+        except Exception:
+            import numpy as _np
+            sk = types.ModuleType("skimage")
+            mo = types.ModuleType("skimage.morphology")
+
+            def _disk(radius, dtype=_np.uint8):
+                L = _np.arange(-radius, radius + 1)
+                X, Y = _np.meshgrid(L, L)
+                return _np.array((X ** 2 + Y ** 2) <= radius ** 2, dtype=dtype)
+
+            mo.disk = _disk
+            sk.morphology = mo
+            sys.modules["skimage"] = sk
+            sys.modules["skimage.morphology"] = mo
     try:
         import torchvision  # noqa: F401  (networks/SEG.py imports it, never uses it)
     except Exception:
@@ -98,8 +117,9 @@ def load(device="cpu"):
     import fcn.test_dataset as test_dataset
     import networks
 
+    import utils.evaluation as evaluation
     _loaded.update(cfg=cfg, mean_shift=mean_shift, test_dataset=test_dataset, networks=networks,
-                   mask_utils=mask_utils)
+                   mask_utils=mask_utils, evaluation=evaluation)
     return types.SimpleNamespace(**_loaded)
 
 

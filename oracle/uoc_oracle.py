@@ -478,3 +478,128 @@ def read_sample_arrays(im_bgr_u8, depth_u16, camera_params, pixel_means=PIXEL_ME
     im_tensor -= torch.tensor(pixel_means / 255.0).float()
     return im_tensor.permute(2, 0, 1).unsqueeze(0), torch.from_numpy(xyz).permute(2, 0, 1).unsqueeze(0)
 
+
+
+# --------------------------------------------------------------------------------------------
+# evaluation tail  (lib/utils/evaluation.py)
+# --------------------------------------------------------------------------------------------
+
+def disk(radius):
+    """skimage.morphology.disk as used at lib/utils/evaluation.py:94-98 (skimage is not installed here):
+    a (2r+1)x(2r+1) uint8 footprint of the pixels with x^2 + y^2 <= r^2."""
+    L = np.arange(-radius, radius + 1)
+    X, Y = np.meshgrid(L, L)
+    return np.array((X ** 2 + Y ** 2) <= radius ** 2, dtype=np.uint8)
+
+
+def seg2bmap(seg):
+    """lib/utils/evaluation.py:15-70 at full resolution: one-pixel boundary map of a binary mask."""
+    seg = seg.astype(bool)
+    e = np.zeros_like(seg)
+    s = np.zeros_like(seg)
+    se = np.zeros_like(seg)
+    e[:, :-1] = seg[:, 1:]
+    s[:-1, :] = seg[1:, :]
+    se[:-1, :-1] = seg[1:, 1:]
+    b = seg ^ e | seg ^ s | seg ^ se
+    b[-1, :] = seg[-1, :] ^ e[-1, :]
+    b[:, -1] = seg[:, -1] ^ s[:, -1]
+    b[-1, -1] = 0
+    return b
+
+
+def boundary_overlap(predicted_mask, gt_mask, bound_th=0.003):
+    """lib/utils/evaluation.py:73-106: (precision true positives, recall true positives) of the dilated boundaries."""
+    import cv2
+    bound_pix = bound_th if bound_th >= 1 else np.ceil(bound_th * np.linalg.norm(predicted_mask.shape))
+    fg_boundary = seg2bmap(predicted_mask)
+    gt_boundary = seg2bmap(gt_mask)
+    gt_dil = cv2.dilate(gt_boundary.astype(np.uint8), disk(bound_pix), iterations=1)
+    fg_dil = cv2.dilate(fg_boundary.astype(np.uint8), disk(bound_pix), iterations=1)
+    return np.sum(np.logical_and(fg_boundary, gt_dil)), np.sum(np.logical_and(gt_boundary, fg_dil))
+
+
+def multilabel_metrics(prediction, gt, obj_detect_threshold=0.75):
+    """lib/utils/evaluation.py:109-257, statement by statement; the Hungarian step (utils.munkres, :221-223) through
+    scipy.optimize.linear_sum_assignment (same optimum; the pairs can differ only between equally good assignments)."""
+    from scipy.optimize import linear_sum_assignment
+    labels_gt = np.unique(gt)
+    labels_gt = labels_gt[~np.isin(labels_gt, [0])]
+    labels_pred = np.unique(prediction)
+    labels_pred = labels_pred[~np.isin(labels_pred, [0])]
+    ng, npred = labels_gt.shape[0], labels_pred.shape[0]
+
+    def edge(f, p, r, pct):
+        return {'Objects F-measure': f, 'Objects Precision': p, 'Objects Recall': r, 'Boundary F-measure': f,
+                'Boundary Precision': p, 'Boundary Recall': r, 'obj_detected': npred, 'obj_detected_075': 0.,
+                'obj_gt': ng, 'obj_detected_075_percentage': pct}
+
+    if npred == 0 and ng > 0:
+        return edge(0., 1., 0., 0.)
+    if npred > 0 and ng == 0:
+        return edge(0., 0., 1., 0.)
+    if npred == 0 and ng == 0:
+        return edge(1., 1., 1., 1.)
+    F = np.zeros((ng, npred))
+    true_positives = np.zeros((ng, npred))
+    boundary_stuff = np.zeros((ng, npred, 2))
+    for i, gt_i in enumerate(labels_gt):
+        gt_i_mask = (gt == gt_i)
+        for j, pred_j in enumerate(labels_pred):
+            pred_j_mask = (prediction == pred_j)
+            tp = np.int64(np.count_nonzero(np.logical_and(pred_j_mask, gt_i_mask)))
+            true_positives[i, j] = tp
+            prec = tp / np.count_nonzero(pred_j_mask)
+            rec = tp / np.count_nonzero(gt_i_mask)
+            if prec + rec > 0:
+                F[i, j] = (2 * prec * rec) / (prec + rec)
+            boundary_stuff[i, j] = boundary_overlap(pred_j_mask, gt_i_mask)
+    boundary_prec_denom = sum(float(np.sum(seg2bmap(prediction == pred_j))) for pred_j in labels_pred)
+    boundary_rec_denom = sum(float(np.sum(seg2bmap(gt == gt_i))) for gt_i in labels_gt)
+    F[np.isnan(F)] = 0
+    r, c = linear_sum_assignment(F.max() - F.copy())
+    assignments = list(zip(r.tolist(), c.tolist()))
+    num_obj_detected = sum(1 for a in assignments if F[a] > obj_detect_threshold)
+    idx = tuple(np.array(assignments).T)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        precision = np.sum(true_positives[idx]) / np.sum(prediction.clip(0, 1) == 1)
+        recall = np.sum(true_positives[idx]) / np.sum(gt.clip(0, 1) == 1)
+        F_measure = (2 * precision * recall) / (precision + recall)
+        if np.isnan(F_measure):
+            F_measure = 0
+        boundary_precision = np.sum(boundary_stuff[idx][:, 0]) / boundary_prec_denom
+        boundary_recall = np.sum(boundary_stuff[idx][:, 1]) / boundary_rec_denom
+        boundary_F_measure = (2 * boundary_precision * boundary_recall) / (boundary_precision + boundary_recall)
+        if np.isnan(boundary_F_measure):
+            boundary_F_measure = 0
+    return {'Objects F-measure': F_measure, 'Objects Precision': precision, 'Objects Recall': recall,
+            'Boundary F-measure': boundary_F_measure, 'Boundary Precision': boundary_precision,
+            'Boundary Recall': boundary_recall, 'obj_detected': npred, 'obj_detected_075': num_obj_detected,
+            'obj_gt': ng, 'obj_detected_075_percentage': num_obj_detected / ng}
+
+
+def synthetic_prediction(gt, seed):
+    """A plausible prediction for the label map `gt` ([H,W] ints): masks shifted by a few pixels, one object split in two,
+    one dropped, one false positive, ids permuted."""
+    rng = np.random.RandomState(seed)
+    gt = np.asarray(gt)
+    H, W = gt.shape
+    pred = np.zeros_like(gt)
+    ids = [l for l in np.unique(gt) if l != 0]
+    nxt = 1
+    for k, l in enumerate(ids):
+        if k == 1 and len(ids) > 2 and seed % 2 == 0:
+            continue                                   # a missed object
+        m = np.roll(np.roll(gt == l, rng.randint(-3, 4), axis=0), rng.randint(-3, 4), axis=1)
+        if k == 0 and seed % 3 != 2:                   # an over-segmented object
+            ys = np.nonzero(m.any(1))[0]
+            mid = (ys[0] + ys[-1]) // 2
+            top = m.copy(); top[mid:] = False
+            pred[top] = nxt; nxt += 1
+            m = m & ~top
+        pred[m] = nxt; nxt += 1
+    y0, x0 = rng.randint(0, H - 8), rng.randint(0, W - 8)
+    pred[y0:y0 + 6, x0:x0 + 7] = nxt                    # a false positive
+    perm = rng.permutation(np.arange(1, nxt + 1)) + 3   # arbitrary ids, gaps included
+    lut = np.zeros(nxt + 1, dtype=gt.dtype); lut[1:] = perm
+    return lut[pred]

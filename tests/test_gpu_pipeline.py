@@ -289,3 +289,42 @@ def test_match_label_crop_kernel_matches_oracle(seed, with_depth):
     assert not got_ref.is_cuda and torch.equal(got_ref, want_ref)
     assert torch.equal(got_lc.cpu(), want_lc)
     assert len(torch.unique(want_ref)) > 2
+
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluation tail (csrc/metrics.cu + evaluation.py) against the reference's own numbers
+# ----------------------------------------------------------------------------------------------
+def test_multilabel_metrics_match_reference_golden():
+    """utils.evaluation.multilabel_metrics: every entry of the dictionary equals the unmodified reference's
+    (tests/golden/metrics.npz) to 1e-12 -- the counts are exact integers, the ratios float64 like the reference's."""
+    import test_oracle as TO
+    from unseenobjectclustering_b200 import evaluation as EV
+    n = 0
+    for pred, gt, want in TO._metric_cases():
+        got = EV.multilabel_metrics(pred, gt)
+        assert set(got) == set(want)
+        for k, v in want.items():
+            assert abs(float(got[k]) - float(v)) < 1e-12, (pred.shape, k, got[k], v)
+        n += 1
+    assert n == 9
+
+
+def test_multilabel_counts_match_oracle_pairwise():
+    """The device counts for EVERY (gt, prediction) label pair against the oracle's per-pair masks, boundary maps and
+    cv2 dilations (not only the matched pairs the metrics use); tensors on the device as input."""
+    from unseenobjectclustering_b200 import evaluation as EV
+    _, gt = O.synthetic_clustered_features(90, 121, 8, 5, 0.05, 400)
+    gt = gt.numpy().astype(np.int64)
+    pred = O.synthetic_prediction(gt, 3)
+    tp, bp, br, (dp, dg) = EV.multilabel_counts(torch.from_numpy(pred).to(DEV), torch.from_numpy(gt).to(DEV))
+    for i in np.unique(gt):
+        for j in np.unique(pred):
+            assert tp[i, j] == np.count_nonzero((gt == i) & (pred == j))
+            if i and j:
+                a, b = O.boundary_overlap(pred == j, gt == i)
+                assert (bp[i, j], br[i, j]) == (a, b), (i, j)
+    assert dp == sum(int(O.seg2bmap(pred == j).sum()) for j in np.unique(pred) if j)
+    assert dg == sum(int(O.seg2bmap(gt == i).sum()) for i in np.unique(gt) if i)
+    with pytest.raises(_lib.UocError):
+        EV.multilabel_counts(torch.full((8, 8), 300).to(DEV), torch.zeros(8, 8).to(DEV))

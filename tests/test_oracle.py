@@ -258,3 +258,40 @@ def test_input_prep_oracle_matches_the_live_reference_tool():
     got = O.compute_xyz(depth, 612.937, 613.173, 322.549, 248.158, 20, 30)
     assert want.dtype == got.dtype == np.float32 and np.array_equal(want, got)
 
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluation tail: utils.evaluation.multilabel_metrics
+# ----------------------------------------------------------------------------------------------
+def _metric_cases():
+    import make_golden as MG
+    g = _load(os.path.join(GOLDEN, "metrics.npz"))
+    for k in range(int(g["cases"])):
+        H, W, K, seed = (int(v) for v in g["meta%d" % k])
+        _, gt = O.synthetic_clustered_features(H, W, 8, K, 0.05, 200 + seed)
+        gt = gt.numpy().astype(np.float32)
+        pred = O.synthetic_prediction(gt.astype(np.int64), seed).astype(np.float32)
+        yield pred, gt, dict(zip(MG.METRIC_KEYS, g["values%d" % k]))
+    z = np.zeros((40, 48), dtype=np.float32)
+    one = z.copy(); one[5:20, 6:30] = 3
+    for name, (p, q) in (("none_pred", (z, one)), ("none_gt", (one, z)), ("none_both", (z, z))):
+        yield p, q, dict(zip(MG.METRIC_KEYS, g[name]))
+
+
+def test_metrics_oracle_matches_reference_golden():
+    for pred, gt, want in _metric_cases():
+        if pred.shape[0] >= 480:
+            continue                                   # the per-pair CPU loop of the full frame runs in the GPU test only
+        got = O.multilabel_metrics(pred, gt)
+        for k, v in want.items():
+            assert abs(float(got[k]) - float(v)) < 1e-12, (k, got[k], v)
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not present (GPU box)")
+def test_metrics_oracle_equals_the_live_reference():
+    ref = rh.load()
+    _, gt = O.synthetic_clustered_features(80, 100, 8, 5, 0.05, 321)
+    gt = gt.numpy().astype(np.float32)
+    pred = O.synthetic_prediction(gt.astype(np.int64), 7).astype(np.float32)
+    a, b = ref.evaluation.multilabel_metrics(pred, gt), O.multilabel_metrics(pred, gt)
+    assert set(a) == set(b) and all(abs(float(a[k]) - float(b[k])) < 1e-12 for k in a)

@@ -57,6 +57,8 @@ SIGNATURES = {
     "uoc_crop_boxes": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "uoc_crop_resize": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "uoc_match_label_crop": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "uoc_metrics_workspace_bytes": (_sz, [_i, _i]),
+    "uoc_multilabel_counts": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "uoc_prepare_inputs": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _f, _vp, _vp, _vp]),
     "uoc_compute_xyz": (_i, [_vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp]),
 }

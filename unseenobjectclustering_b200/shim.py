@@ -18,6 +18,7 @@ import sys
 from . import networks as _networks
 from . import test_dataset as _td
 from . import mean_shift as _ms
+from . import evaluation as _ev
 
 
 def install(verbose=False):
@@ -40,6 +41,13 @@ def install(verbose=False):
         for name in ("clustering_features", "crop_rois", "match_label_crop", "filter_labels_depth", "test_sample"):
             setattr(ref_td, name, getattr(_td, name))
             patched.append("fcn.test_dataset." + name)
+    if ref_td is not None and hasattr(ref_td, "multilabel_metrics"):
+        ref_td.multilabel_metrics = _ev.multilabel_metrics        # the evaluation tail of test_segnet (:310, :328)
+        patched.append("fcn.test_dataset.multilabel_metrics")
+    ref_ev = sys.modules.get("utils.evaluation")
+    if ref_ev is not None:
+        ref_ev.multilabel_metrics = _ev.multilabel_metrics
+        patched.append("utils.evaluation.multilabel_metrics")
     ref_ms = sys.modules.get("utils.mean_shift")
     if ref_ms is not None:
         for name in ("mean_shift_smart_init", "select_smart_seeds", "seed_hill_climbing_ball", "connected_components"):
