@@ -134,3 +134,44 @@ def test_variant_configuration_and_factories():
     net = N.seg_resnet34_8s_embedding(2, 64, {"module." + k: v for k, v in sd.items()})
     assert not torch.equal(net.state_dict()["fcn.resnet34_8s.conv1.weight"][:, :3], sd["fcn.resnet34_8s.conv1.weight"][:, :3])
     assert torch.equal(net.state_dict()["fcn.resnet34_8s.layer1.0.conv1.weight"], sd["fcn.resnet34_8s.layer1.0.conv1.weight"])
+
+
+def test_shim_rebinds_the_reference_call_sites_and_reads_its_cfg_live():
+    """shim.install(): every reference call site of the path points at this package afterwards, and the factories /
+    clustering_features read INPUT, FUSION_TYPE, EMBEDDING_NORMALIZATION, EMBEDDING_METRIC from the reference's own cfg
+    object at construction / call time (the tools call cfg_from_file() after the imports)."""
+    import sys
+    import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference tree not present (GPU box)")
+    from unseenobjectclustering_b200 import shim, mean_shift as MS, evaluation as EV
+    ref = rh.load()
+    mods = [sys.modules[n] for n in ("networks", "fcn.test_dataset", "utils.mean_shift", "utils.evaluation")]
+    saved = [dict(m.__dict__) for m in mods]
+    cfg_saved = (ref.cfg.INPUT, ref.cfg.TRAIN.FUSION_TYPE, ref.cfg.TRAIN.EMBEDDING_METRIC)
+    try:
+        patched = shim.install()
+        assert ref.networks.__dict__["seg_resnet34_8s_embedding"] is N.seg_resnet34_8s_embedding
+        assert ref.networks.__dict__["seg_resnet34_8s_embedding_early"] is N.seg_resnet34_8s_embedding_early
+        for name in ("clustering_features", "crop_rois", "match_label_crop", "filter_labels_depth", "test_sample"):
+            assert getattr(ref.test_dataset, name) is getattr(TD, name), name
+        assert ref.test_dataset.multilabel_metrics is EV.multilabel_metrics
+        assert ref.mean_shift.mean_shift_smart_init is MS.mean_shift_smart_init
+        assert any("cfg" in p for p in patched)
+        ref.cfg.INPUT, ref.cfg.TRAIN.FUSION_TYPE = "COLOR", "add"          # as cfg_from_file() would, after install()
+        net = ref.networks.__dict__["seg_resnet34_8s_embedding"](2, 64, None)
+        assert net.input_type == "COLOR" and len(net.state_dict()) == 218
+        ref.cfg.INPUT, ref.cfg.TRAIN.FUSION_TYPE = "RGBD", "cat"
+        assert ref.networks.__dict__["seg_resnet34_8s_embedding"](2, 64, None).feature_dim == 128
+        ref.cfg.TRAIN.EMBEDDING_METRIC = "euclidean"
+        assert TD._metric() == "euclidean"
+    finally:
+        ref.cfg.INPUT, ref.cfg.TRAIN.FUSION_TYPE, ref.cfg.TRAIN.EMBEDDING_METRIC = cfg_saved
+        for m, d in zip(mods, saved):
+            for k, v in d.items():
+                if m.__dict__.get(k) is not v:
+                    m.__dict__[k] = v
+        N._LIVE_CFG[0] = None
+        TD._LIVE_CFG[0] = None
+        N.CONFIG.update({"INPUT": "RGBD", "FUSION_TYPE": "add", "EMBEDDING_NORMALIZATION": True})
+    assert ref.test_dataset.clustering_features is not TD.clustering_features
