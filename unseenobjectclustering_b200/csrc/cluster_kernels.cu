@@ -819,18 +819,24 @@ __global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restric
       float zj[DREG > 0 ? DREG : 1];
 #pragma unroll
       for (int k = 0; k < DREG; ++k) zj[k] = (j < m) ? zs[j * ld + k] : 0.f;
-      for (int i = iq; i < m; i += 4) {
-        float acc = 0.f;
-        if (metric == METRIC_EUCLIDEAN) {      // ||z_j - z_i|| <= eps  (mean_shift.py:58-60)
+      if (metric == METRIC_EUCLIDEAN) {        // ||z_j - z_i|| <= eps  (mean_shift.py:58-60)
+        for (int i = iq; i < m; i += 4) {
+          float acc = 0.f;
 #pragma unroll
           for (int k = 0; k < DREG; ++k) { const float t = zj[k] - zs[i * ld + k]; acc = fmaf(t, t, acc); }
-        } else {
+          const bool in = (j < m) && (sqrtf(acc) <= eps);
+          const unsigned int bits = __ballot_sync(0xffffffffu, in);
+          if ((tid & 31) == 0) adj[i][w4] = bits;
+        }
+      } else {
+        for (int i = iq; i < m; i += 4) {
+          float acc = 0.f;
 #pragma unroll
           for (int k = 0; k < DREG; ++k) acc = fmaf(zj[k], zs[i * ld + k], acc);
+          const bool in = (j < m) && ((0.5f * (1.0f - acc)) <= eps);
+          const unsigned int bits = __ballot_sync(0xffffffffu, in);
+          if ((tid & 31) == 0) adj[i][w4] = bits;
         }
-        const bool in = (j < m) && ((metric == METRIC_EUCLIDEAN ? sqrtf(acc) : 0.5f * (1.0f - acc)) <= eps);
-        const unsigned int bits = __ballot_sync(0xffffffffu, in);
-        if ((tid & 31) == 0) adj[i][w4] = bits;
       }
     } else {
       for (int i = iq; i < m; i += 4) {
