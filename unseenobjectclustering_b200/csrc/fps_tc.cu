@@ -58,6 +58,7 @@ struct Fps4Params {
   int T;                    // tiles of the busiest CTA (accumulator columns: 16 * T)
   int TA;                   // tiles kept in tensor memory (the rest in shared memory)
   float rel_margin;         // screening margin per unit |x||s| (kRelMargin4, or half of it for round-to-nearest copies)
+  unsigned int* stats;      // debug (UOC_FPS_TC_STATS=1): per pass {exact rounds, lanes in them, max rounds of one warp, rounds with <= 4 lanes}
   long long* trace;         // debug (UOC_FPS_TC_TRACE=<cta>): per pass {start, screened, local arg-max, exchanged+seed, fp32 rounds}
   int trace_cta;
 };
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
     tmem_wait_ld();
     if (trc) p.trace[i * 6 + 1] = clock64();
     const float ns = s_ns;
-    int n_exact = 0;
+    int n_exact = 0, n_lanes = 0, n_small = 0;
     bool changed = (i == 0);                  // r[] of this thread changed: its cached arg-max key is stale
 #pragma unroll
     for (int s = 0; s < kMaxSlots; ++s) {
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
         }
         if (__any_sync(0xffffffffu, need)) {
           ++n_exact;
+          if (p.stats) { const int c = __popc(__ballot_sync(0xffffffffu, need)); n_lanes += c; n_small += (c <= 4) ? 1 : 0; }
           if (need) {
             // canonical fp32 chain (bit-identical to fps_kernel / fps2_kernel / the oracle)
             const float* xp = Xb + gp;
@@ -276,6 +278,10 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
     }
     if (lane == 0) s_red[warp] = best;
     if (trc) { p.trace[i * 6 + 2] = clock64(); p.trace[i * 6 + 4] = n_exact; }
+    if (p.stats && lane == 0 && n_exact) {
+      atomicAdd(p.stats + i * 4 + 0, (unsigned int)n_exact); atomicAdd(p.stats + i * 4 + 1, (unsigned int)n_lanes);
+      atomicMax(p.stats + i * 4 + 2, (unsigned int)n_exact); atomicAdd(p.stats + i * 4 + 3, (unsigned int)n_small);
+    }
     tc_fence_before();
     __syncthreads();                          // everybody is done with s_seed, s_ns and the accumulators of this pass
     if (trc) p.trace[i * 6 + 5] = clock64();
@@ -585,7 +591,7 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
     p5.slots = w.slots;
     p5.nb = nb; p5.T = 0; p5.TA = 0;
     p5.rel_margin = rel_margin;
-    p5.trace = nullptr; p5.trace_cta = 0;
+    p5.trace = nullptr; p5.trace_cta = 0; p5.stats = nullptr;
     UOC_CUDA(cudaMemsetAsync(w.slots, 0, slot_need5, stream_));
     void* args5[] = {&p5};
     UOC_CUDA(cudaLaunchCooperativeKernel(kern5, dim3(nb * s.batch), dim3(kThreads4), args5, smem5, stream_));
@@ -621,6 +627,11 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   p.rel_margin = rel_margin;
   p.trace = nullptr;
   p.trace_cta = 0;
+  p.stats = nullptr;
+  if (getenv("UOC_FPS_TC_STATS")) {
+    UOC_CUDA(cudaMalloc(&p.stats, sizeof(unsigned int) * 4 * s.m));
+    UOC_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(unsigned int) * 4 * s.m, stream));
+  }
   if (const char* e = getenv("UOC_FPS_TC_TRACE")) {
     p.trace_cta = atoi(e);
     UOC_CUDA(cudaMalloc(&p.trace, sizeof(long long) * 6 * s.m));
@@ -630,6 +641,21 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   void* args[] = {&p};
   UOC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(nb * s.batch), dim3(kThreads4), args, smem, stream));
   count_launch();
+  if (p.stats) {
+    std::vector<unsigned int> hs(size_t(4) * s.m);
+    UOC_CUDA(cudaStreamSynchronize(stream));
+    UOC_CUDA(cudaMemcpy(hs.data(), p.stats, sizeof(unsigned int) * hs.size(), cudaMemcpyDeviceToHost));
+    cudaFree(p.stats);
+    unsigned long long tr = 0, tl = 0, tsm = 0, tmax = 0; int none = 0;
+    for (int i = 1; i + 1 < s.m; ++i) {
+      tr += hs[i * 4]; tl += hs[i * 4 + 1]; tmax += hs[i * 4 + 2]; tsm += hs[i * 4 + 3]; none += hs[i * 4] == 0;
+      if (i < 6 || i % 10 == 0)
+        fprintf(stderr, "[fps tc stats] pass %d: %u exact rounds in the grid, %u lanes, busiest warp %u rounds, %u rounds with <= 4 lanes\n",
+                i, hs[i * 4], hs[i * 4 + 1], hs[i * 4 + 2], hs[i * 4 + 3]);
+    }
+    fprintf(stderr, "[fps tc stats] passes 1..%d: %.1f rounds / pass (%.1f lanes each), busiest warp %.2f rounds on average, %.0f %% of the rounds have <= 4 lanes, %d passes without any round\n",
+            s.m - 2, double(tr) / (s.m - 2), tr ? double(tl) / tr : 0.0, double(tmax) / (s.m - 2), tr ? 100.0 * tsm / tr : 0.0, none);
+  }
   if (p.trace) {
     std::vector<long long> h(size_t(6) * s.m);
     UOC_CUDA(cudaStreamSynchronize(stream));
