@@ -58,6 +58,7 @@ struct Fps4Params {
   int T;                    // tiles of the busiest CTA (accumulator columns: 16 * T)
   int TA;                   // tiles kept in tensor memory (the rest in shared memory)
   float rel_margin;         // screening margin per unit |x||s| (kRelMargin4, or half of it for round-to-nearest copies)
+  int prefetch;             // exact chain: prefetch the later channel batches into L1 (UOC_FPS_PREFETCH, A/B)
   unsigned int* stats;      // debug (UOC_FPS_TC_STATS=1): per pass {exact rounds, lanes in them, max rounds of one warp, rounds with <= 4 lanes}
   long long* trace;         // debug (UOC_FPS_TC_TRACE=<cta>): per pass {start, screened, local arg-max, exchanged+seed, fp32 rounds}
   int trace_cta;
@@ -235,6 +236,12 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
             const float* xp = Xb + gp;
             float acc = 0.f, sq = 0.f;
             constexpr int XB = 32;                    // loads in flight per lane (64 is slower: measured)
+            if (p.prefetch) {
+              // the later load batches depend on the registers of the first one: pull their lines into L1 now, so that
+              // a round costs ONE L2 round trip instead of D / 32
+#pragma unroll
+              for (int k = XB; k < D; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(xp + k * p.sd));
+            }
 #pragma unroll 1
             for (int k0 = 0; k0 < D; k0 += XB) {
               float x[XB];
@@ -591,7 +598,7 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
     p5.slots = w.slots;
     p5.nb = nb; p5.T = 0; p5.TA = 0;
     p5.rel_margin = rel_margin;
-    p5.trace = nullptr; p5.trace_cta = 0; p5.stats = nullptr;
+    p5.trace = nullptr; p5.trace_cta = 0; p5.stats = nullptr; p5.prefetch = 0;
     UOC_CUDA(cudaMemsetAsync(w.slots, 0, slot_need5, stream_));
     void* args5[] = {&p5};
     UOC_CUDA(cudaLaunchCooperativeKernel(kern5, dim3(nb * s.batch), dim3(kThreads4), args5, smem5, stream_));
@@ -627,6 +634,8 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   p.rel_margin = rel_margin;
   p.trace = nullptr;
   p.trace_cta = 0;
+  p.prefetch = 0;
+  if (const char* e = getenv("UOC_FPS_PREFETCH")) p.prefetch = atoi(e);
   p.stats = nullptr;
   if (getenv("UOC_FPS_TC_STATS")) {
     UOC_CUDA(cudaMalloc(&p.stats, sizeof(unsigned int) * 4 * s.m));
