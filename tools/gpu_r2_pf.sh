@@ -5,3 +5,5 @@ for v in 0 1; do
   UOC_FPS_PREFETCH=$v timeout 300 python tools/batch_ab.py 1 2>&1 | tail -1
   UOC_FPS_PREFETCH=$v timeout 300 python tools/two_stage_profile.py 2>&1 | grep -E "^clustering"
 done
+# then the full validation of the tree as it is (prefetch off by default)
+bash tools/gpu_final_s2.sh
