@@ -328,3 +328,50 @@ def test_multilabel_counts_match_oracle_pairwise():
     assert dg == sum(int(O.seg2bmap(gt == i).sum()) for i in np.unique(gt) if i)
     with pytest.raises(_lib.UocError):
         EV.multilabel_counts(torch.full((8, 8), 300).to(DEV), torch.zeros(8, 8).to(DEV))
+
+
+def test_two_stage_plumbing_edge_cases():
+    """Objects touching the frame border (clamped boxes), a single-pixel object (extent 0: no padding, a 1x1 crop),
+    one-object frames, label maps without objects -- device kernels against the oracle."""
+    H, W = 40, 56
+    lab = torch.zeros(1, H, W)
+    lab[0, 0:9, 0:13] = 2            # top-left corner: padding is clamped at 0
+    lab[0, 30:40, 44:56] = 5         # bottom-right corner: clamped at H-1 / W-1
+    lab[0, 20, 30] = 7               # a single pixel
+    img, xyz = O.synthetic_rgbd_frame(H, W, 3)
+    ra, ma, roa, da = O.crop_rois(img, lab.clone(), xyz)
+    rb, mb, rob, db = TD.crop_rois(img.to(DEV), lab.to(DEV), xyz.to(DEV))
+    assert roa.shape[0] == 3 and torch.equal(roa, rob.cpu()) and torch.equal(ma, mb.cpu())
+    assert torch.allclose(ra, rb.cpu(), atol=2e-6, rtol=1e-6) and torch.allclose(da, db.cpu(), atol=2e-6, rtol=1e-6)
+    crops = ma + 1                                          # cluster 2 = the object, cluster 1 = the rest (dropped)
+    want_ref, want_lc = O.match_label_crop(lab.clone(), crops.clone(), ma, roa, da)
+    got_ref, got_lc = TD.match_label_crop(lab.clone(), crops.to(DEV), mb, rob, db)
+    assert torch.equal(got_ref, want_ref) and torch.equal(got_lc.cpu(), want_lc)
+    # one object only, no depth
+    one = torch.zeros(1, H, W)
+    one[0, 5:25, 10:40] = 1
+    r1, m1, ro1, d1 = TD.crop_rois(img.to(DEV), one.to(DEV), None)
+    ro, mo, roo, do = O.crop_rois(img, one.clone(), None)
+    assert torch.equal(roo, ro1.cpu()) and torch.equal(mo, m1.cpu()) and d1 is None
+    a, _ = O.match_label_crop(one.clone(), (mo + 1).clone(), mo, roo, None)
+    b, _ = TD.match_label_crop(one.clone(), (m1 + 1), m1, ro1, None)
+    assert torch.equal(a, b)
+    # nothing to filter / nothing to crop
+    z = torch.zeros(1, H, W)
+    assert torch.equal(TD.filter_labels_depth(z.to(DEV), xyz.to(DEV), 0.8).cpu(), z)
+    assert TD.crop_rois(img.to(DEV), z.to(DEV), xyz.to(DEV))[0].shape[0] == 0
+
+
+def test_multilabel_metrics_edge_cases():
+    """Perfect prediction (every ratio 1), permuted ids, and a prediction with more objects than the ground truth."""
+    from unseenobjectclustering_b200 import evaluation as EV
+    _, gt = O.synthetic_clustered_features(72, 88, 8, 4, 0.05, 500)
+    gt = gt.numpy().astype(np.float32)
+    m = EV.multilabel_metrics(gt.copy(), gt)
+    assert m['Objects F-measure'] == 1.0 and m['Boundary F-measure'] == 1.0 and m['obj_detected_075'] == m['obj_gt'] == 4
+    perm = np.array([0, 9, 3, 17, 4], dtype=np.float32)[gt.astype(np.int64)]
+    assert EV.multilabel_metrics(perm, gt) == m | {}
+    pred = gt.copy()
+    pred[:, 44:][pred[:, 44:] > 0] += 20                   # every object split in two along a vertical line
+    got, want = EV.multilabel_metrics(pred, gt), O.multilabel_metrics(pred, gt)
+    assert all(abs(float(got[k]) - float(want[k])) < 1e-12 for k in want) and got['obj_detected'] > got['obj_gt']
