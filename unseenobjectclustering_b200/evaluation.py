@@ -40,8 +40,9 @@ def multilabel_counts(prediction, gt, device=None):
         t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
         if t.dim() != 2:
             raise ValueError("prediction / gt must be [H, W] label maps")
-        ti = t.to(device=device, dtype=torch.int32).contiguous()
-        if not torch.equal(ti.to(t.dtype).cpu() if not t.is_cuda else ti.to(t.dtype), t.to(device) if t.is_cuda else t):
+        td = t.to(device=device)
+        ti = td.to(torch.int32).contiguous()
+        if not torch.equal(ti.to(torch.float64), td.to(torch.float64)):
             raise ValueError("label maps must hold integers")
         return ti
 
