@@ -28,6 +28,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    # NCCL prints its version banner to STDOUT at the VERSION (and WARN) level; stdout is meant to be the one JSON line.
+    # INFO / TRACE settings are left alone.
+    os.environ.pop("NCCL_DEBUG")
 
 H, W, D, M, ITERS, KAPPA = 480, 640, 64, 100, 10, 20.0
 METRIC = "frames/sec 640x480 RGB-D seg"
