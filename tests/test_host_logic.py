@@ -175,3 +175,36 @@ def test_shim_rebinds_the_reference_call_sites_and_reads_its_cfg_live():
         TD._LIVE_CFG[0] = None
         N.CONFIG.update({"INPUT": "RGBD", "FUSION_TYPE": "add", "EMBEDDING_NORMALIZATION": True})
     assert ref.test_dataset.clustering_features is not TD.clustering_features
+
+
+def test_metrics_host_half_matches_oracle_from_exact_counts():
+    """evaluation.metrics_from_counts (Hungarian matching + the reference's float64 ratios) on count tables computed
+    here with the oracle's primitives -- the same tables the device kernels produce (tests/test_gpu_pipeline.py)."""
+    from unseenobjectclustering_b200 import evaluation as EV
+    for seed in range(3):
+        _, gt = O.synthetic_clustered_features(60, 76, 8, 3 + seed, 0.05, 600 + seed)
+        gt = gt.numpy().astype(np.int64)
+        pred = O.synthetic_prediction(gt, seed)
+        tp = np.zeros((256, 256), dtype=np.int64)
+        bp = np.zeros((256, 256), dtype=np.int64)
+        br = np.zeros((256, 256), dtype=np.int64)
+        np.add.at(tp, (gt.ravel(), pred.ravel()), 1)
+        for i in np.unique(gt):
+            for j in np.unique(pred):
+                if i and j:
+                    bp[i, j], br[i, j] = O.boundary_overlap(pred == j, gt == i)
+        dp = sum(int(O.seg2bmap(pred == j).sum()) for j in np.unique(pred) if j)
+        dg = sum(int(O.seg2bmap(gt == i).sum()) for i in np.unique(gt) if i)
+        got = EV.metrics_from_counts(tp, bp, br, (dp, dg))
+        want = O.multilabel_metrics(pred.astype(np.float32), gt.astype(np.float32))
+        assert set(got) == set(want)
+        for k in want:
+            assert abs(float(got[k]) - float(want[k])) < 1e-12, (seed, k)
+    # degenerate cases (evaluation.py:139-174)
+    z = np.zeros((256, 256), dtype=np.int64)
+    only_gt = z.copy(); only_gt[3, 0] = 50; only_gt[0, 0] = 100
+    assert EV.metrics_from_counts(only_gt, z, z, (0, 10))['Objects Recall'] == 0.
+    only_pred = z.copy(); only_pred[0, 4] = 50; only_pred[0, 0] = 100
+    assert EV.metrics_from_counts(only_pred, z, z, (10, 0))['Objects Precision'] == 0.
+    none = z.copy(); none[0, 0] = 100
+    assert EV.metrics_from_counts(none, z, z, (0, 0))['obj_detected_075_percentage'] == 1.

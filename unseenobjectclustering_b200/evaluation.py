@@ -70,7 +70,14 @@ def multilabel_counts(prediction, gt, device=None):
 
 def multilabel_metrics(prediction, gt, obj_detect_threshold=0.75):
     """lib/utils/evaluation.py:109-257.  prediction, gt: [H, W] numpy arrays (or tensors) of label ids, 0 = background."""
-    tp_all, bprec_all, brec_all, (bden_p, bden_g) = multilabel_counts(prediction, gt)
+    tp_all, bprec_all, brec_all, dens = multilabel_counts(prediction, gt)
+    return metrics_from_counts(tp_all, bprec_all, brec_all, dens, obj_detect_threshold)
+
+
+def metrics_from_counts(tp_all, bprec_all, brec_all, dens, obj_detect_threshold=0.75):
+    """The host half of multilabel_metrics: from the [256,256] count tables (indexed [gt label][predicted label]) and the
+    two boundary denominators to the reference's dictionary, in its float64 arithmetic (evaluation.py:139-257)."""
+    bden_p, bden_g = dens
     area_gt = tp_all.sum(axis=1)                 # pixels per ground-truth label
     area_pred = tp_all.sum(axis=0)               # pixels per predicted label
     labels_gt = [l for l in range(1, _KL) if area_gt[l] > 0]
