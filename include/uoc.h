@@ -67,6 +67,15 @@ UOC_API unsigned long long uoc_launch_count(void);
 /* sm count / compute capability of the current device; UOC_ERR_UNSUPPORTED if it is not sm_100. */
 UOC_API int uoc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Kernels report pipeline time-outs / bad configurations in a per-device error word instead of hanging; the compute
+ * entry points read it only under UOC_FLAG_SYNC_CHECK (that needs a stream synchronisation).  Callers that synchronise
+ * anyway (the .cpu() of lib/fcn/test_dataset.py:57, :255) check it there:
+ *   uoc_check_device_error        synchronises `stream`, returns UOC_ERR_DEVICE (and clears the word) if it is non-zero
+ *   uoc_peek_device_error_async   enqueues a copy of the word into *word_host (pinned host memory; stream-ordered,
+ *                                 capturable in a CUDA graph); the caller inspects it after its own synchronisation */
+UOC_API int uoc_check_device_error(uoc_stream_t stream);
+UOC_API int uoc_peek_device_error_async(uint32_t* word_host, uoc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Clustering: replaces utils.mean_shift.mean_shift_smart_init (lib/utils/mean_shift.py:192-229)
  * as called per batch item by fcn.test_dataset.clustering_features (lib/fcn/test_dataset.py:44-59).

@@ -14,57 +14,59 @@ def _labels(H, W, K, seed):
     return gt
 
 
-@pytest.mark.parametrize("seed", [0, 1, 2, 3])
-def test_filter_labels_depth_matches_oracle(seed):
-    H, W = 60, 80
-    lab = _labels(H, W, 5, seed).float()[None]
-    _, xyz = O.synthetic_rgbd_frame(H, W, seed)
-    g = torch.Generator().manual_seed(seed)
-    xyz[:, 2][torch.rand(1, H, W, generator=g) < 0.3] = 0
-    xyz[:, 2, : H // 2, : W // 2] = 0
-    for thr in (0.5, 0.8):
-        a = O.filter_labels_depth(lab, xyz, thr)
-        b = TD.filter_labels_depth(lab, xyz, thr)
-        assert torch.equal(a, b)
+def test_two_stage_plumbing_has_no_cpu_path():
+    """filter_labels_depth / crop_rois / match_label_crop run in csrc/refine.cu only: CPU pixel tensors are refused
+    (the kernels themselves are checked against the oracle by tests/test_gpu_pipeline.py)."""
+    from unseenobjectclustering_b200 import _lib
+    H, W = 32, 48
+    lab = _labels(H, W, 3, 0).float()[None]
+    img, xyz = O.synthetic_rgbd_frame(H, W, 0)
+    with pytest.raises(_lib.UocError):
+        TD.filter_labels_depth(lab, xyz, 0.8)
+    with pytest.raises(_lib.UocError):
+        TD.crop_rois(img, lab, xyz)
+    with pytest.raises(_lib.UocError):
+        TD.match_label_crop(lab, torch.zeros(1, 224, 224), torch.zeros(1, 224, 224), torch.zeros(1, 4), None)
+    src = open(TD.__file__).read()
+    assert "torch.nn.functional" not in src and "F.interpolate" not in src
 
 
-@pytest.mark.parametrize("seed", [0, 1, 2])
-def test_crop_rois_matches_oracle(seed):
-    H, W = 96, 128
-    lab = _labels(H, W, 4, seed).float()[None]
-    img, xyz = O.synthetic_rgbd_frame(H, W, seed)
-    ra, ma, roa, da = O.crop_rois(img, lab.clone(), xyz)
-    rb, mb, rob, db = TD.crop_rois(img, lab.clone(), xyz)
-    assert torch.equal(roa, rob)
-    assert torch.equal(ma, mb)
-    assert torch.allclose(ra, rb, atol=1e-6) and torch.allclose(da, db, atol=1e-6)
-    # no depth
-    ra, ma, roa, da = O.crop_rois(img, lab.clone(), None)
-    rb, mb, rob, db = TD.crop_rois(img, lab.clone(), None)
-    assert da is None and db is None and torch.equal(roa, rob)
+def test_depth_is_gated_on_the_network_input_type():
+    """lib/fcn/test_dataset.py:236-239: depth is used iff cfg.INPUT is DEPTH / RGBD."""
+    class _Net(object):
+        def __init__(self, it):
+            self.input_type = it
+    assert TD._uses_depth(_Net("RGBD")) and TD._uses_depth(_Net("DEPTH")) and not TD._uses_depth(_Net("COLOR"))
+    wrapped = type("DP", (), {"module": _Net("COLOR")})()
+    assert not TD._uses_depth(wrapped)
+    assert TD._uses_depth(lambda *a: None)           # foreign callable, no live cfg: the reference default (RGBD configs)
 
 
-def test_crop_rois_empty():
-    img, xyz = O.synthetic_rgbd_frame(32, 48, 0)
-    r, m, rois, d = TD.crop_rois(img, torch.zeros(1, 32, 48), xyz)
-    assert r.shape[0] == 0 and rois.shape == (0, 4)
-
-
-@pytest.mark.parametrize("seed", [0, 1, 2])
-def test_match_label_crop_matches_oracle(seed):
-    H, W = 96, 128
-    lab = _labels(H, W, 4, seed).float()[None]
-    img, xyz = O.synthetic_rgbd_frame(H, W, seed)
-    rgb_c, mask_c, rois, depth_c = O.crop_rois(img, lab.clone(), xyz)
-    K = rgb_c.shape[0]
-    crops = torch.stack([_labels(224, 224, 3, 50 + seed * 10 + k).float() for k in range(K)])
-    a, la = O.match_label_crop(lab, crops.clone(), mask_c, rois, depth_c)
-    b, lb = TD.match_label_crop(lab, crops.clone(), mask_c, rois, depth_c)
-    assert torch.equal(a, b)
-    assert torch.equal(la, lb)
-    a, _ = O.match_label_crop(lab, crops.clone(), mask_c, rois, None)
-    b, _ = TD.match_label_crop(lab, crops.clone(), mask_c, rois, None)
-    assert torch.equal(a, b)
+def test_bf16_registry_cannot_alias_a_foreign_tensor():
+    """The side channel from the backbone to clustering_features is keyed by identity, storage and version."""
+    from unseenobjectclustering_b200 import mean_shift as MS
+    MS.clear_bf16_registry()
+    f = torch.zeros(1, 4, 2, 3)
+    xb = torch.zeros(1, 6, 4, dtype=torch.bfloat16)
+    MS.register_bf16_copy(f, xb)
+    assert MS._lookup_bf16(f) is xb
+    assert MS._lookup_bf16(f.detach()) is xb                       # an alias of the same storage (test_dataset.py:247)
+    assert MS._lookup_bf16(f[:, :2]) is None                       # a view with another shape
+    assert MS._lookup_bf16(torch.zeros(1, 4, 2, 3)) is None        # a foreign tensor
+    f.add_(1.0)                                                    # modified in place: the copy is stale
+    assert MS._lookup_bf16(f) is None and MS._lookup_bf16(f) is None
+    # the registry keeps the registered tensor alive, so its address cannot be recycled while the entry is live
+    g = torch.zeros(1, 4, 2, 3)
+    addr = g.data_ptr()
+    MS.register_bf16_copy(g, xb)
+    del g
+    others = [torch.zeros(1, 4, 2, 3) for _ in range(64)]
+    assert all(o.data_ptr() != addr for o in others)
+    assert all(MS._lookup_bf16(o) is None for o in others)
+    for k in range(MS._BF16_REGISTRY_SIZE + 3):                    # bounded
+        MS.register_bf16_copy(torch.zeros(1, 4, 2, 3), xb)
+    assert len(MS._bf16_registry) == MS._BF16_REGISTRY_SIZE
+    MS.clear_bf16_registry()
 
 
 def test_module_state_dict_roundtrip_and_key_filter():

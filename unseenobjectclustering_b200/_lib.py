@@ -34,6 +34,8 @@ SIGNATURES = {
     "uoc_version": (_i, []),
     "uoc_launch_count": (_c.c_uint64, []),
     "uoc_device_info": (_i, [_c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
+    "uoc_check_device_error": (_i, [_vp]),
+    "uoc_peek_device_error_async": (_i, [_vp, _vp]),
     "uoc_meanshift_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "uoc_meanshift_cluster": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                    _i, _vp]),
@@ -98,6 +100,15 @@ def device_info():
     a, b, c = _i(0), _i(0), _i(0)
     check(lib.uoc_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "uoc_device_info")
     return a.value, b.value, c.value
+
+
+def raise_on_device_error(device=None):
+    """Read (and clear) the device error word of `device` on its current stream; raises UocError if a kernel reported a
+    pipeline time-out or a bad configuration.  Synchronises the stream: call it where the host has just synchronised
+    anyway (a .cpu() / .item()), never on the hot path."""
+    import torch
+    with torch.cuda.device(device):
+        check(load().uoc_check_device_error(stream_ptr(device)), "device error check")
 
 
 def ptr(t):

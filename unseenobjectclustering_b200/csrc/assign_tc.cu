@@ -222,10 +222,9 @@ template <int D>
 int launch_tc(const CUtensorMap& tmap, const ClusterShape& s, const float* Z, const int* seed_labels, int P, int* labels_tmp,
               int* hist, unsigned int* ucount, int* ulist, cudaStream_t stream) {
   using Cfg = AsCfg<D>;
-  static bool attr = false;
-  if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(assign_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&assign_tc_kernel<D>), int(Cfg::kSmemBytes));
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   assign_tc_kernel<D><<<dim3(P, s.batch), kThreads, Cfg::kSmemBytes, stream>>>(tmap, Z, seed_labels, s.m, s.n, P, labels_tmp,
                                                                                hist, ucount, ulist, device_error_word());
@@ -255,10 +254,9 @@ int launch_assign_tc(const float* X, const __nv_bfloat16* xb, const ClusterShape
                    : launch_tc<128>(tmap, s, Z, seed_labels, P, labels_tmp, hist, ucount, ulist, stream);
   if (rc != UOC_OK) return rc;
   const size_t smem = sizeof(float) * size_t(s.m) * s.d;
-  static bool attr = false;
-  if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(assign_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&assign_fix_kernel), int(100 * 1024));
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   assign_fix_kernel<<<dim3(sm_count() > 0 ? sm_count() : 148, s.batch), 128, smem, stream>>>(
       X, s.stride_b, s.stride_d, s.n, s.d, s.m, Z, seed_labels, ucount, ulist, hist, labels_tmp);

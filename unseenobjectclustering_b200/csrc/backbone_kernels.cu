@@ -153,10 +153,9 @@ __global__ void __launch_bounds__(256) stem_kernel(StemParams p) {
 template <int CIN>
 static int launch_stem_t(const StemParams& p, int groups, cudaStream_t stream) {
   const size_t smem = sizeof(float) * (49 * CIN * 64 + CIN * kStemPatch * 38);
-  static bool attr = false;
-  if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(stem_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&stem_kernel<CIN>), int(int(smem)));
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   stem_kernel<CIN><<<dim3((p.Wo + 15) / 16, (p.Ho + 15) / 16, groups * p.N), 256, smem, stream>>>(p);
   UOC_CHECK_LAUNCH();
@@ -497,10 +496,9 @@ __global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(StemTc
 template <int CIN>
 static int launch_stem_tc_t(const StemTcParams& p, cudaStream_t stream) {
   using Cfg = StemTcCfg<CIN>;
-  static bool attr = false;
-  if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(stem_tc_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    attr = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&stem_tc_kernel<CIN>), int(Cfg::kSmem));
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   const int per_sm = (CIN == 3) ? 2 : 1;
   int grid = per_sm * (sm_count() > 0 ? sm_count() : 148);

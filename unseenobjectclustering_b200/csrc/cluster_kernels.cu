@@ -544,15 +544,7 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
   else if (gpt_t == 2) kern = UOC_FPS_PICK(2, 1024, 8);
   else kern = UOC_FPS_PICK(4, 1024, 8);
 #undef UOC_FPS_PICK
-  {
-    static void* configured_kern = nullptr;
-    static size_t configured_smem = 0;
-    if (configured_kern != kern || smem > configured_smem) {
-      UOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      configured_kern = kern;
-      configured_smem = smem;
-    }
-  }
+  UOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));   // per device, cheap
   if (variant == 0 || variant == 2) {
     UOC_CUDA(cudaMemsetAsync(slots, 0, slot_need + (variant == 0 ? mail_need : 0), stream));
   } else {
@@ -915,12 +907,12 @@ __global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restric
 int launch_label_seeds(const float* Z, int batch, int m, int d, float epsilon, int* seed_labels, int* num_unique,
                        cudaStream_t stream, int metric) {
   const size_t smem = sizeof(float) * size_t(m) * (d + 1);
-  static bool configured = false;
-  if (!configured) {
-    UOC_CUDA(cudaFuncSetAttribute(label_seeds_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    UOC_CUDA(cudaFuncSetAttribute(label_seeds_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    UOC_CUDA(cudaFuncSetAttribute(label_seeds_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
+  {
+    const void* kern = d == 64 ? reinterpret_cast<const void*>(&label_seeds_kernel<64>)
+                     : d == 128 ? reinterpret_cast<const void*>(&label_seeds_kernel<128>)
+                                : reinterpret_cast<const void*>(&label_seeds_kernel<0>);
+    const int rc_attr = ensure_dynamic_smem(kern, 160 * 1024);
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   if (d == 64) label_seeds_kernel<64><<<batch, 512, smem, stream>>>(Z, m, d, epsilon, metric, seed_labels, num_unique);
   else if (d == 128) label_seeds_kernel<128><<<batch, 512, smem, stream>>>(Z, m, d, epsilon, metric, seed_labels, num_unique);
@@ -1051,12 +1043,12 @@ int launch_assign(const float* X, const __nv_bfloat16* xb, const ClusterShape& s
   }
   const size_t smem = sizeof(float) * size_t(s.m) * s.d;
   const dim3 grid(static_cast<unsigned int>((s.n + 127) / 128), s.batch);
-  static bool attr_done = false;
-  if (!attr_done) {
-    UOC_CUDA(cudaFuncSetAttribute(assign_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    UOC_CUDA(cudaFuncSetAttribute(assign_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    UOC_CUDA(cudaFuncSetAttribute(assign_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_done = true;
+  {
+    const void* kern = s.d == 64 ? reinterpret_cast<const void*>(&assign_kernel<64>)
+                     : s.d == 128 ? reinterpret_cast<const void*>(&assign_kernel<128>)
+                                  : reinterpret_cast<const void*>(&assign_kernel<0>);
+    const int rc_attr = ensure_dynamic_smem(kern, (s.d == 64 || s.d == 128) ? 100 * 1024 : 160 * 1024);
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   if (s.d == 64)
     assign_kernel<64><<<grid, 128, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, metric, Z, seed_labels, hist, labels_tmp);
@@ -1096,10 +1088,9 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict_
 int launch_pack_bf16(const float* X, const ClusterShape& s, __nv_bfloat16* xb, cudaStream_t stream) {
   if (s.d % 2 != 0) return fail(UOC_ERR_UNSUPPORTED, "d must be even");
   const size_t smem = sizeof(float) * size_t(s.d) * 65;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    UOC_CUDA(cudaFuncSetAttribute(pack_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = smem;
+  if (smem > 48 * 1024) {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&pack_bf16_kernel), int(smem));
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   const dim3 grid(static_cast<unsigned int>((s.n + 63) / 64), s.batch);
   pack_bf16_kernel<<<grid, 256, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, xb);

@@ -259,10 +259,9 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
 template <int BLOCK_N, int SUB, bool XHALO>
 int launch(HaloParams prm, int ctas, int groups, cudaStream_t stream) {
   using Cfg = HaloCfg<BLOCK_N, SUB, XHALO>;
-  static bool attr = false;
-  if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BLOCK_N, SUB, XHALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    attr = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&conv_halo_kernel<BLOCK_N, SUB, XHALO>), int(kSmemBudget));
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   prm.a_stride = (prm.a_bytes + 1023) / 1024 * 1024;
   int budget = kSmemBudget;

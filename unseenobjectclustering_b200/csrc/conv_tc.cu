@@ -207,10 +207,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
 template <int BLOCK_N, int CLUSTER>
 int launch(const ConvTcParams& prm, int m_tiles, int groups, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
-  static bool attr = false;
-  if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&conv_tc_kernel<BLOCK_N, CLUSTER>), int(Cfg::kSmemBytes));
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   const int m_clusters = (m_tiles + CLUSTER - 1) / CLUSTER;
   cudaLaunchConfig_t cfg;
@@ -414,10 +413,9 @@ conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
 template <int BLOCK_N>
 int launch_pair(const ConvTcParams& prm, int m_tiles, int groups, cudaStream_t stream) {
   using Cfg = Conv2Cfg<BLOCK_N>;
-  static bool attr = false;
-  if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&conv_tc2_kernel<BLOCK_N>), int(Cfg::kSmemBytes));
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   const int m_pairs = (m_tiles + 1) / 2;
   cudaLaunchConfig_t cfg;

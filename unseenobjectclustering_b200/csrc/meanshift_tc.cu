@@ -242,10 +242,9 @@ template <int D>
 int launch_iter(const CUtensorMap& tmap, const ClusterShape& s, const ClusterWorkspace& w, const float* Z, int P,
                 float kappa, cudaStream_t stream) {
   using Cfg = MsCfg<D>;
-  static bool attr = false;
-  if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(meanshift_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&meanshift_tc_kernel<D>), int(Cfg::kSmemBytes));
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   const float c1 = kappa * 1.4426950408889634f;
   cudaLaunchConfig_t cfg;
@@ -597,11 +596,9 @@ template <int D, int POLY>
 int launch_persistent(const CUtensorMap& tmap, const ClusterShape& s, const ClusterWorkspace& w, float* Z, int P,
                       float kappa, int iters, cudaStream_t stream) {
   using Cfg = MsCfg<D>;
-  static bool attr = false;
-  if (!attr) {
-    UOC_CUDA(cudaFuncSetAttribute(meanshift_tc_persistent_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
-    attr = true;
+  {
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&meanshift_tc_persistent_kernel<D, POLY>), int(Cfg::kSmemBytes));
+    if (rc_attr != UOC_OK) return rc_attr;
   }
   unsigned int* done = reinterpret_cast<unsigned int*>(w.slots);   // two counters per batch item, 128 bytes apart
   unsigned int* rowflag = nullptr;

@@ -38,6 +38,8 @@ int sm_count();            // cached multiProcessorCount of the current device
 // device-side error word (one per process, lives in global memory); kernels OR error bits into it
 unsigned int* device_error_word();
 int check_device_error(cudaStream_t stream);   // synchronises the stream
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel): the attribute is per device
+int ensure_dynamic_smem(const void* func, int bytes);
 
 // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -4,7 +4,9 @@
 
 #include <atomic>
 #include <cstdio>
+#include <map>
 #include <mutex>
+#include <utility>
 
 namespace uoc {
 
@@ -30,31 +32,34 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 struct DevInfo {
   int ok = -1;  // -1 unknown
-  int device = -1;
   int sms = 0, major = 0, minor = 0;
 };
-static DevInfo g_dev;
+static DevInfo g_devs[64];
 static std::mutex g_mu;
 
-static int query_device() {
-  std::lock_guard<std::mutex> lk(g_mu);
+static int query_device(DevInfo* out = nullptr) {
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__);
-  if (g_dev.ok >= 0 && g_dev.device == dev) return UOC_OK;
-  cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, dev);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__);
-  g_dev.device = dev;
-  g_dev.sms = prop.multiProcessorCount;
-  g_dev.major = prop.major;
-  g_dev.minor = prop.minor;
-  g_dev.ok = (prop.major == 10) ? 1 : 0;
+  if (dev < 0 || dev >= 64) return fail(UOC_ERR_UNSUPPORTED, "device ordinal out of range");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DevInfo& d = g_devs[dev];
+  if (d.ok < 0) {
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__);
+    d.sms = prop.multiProcessorCount;
+    d.major = prop.major;
+    d.minor = prop.minor;
+    d.ok = (prop.major == 10) ? 1 : 0;
+  }
+  if (out) *out = d;
   return UOC_OK;
 }
 
 int require_sm100() {
-  int rc = query_device();
+  DevInfo g_dev;
+  int rc = query_device(&g_dev);
   if (rc != UOC_OK) return rc;
   if (g_dev.ok != 1) {
     char buf[256];
@@ -67,25 +72,42 @@ int require_sm100() {
 }
 
 int sm_count() {
-  if (query_device() != UOC_OK) return 0;
-  return g_dev.sms;
+  DevInfo d;
+  if (query_device(&d) != UOC_OK) return 0;
+  return d.sms;
 }
 
-static unsigned int* g_err_word = nullptr;
-static int g_err_dev = -1;
+// one error word per device (multi-GPU processes: DataParallel replicas, one handle per device)
+static const int kMaxDevices = 64;
+static unsigned int* g_err_word[kMaxDevices] = {nullptr};
 
 unsigned int* device_error_word() {
   int dev = -1;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_err_word == nullptr || g_err_dev != dev) {
+  if (g_err_word[dev] == nullptr) {
     unsigned int* p = nullptr;
     if (cudaMalloc(&p, sizeof(unsigned int)) != cudaSuccess) return nullptr;
     cudaMemset(p, 0, sizeof(unsigned int));
-    g_err_word = p;  // one small allocation per device change; intentionally never freed
-    g_err_dev = dev;
+    g_err_word[dev] = p;  // one small allocation per device; intentionally never freed
   }
-  return g_err_word;
+  return g_err_word[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember (device, kernel) pairs already set
+int ensure_dynamic_smem(const void* func, int bytes) {
+  int dev = -1;
+  UOC_CUDA(cudaGetDevice(&dev));
+  static std::map<std::pair<int, const void*>, int> done;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = done.find(std::make_pair(dev, func));
+    if (it != done.end() && it->second >= bytes) return UOC_OK;
+  }
+  UOC_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  std::lock_guard<std::mutex> lk(g_mu);
+  done[std::make_pair(dev, func)] = bytes;
+  return UOC_OK;
 }
 
 int check_device_error(cudaStream_t stream) {
@@ -156,12 +178,30 @@ int uoc_version(void) { return 100; }
 unsigned long long uoc_launch_count(void) { return uoc::g_launches.load(); }
 
 int uoc_device_info(int* sm_count_out, int* cc_major, int* cc_minor) {
-  int rc = uoc::query_device();
+  uoc::DevInfo d;
+  int rc = uoc::query_device(&d);
   if (rc != UOC_OK) return rc;
-  if (sm_count_out) *sm_count_out = uoc::g_dev.sms;
-  if (cc_major) *cc_major = uoc::g_dev.major;
-  if (cc_minor) *cc_minor = uoc::g_dev.minor;
+  if (sm_count_out) *sm_count_out = d.sms;
+  if (cc_major) *cc_major = d.major;
+  if (cc_minor) *cc_minor = d.minor;
   return uoc::require_sm100();
+}
+
+
+int uoc_check_device_error(uoc_stream_t stream) {
+  int rc = uoc::require_sm100();
+  if (rc != UOC_OK) return rc;
+  return uoc::check_device_error(static_cast<cudaStream_t>(stream));
+}
+
+int uoc_peek_device_error_async(uint32_t* word_host, uoc_stream_t stream) {
+  int rc = uoc::require_sm100();
+  if (rc != UOC_OK) return rc;
+  if (!word_host) return uoc::fail(UOC_ERR_INVALID, "word_host is null");
+  unsigned int* w = uoc::device_error_word();
+  if (!w) return uoc::fail(UOC_ERR_CUDA, "could not allocate the device error word");
+  UOC_CUDA(cudaMemcpyAsync(word_host, w, sizeof(uint32_t), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  return UOC_OK;
 }
 
 }  // extern "C"

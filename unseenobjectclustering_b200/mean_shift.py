@@ -16,7 +16,8 @@ from . import _lib
 EMBEDDING_ALPHA = 0.02   # cfg.TRAIN.EMBEDDING_ALPHA default, lib/fcn/config.py:254
 
 _workspaces = {}
-_bf16_registry = {}      # data_ptr of a feature tensor -> (bf16 pixel-major copy, shape) made by the backbone
+_bf16_registry = {}      # data_ptr -> (the feature tensor itself, its bf16 pixel-major copy, its version) made by the backbone
+_BF16_REGISTRY_SIZE = 8
 
 
 def _workspace(device, nbytes):
@@ -32,16 +33,40 @@ def _workspace(device, nbytes):
 
 
 def register_bf16_copy(features, xb):
-    """Called by the backbone module: remember the bf16 [N, H*W, C] copy written next to `features`."""
-    while len(_bf16_registry) >= 8:          # a handful of live entries is enough (frames in flight)
+    """Called by the backbone module: remember the bf16 [N, H*W, C] copy written next to `features`.
+
+    The entry holds a STRONG reference to `features`, so its address cannot be handed to another tensor by the
+    caching allocator while the entry is live (an entry keyed by a bare data_ptr could silently alias a later,
+    unrelated field of the same shape).  At most _BF16_REGISTRY_SIZE entries (feature maps) are kept alive."""
+    key = features.data_ptr()
+    _bf16_registry.pop(key, None)
+    while len(_bf16_registry) >= _BF16_REGISTRY_SIZE:
         _bf16_registry.pop(next(iter(_bf16_registry)))
-    _bf16_registry[features.data_ptr()] = (xb, tuple(features.shape))
+    _bf16_registry[key] = (features, xb, features._version)
+
+
+def clear_bf16_registry():
+    """Drop every remembered (features, bf16 copy) pair (releases the feature maps the registry keeps alive)."""
+    _bf16_registry.clear()
 
 
 def _lookup_bf16(features):
+    """The bf16 copy the backbone wrote next to `features`, or None.  A hit requires the SAME storage, offset, shape and
+    strides as the registered tensor (the tensor itself or an alias such as .detach()) and an unchanged autograd version
+    counter (an in-place torch op on the field since the forward pass invalidates the copy)."""
     ent = _bf16_registry.get(features.data_ptr())
-    if ent is not None and ent[1] == tuple(features.shape):
-        return ent[0]
+    if ent is None:
+        return None
+    owner, xb, version = ent
+    same = (features is owner or
+            (features.untyped_storage().data_ptr() == owner.untyped_storage().data_ptr()
+             and features.storage_offset() == owner.storage_offset()))
+    if (same and features.dtype == owner.dtype and tuple(features.shape) == tuple(owner.shape)
+            and tuple(features.stride()) == tuple(owner.stride())
+            and features._version == version and owner._version == version):
+        return xb
+    if features is owner or same:
+        _bf16_registry.pop(features.data_ptr(), None)      # modified in place: the copy is stale for good
     return None
 
 
@@ -58,13 +83,15 @@ def _metric_flag(metric):
 
 
 def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indices=None, epsilon=None, flags=0,
-                   return_seeds=False, on_sampling_done=None, metric='cosine'):
+                   return_seeds=False, on_sampling_done=None, metric='cosine', x_bf16=None):
     """Cluster a batch of embedding fields in ONE library call.
 
     features: [N, C, H, W] float32 CUDA tensor, unit norm over C (any batch stride; each item must
     be planar-contiguous like the reference's network output).
     first_indices: the per-item first seed (np.random.randint(0, n) of mean_shift.py:155); drawn
     here from numpy's global RNG, in item order, when None.
+    x_bf16: the bf16 pixel-major copy [N, H*W, C] of `features` when the caller owns it (SEGNET_B200.forward_ex);
+    None -> the copy the backbone registered for exactly this tensor, else it is made inside the library.
     Returns (labels int32 [N, H*W] CUDA, selected int64 [N, num_seeds] CUDA[, seeds, seed_labels]).
     """
     if not features.is_cuda:
@@ -73,6 +100,12 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
         raise _lib.UocError("features must be float32")
     N, C, H, W = features.shape
     n = H * W
+    xb = None
+    if metric == 'cosine':
+        xb = x_bf16 if x_bf16 is not None else _lookup_bf16(features)
+        if xb is not None and (xb.dtype != torch.bfloat16 or tuple(xb.shape) != (N, n, C) or not xb.is_contiguous()
+                               or xb.device != features.device):
+            raise _lib.UocError("x_bf16 must be a contiguous bfloat16 [N, H*W, C] tensor on the features' device")
     if not (features.stride(3) == 1 and features.stride(2) == W and features.stride(1) == n):
         features = features.contiguous()
     lib = _lib.load()
@@ -83,7 +116,6 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
         raise ValueError("first_indices has %d entries for %d fields" % (len(first_indices), N))
     first = (ctypes.c_int64 * N)(*[int(v) for v in list(first_indices)[:N]])     # extra entries are left unused
     flags = int(flags) | _metric_flag(metric)
-    xb = _lookup_bf16(features) if metric == 'cosine' else None
     with torch.cuda.device(dev):
         nbytes = lib.uoc_meanshift_workspace_bytes(N, n, C, num_seeds)
         ws = _workspace(dev, nbytes)

@@ -155,8 +155,8 @@ class SEGNET_B200(nn.Module):
         self._names = list(sd.keys())
         for k, v in sd.items():
             self.register_buffer(k.replace(".", "__"), v, persistent=True)
-        self._handle = None
-        self._handle_dev = None
+        self._handles = {}          # device -> uoc_backbone handle; shared (by reference) with DataParallel replicas
+        self._owner = True          # replicas never destroy handles
         self._ws = None
         self._ws_by_stream = {}
         self.keep_bf16 = True
@@ -175,9 +175,20 @@ class SEGNET_B200(nn.Module):
         return res
 
     def _release(self):
-        if self._handle is not None:
-            _lib.load().uoc_backbone_destroy(self._handle)
-            self._handle = None
+        if not getattr(self, "_owner", False):
+            return
+        handles, self._handles = self._handles, {}
+        for h in handles.values():
+            _lib.load().uoc_backbone_destroy(h)
+
+    def _replicate_for_data_parallel(self):
+        # torch.nn.DataParallel over several devices: replicas share the per-device handle table (one handle per
+        # device, built once from the host copy of the weights) and own nothing themselves
+        replica = super()._replicate_for_data_parallel()
+        replica._owner = False
+        replica._ws = None
+        replica._ws_by_stream = {}
+        return replica
 
     def __del__(self):
         try:
@@ -198,9 +209,9 @@ class SEGNET_B200(nn.Module):
 
     # handle ------------------------------------------------------------------------------------
     def _ensure_handle(self, device):
-        if self._handle is not None and self._handle_dev == device:
-            return
-        self._release()
+        h = self._handles.get(device)
+        if h is not None:
+            return h
         lib = _lib.load()
         keep = []
         descs = []
@@ -216,10 +227,20 @@ class SEGNET_B200(nn.Module):
             _lib.check(lib.uoc_backbone_create_ex(ctypes.byref(h), arr, len(descs), self.num_units,
                                                   _INPUT_IDS[self.input_type], _FUSION_IDS[self.fusion_type],
                                                   int(self.normalize)), "uoc_backbone_create_ex")
-        self._handle = h
-        self._handle_dev = device
+        self._handles[device] = h
+        return h
 
     def forward(self, img, label=None, depth=None):
+        """features [N, C, H, W] float32 (the reference's return value).  The bf16 pixel-major copy written by the same
+        kernel is remembered for exactly this tensor (mean_shift.register_bf16_copy) so that clustering_features(features)
+        finds it; callers that own both use forward_ex."""
+        out, xb = self.forward_ex(img, label, depth)
+        if xb is not None:
+            _ms.register_bf16_copy(out, xb)
+        return out
+
+    def forward_ex(self, img, label=None, depth=None):
+        """(features [N, C, H, W] float32, bf16 pixel-major copy [N, H*W, C] or None when keep_bf16 is off)."""
         need_img, need_depth = self.input_type != "DEPTH", self.input_type != "COLOR"
         if need_depth and depth is None:
             raise _lib.UocError("INPUT=%r needs the depth (XYZ) tensor" % self.input_type)
@@ -229,13 +250,13 @@ class SEGNET_B200(nn.Module):
         if not lead.is_cuda:
             raise _lib.UocError("inputs must be CUDA tensors: there is no CPU path in this package")
         dev = lead.device
-        self._ensure_handle(dev)
+        handle = self._ensure_handle(dev)
         lib = _lib.load()
         img = img.detach().to(device=dev, dtype=torch.float32).contiguous() if need_img else None
         depth = depth.detach().to(device=dev, dtype=torch.float32).contiguous() if need_depth else None
         N, _, H, W = lead.shape
         with torch.cuda.device(dev):
-            nbytes = lib.uoc_backbone_workspace_bytes(self._handle, N, H, W)
+            nbytes = lib.uoc_backbone_workspace_bytes(handle, N, H, W)
             sid = torch.cuda.current_stream(dev).cuda_stream       # one activation workspace per stream in flight
             self._ws = self._ws_by_stream.get(sid)
             if self._ws is None or self._ws.device != dev or self._ws.numel() < nbytes + 1024:
@@ -245,13 +266,11 @@ class SEGNET_B200(nn.Module):
             ws_ptr = ctypes.c_void_p(self._ws.data_ptr() + off)
             out = torch.empty((N, self.feature_dim, H, W), dtype=torch.float32, device=dev)
             xb = torch.empty((N, H * W, self.feature_dim), dtype=torch.bfloat16, device=dev) if self.keep_bf16 else None
-            st = lib.uoc_backbone_forward(self._handle, _lib.ptr(img), _lib.ptr(depth), N, H, W, _lib.ptr(out),
+            st = lib.uoc_backbone_forward(handle, _lib.ptr(img), _lib.ptr(depth), N, H, W, _lib.ptr(out),
                                           _lib.ptr(xb), ws_ptr, self._ws.numel() - off, self.flags,
                                           _lib.stream_ptr(dev))
             _lib.check(st, "uoc_backbone_forward")
-        if xb is not None:
-            _ms.register_bf16_copy(out, xb)
-        return out
+        return out, xb
 
     def read_trunk(self, branch, N, H, W):
         """Test hook: trunk output [N, num_units, H/8, W/8] of one branch from the last forward."""
@@ -262,7 +281,7 @@ class SEGNET_B200(nn.Module):
         out = torch.empty((N, self.num_units, h3, w3), dtype=torch.float32, device=dev)
         off = (-self._ws.data_ptr()) % 1024
         with torch.cuda.device(dev):
-            _lib.check(lib.uoc_backbone_read_trunk(self._handle, branch, N, H, W,
+            _lib.check(lib.uoc_backbone_read_trunk(self._handles[dev], branch, N, H, W,
                                                    ctypes.c_void_p(self._ws.data_ptr() + off), _lib.ptr(out),
                                                    _lib.stream_ptr(dev)), "uoc_backbone_read_trunk")
         return out

@@ -41,6 +41,7 @@ class _Slot(object):
         self.fill = 0                # frames copied into the slot so far (frames_per_slot > 1)
         self.firsts = []
         self.done = torch.cuda.Event()
+        self.err_pin = torch.zeros((1,), dtype=torch.int32).pin_memory()   # copy of the device error word, read after `done`
         self.labels = None
         self.busy = False
         self.graph_a = None
@@ -63,12 +64,21 @@ class FramePipeline(object):
         self.next = 0
         self.coop_tail = None          # event after the last cooperative sampling kernel
         self.pending = []
+        self.collected = []            # results of slots that had to be recycled before the caller collected them
         self.use_graphs = bool(use_graphs) and isinstance(network, torch.nn.Module)
         self.graph_error = None
 
     # -- eager path (also the warm-up of the graph path) ----------------------------------------------
-    def _run_eager(self, slot, firsts):
+    def _forward(self, slot):
+        """(features, bf16 copy or None): the network's explicit two-output form when it has one (SEGNET_B200)."""
+        net = getattr(self.network, "module", self.network)
+        if hasattr(net, "forward_ex"):
+            return net.forward_ex(slot.img_dev, None, slot.xyz_dev)
         feats = self.network(slot.img_dev, None, slot.xyz_dev)
+        return feats, _ms._lookup_bf16(feats)
+
+    def _run_eager(self, slot, firsts):
+        feats, xb = self._forward(slot)
         if self.coop_tail is not None:
             slot.stream.wait_event(self.coop_tail)          # sampling kernels never overlap each other
 
@@ -78,7 +88,7 @@ class FramePipeline(object):
             self.coop_tail = ev
 
         labels, _ = _ms.cluster_fields(feats, self.num_seeds, self.kappa, self.max_iters, [int(v) for v in firsts],
-                                       epsilon=self.eps, on_sampling_done=sampled)
+                                       epsilon=self.eps, on_sampling_done=sampled, x_bf16=xb)
         return labels
 
     # -- graph path -------------------------------------------------------------------------------------
@@ -87,8 +97,7 @@ class FramePipeline(object):
         dev, n, m, B = self.dev, self.H * self.W, self.num_seeds, self.B
         ga = torch.cuda.CUDAGraph()
         with torch.cuda.graph(ga, stream=slot.stream):
-            slot.feats = self.network(slot.img_dev, None, slot.xyz_dev)
-        slot.xb = _ms._lookup_bf16(slot.feats)
+            slot.feats, slot.xb = self._forward(slot)
         C = slot.feats.shape[1]
         slot.C = C
         slot.sel = torch.empty((B, m), dtype=torch.int64, device=dev)
@@ -109,6 +118,7 @@ class FramePipeline(object):
                                              _lib.ptr(slot.Z), _lib.ptr(slot.sl), _lib.ptr(slot.nu), _lib.ptr(slot.lab),
                                              _lib.ptr(slot.ws_b), slot.ws_b.numel(), sp), "uoc_assign_labels")
             slot.out_pin.copy_(slot.lab.view(B, self.H, self.W).to(torch.float32), non_blocking=True)
+            _lib.check(lib.uoc_peek_device_error_async(ctypes.c_void_p(slot.err_pin.data_ptr()), sp), "uoc_peek_device_error_async")
         slot.graph_a, slot.graph_b = ga, gb
 
     def _run_graph(self, slot, firsts):
@@ -146,7 +156,10 @@ class FramePipeline(object):
         (resident=True).  Returns the slot; collect results with collect_one() / drain() in submission order."""
         slot = self.slots[self.next % len(self.slots)]
         if slot.busy:
-            self.collect_one()
+            # the caller submitted more steps than there are slots without collecting: keep the oldest result (a copy --
+            # the slot's pinned buffer is about to be reused) and hand it out from the next collect_one() / drain()
+            out_pin, labels = self._collect_slot()
+            self.collected.append((out_pin.clone(), labels.clone()))
         if first_index is None:
             first_index = np.random.randint(0, self.H * self.W)     # lib/utils/mean_shift.py:155, drawn in frame order
         k = slot.fill                                               # position of this frame inside the slot's batch
@@ -195,17 +208,35 @@ class FramePipeline(object):
             else:
                 slot.labels = self._run_eager(slot, slot.firsts)
                 slot.out_pin.copy_(slot.labels.view(self.B, self.H, self.W).to(torch.float32), non_blocking=True)
+                self._peek_error(slot)
             slot.runs += 1
             slot.done.record(slot.stream)
         slot.busy = True
         self.pending.append(slot)
         return slot
 
-    def collect_one(self):
+    def _peek_error(self, slot):
+        _lib.check(_lib.load().uoc_peek_device_error_async(ctypes.c_void_p(slot.err_pin.data_ptr()), _lib.stream_ptr(self.dev)),
+                   "uoc_peek_device_error_async")
+
+    def _collect_slot(self):
         slot = self.pending.pop(0)
         slot.done.synchronize()
         slot.busy = False
+        word = int(slot.err_pin[0])
+        if word != 0:                  # a kernel of this step timed out / rejected its configuration: the labels are garbage
+            with torch.cuda.device(self.dev):
+                _lib.load().uoc_check_device_error(_lib.stream_ptr(self.dev))      # clears the word
+            raise _lib.UocError("device-side pipeline error word 0x%x in a FramePipeline step (1=mbarrier time-out, "
+                                "2=grid-barrier time-out, 4=bad config)" % word)
         return slot.out_pin, slot.labels
+
+    def collect_one(self):
+        """Oldest uncollected step: (float32 CPU label maps [B,H,W] -- the slot's pinned buffer, valid until the slot is
+        reused `depth` steps later: copy it if it must live longer --, int32 device labels [B, H*W])."""
+        if self.collected:
+            return self.collected.pop(0)
+        return self._collect_slot()
 
     def flush(self):
         """frames_per_slot > 1: run a partially filled slot now (the missing positions repeat the last frame and their
@@ -224,6 +255,7 @@ class FramePipeline(object):
             slot.labels = (self._run_graph if slot.graph_a is not None else self._run_eager)(slot, slot.firsts)
             if slot.graph_a is None:
                 slot.out_pin.copy_(slot.labels.view(self.B, self.H, self.W).to(torch.float32), non_blocking=True)
+                self._peek_error(slot)
             slot.runs += 1
             slot.done.record(slot.stream)
         slot.busy = True
@@ -233,6 +265,6 @@ class FramePipeline(object):
     def drain(self):
         self.flush()
         out = []
-        while self.pending:
+        while self.collected or self.pending:
             out.append(self.collect_one())
         return out
