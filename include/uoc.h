@@ -107,6 +107,16 @@ UOC_API int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stri
                                   float* seeds_out, int32_t* seed_labels_out, void* workspace, size_t workspace_bytes,
                                   int flags, uoc_stream_t stream);
 
+/* Same, with the label map also written as float32 (the reference's API type: out_label is a float tensor,
+ * lib/fcn/test_dataset.py:48,57) and / or uint8 (the wire type of the multi-GPU label gather; ids < m <= 128) by the same
+ * final pass -- either may be NULL. */
+UOC_API int uoc_meanshift_cluster_ex(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16,
+                                     int batch, int64_t n, int d, int m, float kappa, int iters, float epsilon,
+                                     const int64_t* first_seed_host, int32_t* labels_out, float* labels_f32_out,
+                                     uint8_t* labels_u8_out, int64_t* selected_out, float* seeds_out,
+                                     int32_t* seed_labels_out, void* workspace, size_t workspace_bytes, int flags,
+                                     uoc_stream_t stream);
+
 /* Stage entry points (same semantics as the matching reference functions; used by the parity
  * tests and by callers that want one stage only). */
 
@@ -141,6 +151,13 @@ UOC_API int uoc_assign_labels(const float* X, int64_t stride_b, int64_t stride_d
 UOC_API int uoc_assign_labels_ex(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n,
                                  int d, int m, const float* Z, const int32_t* seed_labels, const int32_t* num_unique,
                                  int32_t* labels_out, void* workspace, size_t workspace_bytes, int flags, uoc_stream_t stream);
+
+/* same, with optional float32 / uint8 copies of the label map written by the final pass (see uoc_meanshift_cluster_ex) */
+UOC_API int uoc_assign_labels_typed(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch,
+                                    int64_t n, int d, int m, const float* Z, const int32_t* seed_labels,
+                                    const int32_t* num_unique, int32_t* labels_out, float* labels_f32_out,
+                                    uint8_t* labels_u8_out, void* workspace, size_t workspace_bytes, int flags,
+                                    uoc_stream_t stream);
 
 /* fp32 planar [batch][d][n] -> bf16 pixel-major [batch][n][d] (the layout the tcgen05 loop streams). */
 UOC_API int uoc_pack_bf16(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d,

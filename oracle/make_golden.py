@@ -215,6 +215,118 @@ def gen_input_prep(ref):
                         x_offset=cam["x_offset"], y_offset=cam["y_offset"], **out)
 
 
+FULL_CASES = [
+    # name, H, W, d, objects, noise, first generator seed to try, num_seeds, max_iters, np_seed
+    ("full_cfg2", 480, 640, 64, 6, 0.05, 100, 100, 10, 3),          # BASELINE config 2
+    ("full_cfg5", 720, 960, 128, 12, 0.05, 500, 100, 30, 3),        # BASELINE config 5 (one GPU's share)
+]
+
+
+def _planar_to_X(Xp):
+    """[d, n] planar float32 -> the reference's X: a [n, d] view with strides (1, n) (test_dataset.py:54-55)."""
+    return torch.from_numpy(Xp).t()
+
+
+def _margin_seed(ref, H, W, d, K, noise, seed0, m, first, tries=20):
+    """First generator seed >= seed0 whose farthest-point sequence is the same in the reference (torch CPU, library
+    summation order) and in the canonical-order C oracle: such an input has decision margins larger than fp32
+    summation-order noise, so ANY correct fp32 implementation must reproduce all m indices (goldens are exact
+    only for integer outputs on inputs with margin)."""
+    import uoc_oracle_c as OC
+    for seed in range(seed0, seed0 + tries):
+        Xp, gt = O.exact_clustered_field(H, W, d, K, noise, seed)
+        X = _planar_to_X(Xp)
+        seeds, sel = _ref_select(ref, X, m, first)
+        sel_c, _ = OC.select_seeds(Xp, m, first)
+        if np.array_equal(sel.numpy(), sel_c):
+            return seed, Xp, gt
+        print("   seed", seed, "has a marginless farthest-point decision (reference != canonical order); next")
+    raise RuntimeError("no seed with margin found")
+
+
+def _ref_select(ref, X, m, first):
+    """The reference's select_smart_seeds with its np.random.randint(0, n) draw (mean_shift.py:155) pinned to `first`."""
+    saved = np.random.randint
+    np.random.randint = lambda *a, **k: first
+    try:
+        return ref.mean_shift.select_smart_seeds(X, m, return_selected_indices=True, metric='cosine')
+    finally:
+        np.random.randint = saved
+
+
+def _ref_cluster(ref, X, m, iters, first):
+    saved = np.random.randint
+    np.random.randint = lambda *a, **k: first
+    try:
+        labels, selected = ref.mean_shift.mean_shift_smart_init(X, kappa=20, num_seeds=m, max_iters=iters, metric='cosine')
+        seeds, sel2 = ref.mean_shift.select_smart_seeds(X, m, return_selected_indices=True, metric='cosine')
+        assert torch.equal(sel2, selected)
+        seed_labels, Z = ref.mean_shift.mean_shift_with_seeds(X, seeds, 20, max_iters=iters, metric='cosine')
+    finally:
+        np.random.randint = saved
+    return labels, selected, seed_labels, Z
+
+
+def gen_full(ref):
+    """BASELINE-size fixtures: the UNMODIFIED reference on 640x480x64 (config 2) and 960x720x128 with
+    30 updates (config 5).  Only the outputs are stored (labels as uint8); the inputs are regenerated bit-identically from
+    the seed by O.exact_clustered_field and checked by CRC."""
+    for name, H, W, d, K, noise, seed0, m, iters, npseed in FULL_CASES:
+        np.random.seed(npseed)
+        first = int(np.random.randint(0, H * W))
+        seed, Xp, gt = _margin_seed(ref, H, W, d, K, noise, seed0, m, first)
+        X = _planar_to_X(Xp)
+        labels, selected, seed_labels, Z = _ref_cluster(ref, X, m, iters, first)
+        assert int(labels.max()) < 256
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), H=H, W=W, d=d, objects=K, noise=noise, seed=seed, num_seeds=m,
+                            max_iters=iters, first_index=first, crc32=O.field_crc32(Xp), gt=gt.astype(np.uint8),
+                            labels=labels.numpy().astype(np.uint8), selected=selected.numpy(), Z=Z.numpy(),
+                            seed_labels=seed_labels.numpy())
+        print(name, "seed", seed, "labels", np.unique(labels.numpy(), return_counts=True))
+
+
+def gen_full_two_stage(ref):
+    """BASELINE config 3 at full size: the reference's own test_sample (lib/fcn/test_dataset.py:232-267) on a 640x480
+    frame whose stage-1 field has 6 objects, 224x224 crop fields from the same generator (fake networks, as SURVEY 8c
+    advises: random-init embeddings collapse)."""
+    H, W, K = 480, 640, 6
+    np.random.seed(3)
+    first = int(np.random.randint(0, H * W))
+    seed, Xp, gt = _margin_seed(ref, H, W, 64, K, 0.05, 300, 100, first)
+    feats = torch.from_numpy(Xp).view(1, 64, H, W)
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed=22)
+    xyz[:, 2, :40, :] = 0          # invalid depth on top: filter_labels_depth has something to see
+
+    # crops: one field per crop; first indices pinned; each checked for margin like the stage-1 field
+    firsts_crop, crop_seeds, crop_fields = [], [], []
+    rs = np.random.RandomState(5)
+    for k in range(K):
+        fc = int(rs.randint(0, 224 * 224))
+        sc, Xc, _ = _margin_seed(ref, 224, 224, 64, 2, 0.05, 700 + 20 * k, 100, fc)
+        firsts_crop.append(fc); crop_seeds.append(sc); crop_fields.append(torch.from_numpy(Xc).view(1, 64, 224, 224))
+
+    def net(i, l, dd):
+        return feats
+
+    def net_crop(i, l, dd):
+        return torch.cat(crop_fields[:i.shape[0]], 0)
+
+    draws = [first] + firsts_crop
+    saved = np.random.randint
+    np.random.randint = lambda *a, **k: draws.pop(0)
+    try:
+        with rh.cpu_cuda_identity():
+            out_label, refined = ref.test_dataset.test_sample({'image_color': img, 'depth': xyz}, net, net_crop)
+    finally:
+        np.random.randint = saved
+    rgb_c, mask_c, rois, depth_c = ref.test_dataset.crop_rois(img, out_label.clone(), xyz)
+    np.savez_compressed(os.path.join(OUT, "full_cfg3.npz"), H=H, W=W, objects=K, seed=seed, frame_seed=22, first_index=first,
+                        crc32=O.field_crc32(Xp), crop_seeds=np.array(crop_seeds), first_indices_crop=np.array(firsts_crop),
+                        num_crops=rgb_c.shape[0], out_label=out_label.numpy().astype(np.uint8),
+                        refined=refined.numpy().astype(np.uint8), rois=rois.numpy())
+    print("full_cfg3 seed", seed, "crops", rgb_c.shape[0], np.unique(out_label.numpy()).tolist(), np.unique(refined.numpy()).tolist())
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = rh.load()
@@ -233,3 +345,7 @@ if __name__ == "__main__":
         gen_euclid(ref)
     if not only or "metrics" in only:
         gen_metrics(ref)
+    if not only or "full" in only:
+        gen_full(ref)
+    if not only or "full_two_stage" in only:
+        gen_full_two_stage(ref)

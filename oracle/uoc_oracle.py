@@ -406,6 +406,41 @@ def synthetic_clustered_features(H, W, d=64, num_objects=6, noise=0.05, seed=0):
     return feats, gt
 
 
+def exact_clustered_field(H, W, d=64, num_objects=6, noise=0.05, seed=0, chunk_rows=32768):
+    """Platform-independent cfg2 / cfg5 generator for the FULL-SIZE fixtures (tests/golden/full_*.npz store only the
+    reference's outputs; the 79 - 354 MB inputs are regenerated from the seed on the box that runs the test, so the
+    generator must give the same bits everywhere): MT19937 integers only; noise = Irwin-Hall sum of four 16-bit uniforms
+    (an integer); rows are quantised to 2^-20 and normalised by an EXACT integer sum of squares, so every float
+    operation is a single correctly rounded IEEE op (no vectorised reductions whose order depends on the CPU).
+    Returns (X_planar float32 [d, H*W] (row k = channel k, the reference's memory layout), gt int64 [H, W])."""
+    rs = np.random.RandomState(int(seed))
+    ci = rs.randint(-1000, 1001, size=(num_objects + 1, d)).astype(np.int64)
+    c = ci / np.sqrt((ci * ci).sum(1).astype(np.float64))[:, None]
+    gt = np.zeros((H, W), dtype=np.int64)
+    for k in range(1, num_objects + 1):
+        h = int(rs.randint(H // 8, H // 3)); w = int(rs.randint(W // 8, W // 3))
+        y = int(rs.randint(0, H - h)); x = int(rs.randint(0, W - w))
+        gt[y:y + h, x:x + w] = k
+    n = H * W
+    flat = gt.reshape(-1)
+    inv_sigma = 1.0 / math.sqrt(4.0 * (65536.0 ** 2 - 1.0) / 12.0)
+    out = np.empty((d, n), dtype=np.float32)
+    for r0 in range(0, n, chunk_rows):
+        r1 = min(n, r0 + chunk_rows)
+        u = rs.randint(0, 65536, size=(r1 - r0, d, 4)).astype(np.int64).sum(-1)
+        z = (u - 131070).astype(np.float64) * inv_sigma
+        x = c[flat[r0:r1]] + noise * z
+        xi = np.rint(x * 1048576.0).astype(np.int64)
+        ss = (xi * xi).sum(1)
+        out[:, r0:r1] = (xi / np.sqrt(ss.astype(np.float64))[:, None]).astype(np.float32).T
+    return out, gt
+
+
+def field_crc32(X_planar):
+    import zlib
+    return zlib.crc32(np.ascontiguousarray(X_planar).tobytes()) & 0xFFFFFFFF
+
+
 def synthetic_rgbd_frame(H=480, W=640, seed=0):
     """cfg1 generator: image ~ U(-0.5, 0.6); XYZ from Z ~ U(0.3, 1.5) m with the demo intrinsics
     (data/demo/camera_params.json: fx 612.937 fy 613.173 cx 322.549 cy 248.158, scaled to HxW)."""
@@ -418,6 +453,80 @@ def synthetic_rgbd_frame(H=480, W=640, seed=0):
     v = torch.arange(H, dtype=torch.float32).view(1, 1, H, 1)
     xyz = torch.cat([(u - cx) / fx * z, (v - cy) / fy * z, z], dim=1)
     return img, xyz
+
+
+def structured_rgbd_frame(H=480, W=640, num_objects=6, seed=0):
+    """A frame with STRUCTURE for the label flip-rate test (SURVEY section 7 "report the flip rate"): num_objects
+    rectangles on a background, each region with its own constant colour and its own constant 3-vector in the depth
+    tensor (piece-wise constant network inputs; not a physical XYZ map -- spatial ramps would give a continuum of
+    embeddings).  Returns (img [1,3,H,W], xyz [1,3,H,W], gt [H,W])."""
+    g = torch.Generator().manual_seed(int(seed))
+    gt = torch.zeros(H, W, dtype=torch.long)
+    for k in range(1, num_objects + 1):
+        h = int(torch.randint(H // 6, H // 3, (1,), generator=g))
+        w = int(torch.randint(W // 6, W // 3, (1,), generator=g))
+        y = int(torch.randint(0, H - h, (1,), generator=g))
+        x = int(torch.randint(0, W - w, (1,), generator=g))
+        gt[y:y + h, x:x + w] = k
+    col = torch.rand(num_objects + 1, 3, generator=g) * 1.1 - 0.5
+    pc = torch.rand(num_objects + 1, 3, generator=g) * 1.0 + 0.2
+    img = col[gt].permute(2, 0, 1)[None].contiguous()
+    xyz = pc[gt].permute(2, 0, 1)[None].contiguous()
+    return img, xyz, gt
+
+
+def calibrated_state_dict_(sd, img, xyz, residual_gain=0.05):
+    """Turn a random-init reference-format state_dict into one whose embeddings of (img, xyz) are NOT collapsed (random
+    init gives one cluster): the residual branches are scaled down (bn2.weight *= residual_gain, so the
+    identity / down-sample path carries the regions' piece-wise constant signal), every BatchNorm gets the batch
+    statistics of this very input as running statistics (layer by layer, as a training-mode pass would accumulate them),
+    and the fc bias centres the trunk output.  In place; returns sd.  Test infrastructure (fp32 torch on the CPU)."""
+    for k in list(sd.keys()):
+        if k.endswith("bn2.weight"):
+            sd[k] = sd[k] * residual_gain
+
+    def bn(x, p):
+        m = x.mean((0, 2, 3))
+        v = x.var((0, 2, 3), unbiased=False)
+        sd[p + ".running_mean"] = m.clone()
+        sd[p + ".running_var"] = v.clone()
+        return F.batch_norm(x, m, v, sd[p + ".weight"], sd[p + ".bias"], False, 0.0, BN_EPS)
+
+    with torch.no_grad():
+        for x, p in ((img, "fcn.resnet34_8s."), (xyz, "fcn_depth.resnet34_8s.")):
+            x = F.conv2d(x, sd[p + "conv1.weight"], None, stride=2, padding=3)
+            x = F.max_pool2d(F.relu(bn(x, p + "bn1")), kernel_size=3, stride=2, padding=1)
+            for li, (planes, blocks, stride, dil) in enumerate(RESNET34_8S_LAYERS, start=1):
+                for b in range(blocks):
+                    q = "%slayer%d.%d." % (p, li, b)
+                    s = stride if b == 0 else 1
+                    out = F.relu(bn(F.conv2d(x, sd[q + "conv1.weight"], None, stride=s, padding=dil, dilation=dil), q + "bn1"))
+                    out = bn(F.conv2d(out, sd[q + "conv2.weight"], None, stride=1, padding=dil, dilation=dil), q + "bn2")
+                    if (q + "downsample.0.weight") in sd:
+                        res = bn(F.conv2d(x, sd[q + "downsample.0.weight"], None, stride=s), q + "downsample.1")
+                    else:
+                        res = x
+                    x = F.relu(out + res)
+            y = F.conv2d(x, sd[p + "fc.weight"], None)
+            sd[p + "fc.bias"] = -y.mean((0, 2, 3))
+    return sd
+
+
+def best_label_agreement(a, b):
+    """Fraction of pixels on which label maps a and b agree under the best one-to-one relabelling of b that keeps
+    label 0 fixed (Hungarian assignment on the contingency table of the non-zero ids)."""
+    from scipy.optimize import linear_sum_assignment
+    a = np.asarray(a).astype(np.int64).ravel()
+    b = np.asarray(b).astype(np.int64).ravel()
+    ka, kb = int(a.max()) + 1, int(b.max()) + 1
+    table = np.zeros((ka, kb), dtype=np.int64)
+    np.add.at(table, (a, b), 1)
+    agree = int(table[0, 0])
+    if ka > 1 and kb > 1:
+        sub = table[1:, 1:]
+        r, c = linear_sum_assignment(-sub)
+        agree += int(sub[r, c].sum())
+    return agree / float(a.size)
 
 
 def randomise_bn_(sd, seed):

@@ -339,3 +339,80 @@ def test_euclidean_clustering_features_and_batch():
         assert O.labels_equal_up_to_permutation(out[j].numpy().ravel(), want[j].numpy().ravel())
     with pytest.raises(ValueError):
         TD.clustering_features(feats.to(DEV), 60, [11, 700], metric="manhattan")
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE-size fixtures written by the unmodified reference (oracle/make_golden.py gen_full)
+# ---------------------------------------------------------------------------------------------
+def _full_case(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    Xp, gt = O.exact_clustered_field(int(g["H"]), int(g["W"]), int(g["d"]), int(g["objects"]), float(g["noise"]), int(g["seed"]))
+    assert O.field_crc32(Xp) == int(g["crc32"]), "exact_clustered_field is not bit-reproducible on this platform"
+    feats = torch.from_numpy(Xp).view(1, int(g["d"]), int(g["H"]), int(g["W"]))
+    return g, feats, gt
+
+
+@pytest.mark.parametrize("name", ["full_cfg2", "full_cfg5"])
+def test_full_size_clustering_matches_reference_golden(name):
+    """640x480x64 / 10 updates (config 2) and 960x720x128 / 30 updates (config 5): ALL 100 selected indices, the converged
+    seeds (<= 5e-5 cosine distance: bf16 operands in the tcgen05 loop) and all pixel labels against the reference's output."""
+    g, feats, gt = _full_case(name)
+    m = int(g["num_seeds"])
+    labels, sel, Z, sl = MS.cluster_fields(feats.to(DEV), m, max_iters=int(g["max_iters"]), first_indices=[int(g["first_index"])],
+                                           flags=_lib.FLAG_SYNC_CHECK, return_seeds=True)
+    assert np.array_equal(sel[0].cpu().numpy(), g["selected"])
+    cosd = 1.0 - (Z[0].cpu().numpy().astype(np.float64) * g["Z"].astype(np.float64)).sum(1)
+    assert np.abs(cosd).max() < 5e-5, np.abs(cosd).max()
+    lab = labels[0].cpu().numpy()
+    assert O.labels_equal_up_to_permutation(lab, g["labels"])
+    assert O.labels_equal_up_to_permutation(lab, gt.ravel())
+    assert np.array_equal(sl[0].cpu().numpy(), g["seed_labels"])           # on these inputs even the ids agree
+    assert np.array_equal(lab, g["labels"].astype(np.int32))
+
+
+def test_full_size_loop_vs_double_oracle():
+    """The mean-shift loop at 640x480x64 against the double-precision C oracle (same seeds in, 10 updates)."""
+    g, feats, _ = _full_case("full_cfg2")
+    Xp = feats[0].reshape(64, -1).numpy()
+    X = feats.to(DEV)[0].view(64, -1).t()
+    _, seeds_o = C.select_seeds(Xp, 100, int(g["first_index"]))
+    Zo = C.hill_climb(Xp, seeds_o, 20.0, 10)
+    Z = MS.seed_hill_climbing_ball(X, torch.from_numpy(seeds_o).to(DEV), 20.0, 10)
+    cosd = 1.0 - (Z.cpu().numpy().astype(np.float64) * Zo.astype(np.float64)).sum(1)
+    assert np.abs(cosd).max() < 5e-5, np.abs(cosd).max()
+
+
+def test_bf16_side_channel_cannot_go_stale():
+    """the bf16 copy of a backbone output must never be served for a different tensor that happens to get the
+    same address.  Free a backbone output, allocate a same-shape foreign field, cluster it: the lookup must miss and the
+    labels must be those of the foreign field."""
+    from unseenobjectclustering_b200 import networks as NW
+    MS.clear_bf16_registry()
+    H, W = 64, 96
+    net = NW.seg_resnet34_8s_embedding(2, 64, NW.random_state_dict(64, seed=0)).to(DEV)
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed=1)
+    f = net(img.to(DEV), None, xyz.to(DEV))
+    assert MS._lookup_bf16(f) is not None and MS._lookup_bf16(f.detach()) is not None
+    addr = f.data_ptr()
+    del f
+    torch.cuda.synchronize()
+    foreign, gt = O.synthetic_clustered_features(H, W, 64, 4, 0.05, seed=9)
+    cands = [foreign.to(DEV) for _ in range(4)]
+    assert all(c.data_ptr() != addr for c in cands), "the registered tensor is kept alive: its address cannot be recycled"
+    for c in cands:
+        assert MS._lookup_bf16(c) is None
+    lab, _ = MS.cluster_fields(cands[0], 100, first_indices=[7], flags=_lib.FLAG_SYNC_CHECK)
+    assert O.labels_equal_up_to_permutation(lab[0].cpu().numpy(), gt.numpy().ravel())
+    # after eviction the address may be recycled -- and then there is no entry to hit
+    MS.clear_bf16_registry()
+    torch.cuda.empty_cache()
+    again = [foreign.to(DEV) for _ in range(8)]
+    assert all(MS._lookup_bf16(c) is None for c in again)
+    lab2, _ = MS.cluster_fields(again[0], 100, first_indices=[7], flags=_lib.FLAG_SYNC_CHECK)
+    assert torch.equal(lab, lab2)
+    # in-place modification of a registered field invalidates its copy
+    f = net(img.to(DEV), None, xyz.to(DEV))
+    f.copy_(cands[0])
+    assert MS._lookup_bf16(f) is None
+    lab3, _ = MS.cluster_fields(f, 100, first_indices=[7], flags=_lib.FLAG_SYNC_CHECK)
+    assert torch.equal(lab, lab3)

@@ -1,0 +1,48 @@
+"""Label flip rate of the bf16 tcgen05 backbone against the fp32 oracle backbone on a STRUCTURED field (VERDICT r1 item
+3c; SURVEY section 7: "report the flip rate").  The same frame goes through (a) the oracle network in fp32 on the CPU and
+(b) the B200 backbone; both embedding fields go through the SAME clustering (this package's, same first seed).  The
+embeddings must agree within BASELINE.json's 1e-3 cosine distance; the label agreement under the best relabelling that
+keeps label 0 fixed is reported and bounded."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import uoc_oracle as O
+from conftest import ROOT
+from unseenobjectclustering_b200 import _lib
+from unseenobjectclustering_b200 import mean_shift as MS
+from unseenobjectclustering_b200 import networks as NW
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("H,W,seed", [(480, 640, 5), (240, 320, 6)])
+def test_label_flip_rate_bf16_vs_fp32_backbone(H, W, seed):
+    img, xyz, gt = O.structured_rgbd_frame(H, W, 6, seed)
+    sd = O.calibrated_state_dict_(NW.random_state_dict(64, seed=0), img, xyz)
+    want = O.OracleSegNet(sd)(img, None, xyz)                                  # fp32, CPU
+    net = NW.seg_resnet34_8s_embedding(2, 64, sd).to(DEV)
+    net.flags = _lib.FLAG_SYNC_CHECK
+    got = net(img.to(DEV), None, xyz.to(DEV))
+    cosd = float((1.0 - (got.cpu() * want).sum(1)).abs().max())
+    assert cosd < 1e-3, cosd                                                     # BASELINE.json: embeddings within 1e-3
+    first = (H * W) // 2 + 17
+    lab_b, sel_b = MS.cluster_fields(got, 100, first_indices=[first], flags=_lib.FLAG_SYNC_CHECK)
+    lab_a, sel_a = MS.cluster_fields(want.to(DEV), 100, first_indices=[first], flags=_lib.FLAG_SYNC_CHECK)
+    a, b = lab_a[0].cpu().numpy(), lab_b[0].cpu().numpy()
+    agree = O.best_label_agreement(a, b)
+    same_seeds = int((sel_a[0] == sel_b[0]).sum())
+    rec = {"H": H, "W": W, "clusters_fp32": int(len(np.unique(a))), "clusters_bf16": int(len(np.unique(b))),
+           "label_agreement": agree, "flip_rate": 1.0 - agree, "identical_seed_indices": same_seeds,
+           "embedding_max_cosine_distance": cosd}
+    print("flip rate:", json.dumps(rec))
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "flip_rate_%dx%d.json" % (W, H)), "w") as f:
+            json.dump(rec, f)
+    assert len(np.unique(a)) > 3, "the structured field must not collapse"
+    assert agree > 0.90, rec

@@ -375,3 +375,32 @@ def test_multilabel_metrics_edge_cases():
     pred[:, 44:][pred[:, 44:] > 0] += 20                   # every object split in two along a vertical line
     got, want = EV.multilabel_metrics(pred, gt), O.multilabel_metrics(pred, gt)
     assert all(abs(float(got[k]) - float(want[k])) < 1e-12 for k in want) and got['obj_detected'] > got['obj_gt']
+
+
+def test_two_stage_full_size_matches_reference_golden():
+    """BASELINE config 3 at full size: 640x480 frame, 6 objects -> 6 crops of 224x224 through test_sample against the
+    output of the unmodified reference's test_sample (tests/golden/full_cfg3.npz, oracle/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, "full_cfg3.npz"))
+    H, W, K = int(g["H"]), int(g["W"]), int(g["objects"])
+    Xp, _ = O.exact_clustered_field(H, W, 64, K, 0.05, int(g["seed"]))
+    assert O.field_crc32(Xp) == int(g["crc32"])
+    fd = torch.from_numpy(Xp).view(1, 64, H, W).to(DEV)
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed=int(g["frame_seed"]))
+    xyz[:, 2, :40, :] = 0
+    crops = [torch.from_numpy(O.exact_clustered_field(224, 224, 64, 2, 0.05, int(s))[0]).view(1, 64, 224, 224).to(DEV)
+             for s in g["crop_seeds"]]
+
+    def net(i, l, dd):
+        return fd
+
+    def net_crop(i, l, dd):
+        return torch.cat(crops[:i.shape[0]], 0)
+
+    out_label, refined = TD.test_sample({'image_color': img, 'depth': xyz}, net, net_crop, [int(g["first_index"])],
+                                        g["first_indices_crop"].tolist(), flags=_lib.FLAG_SYNC_CHECK)
+    assert out_label.shape == (1, H, W) and refined is not None
+    assert O.labels_equal_up_to_permutation(out_label.numpy(), g["out_label"])
+    assert np.array_equal(out_label.numpy(), g["out_label"].astype(np.float32))
+    assert np.array_equal(refined.numpy(), g["refined"].astype(np.float32))    # stage-2 ids are deterministic (1..K far to near)
+    rgb_c, mask_c, rois, depth_c = TD.crop_rois(img.to(DEV), out_label, xyz.to(DEV))
+    assert rgb_c.shape[0] == int(g["num_crops"]) and np.array_equal(rois.cpu().numpy(), g["rois"])

@@ -295,3 +295,58 @@ def test_metrics_oracle_equals_the_live_reference():
     pred = O.synthetic_prediction(gt.astype(np.int64), 7).astype(np.float32)
     a, b = ref.evaluation.multilabel_metrics(pred, gt), O.multilabel_metrics(pred, gt)
     assert set(a) == set(b) and all(abs(float(a[k]) - float(b[k])) < 1e-12 for k in a)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE-size fixtures (tests/golden/full_*.npz: outputs of the unmodified reference; inputs regenerated from the seed)
+# ---------------------------------------------------------------------------------------------
+def _full_field(g):
+    Xp, gt = O.exact_clustered_field(int(g["H"]), int(g["W"]), int(g["d"]) if "d" in g else 64, int(g["objects"]),
+                                     float(g["noise"]) if "noise" in g else 0.05, int(g["seed"]))
+    assert O.field_crc32(Xp) == int(g["crc32"]), "exact_clustered_field is not bit-reproducible on this platform"
+    return Xp, gt
+
+
+def test_exact_generator_is_pinned():
+    """A small field with a CRC committed here: the generator of the full-size fixtures gives the same bits everywhere."""
+    Xp, gt = O.exact_clustered_field(24, 40, 64, 3, 0.05, 7)
+    assert Xp.shape == (64, 960) and Xp.dtype == np.float32
+    assert np.abs((Xp.astype(np.float64) ** 2).sum(0) - 1.0).max() < 2e-7
+    assert O.field_crc32(Xp) == 0x15131BCC, hex(O.field_crc32(Xp))
+
+
+def test_oracles_match_reference_golden_at_baseline_size_config2():
+    """640x480x64, 100 seeds, 10 updates (BASELINE config 2): torch oracle bit-identical to the reference's output, C
+    oracle identical in every discrete decision (all 100 indices, seed labels, 307 200 pixel labels)."""
+    g = _load(os.path.join(GOLDEN, "full_cfg2.npz"))
+    Xp, gt = _full_field(g)
+    m, first = int(g["num_seeds"]), int(g["first_index"])
+    X = torch.from_numpy(Xp).t()
+    labels, sel, seeds, Z, sl = O.mean_shift_smart_init(X, num_seeds=m, max_iters=int(g["max_iters"]), first_index=first,
+                                                        return_all=True)
+    assert np.array_equal(sel.numpy(), g["selected"])
+    assert np.array_equal(labels.numpy(), g["labels"].astype(np.int64))
+    assert np.array_equal(sl.numpy(), g["seed_labels"])
+    assert np.allclose(Z.numpy(), g["Z"], atol=1e-6)
+    assert O.labels_equal_up_to_permutation(labels.numpy(), gt.ravel())
+    res = C.cluster(Xp, m, first, iters=int(g["max_iters"]))
+    assert np.array_equal(res["selected"], g["selected"])
+    assert np.abs(1.0 - (res["Z"] * g["Z"]).sum(1)).max() < 1e-5
+    assert np.array_equal(res["seed_labels"], g["seed_labels"])
+    assert np.array_equal(res["labels"], g["labels"].astype(np.int32))
+
+
+def test_c_oracle_matches_reference_golden_at_baseline_size_config5():
+    """960x720x128, 30 updates (BASELINE config 5, one GPU's share): the discrete stages of the canonical-order C oracle
+    against the reference's output -- all 100 farthest-point indices, and seed labels / 691 200 pixel labels from the
+    reference's converged seeds (the 30-update double-precision loop of the C oracle is exercised at this size by the GPU
+    test; make_golden.py pins the torch oracle at this size where the reference is importable)."""
+    g = _load(os.path.join(GOLDEN, "full_cfg5.npz"))
+    Xp, gt = _full_field(g)
+    sel, seeds = C.select_seeds(Xp, int(g["num_seeds"]), int(g["first_index"]))
+    assert np.array_equal(sel, g["selected"])
+    sl, uniq = C.label_seeds(g["Z"], 0.04)
+    assert np.array_equal(sl, g["seed_labels"])
+    labels = C.assign(Xp, g["Z"], sl, uniq)
+    assert np.array_equal(labels, g["labels"].astype(np.int32))
+    assert O.labels_equal_up_to_permutation(labels, gt.ravel())

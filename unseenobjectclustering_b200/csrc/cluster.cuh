@@ -62,7 +62,8 @@ int launch_label_seeds(const float* Z, int batch, int m, int d, float epsilon, i
 // the uncertified points (assign_tc.cu); otherwise the fp32 SIMT kernel.  Identical labels either way.
 int launch_assign(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w, const float* Z,
                   const int* seed_labels, const int* num_unique, int* hist, int* labels_tmp, int* labels_out,
-                  cudaStream_t stream, int metric = METRIC_COSINE);
+                  cudaStream_t stream, int metric = METRIC_COSINE, float* labels_f32_out = nullptr,
+                  unsigned char* labels_u8_out = nullptr);
 int launch_assign_tc(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w, const float* Z,
                      const int* seed_labels, int* hist, int* labels_tmp, cudaStream_t stream);
 // fp32 planar -> bf16 pixel-major

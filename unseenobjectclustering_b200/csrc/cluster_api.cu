@@ -56,6 +56,16 @@ int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stride_d, co
                           int d, int m, float kappa, int iters, float epsilon, const int64_t* first_seed_host,
                           int32_t* labels_out, int64_t* selected_out, float* seeds_out, int32_t* seed_labels_out,
                           void* workspace, size_t workspace_bytes, int flags, uoc_stream_t stream) {
+  return uoc_meanshift_cluster_ex(X, stride_b, stride_d, x_bf16, batch, n, d, m, kappa, iters, epsilon, first_seed_host, labels_out,
+                                  nullptr, nullptr, selected_out, seeds_out, seed_labels_out, workspace, workspace_bytes, flags,
+                                  stream);
+}
+
+int uoc_meanshift_cluster_ex(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n,
+                             int d, int m, float kappa, int iters, float epsilon, const int64_t* first_seed_host,
+                             int32_t* labels_out, float* labels_f32_out, uint8_t* labels_u8_out, int64_t* selected_out,
+                             float* seeds_out, int32_t* seed_labels_out, void* workspace, size_t workspace_bytes, int flags,
+                             uoc_stream_t stream) {
   int rc = require_sm100();
   if (rc != UOC_OK) return rc;
   rc = check_shape(X, batch, n, d, m, stride_b, stride_d);
@@ -84,7 +94,8 @@ int uoc_meanshift_cluster(const float* X, int64_t stride_b, int64_t stride_d, co
   if (metric == METRIC_EUCLIDEAN) xb = nullptr;
   rc = launch_label_seeds(w.Z, batch, m, d, epsilon, w.seed_labels, w.num_unique, st, metric);
   if (rc != UOC_OK) return rc;
-  rc = launch_assign(X, xb, s, w, w.Z, w.seed_labels, w.num_unique, w.hist, w.labels_tmp, labels_out, st, metric);
+  rc = launch_assign(X, xb, s, w, w.Z, w.seed_labels, w.num_unique, w.hist, w.labels_tmp, labels_out, st, metric,
+                     labels_f32_out, labels_u8_out);
   if (rc != UOC_OK) return rc;
   if (seeds_out)
     UOC_CUDA(cudaMemcpyAsync(seeds_out, w.Z, sizeof(float) * size_t(batch) * m * d, cudaMemcpyDeviceToDevice, st));
@@ -160,6 +171,14 @@ int uoc_assign_labels(const float* X, int64_t stride_b, int64_t stride_d, const 
 int uoc_assign_labels_ex(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n, int d,
                          int m, const float* Z, const int32_t* seed_labels, const int32_t* num_unique, int32_t* labels_out,
                          void* workspace, size_t workspace_bytes, int flags, uoc_stream_t stream) {
+  return uoc_assign_labels_typed(X, stride_b, stride_d, x_bf16, batch, n, d, m, Z, seed_labels, num_unique, labels_out, nullptr,
+                                 nullptr, workspace, workspace_bytes, flags, stream);
+}
+
+int uoc_assign_labels_typed(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n, int d,
+                            int m, const float* Z, const int32_t* seed_labels, const int32_t* num_unique, int32_t* labels_out,
+                            float* labels_f32_out, uint8_t* labels_u8_out, void* workspace, size_t workspace_bytes, int flags,
+                            uoc_stream_t stream) {
   int rc = require_sm100();
   if (rc != UOC_OK) return rc;
   rc = check_shape(X, batch, n, d, m, stride_b, stride_d);
@@ -170,7 +189,7 @@ int uoc_assign_labels_ex(const float* X, int64_t stride_b, int64_t stride_d, con
   if (rc != UOC_OK) return rc;
   ClusterShape s{batch, n, d, m, stride_b, stride_d};
   return launch_assign(X, static_cast<const __nv_bfloat16*>(x_bf16), s, w, Z, seed_labels, num_unique, w.hist, w.labels_tmp,
-                       labels_out, static_cast<cudaStream_t>(stream), metric_of(flags));
+                       labels_out, static_cast<cudaStream_t>(stream), metric_of(flags), labels_f32_out, labels_u8_out);
 }
 
 int uoc_pack_bf16(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, void* x_bf16_out,

@@ -1001,7 +1001,8 @@ __global__ void __launch_bounds__(128) assign_kernel(const float* __restrict__ X
 // swap label 0 <-> argmax_i count[i], i in range(num_unique)   (mean_shift.py:217-227)
 __global__ void __launch_bounds__(256) relabel_kernel(const int* __restrict__ labels_tmp, const int* __restrict__ hist,
                                                       const int* __restrict__ num_unique, long long n, int m,
-                                                      int* __restrict__ labels_out) {
+                                                      int* __restrict__ labels_out, float* __restrict__ labels_f32_out,
+                                                      unsigned char* __restrict__ labels_u8_out) {
   __shared__ int s_max;
   const int b = blockIdx.y;
   if (threadIdx.x == 0) {
@@ -1024,12 +1025,16 @@ __global__ void __launch_bounds__(256) relabel_kernel(const int* __restrict__ la
       else if (l == lm) l = 0;
     }
     labels_out[size_t(b) * n + pnt] = l;
+    // the reference's API type (float32 label maps, test_dataset.py:48) and the wire type of the label all-gather
+    // (uint8: ids < num_seeds <= 128) written by the same pass instead of separate conversion kernels
+    if (labels_f32_out) labels_f32_out[size_t(b) * n + pnt] = float(l);
+    if (labels_u8_out) labels_u8_out[size_t(b) * n + pnt] = static_cast<unsigned char>(l);
   }
 }
 
 int launch_assign(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w, const float* Z,
                   const int* seed_labels, const int* num_unique, int* hist, int* labels_tmp, int* labels_out,
-                  cudaStream_t stream, int metric) {
+                  cudaStream_t stream, int metric, float* labels_f32_out, unsigned char* labels_u8_out) {
   UOC_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * size_t(s.batch) * s.m, stream));
   bool use_tc = xb != nullptr && (s.d == 64 || s.d == 128) && metric == METRIC_COSINE;
   if (const char* e = getenv("UOC_ASSIGN_SIMT")) { if (atoi(e) != 0) use_tc = false; }
@@ -1037,7 +1042,7 @@ int launch_assign(const float* X, const __nv_bfloat16* xb, const ClusterShape& s
     int rc = launch_assign_tc(X, xb, s, w, Z, seed_labels, hist, labels_tmp, stream);
     if (rc != UOC_OK) return rc;
     const dim3 grid2(static_cast<unsigned int>((s.n + 255) / 256), s.batch);
-    relabel_kernel<<<grid2, 256, 0, stream>>>(labels_tmp, hist, num_unique, s.n, s.m, labels_out);
+    relabel_kernel<<<grid2, 256, 0, stream>>>(labels_tmp, hist, num_unique, s.n, s.m, labels_out, labels_f32_out, labels_u8_out);
     UOC_CHECK_LAUNCH();
     return UOC_OK;
   }
@@ -1058,7 +1063,7 @@ int launch_assign(const float* X, const __nv_bfloat16* xb, const ClusterShape& s
     assign_kernel<0><<<grid, 128, smem, stream>>>(X, s.stride_b, s.stride_d, s.n, s.d, s.m, metric, Z, seed_labels, hist, labels_tmp);
   UOC_CHECK_LAUNCH();
   const dim3 grid2(static_cast<unsigned int>((s.n + 255) / 256), s.batch);
-  relabel_kernel<<<grid2, 256, 0, stream>>>(labels_tmp, hist, num_unique, s.n, s.m, labels_out);
+  relabel_kernel<<<grid2, 256, 0, stream>>>(labels_tmp, hist, num_unique, s.n, s.m, labels_out, labels_f32_out, labels_u8_out);
   UOC_CHECK_LAUNCH();
   return UOC_OK;
 }

@@ -83,7 +83,8 @@ def _metric_flag(metric):
 
 
 def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indices=None, epsilon=None, flags=0,
-                   return_seeds=False, on_sampling_done=None, metric='cosine', x_bf16=None):
+                   return_seeds=False, on_sampling_done=None, metric='cosine', x_bf16=None, labels_f32_out=None,
+                   labels_u8_out=None):
     """Cluster a batch of embedding fields in ONE library call.
 
     features: [N, C, H, W] float32 CUDA tensor, unit norm over C (any batch stride; each item must
@@ -92,6 +93,8 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
     here from numpy's global RNG, in item order, when None.
     x_bf16: the bf16 pixel-major copy [N, H*W, C] of `features` when the caller owns it (SEGNET_B200.forward_ex);
     None -> the copy the backbone registered for exactly this tensor, else it is made inside the library.
+    labels_f32_out / labels_u8_out: optional contiguous CUDA tensors with N * H*W elements (float32 / uint8) that receive
+    the label map in that type from the same final pass (the reference's out_label is float32; uint8 is the gather type).
     Returns (labels int32 [N, H*W] CUDA, selected int64 [N, num_seeds] CUDA[, seeds, seed_labels]).
     """
     if not features.is_cuda:
@@ -114,6 +117,9 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
         first_indices = [np.random.randint(0, n) for _ in range(N)]
     if len(first_indices) < N:
         raise ValueError("first_indices has %d entries for %d fields" % (len(first_indices), N))
+    for t, dt in ((labels_f32_out, torch.float32), (labels_u8_out, torch.uint8)):
+        if t is not None and (t.dtype != dt or t.numel() != N * n or not t.is_contiguous() or t.device != features.device):
+            raise _lib.UocError("labels_f32_out / labels_u8_out must be contiguous CUDA tensors with N*H*W elements")
     first = (ctypes.c_int64 * N)(*[int(v) for v in list(first_indices)[:N]])     # extra entries are left unused
     flags = int(flags) | _metric_flag(metric)
     with torch.cuda.device(dev):
@@ -139,19 +145,20 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
                        "uoc_hill_climb")
             _lib.check(lib.uoc_label_seeds_ex(_lib.ptr(seeds), N, num_seeds, C, _epsilon(epsilon), int(flags),
                                               _lib.ptr(seed_labels), _lib.ptr(nuniq), sp), "uoc_label_seeds")
-            _lib.check(lib.uoc_assign_labels_ex(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, _lib.ptr(seeds),
-                                                _lib.ptr(seed_labels), _lib.ptr(nuniq), _lib.ptr(labels), _lib.ptr(ws),
-                                                ws.numel(), int(flags), sp), "uoc_assign_labels")
+            _lib.check(lib.uoc_assign_labels_typed(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, _lib.ptr(seeds),
+                                                   _lib.ptr(seed_labels), _lib.ptr(nuniq), _lib.ptr(labels),
+                                                   _lib.ptr(labels_f32_out), _lib.ptr(labels_u8_out), _lib.ptr(ws),
+                                                   ws.numel(), int(flags), sp), "uoc_assign_labels")
             if return_seeds:
                 return labels, selected, seeds, seed_labels
             return labels, selected
         seeds = torch.empty((N, num_seeds, C), dtype=torch.float32, device=dev) if return_seeds else None
         seed_labels = torch.empty((N, num_seeds), dtype=torch.int32, device=dev) if return_seeds else None
-        st = lib.uoc_meanshift_cluster(
+        st = lib.uoc_meanshift_cluster_ex(
             _lib.ptr(features), features.stride(0), features.stride(1), _lib.ptr(xb), N, n, C, num_seeds,
             float(kappa), int(max_iters), _epsilon(epsilon), ctypes.cast(first, ctypes.c_void_p), _lib.ptr(labels),
-            _lib.ptr(selected), _lib.ptr(seeds), _lib.ptr(seed_labels), _lib.ptr(ws), ws.numel(), int(flags),
-            _lib.stream_ptr(dev))
+            _lib.ptr(labels_f32_out), _lib.ptr(labels_u8_out), _lib.ptr(selected), _lib.ptr(seeds), _lib.ptr(seed_labels),
+            _lib.ptr(ws), ws.numel(), int(flags), _lib.stream_ptr(dev))
         _lib.check(st, "uoc_meanshift_cluster")
     if return_seeds:
         return labels, selected, seeds, seed_labels

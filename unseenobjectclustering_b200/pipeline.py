@@ -43,6 +43,8 @@ class _Slot(object):
         self.done = torch.cuda.Event()
         self.err_pin = torch.zeros((1,), dtype=torch.int32).pin_memory()   # copy of the device error word, read after `done`
         self.labels = None
+        self.lab_f32 = None
+        self.lab_u8 = None
         self.busy = False
         self.graph_a = None
         self.graph_b = None
@@ -87,8 +89,12 @@ class FramePipeline(object):
             ev.record(slot.stream)          # right after this frame's sampling kernel: the next frame's may start
             self.coop_tail = ev
 
+        if getattr(slot, "lab_f32", None) is None:
+            slot.lab_f32 = torch.empty((self.B, self.H, self.W), dtype=torch.float32, device=self.dev)
+            slot.lab_u8 = torch.empty((self.B, self.H * self.W), dtype=torch.uint8, device=self.dev)
         labels, _ = _ms.cluster_fields(feats, self.num_seeds, self.kappa, self.max_iters, [int(v) for v in firsts],
-                                       epsilon=self.eps, on_sampling_done=sampled, x_bf16=xb)
+                                       epsilon=self.eps, on_sampling_done=sampled, x_bf16=xb, labels_f32_out=slot.lab_f32,
+                                       labels_u8_out=slot.lab_u8)
         return labels
 
     # -- graph path -------------------------------------------------------------------------------------
@@ -105,6 +111,8 @@ class FramePipeline(object):
         slot.sl = torch.empty((B, m), dtype=torch.int32, device=dev)
         slot.nu = torch.empty((B,), dtype=torch.int32, device=dev)
         slot.lab = torch.empty((B, n), dtype=torch.int32, device=dev)
+        slot.lab_f32 = torch.empty((B, self.H, self.W), dtype=torch.float32, device=dev)
+        slot.lab_u8 = torch.empty((B, n), dtype=torch.uint8, device=dev)       # wire type of the multi-GPU label gather
         nbytes = lib.uoc_meanshift_workspace_bytes(B, n, C, m)
         slot.ws_fps = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=dev)
         slot.ws_b = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=dev)
@@ -114,10 +122,11 @@ class FramePipeline(object):
             f = slot.feats
             _lib.check(lib.uoc_label_seeds(_lib.ptr(slot.Z), B, m, C, self.eps, _lib.ptr(slot.sl), _lib.ptr(slot.nu), sp),
                        "uoc_label_seeds")
-            _lib.check(lib.uoc_assign_labels(_lib.ptr(f), f.stride(0), f.stride(1), _lib.ptr(slot.xb), B, n, C, m,
-                                             _lib.ptr(slot.Z), _lib.ptr(slot.sl), _lib.ptr(slot.nu), _lib.ptr(slot.lab),
-                                             _lib.ptr(slot.ws_b), slot.ws_b.numel(), sp), "uoc_assign_labels")
-            slot.out_pin.copy_(slot.lab.view(B, self.H, self.W).to(torch.float32), non_blocking=True)
+            _lib.check(lib.uoc_assign_labels_typed(_lib.ptr(f), f.stride(0), f.stride(1), _lib.ptr(slot.xb), B, n, C, m,
+                                                   _lib.ptr(slot.Z), _lib.ptr(slot.sl), _lib.ptr(slot.nu), _lib.ptr(slot.lab),
+                                                   _lib.ptr(slot.lab_f32), _lib.ptr(slot.lab_u8), _lib.ptr(slot.ws_b),
+                                                   slot.ws_b.numel(), 0, sp), "uoc_assign_labels")
+            slot.out_pin.copy_(slot.lab_f32, non_blocking=True)
             _lib.check(lib.uoc_peek_device_error_async(ctypes.c_void_p(slot.err_pin.data_ptr()), sp), "uoc_peek_device_error_async")
         slot.graph_a, slot.graph_b = ga, gb
 
@@ -207,7 +216,7 @@ class FramePipeline(object):
                 slot.labels = self._run_graph(slot, slot.firsts)
             else:
                 slot.labels = self._run_eager(slot, slot.firsts)
-                slot.out_pin.copy_(slot.labels.view(self.B, self.H, self.W).to(torch.float32), non_blocking=True)
+                slot.out_pin.copy_(slot.lab_f32, non_blocking=True)
                 self._peek_error(slot)
             slot.runs += 1
             slot.done.record(slot.stream)
@@ -254,7 +263,7 @@ class FramePipeline(object):
             self.next += 1
             slot.labels = (self._run_graph if slot.graph_a is not None else self._run_eager)(slot, slot.firsts)
             if slot.graph_a is None:
-                slot.out_pin.copy_(slot.labels.view(self.B, self.H, self.W).to(torch.float32), non_blocking=True)
+                slot.out_pin.copy_(slot.lab_f32, non_blocking=True)
                 self._peek_error(slot)
             slot.runs += 1
             slot.done.record(slot.stream)

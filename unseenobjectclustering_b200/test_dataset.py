@@ -48,18 +48,19 @@ def clustering_features(features, num_seeds=100, first_indices=None, flags=0, me
     """lib/fcn/test_dataset.py:44-59.  Returns (out_label float32 CPU [N,H,W], list of N int64 CPU
     [num_seeds] tensors).  One np.random.randint(0, n) is consumed per item, in order, exactly like
     the reference (lib/utils/mean_shift.py:155).  metric None -> the module-level METRIC."""
-    labels, selected = clustering_features_device(features, num_seeds, first_indices, flags, metric)
     N, _, H, W = features.shape
-    out_label = labels.view(N, H, W).to(torch.float32).cpu()
+    labels_f32 = torch.empty((N, H, W), dtype=torch.float32, device=features.device) if features.is_cuda else None
+    labels, selected = clustering_features_device(features, num_seeds, first_indices, flags, metric, labels_f32_out=labels_f32)
+    out_label = labels_f32.cpu()                    # the reference's out_label: float32 on the CPU (test_dataset.py:48,57)
     sel = selected.cpu()
     _lib.raise_on_device_error(features.device)      # the host has just synchronised: surface kernel time-outs here
     return out_label, [sel[j] for j in range(N)]
 
 
-def clustering_features_device(features, num_seeds=100, first_indices=None, flags=0, metric=None):
+def clustering_features_device(features, num_seeds=100, first_indices=None, flags=0, metric=None, labels_f32_out=None):
     """Same, but results stay on the device: (int32 [N, H*W], int64 [N, num_seeds])."""
     return _ms.cluster_fields(features, num_seeds=num_seeds, kappa=20.0, max_iters=10, first_indices=first_indices,
-                              flags=flags, metric=_metric(metric))
+                              flags=flags, metric=_metric(metric), labels_f32_out=labels_f32_out)
 
 
 # --------------------------------------------------------------------------------------------
@@ -180,12 +181,14 @@ def test_sample(sample, network, network_crop, first_indices=None, first_indices
     label = sample['label'].cuda() if 'label' in sample else None
 
     features = network(image, label, depth).detach()
-    labels, _ = clustering_features_device(features, 100, first_indices, flags)
     N, _, H, W = features.shape
+    labels_f32 = torch.empty((N, H, W), dtype=torch.float32, device=features.device) if depth is None else None
+    labels, _ = clustering_features_device(features, 100, first_indices, flags, labels_f32_out=labels_f32)
     labels = labels.view(N, H, W)
     if depth is not None:
         labels = _filter_labels_depth_device(labels, depth, 0.8)
-    out_label = labels.to(torch.float32).cpu()
+        labels_f32 = labels.to(torch.float32)
+    out_label = labels_f32.cpu()
     _lib.raise_on_device_error(image.device)
 
     out_label_refined = None
