@@ -31,6 +31,9 @@ CONV_CASES = [
     (512, 512, 3, 1, 4, 60, 80, 1),    # layer4 at 640x480
     (64, 64, 3, 1, 1, 120, 160, 1),    # layer1 at 640x480
     (256, 256, 3, 1, 2, 28, 28, 3),    # layer3 on 224x224 crops, batch 3
+    (128, 128, 3, 1, 1, 60, 80, 8),    # layer2, 4 frames x 2 branches: several stream-K segments per CTA pair
+    (256, 512, 1, 1, 1, 60, 80, 8),    # 1x1 down-sample, 320 whole tiles dealt over 74 pairs (accumulator ring wraps)
+    (256, 256, 3, 1, 2, 60, 80, 2),    # layer3 at 640x480: 38 tiles on 74 pairs, every tile split in two
 ]
 
 
@@ -46,24 +49,14 @@ def _conv_call(x, w, bias, res, N, H, W, Cin, Cout, k, stride, dil, relu, flags)
     return y
 
 
-@pytest.mark.parametrize("variant", ["tc_cluster1", "pair", "halo_x1", "halo_x1_sub1", "halo_small_sub1", "halo_x0", "tc_cluster4", "tc_cluster8", "tc_cluster2_n128", "simt"])
+@pytest.mark.parametrize("variant", ["pair", "tc", "simt"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
 def test_conv_matches_torch(case, variant, monkeypatch):
-    """tcgen05 implicit GEMM with every cluster-multicast width (the library reads UOC_CONV_CLUSTER /
-    UOC_CONV_MAX_BLOCK_N at each launch) and the SIMT validation kernel, against torch's convolution."""
+    """The persistent CTA-pair stream-K kernel (conv_pair.cu, default), the first-generation one-tile-per-CTA kernel
+    (UOC_CONV_PAIR=0) and the SIMT validation kernel, against torch's convolution on the same bf16 operands."""
     Cin, Cout, k, stride, dil, H, W, N = case
     flags = _lib.FLAG_CONV_SIMT if variant == "simt" else 0
-    monkeypatch.setenv("UOC_CONV_2SM", "1" if variant == "pair" else "0")     # CTA pairs (cta_group::2), Cout % 128 == 0
-    if variant.startswith("tc_cluster"):
-        monkeypatch.setenv("UOC_CONV_CLUSTER", variant[len("tc_cluster")])
-    if variant.endswith("_n128"):
-        monkeypatch.setenv("UOC_CONV_MAX_BLOCK_N", "128")
-    if variant.startswith("halo"):
-        monkeypatch.setenv("UOC_CONV_HALO", "1")
-        monkeypatch.setenv("UOC_CONV_XHALO", "0" if "_x0" in variant else "1")
-        if variant.endswith("sub1"):
-            monkeypatch.setenv("UOC_CONV_SUB", "1")
-        monkeypatch.setenv("UOC_CONV_HALO_SMALL", "1" if "small" in variant else "0")
+    monkeypatch.setenv("UOC_CONV_PAIR", "0" if variant == "tc" else "1")
     g = torch.Generator().manual_seed(Cin + Cout + k + H)
     x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(torch.bfloat16)
     w = (torch.randn(Cout, k * k, Cin, generator=g) * (1.0 / np.sqrt(k * k * Cin))).to(torch.bfloat16)
@@ -126,13 +119,18 @@ def test_backbone_full_frame_vs_oracle_and_bf16_copy():
     assert xb is not None and xb.shape == (1, 480 * 640, 64)
     back = xb.float().view(1, 480, 640, 64).permute(0, 3, 1, 2)
     assert (back - f).abs().max().item() < 1e-2
-    # batch of 2 crops-like inputs == two single calls
+    # batch of 2 crops-like inputs vs two single calls: the stream-K convolution cuts the K range of a tile where the
+    # launch's work divides evenly over the CTA pairs, i.e. at batch-dependent places, so the fp32 summation order (and
+    # with it a few bf16 roundings per layer) depends on the batch: equal within a fraction of the embedding tolerance,
+    # and a repeated call is bit-identical
     i2, x2 = O.synthetic_rgbd_frame(224, 224, seed=2)
     i3, x3 = O.synthetic_rgbd_frame(224, 224, seed=3)
     fb = net(torch.cat([i2, i3]).to(DEV), None, torch.cat([x2, x3]).to(DEV)).cpu()
     f2 = net(i2.to(DEV), None, x2.to(DEV)).cpu()
     f3 = net(i3.to(DEV), None, x3.to(DEV)).cpu()
-    assert torch.equal(fb[0], f2[0]) and torch.equal(fb[1], f3[0])
+    assert float((1.0 - (fb[0] * f2[0]).sum(0)).abs().max()) < 2e-4
+    assert float((1.0 - (fb[1] * f3[0]).sum(0)).abs().max()) < 2e-4
+    assert torch.equal(net(i2.to(DEV), None, x2.to(DEV)).cpu(), f2)
 
 
 def test_module_drop_in_behaviour():

@@ -188,7 +188,7 @@ static Dims trunk_dims(int H, int W) {
 }
 
 struct WsPlan {
-  size_t stem[2], buf[2][4], trunk[2], total;
+  size_t stem[2], buf[2][4], trunk[2], scratch, total;
 };
 
 static WsPlan plan_ws(int num_units, int N, int H, int W) {
@@ -204,12 +204,14 @@ static WsPlan plan_ws(int num_units, int N, int H, int W) {
     for (int i = 0; i < 4; ++i) { p.buf[g][i] = off; off = align_up(off + act, 1024); }
     p.trunk[g] = off; off = align_up(off + size_t(N) * d.H3 * d.W3 * num_units * 4, 1024);
   }
+  p.scratch = off;            // stream-K partials + flags of the convolution kernel (private to this workspace = stream)
+  off = align_up(off + conv_pair_scratch_bytes(), 1024);
   p.total = off;
   return p;
 }
 
 static int run_conv(const ConvLayer* L[2], const uoc_backbone* bb, const void* x[2], const void* res[2], void* y[2], int N,
-                    int H, int W, int relu, int out_fp32, int flags, cudaStream_t st) {
+                    int H, int W, int relu, int out_fp32, int flags, cudaStream_t st, void* scratch) {
   ConvProblem p;
   memset(&p, 0, sizeof(p));
   p.groups = bb->groups;
@@ -222,7 +224,7 @@ static int run_conv(const ConvLayer* L[2], const uoc_backbone* bb, const void* x
   }
   p.N = N; p.H = H; p.W = W; p.Cin = L[0]->Cin; p.Cout = L[0]->Cout;
   p.ksize = L[0]->ksize; p.stride = L[0]->stride; p.dilation = L[0]->dil; p.relu = relu; p.out_fp32 = out_fp32;
-  return (flags & UOC_FLAG_CONV_SIMT) ? launch_conv_simt(p, st) : launch_conv_auto(p, st);
+  return (flags & UOC_FLAG_CONV_SIMT) ? launch_conv_simt(p, st) : launch_conv_auto(p, scratch, conv_pair_scratch_bytes(), st);
 }
 
 }  // namespace uoc
@@ -309,6 +311,10 @@ int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, i
   char* ws = static_cast<char*>(workspace);
   const Dims d = trunk_dims(H, W);
   const int G = bb->groups;
+  void* scratch = ws + wp.scratch;
+  // a caller may hand the same memory to another tensor between calls (torch's caching allocator): the stream-K counters are
+  // re-zeroed at the start of every forward pass (4 KB memset, stream ordered)
+  UOC_CUDA(cudaMemsetAsync(scratch, 0, kConvCounterBytes, st));
 
   // SEG.py:97-108: DEPTH -> fcn(depth); COLOR -> fcn(img); early -> fcn(cat(img, depth)); else fcn(img), fcn_depth(depth)
   StemGroup sg[2];
@@ -341,7 +347,7 @@ int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, i
     const void* xin[2] = {ws + wp.buf[0][cur], ws + wp.buf[1][cur]};
     void* tout[2] = {ws + wp.buf[0][t], ws + wp.buf[1][t]};
     const ConvLayer* L1[2] = {&b0.conv1, &b1.conv1};
-    rc = run_conv(L1, bb, xin, nullptr, tout, N, curH, curW, 1, 0, flags, st);
+    rc = run_conv(L1, bb, xin, nullptr, tout, N, curH, curW, 1, 0, flags, st, scratch);
     if (rc != UOC_OK) return rc;
     const int oH = conv_out_dim(curH, 3, b0.conv1.stride, b0.conv1.dil);
     const int oW = conv_out_dim(curW, 3, b0.conv1.stride, b0.conv1.dil);
@@ -349,14 +355,14 @@ int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, i
     if (b0.has_down) {
       void* rout[2] = {ws + wp.buf[0][r], ws + wp.buf[1][r]};
       const ConvLayer* LD[2] = {&b0.down, &b1.down};
-      rc = run_conv(LD, bb, xin, nullptr, rout, N, curH, curW, 0, 0, flags, st);
+      rc = run_conv(LD, bb, xin, nullptr, rout, N, curH, curW, 0, 0, flags, st, scratch);
       if (rc != UOC_OK) return rc;
       res[0] = rout[0]; res[1] = rout[1];
     }
     const void* tin[2] = {tout[0], tout[1]};
     void* yout[2] = {ws + wp.buf[0][y], ws + wp.buf[1][y]};
     const ConvLayer* L2[2] = {&b0.conv2, &b1.conv2};
-    rc = run_conv(L2, bb, tin, res, yout, N, oH, oW, 1, 0, flags, st);
+    rc = run_conv(L2, bb, tin, res, yout, N, oH, oW, 1, 0, flags, st, scratch);
     if (rc != UOC_OK) return rc;
     cur = y; curH = oH; curW = oW;
   }
@@ -364,7 +370,7 @@ int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, i
     const void* xin[2] = {ws + wp.buf[0][cur], ws + wp.buf[1][cur]};
     void* tr[2] = {ws + wp.trunk[0], ws + wp.trunk[1]};
     const ConvLayer* LF[2] = {&bb->br[0].fc, &bb->br[G - 1].fc};
-    rc = run_conv(LF, bb, xin, nullptr, tr, N, curH, curW, 0, 1, flags, st);
+    rc = run_conv(LF, bb, xin, nullptr, tr, N, curH, curW, 0, 1, flags, st, scratch);
     if (rc != UOC_OK) return rc;
   }
   const int mode = (G == 1) ? HEAD_SINGLE : (bb->fusion == UOC_FUSION_CAT ? HEAD_CAT : HEAD_ADD);
@@ -396,7 +402,17 @@ int uoc_conv2d_bf16(const void* x, const void* w, const float* bias, const void*
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.stride = stride; p.dilation = dilation;
   p.relu = relu; p.out_fp32 = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = (flags & UOC_FLAG_CONV_SIMT) ? launch_conv_simt(p, st) : launch_conv_auto(p, st);
+  // test hook: one scratch region per device, allocated on first use (the product path takes it from the caller's workspace)
+  static void* hook_scratch[64] = {nullptr};
+  int devid = 0;
+  UOC_CUDA(cudaGetDevice(&devid));
+  if (devid < 0 || devid >= 64) return fail(UOC_ERR_UNSUPPORTED, "device ordinal out of range");
+  if (!hook_scratch[devid]) {
+    UOC_CUDA(cudaMalloc(&hook_scratch[devid], conv_pair_scratch_bytes()));
+    UOC_CUDA(cudaMemset(hook_scratch[devid], 0, kConvCounterBytes));
+  }
+  rc = (flags & UOC_FLAG_CONV_SIMT) ? launch_conv_simt(p, st)
+                                    : launch_conv_auto(p, hook_scratch[devid], conv_pair_scratch_bytes(), st);
   if (rc != UOC_OK) return rc;
   if (flags & UOC_FLAG_SYNC_CHECK) return check_device_error(st);
   return UOC_OK;

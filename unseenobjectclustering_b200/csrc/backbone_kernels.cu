@@ -294,12 +294,140 @@ __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ a, 
   }
 }
 
+// Second generation of the head: one CTA per output ROW.  The two source rows y0, y1 of the (for add fusion already
+// summed) trunk output are staged ONCE in shared memory (the first generation re-read the four source pixels of every
+// output pixel from global memory: 128 LDG.128 per thread); every thread then owns PX consecutive output pixels x D/4
+// channels: the same interpolation formula from shared memory, the L2 norm over the channels with two warp shuffles,
+// and 16-byte stores on BOTH outputs (fp32 planar NCHW: PX pixels of
+// one channel; bf16 pixel-major: 8 channels of one pixel).  Lane = quarter * 8 + pixel group, so that the eight lanes of
+// a shared-memory phase read at most two different rows (broadcast) and a warp's planar stores are 128-byte runs.
+template <int D, int MODE, int PX>
+__global__ void __launch_bounds__(256, 2) head_row_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w,
+                                                       int H, int W, float sy, float sx, int normalize,
+                                                       float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_bf16) {
+  constexpr int DU = (MODE == HEAD_CAT) ? D / 2 : D;     // channels of one trunk output
+  constexpr int CPT = D / 4;                             // channels per thread
+  constexpr int PITCH = D + 4;                           // floats per source pixel in shared memory (16-byte aligned, bank shift 4)
+  extern __shared__ float vrow[];                        // [2][w][PITCH]: source rows y0, y1
+  const int n = blockIdx.y, oy = blockIdx.x, tid = threadIdx.x;
+  const float fy = sy * float(oy);
+  const int y0 = int(fy);
+  const int y1 = y0 + ((y0 < h - 1) ? 1 : 0);
+  const float ly1 = fy - float(y0), ly0 = 1.f - ly1;
+  const size_t base = size_t(n) * h * w;
+  for (int e = tid; e < w * (D / 4); e += 256) {
+    const int x = e / (D / 4), k4 = e - x * (D / 4);
+    const float* src = (MODE == HEAD_CAT && k4 >= DU / 4) ? b : a;
+    const int kk = (MODE == HEAD_CAT && k4 >= DU / 4) ? k4 - DU / 4 : k4;
+    const size_t o0 = (base + size_t(y0) * w + x) * DU, o1 = (base + size_t(y1) * w + x) * DU;
+    float4 v0 = __ldg(reinterpret_cast<const float4*>(src + o0) + kk), v1 = __ldg(reinterpret_cast<const float4*>(src + o1) + kk);
+    if (MODE == HEAD_ADD) {
+      const float4 u0 = __ldg(reinterpret_cast<const float4*>(b + o0) + kk), u1 = __ldg(reinterpret_cast<const float4*>(b + o1) + kk);
+      v0.x += u0.x; v0.y += u0.y; v0.z += u0.z; v0.w += u0.w;
+      v1.x += u1.x; v1.y += u1.y; v1.z += u1.z; v1.w += u1.w;
+    }
+    *reinterpret_cast<float4*>(vrow + x * PITCH + 4 * k4) = v0;                  // row y0
+    *reinterpret_cast<float4*>(vrow + (w + x) * PITCH + 4 * k4) = v1;            // row y1
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const int q = lane >> 3, gi = lane & 7;                // channel quarter, pixel group inside the warp
+  const size_t HW = size_t(H) * W;
+  const int groups = W / PX;                             // W % PX == 0 (W is a multiple of 8)
+  for (int g0 = warp * 8; g0 < groups; g0 += 8 * 8) {
+    const int grp = g0 + gi;
+    const bool live = grp < groups;
+    float f[PX][CPT];
+    float ss[PX];
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+      const int ox = (live ? grp : 0) * PX + i;
+      const float fx = sx * float(ox);
+      const int x0 = int(fx);
+      const int x1 = x0 + ((x0 < w - 1) ? 1 : 0);
+      const float lx1 = fx - float(x0), lx0 = 1.f - lx1;
+      const float* r00 = vrow + x0 * PITCH + q * CPT;
+      const float* r01 = vrow + x1 * PITCH + q * CPT;
+      const float* r10 = vrow + (w + x0) * PITCH + q * CPT;
+      const float* r11 = vrow + (w + x1) * PITCH + q * CPT;
+      ss[i] = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < CPT / 4; ++c4) {
+        const float4 v00 = *reinterpret_cast<const float4*>(r00 + 4 * c4), v01 = *reinterpret_cast<const float4*>(r01 + 4 * c4);
+        const float4 v10 = *reinterpret_cast<const float4*>(r10 + 4 * c4), v11 = *reinterpret_cast<const float4*>(r11 + 4 * c4);
+        f[i][4 * c4 + 0] = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+        f[i][4 * c4 + 1] = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+        f[i][4 * c4 + 2] = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+        f[i][4 * c4 + 3] = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+      }
+    }
+    // sum of squares in channel order 0..D-1 (the order of the first generation and of the oracle's reduction is not
+    // defined; the tolerance of the embeddings is 1e-3 cosine distance): per-thread partial, then the four quarters
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) ss[i] = fmaf(f[i][c], f[i][c], ss[i]);
+      ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 8);
+      ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 16);
+    }
+    if (!live) continue;
+    float inv[PX];
+#pragma unroll
+    for (int i = 0; i < PX; ++i) inv[i] = normalize ? 1.0f / fmaxf(sqrtf(ss[i]), 1e-12f) : 1.0f;
+    const size_t pix0 = size_t(oy) * W + size_t(grp) * PX;
+    float* o = out_nchw + size_t(n) * D * HW + size_t(q * CPT) * HW + pix0;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      if (PX == 4) {
+        __stcs(reinterpret_cast<float4*>(o + size_t(c) * HW),
+               make_float4(f[0][c] * inv[0], f[1][c] * inv[1], f[2 % PX][c] * inv[2 % PX], f[3 % PX][c] * inv[3 % PX]));
+      } else {
+        __stcs(reinterpret_cast<float2*>(o + size_t(c) * HW), make_float2(f[0][c] * inv[0], f[1 % PX][c] * inv[1 % PX]));
+      }
+    }
+    if (out_bf16) {
+#pragma unroll
+      for (int i = 0; i < PX; ++i) {
+        uint4* ob = reinterpret_cast<uint4*>(out_bf16 + (size_t(n) * HW + pix0 + i) * D + q * CPT);
+#pragma unroll
+        for (int e = 0; e < CPT / 8; ++e)
+          ob[e] = make_uint4(pack_bf16x2(f[i][8 * e + 0] * inv[i], f[i][8 * e + 1] * inv[i]),
+                             pack_bf16x2(f[i][8 * e + 2] * inv[i], f[i][8 * e + 3] * inv[i]),
+                             pack_bf16x2(f[i][8 * e + 4] * inv[i], f[i][8 * e + 5] * inv[i]),
+                             pack_bf16x2(f[i][8 * e + 6] * inv[i], f[i][8 * e + 7] * inv[i]));
+      }
+    }
+  }
+}
+
+template <int D, int MODE, int PX>
+static int launch_head_row(const float* a, const float* b, int normalize, int N, int h, int w, int H, int W, float sy, float sx,
+                           float* out_nchw, __nv_bfloat16* ob, cudaStream_t stream) {
+  const size_t smem = size_t(2) * w * (D + 4) * sizeof(float);
+  if (smem > 48 * 1024) {
+    const int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&head_row_kernel<D, MODE, PX>), int(smem));
+    if (rc != UOC_OK) return rc;
+  }
+  head_row_kernel<D, MODE, PX><<<dim3(H, N), 256, smem, stream>>>(a, b, h, w, H, W, sy, sx, normalize, out_nchw, ob);
+  UOC_CHECK_LAUNCH();
+  return UOC_OK;
+}
+
 int launch_head(const float* a, const float* b, int mode, int normalize, int N, int h, int w, int d, int H, int W,
                 float* out_nchw, void* out_bf16, cudaStream_t stream) {
   const float sy = (H > 1) ? float(h - 1) / float(H - 1) : 0.f;
   const float sx = (W > 1) ? float(w - 1) / float(W - 1) : 0.f;
-  const dim3 grid((W + 127) / 128, H, N);
   __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  const size_t smem_row = size_t(2) * w * (d + 4) * sizeof(float);
+  if (W % 4 == 0 && smem_row <= 200 * 1024) {
+    if (mode == HEAD_ADD && d == 64) return launch_head_row<64, HEAD_ADD, 4>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_ADD && d == 128) return launch_head_row<128, HEAD_ADD, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_SINGLE && d == 64) return launch_head_row<64, HEAD_SINGLE, 4>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_SINGLE && d == 128) return launch_head_row<128, HEAD_SINGLE, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_CAT && d == 128) return launch_head_row<128, HEAD_CAT, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    return fail(UOC_ERR_UNSUPPORTED, "head supports 64 or 128 output channels (cat fusion: 2 x 64)");
+  }
+  const dim3 grid((W + 127) / 128, H, N);
 #define UOC_HEAD(DD, MM) head_kernel<DD, MM><<<grid, 128, 0, stream>>>(a, b, h, w, H, W, sy, sx, normalize, out_nchw, ob)
   if (mode == HEAD_ADD && d == 64) UOC_HEAD(64, HEAD_ADD);
   else if (mode == HEAD_ADD && d == 128) UOC_HEAD(128, HEAD_ADD);

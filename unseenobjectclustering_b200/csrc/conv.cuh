@@ -32,13 +32,18 @@ static inline int conv_out_dim(int in, int ksize, int stride, int dilation) {
   return (in + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1;
 }
 
-// tcgen05 implicit-GEMM convolution (Cin % 64 == 0, Cout % 64 == 0)
+// tcgen05 implicit-GEMM convolution, first generation: one 128 x BLOCK_N tile per CTA (Cin % 64 == 0, Cout % 64 == 0)
 int launch_conv_tc(const ConvProblem& p, cudaStream_t stream);
-// second generation for 3x3 stride-1 convolutions: one halo fetch per 64-channel block serves all nine taps (conv_halo.cu)
-bool conv_halo_supported(const ConvProblem& p);
-int launch_conv_halo(const ConvProblem& p, cudaStream_t stream);
-// picks conv_halo / conv_tc (UOC_CONV_HALO=0 forces the first generation everywhere)
-int launch_conv_auto(const ConvProblem& p, cudaStream_t stream);
+// second generation (conv_pair.cu): persistent CTA pairs (cta_group::2, M = 256), stream-K, two TMEM accumulators.
+// scratch: conv_pair_scratch_bytes() of device memory private to the calling stream (stream-K counters + partials; the
+// first kConvCounterBytes must be zero before the first use and are left zero by every launch).
+constexpr int kConvMaxPairs = 96;
+constexpr size_t kConvCounterBytes = 64 * 1024;
+size_t conv_pair_scratch_bytes();
+bool conv_pair_supported(const ConvProblem& p);
+int launch_conv_pair(const ConvProblem& p, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+// the default path: the pair kernel (scratch given and UOC_CONV_PAIR != 0), else the first generation
+int launch_conv_auto(const ConvProblem& p, void* scratch, size_t scratch_bytes, cudaStream_t stream);
 // fp32-accumulate SIMT validation convolution, same interface and data types
 int launch_conv_simt(const ConvProblem& p, cudaStream_t stream);
 

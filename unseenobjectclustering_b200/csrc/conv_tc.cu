@@ -495,13 +495,25 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
   return launch_n<64>(prm, cluster, m_tiles, p.groups, stream);
 }
 
-int launch_conv_auto(const ConvProblem& p, cudaStream_t stream) {
-  // Measured per layer on B200 (profiles/r01_conv_halo_vs_tc.md): the halo kernel moves 2.2x fewer bytes per MAC but its
-  // single 200+ KB CTA per SM is latency-bound (tensor pipe 36 % active, 16 B/clk of TMA traffic) and loses to the
-  // first generation's two co-resident CTAs on every layer of this network, so it is opt-in: UOC_CONV_HALO=1.
-  int halo = 0;
-  if (const char* e = getenv("UOC_CONV_HALO")) halo = atoi(e);
-  if (halo > 0 && conv_halo_supported(p)) return launch_conv_halo(p, stream);
+int launch_conv_auto(const ConvProblem& p, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+  // Two live kernels, chosen per layer by the amount of work (profiles/r02_conv_layers.txt): the persistent CTA-pair
+  // stream-K kernel wins where a pair gets a long K range of a wide tile (layers 3 / 4; every layer-3 / 4 convolution when
+  // several frames share a launch); the one-tile-per-CTA kernel wins on the small layers (Cout <= 128, and everything
+  // short at batch 1), where fixed per-pair costs dominate.  UOC_CONV_PAIR=0 / 1 forces one of them (parity tests).
+  int use_pair = -1;
+  if (const char* e = getenv("UOC_CONV_PAIR")) use_pair = atoi(e) != 0 ? 1 : 0;
+  if (!scratch || !conv_pair_supported(p)) use_pair = 0;
+  if (use_pair < 0) {
+    const int Ho = conv_out_dim(p.H, p.ksize, p.stride, p.dilation), Wo = conv_out_dim(p.W, p.ksize, p.stride, p.dilation);
+    const long long m_pairs = ((long long)p.N * ((Ho + 7) / 8) * ((Wo + 15) / 16) + 1) / 2;
+    const long long tiles = m_pairs * (p.Cout / 256) * p.groups;
+    const long long units = tiles * p.ksize * p.ksize * (p.Cin / 64);
+    int pairs = sm_count() / 2;
+    if (pairs < 1) pairs = 1;
+    const long long per_pair = units / pairs;
+    use_pair = (p.Cout % 256 == 0 && !p.out_fp32 && per_pair >= (p.ksize == 3 ? 32 : 16)) ? 1 : 0;
+  }
+  if (use_pair) return launch_conv_pair(p, scratch, scratch_bytes, stream);
   return launch_conv_tc(p, stream);
 }
 

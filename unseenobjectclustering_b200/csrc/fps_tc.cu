@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
 // two-term split is needed); everything the screen cannot prove unchanged runs the canonical fp32 chain -> bit-identical
 // indices.  32-point tiles are dealt round-robin to all warps of the item, running minima live in registers.
 // ----------------------------------------------------------------------------------------------
-constexpr int kMaxSlots5 = 12;             // 32-point tiles per warp: n <= 148 * 16 * 32 * 12 = 909k points
+constexpr int kMaxSlots5 = 18;             // 32-point tiles per warp: n <= 148 * 16 * 32 * 18 = 1.36M points (4 x 640x480 on 37 CTAs each)
 
 // canonical fp32 chain over the channels of point xp (planar field, channel stride sd): out of line so that the twelve
 // unrolled slots of fps5_kernel do not each carry their own 32-register load batch
@@ -563,6 +563,14 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   if (const char* e = getenv("UOC_FPS_TC")) { if (atoi(e) == 0) return UOC_OK; }
   const int sms = sm_count();
   if (sms <= 0 || s.batch > sms) return UOC_OK;
+  // a batch of fields that do not fit on chip together: the fields take turns in the resident-slice kernel
+  // (launch_select_seeds); UOC_FPS_BATCH_STREAM=1 streams them side by side instead (A/B knob: slower)
+  if (s.batch > 1) {
+    const char* e = getenv("UOC_FPS_BATCH_STREAM");
+    const bool side_by_side = e ? atoi(e) != 0 : false;   // measured (profiles/r02_fps_batch.txt): turns 0.72 ms / field, side by side 1.25 - 1.40
+    const long long tiles_per_cta = ((s.n + 127) / 128 + (sms / s.batch) - 1) / (sms / s.batch);
+    if (tiles_per_cta > 4 * kMaxSlots && !side_by_side) return UOC_OK;
+  }
   const int nb = sms / s.batch;
   if (nb > 160) return UOC_OK;                      // the poll loop reads at most 5 keys per lane
   float rel_margin = kRelMargin4;
