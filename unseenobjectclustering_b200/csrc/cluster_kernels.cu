@@ -53,10 +53,10 @@ static WsLayout ws_layout(int batch, int64_t n, int d, int m) {
     if (sms <= 0) sms = 148;
     const int nb = batch <= sms ? sms / batch : 1;
     size_t per_pass = size_t(nb) * 128;                               // leader protocol: one line per CTA
-    if (size_t(nb) * nb * 8 > per_pass) per_pass = size_t(nb) * nb * 8;   // all-to-all protocol: nb x nb key matrix
+    if (size_t(nb) * nb * 16 > per_pass) per_pass = size_t(nb) * nb * 16;   // all-to-all protocol: nb x nb matrix of (first, second) keys
     L.slot_bytes = size_t(batch) * m * per_pass + size_t(batch) * m * d * 8;   // key slots + seed mailboxes
     // a batch whose fields do not fit on chip together is sampled one field at a time at full width (nb = all SMs)
-    const size_t single = size_t(m) * size_t(sms) * sms * 8 + size_t(m) * d * 8;
+    const size_t single = size_t(m) * size_t(sms) * sms * 16 + size_t(m) * d * 8;
     if (batch > 1 && single > L.slot_bytes) L.slot_bytes = single;
     L.slots = carve(off, L.slot_bytes);
   }

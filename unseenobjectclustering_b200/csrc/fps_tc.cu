@@ -58,10 +58,7 @@ struct Fps4Params {
   int T;                    // tiles of the busiest CTA (accumulator columns: 16 * T)
   int TA;                   // tiles kept in tensor memory (the rest in shared memory)
   float rel_margin;         // screening margin per unit |x||s| (kRelMargin4, or half of it for round-to-nearest copies)
-  int prefetch;             // exact chain: prefetch the later channel batches into L1 (UOC_FPS_PREFETCH, A/B)
-  unsigned int* stats;      // debug (UOC_FPS_TC_STATS=1): per pass {exact rounds, lanes in them, max rounds of one warp, rounds with <= 4 lanes}
-  long long* trace;         // debug (UOC_FPS_TC_TRACE=<cta>): per pass {start, screened, local arg-max, exchanged+seed, fp32 rounds}
-  int trace_cta;
+  unsigned long long* passlog;  // debug (UOC_FPS_STATS): [m] per pass of CTA 0: (exchange ? 1 << 63 : 0) | clock64 at the pass end
 };
 
 __device__ __forceinline__ unsigned int orderable4(float f) {
@@ -75,21 +72,49 @@ __device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t& a, u
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
 }
 
+// top-2 keys of two (first, second) pairs
+__device__ __forceinline__ void merge_top2(unsigned long long& a1, unsigned long long& a2, unsigned long long b1,
+                                           unsigned long long b2) {
+  const unsigned long long hi = a1 > b1 ? a1 : b1;
+  const unsigned long long lo = a1 > b1 ? b1 : a1;
+  const unsigned long long s2 = a2 > b2 ? a2 : b2;
+  a1 = hi;
+  a2 = lo > s2 ? lo : s2;
+}
+__device__ __forceinline__ float key_r(unsigned long long key) {      // inverse of orderable4 on the high word
+  const unsigned int u = static_cast<unsigned int>(key >> 32);
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// Speculative seed chain (round 2).  A pass used to end with an all-to-all exchange of every CTA's arg-max key (~3.2k clk
+// plus the wait for the slowest CTA) although the answer is usually known in advance: r[] only ever DECREASES, so the
+// exchange of pass i also tells every CTA the runners-up.  Every CTA publishes its TOP-2 keys; all CTAs derive the same
+//   list  = the first keys k1 that exceed   bound = max over CTAs of the second key k2   (<= 32 entries), and
+//   bound = an upper bound, for ever, of every point that is not in the list.
+// After a new seed s every CTA re-evaluates the list entries exactly (canonical fp32 chain on x_q, s -- any CTA can do
+// that, it is 64 loads per entry) and takes the largest; if it is still above `bound` it IS the global arg-max (same key
+// order, same tie-break) and becomes the next seed WITHOUT any exchange: the CTAs run such passes uncoupled.  Only when the
+// list runs dry, or its best entry drops to the bound, a real exchange rebuilds it.  Indices are bit-identical by
+// construction: every decision is taken on exact keys.
 template <int D>
 __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
   constexpr int KB = D / 64;                 // 64-channel blocks: one 128-byte swizzled row per point and block
   constexpr int NL = D / 8;                  // 16-byte units per point
   constexpr int ACOLS = D / 2;               // tensor-memory columns of one A tile (two bf16 per column)
   extern __shared__ uint8_t smem_raw[];
-  __shared__ float s_seed[D];
-  __shared__ float s_ns;
-  __shared__ unsigned long long s_red[kWarps4];
-  __shared__ uint64_t s_bar;
+  __shared__ float s_seed[2][D];             // seed i lives in buffer i & 1: the next seed is staged while pass i runs
+  __shared__ float s_ns[2];
+  __shared__ unsigned long long s_red[2 * kWarps4];
+  __shared__ unsigned long long s_list[32];
+  __shared__ unsigned long long s_drop, s_bound;
+  __shared__ int s_cnt, s_newlist;
+  __shared__ long long s_next[2];            // [pass parity] next seed index decided by the speculative chain, -1: exchange needed
+  __shared__ uint64_t s_bar[2];              // the screen is committed in two halves (tile slots 0-1 / 2-4)
   __shared__ uint32_t s_tmem;
   __shared__ int s_fail;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bsm = smem;                       // B operand: KB blocks of [16 rows][128 B]
-  uint8_t* atiles = smem + KB * 2048;        // shared-memory A tiles: [tile][KB][128 rows][128 B]
+  uint8_t* bsm = smem;                       // B operand, two buffers (seed parity): KB blocks of [16 rows][128 B] each
+  uint8_t* atiles = smem + 2 * KB * 2048;    // shared-memory A tiles: [tile][KB][128 rows][128 B]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, gi = warp >> 2;    // TMEM lane quadrant this warp may access; tile group
@@ -106,9 +131,9 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
   if (warp == 0) {
     tmem_alloc(&s_tmem, 512);
     tmem_relinquish();
-    if (lane == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); s_fail = 0; }
+    if (lane == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); s_fail = 0; s_next[0] = s_next[1] = -1; s_newlist = 0; }
   }
-  for (int e = tid; e < KB * 2048 / 16; e += kThreads4) reinterpret_cast<uint4*>(bsm)[e] = make_uint4(0u, 0u, 0u, 0u);
+  for (int e = tid; e < 2 * KB * 2048 / 16; e += kThreads4) reinterpret_cast<uint4*>(bsm)[e] = make_uint4(0u, 0u, 0u, 0u);
   // shared-memory A tiles: chunk c (8 channels) of row r of block kb goes to ((c ^ (r & 7)) << 4) of its 128-byte row
   for (int e = tid; e < (T - TA) * 128 * NL; e += kThreads4) {
     const int ts = e / (128 * NL), row = (e / NL) % 128, chunk = e % NL;
@@ -139,25 +164,30 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
   }
   tmem_wait_st();
 
-  unsigned long long mybest = 1ull;
   float r[kMaxSlots], nx[kMaxSlots];
 #pragma unroll
   for (int s = 0; s < kMaxSlots; ++s) { r[s] = 0.f; nx[s] = 0.f; }
+  // warp 1 (idle while warp 0 issues the MMAs of the screen), lane j: entry j of the candidate list (exact current key,
+  // 0 = empty); `bound` is warp-uniform
+  unsigned long long cand = 0ull, bound = ~0ull;
 
-  // warp 0: fetch seed `idx` (fp32), its norm, and the B operand {bf16(s), bf16(s - bf16(s))} of the screen
+  // one warp: fetch seed `idx` = seed number i (fp32), its norm, and the B operand {bf16(s), bf16(s - bf16(s))} of the
+  // screen into the buffers of parity i & 1
   auto stage_seed = [&](long long idx, int i) {
+    float* seedbuf = s_seed[i & 1];
+    uint8_t* bbuf = bsm + (i & 1) * KB * 2048;
     float sq = 0.f;
 #pragma unroll
     for (int h = 0; h < D / 64; ++h) {
       const int c0 = h * 64 + 2 * lane;
       const float v0 = __ldg(Xb + c0 * p.sd + idx), v1 = __ldg(Xb + (c0 + 1) * p.sd + idx);
-      s_seed[c0] = v0; s_seed[c0 + 1] = v1;
+      seedbuf[c0] = v0; seedbuf[c0 + 1] = v1;
       sq = fmaf(v0, v0, fmaf(v1, v1, sq));
       const float h0 = __bfloat162float(__float2bfloat16_rn(v0)), h1 = __bfloat162float(__float2bfloat16_rn(v1));
       const int chunk = lane >> 2, off = (lane & 3) * 4;          // channels 2*lane, 2*lane+1 of block h
       // row r (= column of B), chunk c of block h at h * 2048 + r * 128 + ((c ^ (r & 7)) << 4)
-      *reinterpret_cast<uint32_t*>(bsm + h * 2048 + 0 * 128 + ((chunk ^ 0) << 4) + off) = pack_bf16x2(h0, h1);
-      *reinterpret_cast<uint32_t*>(bsm + h * 2048 + 1 * 128 + ((chunk ^ 1) << 4) + off) = pack_bf16x2(v0 - h0, v1 - h1);
+      *reinterpret_cast<uint32_t*>(bbuf + h * 2048 + 0 * 128 + ((chunk ^ 0) << 4) + off) = pack_bf16x2(h0, h1);
+      *reinterpret_cast<uint32_t*>(bbuf + h * 2048 + 1 * 128 + ((chunk ^ 1) << 4) + off) = pack_bf16x2(v0 - h0, v1 - h1);
       if (rank == 0) {
         float* so = p.seeds_out + (size_t(b) * p.m + i) * D;
         so[c0] = v0; so[c0 + 1] = v1;
@@ -166,7 +196,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     if (lane == 0) {
-      s_ns = sqrtf(sq) * 1.000001f;
+      s_ns[i & 1] = sqrtf(sq) * 1.000001f;
       if (rank == 0) p.selected_out[size_t(b) * p.m + i] = idx;
     }
     fence_proxy_async();
@@ -177,71 +207,109 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
 
   constexpr uint32_t idesc = make_idesc_bf16(128, 16, 0, 0);
   const uint32_t bsm_addr = smem_u32(bsm), at_addr = smem_u32(atiles);
-  const bool trc = p.trace && int(blockIdx.x) == p.trace_cta && tid == 0;
 
   for (int i = 0; i + 1 < p.m; ++i) {
-    if (trc) p.trace[i * 6 + 0] = clock64();
     // ---- screen: all tiles of the CTA against seed i
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
+        // two halves, one commit each: the warps start on the tiles of slots 0-1 while the tensor core still works on the rest
+        const uint32_t bcur = bsm_addr + uint32_t(i & 1) * KB * 2048;
+        const int T0 = T < 8 ? T : 8;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int tb = half ? T0 : 0, te = half ? T : T0;
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
+          for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {           // k-step major: consecutive MMAs accumulate into different tiles
-            const uint64_t bd = make_smem_desc_sw128(bsm_addr + kb * 2048 + ks * 32, 16, 1024);
-            const uint32_t accumulate = (kb | ks) ? 1u : 0u;
-            for (int t = 0; t < TA; ++t)
-              umma_ts_f16(tmem_base + dcol0 + 16u * t, tmem_base + acol0 + uint32_t(t) * ACOLS + kb * 32 + ks * 8, bd, idesc, accumulate);
-            for (int t = TA; t < T; ++t) {
-              const uint64_t ad = make_smem_desc_sw128(at_addr + uint32_t((t - TA) * KB + kb) * 16384u + ks * 32, 16, 1024);
-              umma_ss_f16(tmem_base + dcol0 + 16u * t, ad, bd, idesc, accumulate);
+            for (int ks = 0; ks < 4; ++ks) {         // k-step major: consecutive MMAs accumulate into different tiles
+              const uint64_t bd = make_smem_desc_sw128(bcur + kb * 2048 + ks * 32, 16, 1024);
+              const uint32_t accumulate = (kb | ks) ? 1u : 0u;
+              for (int t = tb; t < te && t < TA; ++t)
+                umma_ts_f16(tmem_base + dcol0 + 16u * t, tmem_base + acol0 + uint32_t(t) * ACOLS + kb * 32 + ks * 8, bd, idesc, accumulate);
+              for (int t = (tb > TA ? tb : TA); t < te; ++t) {
+                const uint64_t ad = make_smem_desc_sw128(at_addr + uint32_t((t - TA) * KB + kb) * 16384u + ks * 32, 16, 1024);
+                umma_ss_f16(tmem_base + dcol0 + 16u * t, ad, bd, idesc, accumulate);
+              }
             }
           }
+          umma_commit(&s_bar[half]);
         }
-        umma_commit(&s_bar);
       }
       __syncwarp();
+    } else if (warp == 1) {
+      // ---- speculative chain (while warp 0 issues the screen): exact keys of the candidates after seed i
+      if (s_newlist) {                            // the last pass ended with an exchange: take the rebuilt list
+        const int cnt = s_cnt < 32 ? s_cnt : 32;
+        cand = lane < cnt ? s_list[lane] : 0ull;
+        bound = s_bound;
+        __syncwarp();
+        if (lane == 0) s_newlist = 0;
+      }
+      if (__any_sync(0xffffffffu, cand != 0ull)) {
+        if (cand != 0ull) {
+          const unsigned int idx = 0xFFFFFFFFu - static_cast<unsigned int>(cand & 0xFFFFFFFFull);
+          const float* xp = Xb + idx;
+          float acc = 0.f;
+#pragma unroll 1
+          for (int k0 = 0; k0 < D; k0 += 32) {
+            float x[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) x[k] = __ldg(xp + (k0 + k) * p.sd);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc = fmaf(x[k], s_seed[i & 1][k0 + k], acc);
+          }
+          const float dist = 0.5f * (1.0f - acc);
+          const float rq = key_r(cand);
+          cand = pack_key4(dist < rq ? dist : rq, idx);
+        }
+        unsigned long long best = cand;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+          best = other > best ? other : best;
+        }
+        if (best > bound) {                       // above everything that is not in the list: the global arg-max
+          if (cand == best) cand = 0ull;          // consumed (keys are unique: they carry the point index)
+          const long long nidx = static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(best & 0xFFFFFFFFull));
+          if (lane == 0) s_next[i & 1] = nidx;
+          stage_seed(nidx, i + 1);                // into the other buffers, while this pass still runs
+        } else {
+          cand = 0ull;                            // the list is stale beyond use: rebuilt by the exchange
+          if (lane == 0) s_next[i & 1] = -1;
+        }
+      } else if (lane == 0) {
+        s_next[i & 1] = -1;
+      }
     }
-    const bool ok = mbar_wait(&s_bar, uint32_t(i) & 1u, p.err);
-    tc_fence_after();
-    uint32_t c0[kMaxSlots], c1[kMaxSlots];
+    const float ns = s_ns[i & 1];
+    const float* seed = s_seed[i & 1];
+    bool ok = true;
 #pragma unroll
     for (int s = 0; s < kMaxSlots; ++s) {
-      const int t = gi + 4 * s;
-      c0[s] = c1[s] = 0u;
-      if (t < T) tmem_ld_32x32b_x2(lane_addr + dcol0 + 16u * uint32_t(t), c0[s], c1[s]);
-    }
-    tmem_wait_ld();
-    if (trc) p.trace[i * 6 + 1] = clock64();
-    const float ns = s_ns;
-    int n_exact = 0, n_lanes = 0, n_small = 0;
-    bool changed = (i == 0);                  // r[] of this thread changed: its cached arg-max key is stale
-#pragma unroll
-    for (int s = 0; s < kMaxSlots; ++s) {
+      if (s == 0 || s == 2) {                 // slots 0-1 = tiles 0..7 (first commit), slots 2-4 = the rest (second commit)
+        ok = mbar_wait(&s_bar[s == 0 ? 0 : 1], uint32_t(i) & 1u, p.err) && ok;
+        tc_fence_after();
+      }
       const int t = gi + 4 * s;
       if (t < T) {                            // warp-uniform
+        uint32_t c0, c1;
+        tmem_ld_32x32b_x2(lane_addr + dcol0 + 16u * uint32_t(t), c0, c1);
+        tmem_wait_ld();
         const long long gp = tile_base(t) + q * 32 + lane;
         const bool valid = gp < p.n;
         bool need = valid;
         if (i > 0 && ok) {
-          const float dapprox = 0.5f * (1.0f - (__uint_as_float(c0[s]) + __uint_as_float(c1[s])));
+          const float dapprox = 0.5f * (1.0f - (__uint_as_float(c0) + __uint_as_float(c1)));
           need = valid && !((dapprox - fmaf(p.rel_margin * nx[s], ns, kAbsMargin4)) >= r[s]);
         }
         if (__any_sync(0xffffffffu, need)) {
-          ++n_exact;
-          if (p.stats) { const int c = __popc(__ballot_sync(0xffffffffu, need)); n_lanes += c; n_small += (c <= 4) ? 1 : 0; }
           if (need) {
             // canonical fp32 chain (bit-identical to fps_kernel / fps2_kernel / the oracle)
             const float* xp = Xb + gp;
             float acc = 0.f, sq = 0.f;
-            constexpr int XB = 32;                    // loads in flight per lane (64 is slower: measured)
-            if (p.prefetch) {
-              // the later load batches depend on the registers of the first one: pull their lines into L1 now, so that
-              // a round costs ONE L2 round trip instead of D / 32
-#pragma unroll
-              for (int k = XB; k < D; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(xp + k * p.sd));
-            }
+            constexpr int XB = 32;                    // loads in flight per lane (64 were measured slower, also for the
+                                                      // sparse rounds of the later passes: profiles/r02_fps_speculation.txt)
 #pragma unroll 1
             for (int k0 = 0; k0 < D; k0 += XB) {
               float x[XB];
@@ -249,7 +317,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
               for (int k = 0; k < XB; ++k) x[k] = __ldg(xp + (k0 + k) * p.sd);
 #pragma unroll
               for (int k = 0; k < XB; ++k) {
-                acc = fmaf(x[k], s_seed[k0 + k], acc);
+                acc = fmaf(x[k], seed[k0 + k], acc);
                 if (i == 0) sq = fmaf(x[k], x[k], sq);
               }
             }
@@ -258,89 +326,104 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
               r[s] = dist;
               nx[s] = sqrtf(sq) * 1.000001f;
             } else {
-              changed = changed || dist < r[s];
               r[s] = dist < r[s] ? dist : r[s];
             }
           }
         }
       }
     }
-    if (changed) {                            // rare after the first passes: r[] only changes on the fp32 path
-      mybest = 1ull;                          // non-zero sentinel: an empty slice still signals arrival
+    tc_fence_before();
+    __syncthreads();                          // everybody is done with the accumulators of this pass; s_next is final
+    const long long next = s_next[i & 1];     // same decision in every CTA (deterministic)
+    // next >= 0: speculative pass end -- no exchange, the CTAs stay uncoupled; warp 1 has staged the seed already
+    if (next < 0) {
+      // ---- exchange: every CTA publishes its two best keys; everybody rebuilds the candidate list
+      // (four keys per CTA were measured: 66 % instead of 50 % of the passes stay speculative on the bench frame, but the
+      // wider exchange costs more than that returns: 0.74 vs 0.61 ms, profiles/r02_fps_speculation.txt)
+      unsigned long long k1 = 1ull, k2 = 1ull;          // non-zero sentinels: an empty slice still signals arrival
 #pragma unroll
       for (int s = 0; s < kMaxSlots; ++s) {
         const int t = gi + 4 * s;
         const long long gp = tile_base(t) + q * 32 + lane;
-        if (t < T && gp < p.n) {
-          const unsigned long long key = pack_key4(r[s], static_cast<unsigned int>(gp));
-          mybest = key > mybest ? key : mybest;
-        }
+        if (t < T && gp < p.n) merge_top2(k1, k2, pack_key4(r[s], static_cast<unsigned int>(gp)), 1ull);
       }
-    }
-    unsigned long long best = mybest;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-      best = other > best ? other : best;
-    }
-    if (lane == 0) s_red[warp] = best;
-    if (trc) { p.trace[i * 6 + 2] = clock64(); p.trace[i * 6 + 4] = n_exact; }
-    if (p.stats && lane == 0 && n_exact) {
-      atomicAdd(p.stats + i * 4 + 0, (unsigned int)n_exact); atomicAdd(p.stats + i * 4 + 1, (unsigned int)n_lanes);
-      atomicMax(p.stats + i * 4 + 2, (unsigned int)n_exact); atomicAdd(p.stats + i * 4 + 3, (unsigned int)n_small);
-    }
-    tc_fence_before();
-    __syncthreads();                          // everybody is done with s_seed, s_ns and the accumulators of this pass
-    if (trc) p.trace[i * 6 + 5] = clock64();
-    if (warp == 0) {
-      unsigned long long v = (lane < kWarps4) ? s_red[lane] : 0ull;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
-        v = other > v ? other : v;
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        merge_top2(k1, k2, o1, o2);
       }
-      // all-to-all: this CTA's key goes into column `rank` of EVERY CTA's private row; then poll the own row
-      unsigned long long* mat = p.slots + (size_t(b) * p.m + (i + 1)) * nb * nb;
+      if (lane == 0) { s_red[2 * warp] = k1; s_red[2 * warp + 1] = k2; }
+      if (tid == 0) { s_cnt = 0; s_drop = 0ull; }
+      __syncthreads();
+      if (warp == 0) {
+        k1 = (lane < kWarps4) ? s_red[2 * lane] : 1ull;
+        k2 = (lane < kWarps4) ? s_red[2 * lane + 1] : 1ull;
 #pragma unroll
-      for (int c5 = 0; c5 < 5; ++c5) {
-        const int c = lane + 32 * c5;
-        if (c < nb) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mat + size_t(c) * nb + rank), "l"(v) : "memory");
-      }
-      const unsigned long long* row = mat + size_t(rank) * nb;
-      unsigned long long gmax = 0ull;
-      bool done = false;
-      for (unsigned int it = 0; it < (1u << 22) && !done; ++it) {
-        unsigned long long kv[5];
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+          merge_top2(k1, k2, o1, o2);
+        }
+        // all-to-all: this CTA's pair goes into column `rank` of EVERY CTA's private row; then poll the own row
+        unsigned long long* mat = p.slots + (size_t(b) * p.m + (i + 1)) * nb * nb * 2;
 #pragma unroll
         for (int c5 = 0; c5 < 5; ++c5) {
           const int c = lane + 32 * c5;
-          kv[c5] = 1ull;
-          if (c < nb) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(kv[c5]) : "l"(row + c));
+          if (c < nb) {
+            unsigned long long* dst = mat + (size_t(c) * nb + rank) * 2;
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst), "l"(k1) : "memory");
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(k2) : "memory");
+          }
         }
-        bool all = true;
-        gmax = 0ull;
+        const unsigned long long* row = mat + size_t(rank) * nb * 2;
+        unsigned long long kv1[5], kv2[5];
+        bool done = false;
+        for (unsigned int it = 0; it < (1u << 22) && !done; ++it) {
+          bool all = true;
 #pragma unroll
-        for (int c5 = 0; c5 < 5; ++c5) {
-          all = all && (kv[c5] != 0ull);
-          gmax = kv[c5] > gmax ? kv[c5] : gmax;
+          for (int c5 = 0; c5 < 5; ++c5) {
+            const int c = lane + 32 * c5;
+            kv1[c5] = 1ull; kv2[c5] = 1ull;
+            if (c < nb) {
+              asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(kv1[c5]) : "l"(row + 2 * c));
+              asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(kv2[c5]) : "l"(row + 2 * c + 1));
+            }
+            all = all && (kv1[c5] != 0ull) && (kv2[c5] != 0ull);
+          }
+          done = __all_sync(0xffffffffu, all);
         }
-        done = __all_sync(0xffffffffu, all);
-      }
+        if (done && ok) {
+          // bound = the largest SECOND key: every point outside the CTAs' first keys is below it
+          unsigned long long bk = 0ull, gmax = 0ull;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, gmax, o);
-        gmax = other > gmax ? other : gmax;
+          for (int c5 = 0; c5 < 5; ++c5) { bk = kv2[c5] > bk ? kv2[c5] : bk; gmax = kv1[c5] > gmax ? kv1[c5] : gmax; }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bk, o), og = __shfl_xor_sync(0xffffffffu, gmax, o);
+            bk = ob > bk ? ob : bk;
+            gmax = og > gmax ? og : gmax;
+          }
+          // list = the first keys above the bound, except the winner itself (at most 32; the overflow raises the bound)
+#pragma unroll
+          for (int c5 = 0; c5 < 5; ++c5) {
+            if (kv1[c5] > bk && kv1[c5] != gmax) {
+              const int pos = atomicAdd(&s_cnt, 1);
+              if (pos < 32) s_list[pos] = kv1[c5];
+              else atomicMax(&s_drop, kv1[c5]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) { s_bound = s_drop > bk ? s_drop : bk; s_newlist = 1; }
+          stage_seed(static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(gmax & 0xFFFFFFFFull)), i + 1);
+        } else if (lane == 0) {
+          s_fail = 1;
+          atomicOr(p.err, ERR_GRID_BARRIER_TIMEOUT);
+        }
       }
-      if (done && ok) {
-        stage_seed(static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(gmax & 0xFFFFFFFFull)), i + 1);
-      } else if (lane == 0) {
-        s_fail = 1;
-        atomicOr(p.err, ERR_GRID_BARRIER_TIMEOUT);
-      }
+      tc_fence_before();
+      __syncthreads();                        // the exchanged seed is staged
     }
-    tc_fence_before();
-    __syncthreads();
-    if (trc) p.trace[i * 6 + 3] = clock64();
+    if (p.passlog && blockIdx.x == 0 && tid == 0)
+      p.passlog[i] = (next < 0 ? (1ull << 63) : 0ull) | (static_cast<unsigned long long>(clock64()) & ~(1ull << 63));
     if (s_fail) break;
   }
   tc_fence_before();
@@ -585,7 +668,7 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
     int TA0 = int((512 - 16 * T) / acols0);
     if (TA0 > T) TA0 = int(T);
     if (TA0 < 0) TA0 = 0;
-    if (1024 + size_t(kb0) * 2048 + size_t(T - TA0) * kb0 * 16384 > 225 * 1024) streaming = true;
+    if (1024 + 2 * size_t(kb0) * 2048 + size_t(T - TA0) * kb0 * 16384 > 225 * 1024) streaming = true;
   }
   if (streaming) {
     const long long tiles32 = (s.n + 31) / 32;
@@ -606,7 +689,7 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
     p5.slots = w.slots;
     p5.nb = nb; p5.T = 0; p5.TA = 0;
     p5.rel_margin = rel_margin;
-    p5.trace = nullptr; p5.trace_cta = 0; p5.stats = nullptr; p5.prefetch = 0;
+    p5.passlog = nullptr;
     UOC_CUDA(cudaMemsetAsync(w.slots, 0, slot_need5, stream_));
     void* args5[] = {&p5};
     UOC_CUDA(cudaLaunchCooperativeKernel(kern5, dim3(nb * s.batch), dim3(kThreads4), args5, smem5, stream_));
@@ -620,9 +703,9 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   if (TA > T) TA = int(T);
   if (TA < 0) TA = 0;
   if (const char* e = getenv("UOC_FPS_TC_TMEM_TILES")) { const int v = atoi(e); if (v >= 0 && v < TA) TA = v; }   // test / A-B knob
-  const size_t smem = 1024 + size_t(kb) * 2048 + size_t(T - TA) * kb * 16384;
+  const size_t smem = 1024 + 2 * size_t(kb) * 2048 + size_t(T - TA) * kb * 16384;
   if (smem > 225 * 1024) return UOC_OK;
-  const size_t slot_need = size_t(s.batch) * s.m * nb * nb * 8;
+  const size_t slot_need = size_t(s.batch) * s.m * nb * nb * 16;     // (first, second) key per CTA pair and pass
   if (slot_need > w.slot_bytes) return UOC_OK;
   unsigned int* err = device_error_word();
   if (!err) return fail(UOC_ERR_CUDA, "no device error word");
@@ -640,55 +723,24 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   p.slots = w.slots;
   p.nb = nb; p.T = int(T); p.TA = TA;
   p.rel_margin = rel_margin;
-  p.trace = nullptr;
-  p.trace_cta = 0;
-  p.prefetch = 0;
-  if (const char* e = getenv("UOC_FPS_PREFETCH")) p.prefetch = atoi(e);
-  p.stats = nullptr;
-  if (getenv("UOC_FPS_TC_STATS")) {
-    UOC_CUDA(cudaMalloc(&p.stats, sizeof(unsigned int) * 4 * s.m));
-    UOC_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(unsigned int) * 4 * s.m, stream));
-  }
-  if (const char* e = getenv("UOC_FPS_TC_TRACE")) {
-    p.trace_cta = atoi(e);
-    UOC_CUDA(cudaMalloc(&p.trace, sizeof(long long) * 6 * s.m));
-    UOC_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * 6 * s.m, stream));
-  }
+  p.passlog = getenv("UOC_FPS_STATS") ? w.keys : nullptr;      // the key slots of the fp32 kernels are unused here
   UOC_CUDA(cudaMemsetAsync(w.slots, 0, slot_need, stream));
   void* args[] = {&p};
   UOC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(nb * s.batch), dim3(kThreads4), args, smem, stream));
   count_launch();
-  if (p.stats) {
-    std::vector<unsigned int> hs(size_t(4) * s.m);
+  if (p.passlog) {
+    std::vector<unsigned long long> h(s.m);
     UOC_CUDA(cudaStreamSynchronize(stream));
-    UOC_CUDA(cudaMemcpy(hs.data(), p.stats, sizeof(unsigned int) * hs.size(), cudaMemcpyDeviceToHost));
-    cudaFree(p.stats);
-    unsigned long long tr = 0, tl = 0, tsm = 0, tmax = 0; int none = 0;
-    for (int i = 1; i + 1 < s.m; ++i) {
-      tr += hs[i * 4]; tl += hs[i * 4 + 1]; tmax += hs[i * 4 + 2]; tsm += hs[i * 4 + 3]; none += hs[i * 4] == 0;
-      if (i < 6 || i % 10 == 0)
-        fprintf(stderr, "[fps tc stats] pass %d: %u exact rounds in the grid, %u lanes, busiest warp %u rounds, %u rounds with <= 4 lanes\n",
-                i, hs[i * 4], hs[i * 4 + 1], hs[i * 4 + 2], hs[i * 4 + 3]);
+    UOC_CUDA(cudaMemcpy(h.data(), p.passlog, sizeof(unsigned long long) * s.m, cudaMemcpyDeviceToHost));
+    int nx = 0, nsp = 0;
+    double cx = 0, csp = 0;
+    for (int i = 2; i + 1 < s.m; ++i) {
+      const bool ex = (h[i] >> 63) != 0;
+      const double dt = double((h[i] & ~(1ull << 63)) - (h[i - 1] & ~(1ull << 63)));
+      if (ex) { ++nx; cx += dt; } else { ++nsp; csp += dt; }
     }
-    fprintf(stderr, "[fps tc stats] passes 1..%d: %.1f rounds / pass (%.1f lanes each), busiest warp %.2f rounds on average, %.0f %% of the rounds have <= 4 lanes, %d passes without any round\n",
-            s.m - 2, double(tr) / (s.m - 2), tr ? double(tl) / tr : 0.0, double(tmax) / (s.m - 2), tr ? 100.0 * tsm / tr : 0.0, none);
-  }
-  if (p.trace) {
-    std::vector<long long> h(size_t(6) * s.m);
-    UOC_CUDA(cudaStreamSynchronize(stream));
-    UOC_CUDA(cudaMemcpy(h.data(), p.trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
-    cudaFree(p.trace);
-    double sum[4] = {0, 0, 0, 0};
-    for (int i = 0; i + 1 < s.m; ++i) {
-      const long long* q = h.data() + size_t(i) * 6;
-      if (i < 6 || i % 10 == 0)
-        fprintf(stderr, "[fps tc trace] cta %d pass %d: screen %lld  fp32 rounds+arg-max (warp 0) %lld  wait for all warps %lld  exchange+seed %lld clk; fp32 rounds (warp 0) %lld\n",
-                p.trace_cta, i, q[1] - q[0], q[2] - q[1], q[5] - q[2], q[3] - q[5], q[4]);
-      if (i >= 10) { sum[0] += q[1] - q[0]; sum[1] += q[2] - q[1]; sum[2] += q[5] - q[2]; sum[3] += q[3] - q[5]; }
-    }
-    const double cnt = s.m - 11;
-    fprintf(stderr, "[fps tc trace] mean over passes >= 10: screen %.0f  fp32+arg-max (warp 0) %.0f  wait for all warps %.0f  exchange+seed %.0f clk  (T %d, TA %d)\n",
-            sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, int(T), TA);
+    fprintf(stderr, "[fps stats] passes 2..%d of CTA 0: %d ended with an exchange (%.0f clk per pass), %d speculative (%.0f clk per pass)\n",
+            s.m - 2, nx, nx ? cx / nx : 0.0, nsp, nsp ? csp / nsp : 0.0);
   }
   *used = true;
   return UOC_OK;
