@@ -50,6 +50,10 @@ enum {
   UOC_FLAG_CONV_SIMT = 2,   /* backbone convolutions on the fp32 SIMT validation kernel instead of tcgen05 */
   UOC_FLAG_SYNC_CHECK = 4,  /* synchronise the stream and read back the device error word before returning */
   UOC_FLAG_FPS_FP32 = 8,    /* seed selection re-reads the fp32 field in every pass (no bf16 screening pass) */
+  UOC_FLAG_X_F32PM = 32,    /* the x_bf16 / features_bf16_out buffer is a SIDE BUFFER of two parts: the bf16 pixel-major copy
+                               [batch,n,d], then -- at the next multiple of 256 bytes -- an fp32 pixel-major copy [batch,n,d]
+                               (uoc_side_buffer_bytes).  uoc_backbone_forward writes both; the seed selection then reads a
+                               point's exact fp32 row as 256 contiguous bytes instead of d strided channel planes. */
   UOC_FLAG_EUCLIDEAN = 16   /* metric='euclidean' (cfg.TRAIN.EMBEDDING_METRIC, lib/fcn/config.py:261; the euclidean branches
                                of lib/utils/mean_shift.py:21-24,58-60,101-105,159-160,207-209): distances ||x - z||, weights
                                exp(-kappa ||x - z||^2), update divided by max(sum of weights, 1).  X need not be unit norm.
@@ -66,6 +70,12 @@ UOC_API int uoc_version(void);
 UOC_API unsigned long long uoc_launch_count(void);
 /* sm count / compute capability of the current device; UOC_ERR_UNSUPPORTED if it is not sm_100. */
 UOC_API int uoc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Parity-test / measurement knobs (not part of the product contract): the same switches the UOC_* environment variables
+ * set when the library is loaded -- conv_pair, fps_tc, fps_stream, fps_tmem_tiles, fps_batch_stream, fps_rn_margin,
+ * fps_stats, conv_debug, conv_trace, loop_trace, assign_simt (csrc/uoc_common.cuh).  Used by tests/ to run both
+ * convolution kernels and every seed-selection variant on the same inputs. */
+UOC_API int uoc_set_knob(const char* name, int value);
 
 /* Kernels report pipeline time-outs / bad configurations in a per-device error word instead of hanging; the compute
  * entry points read it only under UOC_FLAG_SYNC_CHECK (that needs a stream synchronisation).  Callers that synchronise
@@ -85,6 +95,9 @@ UOC_API int uoc_peek_device_error_async(uint32_t* word_host, uoc_stream_t stream
  * contiguous; the reference's `features[j].view(C,-1).t()` view, test_dataset.py:54-55).
  * Rows must be unit-norm (the network emits F.normalize'd features, lib/networks/SEG.py:114).
  * ------------------------------------------------------------------------------------------ */
+
+/* Bytes of the side buffer (bf16 pixel-major copy, + the fp32 pixel-major copy when with_f32pm) of `batch` fields. */
+UOC_API size_t uoc_side_buffer_bytes(int batch, int64_t n, int d, int with_f32pm);
 
 /* Bytes of device workspace uoc_meanshift_cluster / the stage functions need. */
 UOC_API size_t uoc_meanshift_workspace_bytes(int batch, int64_t n, int d, int m);

@@ -24,3 +24,18 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture
+def knob():
+    """Set library knobs (uoc_set_knob) for one test; every knob is back at its default afterwards."""
+    from unseenobjectclustering_b200 import _lib
+    touched = []
+
+    def setter(name, value):
+        touched.append(name)
+        _lib.set_knob(name, value)
+
+    yield setter
+    for name in touched:
+        _lib.set_knob(name, _lib.KNOB_DEFAULTS[name])

@@ -51,12 +51,12 @@ def _conv_call(x, w, bias, res, N, H, W, Cin, Cout, k, stride, dil, relu, flags)
 
 @pytest.mark.parametrize("variant", ["pair", "tc", "simt"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
-def test_conv_matches_torch(case, variant, monkeypatch):
+def test_conv_matches_torch(case, variant, knob):
     """The persistent CTA-pair stream-K kernel (conv_pair.cu, default), the first-generation one-tile-per-CTA kernel
-    (UOC_CONV_PAIR=0) and the SIMT validation kernel, against torch's convolution on the same bf16 operands."""
+    (knob conv_pair = 0) and the SIMT validation kernel, against torch's convolution on the same bf16 operands."""
     Cin, Cout, k, stride, dil, H, W, N = case
     flags = _lib.FLAG_CONV_SIMT if variant == "simt" else 0
-    monkeypatch.setenv("UOC_CONV_PAIR", "0" if variant == "tc" else "1")
+    knob("conv_pair", 0 if variant == "tc" else 1)
     g = torch.Generator().manual_seed(Cin + Cout + k + H)
     x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(torch.bfloat16)
     w = (torch.randn(Cout, k * k, Cin, generator=g) * (1.0 / np.sqrt(k * k * Cin))).to(torch.bfloat16)

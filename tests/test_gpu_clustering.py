@@ -24,22 +24,22 @@ def _field(H, W, d, K, noise, seed):
     return feats, gt
 
 
-def _fps_mode(monkeypatch, mode):
+def _fps_mode(knob, mode):
     """tc: tcgen05 screen (fps_tc.cu, default: tiles in tensor memory first); tc_smem: same with every tile in shared memory;
     stream: the streaming bf16 screen for fields that do not fit on chip (fps5_kernel), forced on small fields;
     fp32: no screen (fps2_kernel).  Returns bf16_screen."""
-    monkeypatch.setenv("UOC_FPS_TC", "1" if mode in ("tc", "tc_smem", "stream") else "0")
-    monkeypatch.setenv("UOC_FPS_STREAM", "1" if mode == "stream" else "0")
+    knob("fps_tc", 1 if mode in ("tc", "tc_smem", "stream") else 0)
+    knob("fps_stream", 1 if mode == "stream" else 0)
     if mode == "tc_smem":
-        monkeypatch.setenv("UOC_FPS_TC_TMEM_TILES", "0")
+        knob("fps_tmem_tiles", 0)
     return mode != "fp32"
 
 
 @pytest.mark.parametrize("mode", ["tc", "tc_smem", "stream", "fp32"])
 @pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 100), (30, 44, 128, 100), (24, 24, 64, 40),
                                      (60, 80, 32, 17), (120, 160, 64, 100)])
-def test_select_seeds_bit_exact(H, W, d, m, mode, monkeypatch):
-    screen = _fps_mode(monkeypatch, mode)
+def test_select_seeds_bit_exact(H, W, d, m, mode, knob):
+    screen = _fps_mode(knob, mode)
     feats, _ = _field(H, W, d, 4, 0.05, seed=H * 7 + d)
     Xp = feats[0].reshape(d, -1).numpy()
     first = (H * W) // 3
@@ -53,7 +53,7 @@ def test_select_seeds_bit_exact(H, W, d, m, mode, monkeypatch):
 
 @pytest.mark.parametrize("mode", ["tc", "stream"])
 @pytest.mark.parametrize("case", ["isotropic", "scaled", "two_homes", "full_frame", "full_frame_128"])
-def test_select_seeds_bf16_screen_stress(case, mode, monkeypatch):
+def test_select_seeds_bf16_screen_stress(case, mode, knob):
     """The bf16 screening pass of the seed selection (fps_tc.cu) must never change an index:
     isotropic  - no cluster structure: the screen rejects little, nearly every point takes the fp32 path;
     scaled     - rows of norm 3 (the error bound of the screen scales with |x| |s|);
@@ -61,14 +61,14 @@ def test_select_seeds_bf16_screen_stress(case, mode, monkeypatch):
     full_frame - 480x640x64: 17 tiles per CTA (7 in tensor memory + 10 in shared memory for fps_tc);
     full_frame_128 - 240x320x128: the two-block (d = 128) operand layouts at several tiles per CTA.
     mode stream: the same inputs through the streaming screen (fps5_kernel)."""
-    _fps_mode(monkeypatch, mode)
+    _fps_mode(knob, mode)
     if case == "isotropic":
         g = torch.Generator().manual_seed(5)
         feats = torch.nn.functional.normalize(torch.randn(1, 64, 48, 64, generator=g), dim=1)
     elif case == "scaled":
         feats = _field(40, 52, 64, 4, 0.1, seed=12)[0] * 3.0
     elif case == "two_homes":
-        monkeypatch.setenv("UOC_FPS_TC_TMEM_TILES", "1")
+        knob("fps_tmem_tiles", 1)
         feats = _field(120, 160, 64, 5, 0.1, seed=13)[0]
     elif case == "full_frame":
         feats = _field(480, 640, 64, 6, 0.1, seed=14)[0]
@@ -416,3 +416,30 @@ def test_bf16_side_channel_cannot_go_stale():
     assert MS._lookup_bf16(f) is None
     lab3, _ = MS.cluster_fields(f, 100, first_indices=[7], flags=_lib.FLAG_SYNC_CHECK)
     assert torch.equal(lab, lab3)
+
+
+@pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 100), (30, 44, 128, 100), (120, 160, 64, 100), (96, 128, 128, 60)])
+def test_select_seeds_pixel_major_rows_bit_exact(H, W, d, m):
+    """The resident-slice sampler with the fp32 PIXEL-MAJOR side copy (UOC_FLAG_X_F32PM: what the backbone writes next to the
+    features): exact rows are read as 4 d contiguous bytes; same canonical chain, so the indices equal the C oracle's and
+    the planar path's."""
+    feats, _ = _field(H, W, d, 4, 0.05, seed=H * 5 + d)
+    Xp = feats[0].reshape(d, -1).numpy()
+    first = (H * W) // 5
+    sel_o, seeds_o = C.select_seeds(Xp, m, first)
+    f = feats.to(DEV)
+    side = MS.pack_side(f, with_f32pm=True)
+    assert side._uoc_f32pm and torch.equal(MS.side_f32pm(side)[0], f[0].view(d, -1).t())
+    lab, sel, Z, sl = MS.cluster_fields(f, m, first_indices=[first], flags=_lib.FLAG_SYNC_CHECK, return_seeds=True, x_bf16=side)
+    assert np.array_equal(sel[0].cpu().numpy(), sel_o)
+    lab2, sel2, _, _ = MS.cluster_fields(f, m, first_indices=[first], flags=_lib.FLAG_SYNC_CHECK, return_seeds=True,
+                                         x_bf16=MS.pack_side(f, with_f32pm=False))
+    assert torch.equal(sel, sel2) and torch.equal(lab, lab2)
+
+
+def test_full_size_pixel_major_rows_match_reference_golden():
+    g, feats, gt = _full_case("full_cfg2")
+    f = feats.to(DEV)
+    labels, sel = MS.cluster_fields(f, 100, first_indices=[int(g["first_index"])], flags=_lib.FLAG_SYNC_CHECK, x_bf16=MS.pack_side(f))
+    assert np.array_equal(sel[0].cpu().numpy(), g["selected"])
+    assert np.array_equal(labels[0].cpu().numpy(), g["labels"].astype(np.int32))

@@ -1,5 +1,5 @@
 """Per-layer device time of the backbone's convolution shapes through uoc_conv2d_bf16 (CUDA events, L2 flushed), for
-A/B of kernel variants selected by environment knobs.  N images emulate (frames per launch) x (2 branches).
+A/B of kernel variants selected by library knobs (UOC_CONV_LAYERS_VARIANTS="auto;conv_pair=1;conv_pair=0,conv_trace=1").  N images emulate (frames per launch) x (2 branches).
 usage: python tools/conv_layers.py [N ...]   (default 2 and 8 = batch 1 and batch 4 with both branches)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,7 +16,7 @@ LAYERS = [("l1 3x3 64", 120, 160, 64, 64, 3, 1, 1, 6), ("l2 3x3 s2 64>128", 120,
           ("l3 3x3 256 d2", 60, 80, 256, 256, 3, 1, 2, 11), ("l4 3x3 256>512 d4", 60, 80, 256, 512, 3, 1, 4, 1),
           ("l4 1x1 down", 60, 80, 256, 512, 1, 1, 1, 1), ("l4 3x3 512 d4", 60, 80, 512, 512, 3, 1, 4, 5),
           ("fc 1x1 512>64", 60, 80, 512, 64, 1, 1, 1, 1)]
-VARIANTS = [("default", {}), ("2sm", {"UOC_CONV_2SM": "1"})]
+VARIANTS = [("auto", {}), ("pair", {"conv_pair": "1"}), ("tc", {"conv_pair": "0"})]
 if os.environ.get("UOC_CONV_LAYERS_VARIANTS"):
     VARIANTS = [(v, dict(kv.split("=") for kv in v.split(",") if "=" in kv)) for v in os.environ["UOC_CONV_LAYERS_VARIANTS"].split(";")]
 if os.environ.get("UOC_CONV_LAYERS_ONLY"):
@@ -35,9 +35,10 @@ for N in ([int(v) for v in sys.argv[1:]] or [2, 8]):
         flops = 2.0 * N * Ho * Wo * Cout * Cin * k * k
         row = {}
         for vname, env in VARIANTS:
-            for kk in ("UOC_CONV_2SM", "UOC_CONV_BLOCK_N", "UOC_CONV_CLUSTER", "UOC_CONV_MAX_BLOCK_N", "UOC_CONV_PERSIST", "UOC_CONV_PAIR", "UOC_CONV_DEBUG", "UOC_CONV_TRACE"):
-                os.environ.pop(kk, None)
-            os.environ.update(env)
+            for kk in ("conv_pair", "conv_debug", "conv_trace"):        # library knobs (uoc_set_knob), back to their defaults
+                _lib.set_knob(kk, _lib.KNOB_DEFAULTS[kk])
+            for kk, vv in env.items():
+                _lib.set_knob(kk, int(vv))
             ts = []
             for rep in range(7):
                 flush.zero_()

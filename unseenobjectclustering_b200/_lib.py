@@ -14,6 +14,7 @@ FLAG_CONV_SIMT = 2
 FLAG_SYNC_CHECK = 4
 FLAG_FPS_FP32 = 8
 FLAG_EUCLIDEAN = 16
+FLAG_X_F32PM = 32
 MAX_SEEDS = 128
 
 
@@ -34,8 +35,10 @@ SIGNATURES = {
     "uoc_version": (_i, []),
     "uoc_launch_count": (_c.c_uint64, []),
     "uoc_device_info": (_i, [_c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
+    "uoc_set_knob": (_i, [_c.c_char_p, _i]),
     "uoc_check_device_error": (_i, [_vp]),
     "uoc_peek_device_error_async": (_i, [_vp, _vp]),
+    "uoc_side_buffer_bytes": (_sz, [_i, _i64, _i, _i]),
     "uoc_meanshift_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "uoc_meanshift_cluster": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                    _i, _vp]),
@@ -112,6 +115,15 @@ def raise_on_device_error(device=None):
     import torch
     with torch.cuda.device(device):
         check(load().uoc_check_device_error(stream_ptr(device)), "device error check")
+
+
+KNOB_DEFAULTS = {"conv_pair": -1, "conv_debug": 0, "conv_trace": 0, "fps_tc": 1, "fps_stream": 0, "fps_tmem_tiles": -1,
+                 "fps_batch_stream": 0, "fps_rn_margin": 0, "fps_stats": 0, "loop_trace": 0, "assign_simt": 0}
+
+
+def set_knob(name, value):
+    """Parity-test / measurement switch of the library (include/uoc.h uoc_set_knob); not part of the product contract."""
+    check(load().uoc_set_knob(name.encode(), int(value)), "uoc_set_knob(%s)" % name)
 
 
 def ptr(t):

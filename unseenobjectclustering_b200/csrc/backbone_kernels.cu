@@ -236,67 +236,9 @@ int launch_maxpool(const void* const* x, void* const* y, int groups, int N, int 
 // One thread per output pixel, channels in registers.
 // ----------------------------------------------------------------------------------------------
 // D = channels of the output field; MODE: HEAD_ADD (a + b), HEAD_SINGLE (a), HEAD_CAT (a | b, D/2 channels each)
-template <int D, int MODE>
-__global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w,
-                                                   int H, int W, float sy, float sx, int normalize,
-                                                   float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_bf16) {
-  constexpr int DU = (MODE == HEAD_CAT) ? D / 2 : D;     // channels of one trunk output
-  const int n = blockIdx.z;
-  const int oy = blockIdx.y;
-  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ox >= W) return;
-  const float fy = sy * float(oy), fx = sx * float(ox);
-  const int y0 = int(fy), x0 = int(fx);
-  const int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
-  const float ly1 = fy - float(y0), lx1 = fx - float(x0);
-  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-  const size_t base = size_t(n) * h * w;
-  const size_t o00 = (base + size_t(y0) * w + x0) * DU, o01 = (base + size_t(y0) * w + x1) * DU;
-  const size_t o10 = (base + size_t(y1) * w + x0) * DU, o11 = (base + size_t(y1) * w + x1) * DU;
-  float f[D];
-  float ss = 0.f;
-#pragma unroll
-  for (int k4 = 0; k4 < D / 4; ++k4) {
-    const float* src = (MODE == HEAD_CAT && k4 >= DU / 4) ? b : a;
-    const int kk = (MODE == HEAD_CAT && k4 >= DU / 4) ? k4 - DU / 4 : k4;
-    float4 v00 = __ldg(reinterpret_cast<const float4*>(src + o00) + kk), v01 = __ldg(reinterpret_cast<const float4*>(src + o01) + kk);
-    float4 v10 = __ldg(reinterpret_cast<const float4*>(src + o10) + kk), v11 = __ldg(reinterpret_cast<const float4*>(src + o11) + kk);
-    if (MODE == HEAD_ADD) {
-      const float4 u00 = __ldg(reinterpret_cast<const float4*>(b + o00) + kk), u01 = __ldg(reinterpret_cast<const float4*>(b + o01) + kk);
-      const float4 u10 = __ldg(reinterpret_cast<const float4*>(b + o10) + kk), u11 = __ldg(reinterpret_cast<const float4*>(b + o11) + kk);
-      v00.x += u00.x; v00.y += u00.y; v00.z += u00.z; v00.w += u00.w;
-      v01.x += u01.x; v01.y += u01.y; v01.z += u01.z; v01.w += u01.w;
-      v10.x += u10.x; v10.y += u10.y; v10.z += u10.z; v10.w += u10.w;
-      v11.x += u11.x; v11.y += u11.y; v11.z += u11.z; v11.w += u11.w;
-    }
-    f[4 * k4 + 0] = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
-    f[4 * k4 + 1] = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
-    f[4 * k4 + 2] = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
-    f[4 * k4 + 3] = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
-    ss = fmaf(f[4 * k4 + 0], f[4 * k4 + 0], ss); ss = fmaf(f[4 * k4 + 1], f[4 * k4 + 1], ss);
-    ss = fmaf(f[4 * k4 + 2], f[4 * k4 + 2], ss); ss = fmaf(f[4 * k4 + 3], f[4 * k4 + 3], ss);
-  }
-  const float inv = normalize ? 1.0f / fmaxf(sqrtf(ss), 1e-12f) : 1.0f;   // cfg.TRAIN.EMBEDDING_NORMALIZATION (SEG.py:113-114)
-  const size_t HW = size_t(H) * W;
-  const size_t pix = size_t(oy) * W + ox;
-  float* o = out_nchw + size_t(n) * D * HW + pix;
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    f[k] *= inv;
-    __stcs(o + size_t(k) * HW, f[k]);
-  }
-  if (out_bf16) {
-    uint4* ob = reinterpret_cast<uint4*>(out_bf16 + (size_t(n) * HW + pix) * D);
-#pragma unroll
-    for (int e = 0; e < D / 8; ++e)
-      ob[e] = make_uint4(pack_bf16x2(f[8 * e + 0], f[8 * e + 1]), pack_bf16x2(f[8 * e + 2], f[8 * e + 3]),
-                         pack_bf16x2(f[8 * e + 4], f[8 * e + 5]), pack_bf16x2(f[8 * e + 6], f[8 * e + 7]));
-  }
-}
-
-// Second generation of the head: one CTA per output ROW.  The two source rows y0, y1 of the (for add fusion already
-// summed) trunk output are staged ONCE in shared memory (the first generation re-read the four source pixels of every
-// output pixel from global memory: 128 LDG.128 per thread); every thread then owns PX consecutive output pixels x D/4
+// One CTA per output ROW.  The two source rows y0, y1 of the (for add fusion already
+// summed) trunk output are staged ONCE in shared memory (a thread-per-pixel first generation re-read the four source pixels of
+// every output pixel from global memory: 128 LDG.128 per thread, 60 us per frame against 31 us now); every thread then owns PX consecutive output pixels x D/4
 // channels: the same interpolation formula from shared memory, the L2 norm over the channels with two warp shuffles,
 // and 16-byte stores on BOTH outputs (fp32 planar NCHW: PX pixels of
 // one channel; bf16 pixel-major: 8 channels of one pixel).  Lane = quarter * 8 + pixel group, so that the eight lanes of
@@ -304,7 +246,8 @@ __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ a, 
 template <int D, int MODE, int PX>
 __global__ void __launch_bounds__(256, 2) head_row_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w,
                                                        int H, int W, float sy, float sx, int normalize,
-                                                       float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_bf16) {
+                                                       float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_bf16,
+                                                       float* __restrict__ out_f32pm) {
   constexpr int DU = (MODE == HEAD_CAT) ? D / 2 : D;     // channels of one trunk output
   constexpr int CPT = D / 4;                             // channels per thread
   constexpr int PITCH = D + 4;                           // floats per source pixel in shared memory (16-byte aligned, bank shift 4)
@@ -397,47 +340,46 @@ __global__ void __launch_bounds__(256, 2) head_row_kernel(const float* __restric
                              pack_bf16x2(f[i][8 * e + 6] * inv[i], f[i][8 * e + 7] * inv[i]));
       }
     }
+    if (out_f32pm) {                                     // fp32 pixel-major copy (exact rows for the seed selection)
+#pragma unroll
+      for (int i = 0; i < PX; ++i) {
+        float4* of = reinterpret_cast<float4*>(out_f32pm + (size_t(n) * HW + pix0 + i) * D + q * CPT);
+#pragma unroll
+        for (int e = 0; e < CPT / 4; ++e)
+          of[e] = make_float4(f[i][4 * e + 0] * inv[i], f[i][4 * e + 1] * inv[i], f[i][4 * e + 2] * inv[i], f[i][4 * e + 3] * inv[i]);
+      }
+    }
   }
 }
 
 template <int D, int MODE, int PX>
 static int launch_head_row(const float* a, const float* b, int normalize, int N, int h, int w, int H, int W, float sy, float sx,
-                           float* out_nchw, __nv_bfloat16* ob, cudaStream_t stream) {
+                           float* out_nchw, __nv_bfloat16* ob, cudaStream_t stream, float* of) {
   const size_t smem = size_t(2) * w * (D + 4) * sizeof(float);
   if (smem > 48 * 1024) {
     const int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&head_row_kernel<D, MODE, PX>), int(smem));
     if (rc != UOC_OK) return rc;
   }
-  head_row_kernel<D, MODE, PX><<<dim3(H, N), 256, smem, stream>>>(a, b, h, w, H, W, sy, sx, normalize, out_nchw, ob);
+  head_row_kernel<D, MODE, PX><<<dim3(H, N), 256, smem, stream>>>(a, b, h, w, H, W, sy, sx, normalize, out_nchw, ob, of);
   UOC_CHECK_LAUNCH();
   return UOC_OK;
 }
 
 int launch_head(const float* a, const float* b, int mode, int normalize, int N, int h, int w, int d, int H, int W,
-                float* out_nchw, void* out_bf16, cudaStream_t stream) {
+                float* out_nchw, void* out_bf16, cudaStream_t stream, float* out_f32pm) {
   const float sy = (H > 1) ? float(h - 1) / float(H - 1) : 0.f;
   const float sx = (W > 1) ? float(w - 1) / float(W - 1) : 0.f;
   __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
   const size_t smem_row = size_t(2) * w * (d + 4) * sizeof(float);
   if (W % 4 == 0 && smem_row <= 200 * 1024) {
-    if (mode == HEAD_ADD && d == 64) return launch_head_row<64, HEAD_ADD, 4>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
-    if (mode == HEAD_ADD && d == 128) return launch_head_row<128, HEAD_ADD, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
-    if (mode == HEAD_SINGLE && d == 64) return launch_head_row<64, HEAD_SINGLE, 4>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
-    if (mode == HEAD_SINGLE && d == 128) return launch_head_row<128, HEAD_SINGLE, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
-    if (mode == HEAD_CAT && d == 128) return launch_head_row<128, HEAD_CAT, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_ADD && d == 64) return launch_head_row<64, HEAD_ADD, 4>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream, out_f32pm);
+    if (mode == HEAD_ADD && d == 128) return launch_head_row<128, HEAD_ADD, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream, out_f32pm);
+    if (mode == HEAD_SINGLE && d == 64) return launch_head_row<64, HEAD_SINGLE, 4>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream, out_f32pm);
+    if (mode == HEAD_SINGLE && d == 128) return launch_head_row<128, HEAD_SINGLE, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream, out_f32pm);
+    if (mode == HEAD_CAT && d == 128) return launch_head_row<128, HEAD_CAT, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream, out_f32pm);
     return fail(UOC_ERR_UNSUPPORTED, "head supports 64 or 128 output channels (cat fusion: 2 x 64)");
   }
-  const dim3 grid((W + 127) / 128, H, N);
-#define UOC_HEAD(DD, MM) head_kernel<DD, MM><<<grid, 128, 0, stream>>>(a, b, h, w, H, W, sy, sx, normalize, out_nchw, ob)
-  if (mode == HEAD_ADD && d == 64) UOC_HEAD(64, HEAD_ADD);
-  else if (mode == HEAD_ADD && d == 128) UOC_HEAD(128, HEAD_ADD);
-  else if (mode == HEAD_SINGLE && d == 64) UOC_HEAD(64, HEAD_SINGLE);
-  else if (mode == HEAD_SINGLE && d == 128) UOC_HEAD(128, HEAD_SINGLE);
-  else if (mode == HEAD_CAT && d == 128) UOC_HEAD(128, HEAD_CAT);
-  else return fail(UOC_ERR_UNSUPPORTED, "head supports 64 or 128 output channels (cat fusion: 2 x 64)");
-#undef UOC_HEAD
-  UOC_CHECK_LAUNCH();
-  return UOC_OK;
+  return fail(UOC_ERR_UNSUPPORTED, "head: W must be a multiple of 4 and a source row pair must fit in shared memory");
 }
 
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ in, int hw, int d, float* __restrict__ out) {

@@ -503,15 +503,13 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
   *used = false;
   const int sms = sm_count();
   if (sms <= 0 || s.batch > sms) return UOC_OK;
-  if (const char* e = getenv("UOC_FPS_V1")) { if (atoi(e) != 0) return UOC_OK; }
   const int nb = sms / s.batch;
   if (nb > 160) return UOC_OK;                      // the leader's poll loop reads at most 5 slots per lane
   const long long ngroups = s.n / 4;
   const long long chunk_ll = (ngroups + nb - 1) / nb;
   if (chunk_ll > 4096) return UOC_OK;
   const int chunk = int(chunk_ll);
-  int variant = 2;   // 0: leader + mailbox, 1: atomicMax + grid barrier, 2: all-to-all key exchange   (A/B knob)
-  if (const char* e = getenv("UOC_FPS_VARIANT")) variant = atoi(e);
+  constexpr int variant = 2;   // all-to-all key exchange (0: leader + mailbox and 1: atomicMax + grid barrier were measured slower)
   const size_t slot_need = (variant == 2) ? size_t(s.batch) * s.m * nb * nb * 8 : size_t(s.batch) * s.m * nb * 128;
   const size_t mail_need = size_t(s.batch) * s.m * s.d * 8;
   if (slot_need + mail_need > slot_bytes) return UOC_OK;
@@ -519,27 +517,20 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
   // Footprint: the pass time is dominated by the inter-CTA exchange latency, not by the streaming loop, so the default
   // is a LIGHT CTA (<= 320 threads, <= 96 KB shared memory) that leaves room on every SM for the kernels of another
   // frame running on a second stream (see pipeline.py).  UOC_FPS_HEAVY=1 selects the widest configuration instead.
-  bool heavy = true;     // measured: the light footprint costs more in the sampling kernel than the overlap returns
-  if (const char* e = getenv("UOC_FPS_HEAVY")) heavy = atoi(e) != 0;
   int gpt_t, maxt;
-  if (!heavy && chunk <= 640) { gpt_t = 2; maxt = 320; }
-  else if (chunk <= 576) { gpt_t = 1; maxt = 576; }
+  if (chunk <= 576) { gpt_t = 1; maxt = 576; }
   else if (chunk <= 1024) { gpt_t = 1; maxt = 1024; }
   else if (chunk <= 2048) { gpt_t = 2; maxt = 1024; }
   else { gpt_t = 4; maxt = 1024; }
   int threads = ((chunk + gpt_t - 1) / gpt_t + 31) / 32 * 32;
   if (threads < 64) threads = 64;
-  size_t budget = 96 * 1024;     // leaves room for one convolution CTA of another frame on the same SM
-  if (const char* e = getenv("UOC_FPS_SMEM_KB")) budget = size_t(atoi(e)) * 1024;
+  const size_t budget = 96 * 1024;
   int rg = int(budget / (16 * size_t(s.d)));
   if (rg > chunk) rg = chunk;
   const size_t smem = size_t(rg) * s.d * 16 + size_t(s.d) * 4 + 16;
   void* kern;
-#define UOC_FPS_PICK(G, MT, U) (variant == 0 ? reinterpret_cast<void*>(&fps2_kernel<G, MT, U, 0>) \
-                               : (variant == 1 ? reinterpret_cast<void*>(&fps2_kernel<G, MT, U, 1>) \
-                                               : reinterpret_cast<void*>(&fps2_kernel<G, MT, U, 2>)))
-  if (maxt == 320) kern = UOC_FPS_PICK(2, 320, 8);
-  else if (maxt == 576) kern = UOC_FPS_PICK(1, 576, 16);
+#define UOC_FPS_PICK(G, MT, U) reinterpret_cast<void*>(&fps2_kernel<G, MT, U, 2>)
+  if (maxt == 576) kern = UOC_FPS_PICK(1, 576, 16);
   else if (gpt_t == 1) kern = UOC_FPS_PICK(1, 1024, 8);
   else if (gpt_t == 2) kern = UOC_FPS_PICK(2, 1024, 8);
   else kern = UOC_FPS_PICK(4, 1024, 8);
@@ -560,10 +551,10 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
 }
 
 int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
-                        int64_t* selected_out, float* seeds_out, cudaStream_t stream, int metric) {
+                        int64_t* selected_out, float* seeds_out, cudaStream_t stream, int metric, const float* xf) {
   if (xb && metric == METRIC_COSINE) {
     bool used = false;
-    int rc = launch_select_seeds_tc(X, xb, s, w, selected_out, seeds_out, stream, &used);
+    int rc = launch_select_seeds_tc(X, xb, s, w, selected_out, seeds_out, stream, &used, xf);
     if (rc != UOC_OK || used) return rc;
     if (s.batch > 1) {
       // The resident-slice sampler keeps a whole field on chip (tensor + shared memory of all SMs); a batch of large
@@ -575,7 +566,7 @@ int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterSh
         ClusterWorkspace w1 = w;
         w1.first = w.first + b;
         rc = launch_select_seeds_tc(X + b * s.stride_b, xb + size_t(b) * s.n * s.d, s1, w1, selected_out + size_t(b) * s.m,
-                                    seeds_out + size_t(b) * s.m * s.d, stream, &used);
+                                    seeds_out + size_t(b) * s.m * s.d, stream, &used, xf ? xf + size_t(b) * s.n * s.d : nullptr);
         if (rc != UOC_OK) return rc;
         if (!used) break;
       }
@@ -592,12 +583,6 @@ int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterSh
   p.trace = nullptr;
   p.trace_cta = 0;
   p.debug_mode = 0;
-  if (const char* e = getenv("UOC_FPS_DEBUG_MODE")) p.debug_mode = (atoi(e) == 1) ? 1 : 0;   // measurement knob
-  if (const char* e = getenv("UOC_FPS_TRACE")) {
-    // debug: the first 3*m int64 of the r[] scratch (unused by the second-generation kernel) receive the time stamps
-    p.trace = reinterpret_cast<long long*>(w.r);
-    p.trace_cta = atoi(e);
-  }
   UOC_CUDA(cudaMemsetAsync(w.keys, 0, sizeof(unsigned long long) * size_t(s.batch) * s.m, stream));
   UOC_CUDA(cudaMemsetAsync(w.barrier, 0, sizeof(unsigned int), stream));
   const bool vec4 = (s.n % 4 == 0) && (s.stride_d % 4 == 0) && (s.stride_b % 4 == 0) &&
@@ -616,7 +601,6 @@ int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterSh
   UOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) return fail(UOC_ERR_CUDA, "fps kernel does not fit on an SM");
   int want = 2;
-  if (const char* e = getenv("UOC_FPS_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
   if (want > per_sm) want = per_sm;
   const int sms = sm_count();
   long long groups_total = (s.n / (vec4 ? 4 : 1)) * (long long)s.batch;
@@ -1037,7 +1021,7 @@ int launch_assign(const float* X, const __nv_bfloat16* xb, const ClusterShape& s
                   cudaStream_t stream, int metric, float* labels_f32_out, unsigned char* labels_u8_out) {
   UOC_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * size_t(s.batch) * s.m, stream));
   bool use_tc = xb != nullptr && (s.d == 64 || s.d == 128) && metric == METRIC_COSINE;
-  if (const char* e = getenv("UOC_ASSIGN_SIMT")) { if (atoi(e) != 0) use_tc = false; }
+  if (knobs().assign_simt != 0) use_tc = false;
   if (use_tc) {
     int rc = launch_assign_tc(X, xb, s, w, Z, seed_labels, hist, labels_tmp, stream);
     if (rc != UOC_OK) return rc;

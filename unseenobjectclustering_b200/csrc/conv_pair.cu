@@ -564,8 +564,8 @@ int launch_conv_pair(const ConvProblem& p, void* scratch, size_t scratch_bytes, 
   }
   prm.dbg = 0;
   prm.trace = nullptr;
-  if (const char* e = getenv("UOC_CONV_DEBUG")) prm.dbg = atoi(e);
-  const bool want_trace = getenv("UOC_CONV_TRACE") != nullptr;
+  prm.dbg = knobs().conv_debug;
+  const bool want_trace = knobs().conv_trace != 0;
   if (want_trace) {
     UOC_CUDA(cudaMalloc(&prm.trace, 16 * sizeof(long long)));
     UOC_CUDA(cudaMemsetAsync(prm.trace, 0, 16 * sizeof(long long), stream));

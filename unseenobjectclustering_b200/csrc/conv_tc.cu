@@ -11,11 +11,8 @@
 //   warp 0: TMA producer, warp 1: MMA issuer (one thread), warps 2-5: epilogue
 //   (TMEM -> registers -> +bias (+residual) -> ReLU -> bf16/fp32 -> global).
 //
-//   The path is L2->SMEM bandwidth bound at batch 1 (every M tile re-reads the whole weight slab of its
-//   N tile), so CLUSTER consecutive M tiles form a thread-block cluster that shares ONE copy of the
-//   weight tile per K block: each CTA fetches BLOCK_N/CLUSTER rows and TMA-multicasts them into all
-//   CLUSTER shared memories; a stage is recycled only when every CTA of the cluster has consumed it
-//   (tcgen05.commit multicast onto all CTAs' empty barriers).
+//   Two CTAs per SM.  This is the kernel for the SMALL layers (Cout <= 128, and everything short at batch 1); the wide /
+//   long convolutions run on the persistent CTA-pair kernel (conv_pair.cu) -- launch_conv_auto picks per layer.
 #include <cstdlib>
 #include <cstring>
 
@@ -50,13 +47,10 @@ struct ConvCfg {
   static constexpr uint32_t kTmemCols = BLOCK_N;
 };
 
-template <int BLOCK_N, int CLUSTER>
+template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads)
 conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
-  constexpr int kSliceRows = BLOCK_N / CLUSTER;
-  constexpr uint16_t kMask = uint16_t((1u << CLUSTER) - 1u);
-  static_assert(kSliceRows >= 8 && kSliceRows % 8 == 0, "weight slice must be whole 8-row swizzle atoms");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -67,11 +61,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.z;
-  // blockIdx.x = ((m_cluster * n_tiles) + n_tile) * CLUSTER + rank ; the CLUSTER CTAs of a cluster share n_tile
-  const int rank = int(blockIdx.x) % CLUSTER;
-  const int cl = int(blockIdx.x) / CLUSTER;
-  const int n_tile = cl % p.n_tiles;
-  int m_tile = (cl / p.n_tiles) * CLUSTER + rank;       // may exceed the real tile count (padding CTAs): all-zero A, no stores
+  // blockIdx.x = m_tile * n_tiles + n_tile
+  const int n_tile = int(blockIdx.x) % p.n_tiles;
+  int m_tile = int(blockIdx.x) / p.n_tiles;
   const int tx = m_tile % p.tiles_x; m_tile /= p.tiles_x;
   const int ty = m_tile % p.tiles_y;
   const int img = m_tile / p.tiles_y;
@@ -82,7 +74,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_x[g]);
     tma_prefetch_desc(&p.tmap_w[g]);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CLUSTER); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -93,7 +85,6 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (CLUSTER > 1) cluster_sync_all();     // every CTA's barriers are initialised before any remote arrive / multicast
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the
   // previous layer's tail; its activations are complete and visible after the wait.  The next layer may start its own
@@ -113,10 +104,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
         uint8_t* st = smem + s * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
         tma_load_4d(st, &p.tmap_x[g], &full[s], cb * 64, x_base + sx * p.dil, y_base + r * p.dil, img);
-        if (CLUSTER == 1)
-          tma_load_2d(st + kABytes, &p.tmap_w[g], &full[s], kb * 64, n0);
-        else
-          tma_load_2d_mc(st + kABytes + rank * kSliceRows * 128, &p.tmap_w[g], &full[s], kb * 64, n0 + rank * kSliceRows, kMask);
+        tma_load_2d(st + kABytes, &p.tmap_w[g], &full[s], kb * 64, n0);
       }
     }
   } else if (warp == 1) {
@@ -135,8 +123,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
           const uint64_t bd = make_smem_desc_sw128(b_addr + ks * 32, 16, 1024);
           umma_ss_f16(tmem_base, ad, bd, idesc, (kb | ks) ? 1u : 0u);
         }
-        if (CLUSTER == 1) umma_commit(&empty[s]);
-        else umma_commit_mc(&empty[s], kMask);
+        umma_commit(&empty[s]);
       }
       if (ok) umma_commit(acc_full);
     }
@@ -200,240 +187,28 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER > 1) cluster_sync_all();     // no CTA leaves while peers may still multicast into it / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-template <int BLOCK_N, int CLUSTER>
+template <int BLOCK_N>
 int launch(const ConvTcParams& prm, int m_tiles, int groups, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
   {
-    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&conv_tc_kernel<BLOCK_N, CLUSTER>), int(Cfg::kSmemBytes));
+    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&conv_tc_kernel<BLOCK_N>), int(Cfg::kSmemBytes));
     if (rc_attr != UOC_OK) return rc_attr;
   }
-  const int m_clusters = (m_tiles + CLUSTER - 1) / CLUSTER;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(m_clusters * prm.n_tiles * CLUSTER, 1, groups);
+  cfg.gridDim = dim3(m_tiles * prm.n_tiles, 1, groups);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute lattr[2];
-  lattr[0].id = cudaLaunchAttributeClusterDimension;
-  lattr[0].val.clusterDim.x = CLUSTER;
-  lattr[0].val.clusterDim.y = 1;
-  lattr[0].val.clusterDim.z = 1;
-  lattr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the previous layer's tail
-  lattr[1].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the previous layer's tail
+  lattr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = lattr;
   cfg.numAttrs = 1;
-  {
-    static int pdl = -1;
-    if (pdl < 0) { const char* e = getenv("UOC_CONV_PDL"); pdl = (e && atoi(e) == 0) ? 0 : 1; }
-    if (pdl) cfg.numAttrs = 2;
-  }
-  UOC_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, CLUSTER>, prm));
-  count_launch();
-  return UOC_OK;
-}
-
-template <int BLOCK_N>
-int launch_n(const ConvTcParams& prm, int cluster, int m_tiles, int groups, cudaStream_t stream) {
-  switch (cluster) {
-    case 8: if (BLOCK_N >= 64) return launch<BLOCK_N, 8>(prm, m_tiles, groups, stream);
-    case 4: return launch<BLOCK_N, 4>(prm, m_tiles, groups, stream);
-    case 2: return launch<BLOCK_N, 2>(prm, m_tiles, groups, stream);
-    default: return launch<BLOCK_N, 1>(prm, m_tiles, groups, stream);
-  }
-}
-
-
-// ----------------------------------------------------------------------------------------------
-// CTA-pair variant (cta_group::2): the kernel above is bound by the ~48 B/clk an SM can ingest from L2 (a 128x128 tile
-// needs 32 KB per 256 MMA-clk), and multicast does not help because the bytes still enter every SM.  Here two CTAs on
-// the two SMs of a TPC execute ONE tcgen05.mma of M = 256: each stages its own 128 pixels of A and only HALF of the
-// weight rows (BLOCK_N / 2); the tensor core reads the other half from the peer's shared memory.  BLOCK_N = 256:
-// 32 KB per CTA and K block for a 128 x 256 output slab -- half the bytes per MAC of the single-CTA tile.
-//   both CTAs : warp 0 = TMA producer (loads signal the LEADER's full barrier), warps 2-5 = epilogue of the own 128 rows
-//   leader    : warp 1 = MMA issuer; tcgen05.commit multicasts onto both CTAs' empty / accumulator barriers
-// ----------------------------------------------------------------------------------------------
-template <int BLOCK_N>
-struct Conv2Cfg {
-  static constexpr int kBBytes = (BLOCK_N / 2) * 128;       // this CTA's half of the weight tile
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
-  static constexpr uint32_t kTmemCols = BLOCK_N;
-};
-
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
-  using Cfg = Conv2Cfg<BLOCK_N>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + Cfg::kStages;
-  uint64_t* acc_full = bars + 2 * Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.z;
-  const int rank = int(cluster_ctarank());               // 0 = leader
-  const int pair = int(blockIdx.x) >> 1;
-  const int n_tile = pair % p.n_tiles;
-  int m_tile = (pair / p.n_tiles) * 2 + rank;            // may exceed the real tile count (padding CTA): zero A, no stores
-  const int tx = m_tile % p.tiles_x; m_tile /= p.tiles_x;
-  const int ty = m_tile % p.tiles_y;
-  const int img = m_tile / p.tiles_y;
-  const int n0 = n_tile * BLOCK_N;
-  const int cblocks = p.Cin >> 6;
-  const int KB = p.ksize * p.ksize * cblocks;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmap_x[g]);
-    tma_prefetch_desc(&p.tmap_w[g]);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(acc_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish_2sm();
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();        // both CTAs' barriers are initialised and both allocations done before any remote signal
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-  if (warp == 0) {
-    if (elect_one()) {
-      const int x_base = tx * 16 * p.stride - p.pad;
-      const int y_base = ty * 8 * p.stride - p.pad;
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % Cfg::kStages;
-        if (!mbar_wait(&empty[s], ((kb / Cfg::kStages) & 1) ^ 1u, p.err)) break;
-        const int tap = kb / cblocks, cb = kb - tap * cblocks;
-        const int r = tap / p.ksize, sx = tap - r * p.ksize;
-        uint8_t* st = smem + s * Cfg::kStageBytes;
-        if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);     // the bytes of BOTH CTAs
-        const uint32_t lbar = leader_bar_addr(&full[s]);
-        tma_load_4d_2sm(st, &p.tmap_x[g], lbar, cb * 64, x_base + sx * p.dil, y_base + r * p.dil, img);
-        tma_load_2d_2sm(st + kABytes, &p.tmap_w[g], lbar, kb * 64, n0 + rank * (BLOCK_N / 2));
-      }
-    }
-  } else if (warp == 1) {
-    if (rank == 0 && elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 0, 0);
-      bool ok = true;
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % Cfg::kStages;
-        if (!mbar_wait(&full[s], (kb / Cfg::kStages) & 1, p.err)) { ok = false; break; }
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t b_addr = a_addr + kABytes;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ad = make_smem_desc_sw128(a_addr + ks * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc_sw128(b_addr + ks * 32, 16, 1024);
-          umma_ss_f16_2sm(tmem_base, ad, bd, idesc, (kb | ks) ? 1u : 0u);
-        }
-        umma_commit_2sm(&empty[s], 3);
-      }
-      if (ok) umma_commit_2sm(acc_full, 3);
-    }
-  } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int oy = ty * 8 + (row >> 4), ox = tx * 16 + (row & 15);
-    const bool inb = (oy < p.Ho) && (ox < p.Wo) && (img < p.N);
-    const size_t pix = (size_t(img) * p.Ho + oy) * p.Wo + ox;
-    const float* bias = p.bias[g] + n0;
-    if (mbar_wait(acc_full, 0, p.err)) {
-      tc_fence_after();
-      const uint32_t ta = tmem_base + (uint32_t(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(ta + c * 32, v);
-        tmem_wait_ld();
-        if (inb) {
-          float f[32];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + e * 4));
-            f[4 * e + 0] = __uint_as_float(v[4 * e + 0]) + bv.x;
-            f[4 * e + 1] = __uint_as_float(v[4 * e + 1]) + bv.y;
-            f[4 * e + 2] = __uint_as_float(v[4 * e + 2]) + bv.z;
-            f[4 * e + 3] = __uint_as_float(v[4 * e + 3]) + bv.w;
-          }
-          if (p.residual[g]) {
-            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual[g]) +
-                                                             pix * p.Cout + n0 + c * 32);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint4 rv = __ldg(rp + e);
-              const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                f[8 * e + 2 * h + 0] += __uint_as_float(w4[h] << 16);
-                f[8 * e + 2 * h + 1] += __uint_as_float(w4[h] & 0xFFFF0000u);
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] = fmaxf(f[e], 0.f);
-          }
-          if (p.out_fp32) {
-            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.y[g]) + pix * p.Cout + n0 + c * 32);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) op[e] = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y[g]) + pix * p.Cout + n0 + c * 32);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              op[e] = make_uint4(pack_bf16x2(f[8 * e + 0], f[8 * e + 1]), pack_bf16x2(f[8 * e + 2], f[8 * e + 3]),
-                                 pack_bf16x2(f[8 * e + 4], f[8 * e + 5]), pack_bf16x2(f[8 * e + 6], f[8 * e + 7]));
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();        // the peer may still be reading this CTA's weight half / arriving on its barriers
-  if (warp == 1) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
-}
-
-template <int BLOCK_N>
-int launch_pair(const ConvTcParams& prm, int m_tiles, int groups, cudaStream_t stream) {
-  using Cfg = Conv2Cfg<BLOCK_N>;
-  {
-    const int rc_attr = ensure_dynamic_smem(reinterpret_cast<const void*>(&conv_tc2_kernel<BLOCK_N>), int(Cfg::kSmemBytes));
-    if (rc_attr != UOC_OK) return rc_attr;
-  }
-  const int m_pairs = (m_tiles + 1) / 2;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(m_pairs * prm.n_tiles * 2, 1, groups);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute lattr[2];
-  lattr[0].id = cudaLaunchAttributeClusterDimension;
-  lattr[0].val.clusterDim.x = 2;
-  lattr[0].val.clusterDim.y = 1;
-  lattr[0].val.clusterDim.z = 1;
-  lattr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  lattr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = lattr;
-  cfg.numAttrs = 2;
-  UOC_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BLOCK_N>, prm));
+  UOC_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N>, prm));
   count_launch();
   return UOC_OK;
 }
@@ -453,19 +228,7 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
   prm.Cin = p.Cin; prm.Cout = p.Cout; prm.N = p.N;
   prm.tiles_x = (prm.Wo + 15) / 16;
   prm.tiles_y = (prm.Ho + 7) / 8;
-  // Measured on B200 (profiles/r01_conv_notes.md): the kernel is bound by the ~48 B/clk/SM TMA ingest rate, which
-  // multicast does not relieve (the bytes still enter every SM), so the defaults are the plain 128-wide tiles, 2 CTAs/SM.
-  // CTA pairs (cta_group::2) for the wide layers: UOC_CONV_2SM=0 keeps the single-CTA tiles everywhere
-  int pair = 0;
-  if (const char* e = getenv("UOC_CONV_2SM")) pair = atoi(e);
-  if (p.Cout % 128 != 0) pair = 0;
-  int block_n = (p.Cout % 128 == 0) ? 128 : 64;
-  if (pair) block_n = (p.Cout % 256 == 0) ? 256 : 128;
-  if (const char* e = getenv("UOC_CONV_BLOCK_N")) { if (atoi(e) == 256 && p.Cout % 256 == 0) block_n = 256; }
-  int cluster = 1;
-  if (const char* e = getenv("UOC_CONV_CLUSTER")) cluster = atoi(e);
-  if (const char* e = getenv("UOC_CONV_MAX_BLOCK_N")) { int mx = atoi(e); while (block_n > mx && block_n > 64) block_n /= 2; }
-  if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = 1;
+  const int block_n = (p.Cout % 128 == 0) ? 128 : 64;
   prm.n_tiles = p.Cout / block_n;
   prm.ksize = p.ksize; prm.stride = p.stride; prm.dil = p.dilation; prm.pad = pad;
   prm.relu = p.relu; prm.out_fp32 = p.out_fp32;
@@ -481,7 +244,7 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
     if (rc != UOC_OK) return rc;
     const uint64_t wd[2] = {uint64_t(taps) * p.Cin, uint64_t(p.Cout)};
     const uint64_t wsb[1] = {uint64_t(taps) * p.Cin * 2};
-    const uint32_t wb[2] = {64, uint32_t(pair ? block_n / 2 : block_n / cluster)};   // each CTA of a cluster / pair fetches one slice
+    const uint32_t wb[2] = {64, uint32_t(block_n)};
     rc = make_tmap_bf16(&prm.tmap_w[g], p.g[g].w, 2, wd, wsb, wb, nullptr);
     if (rc != UOC_OK) return rc;
     prm.bias[g] = p.g[g].bias;
@@ -489,10 +252,8 @@ int launch_conv_tc(const ConvProblem& p, cudaStream_t stream) {
     prm.y[g] = p.g[g].y;
   }
   const int m_tiles = p.N * prm.tiles_y * prm.tiles_x;
-  if (pair) return (block_n == 256) ? launch_pair<256>(prm, m_tiles, p.groups, stream) : launch_pair<128>(prm, m_tiles, p.groups, stream);
-  if (block_n == 256) return launch_n<256>(prm, cluster, m_tiles, p.groups, stream);
-  if (block_n == 128) return launch_n<128>(prm, cluster, m_tiles, p.groups, stream);
-  return launch_n<64>(prm, cluster, m_tiles, p.groups, stream);
+  if (block_n == 128) return launch<128>(prm, m_tiles, p.groups, stream);
+  return launch<64>(prm, m_tiles, p.groups, stream);
 }
 
 int launch_conv_auto(const ConvProblem& p, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
@@ -500,8 +261,7 @@ int launch_conv_auto(const ConvProblem& p, void* scratch, size_t scratch_bytes, 
   // stream-K kernel wins where a pair gets a long K range of a wide tile (layers 3 / 4; every layer-3 / 4 convolution when
   // several frames share a launch); the one-tile-per-CTA kernel wins on the small layers (Cout <= 128, and everything
   // short at batch 1), where fixed per-pair costs dominate.  UOC_CONV_PAIR=0 / 1 forces one of them (parity tests).
-  int use_pair = -1;
-  if (const char* e = getenv("UOC_CONV_PAIR")) use_pair = atoi(e) != 0 ? 1 : 0;
+  int use_pair = knobs().conv_pair;
   if (!scratch || !conv_pair_supported(p)) use_pair = 0;
   if (use_pair < 0) {
     const int Ho = conv_out_dim(p.H, p.ksize, p.stride, p.dilation), Wo = conv_out_dim(p.W, p.ksize, p.stride, p.dilation);

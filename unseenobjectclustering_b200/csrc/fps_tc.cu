@@ -47,6 +47,7 @@ constexpr float kAbsMargin4 = 2e-6f;
 struct Fps4Params {
   const float* X;
   const uint4* xb;          // bf16 pixel-major copy [batch][n][d], as 16-byte units
+  const float* xf;          // fp32 pixel-major copy [batch][n][d] or null (then exact rows come from the planar field X)
   long long sb, sd, n;
   int d, m, batch;
   const long long* first;
@@ -96,7 +97,49 @@ __device__ __forceinline__ float key_r(unsigned long long key) {      // inverse
 // order, same tie-break) and becomes the next seed WITHOUT any exchange: the CTAs run such passes uncoupled.  Only when the
 // list runs dry, or its best entry drops to the bound, a real exchange rebuilds it.  Indices are bit-identical by
 // construction: every decision is taken on exact keys.
-template <int D>
+// canonical fp32 chain acc = fmaf(x_k, s_k, acc), k = 0 .. D-1 from +0 (bit-identical to fps_kernel / fps2_kernel / the
+// oracle) for ONE point.  PM: its row is 4 D contiguous bytes of the fp32 pixel-major copy -- 16 x 16-byte loads in one
+// batch, ONE L2 round trip and two cache lines per point instead of D strided planes in two dependent batches.
+template <int D, bool PM>
+__device__ __forceinline__ float exact_chain4(const float* __restrict__ xp, long long sd, const float* __restrict__ rowp,
+                                              const float* seed, bool want_sq, float& sq) {
+  float acc = 0.f;
+  sq = 0.f;
+  if (PM) {
+#pragma unroll 1
+    for (int k0 = 0; k0 < D; k0 += 64) {
+      float4 x[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x[k] = __ldg(reinterpret_cast<const float4*>(rowp + k0) + k);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        acc = fmaf(x[k].x, seed[k0 + 4 * k + 0], acc); acc = fmaf(x[k].y, seed[k0 + 4 * k + 1], acc);
+        acc = fmaf(x[k].z, seed[k0 + 4 * k + 2], acc); acc = fmaf(x[k].w, seed[k0 + 4 * k + 3], acc);
+        if (want_sq) {
+          sq = fmaf(x[k].x, x[k].x, sq); sq = fmaf(x[k].y, x[k].y, sq);
+          sq = fmaf(x[k].z, x[k].z, sq); sq = fmaf(x[k].w, x[k].w, sq);
+        }
+      }
+    }
+  } else {
+    constexpr int XB = 32;                    // loads in flight per lane (64 were measured slower, also for the sparse
+                                              // rounds of the later passes: profiles/r02_fps_speculation.txt)
+#pragma unroll 1
+    for (int k0 = 0; k0 < D; k0 += XB) {
+      float x[XB];
+#pragma unroll
+      for (int k = 0; k < XB; ++k) x[k] = __ldg(xp + (k0 + k) * sd);
+#pragma unroll
+      for (int k = 0; k < XB; ++k) {
+        acc = fmaf(x[k], seed[k0 + k], acc);
+        if (want_sq) sq = fmaf(x[k], x[k], sq);
+      }
+    }
+  }
+  return acc;
+}
+
+template <int D, bool PM>
 __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
   constexpr int KB = D / 64;                 // 64-channel blocks: one 128-byte swizzled row per point and block
   constexpr int NL = D / 8;                  // 16-byte units per point
@@ -125,6 +168,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
   const int TA = p.TA < T ? p.TA : T;
   const float* Xb = p.X + b * p.sb;
   const uint4* xbb = p.xb + size_t(b) * p.n * NL;
+  const float* xfb = PM ? p.xf + size_t(b) * p.n * D : nullptr;     // fp32 pixel-major copy of this field
   auto tile_base = [&](int t) { return ((long long)t * nb + rank) * 128; };       // first point of local tile t
   const uint32_t dcol0 = 0, acol0 = 16u * uint32_t(p.T);
 
@@ -180,7 +224,9 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
 #pragma unroll
     for (int h = 0; h < D / 64; ++h) {
       const int c0 = h * 64 + 2 * lane;
-      const float v0 = __ldg(Xb + c0 * p.sd + idx), v1 = __ldg(Xb + (c0 + 1) * p.sd + idx);
+      float v0, v1;
+      if (PM) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(xfb + idx * D + c0)); v0 = t2.x; v1 = t2.y; }
+      else { v0 = __ldg(Xb + c0 * p.sd + idx); v1 = __ldg(Xb + (c0 + 1) * p.sd + idx); }
       seedbuf[c0] = v0; seedbuf[c0 + 1] = v1;
       sq = fmaf(v0, v0, fmaf(v1, v1, sq));
       const float h0 = __bfloat162float(__float2bfloat16_rn(v0)), h1 = __bfloat162float(__float2bfloat16_rn(v1));
@@ -249,16 +295,8 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
       if (__any_sync(0xffffffffu, cand != 0ull)) {
         if (cand != 0ull) {
           const unsigned int idx = 0xFFFFFFFFu - static_cast<unsigned int>(cand & 0xFFFFFFFFull);
-          const float* xp = Xb + idx;
-          float acc = 0.f;
-#pragma unroll 1
-          for (int k0 = 0; k0 < D; k0 += 32) {
-            float x[32];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) x[k] = __ldg(xp + (k0 + k) * p.sd);
-#pragma unroll
-            for (int k = 0; k < 32; ++k) acc = fmaf(x[k], s_seed[i & 1][k0 + k], acc);
-          }
+          float sq_unused;
+          const float acc = exact_chain4<D, PM>(Xb + idx, p.sd, PM ? xfb + size_t(idx) * D : nullptr, s_seed[i & 1], false, sq_unused);
           const float dist = 0.5f * (1.0f - acc);
           const float rq = key_r(cand);
           cand = pack_key4(dist < rq ? dist : rq, idx);
@@ -306,21 +344,8 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
         if (__any_sync(0xffffffffu, need)) {
           if (need) {
             // canonical fp32 chain (bit-identical to fps_kernel / fps2_kernel / the oracle)
-            const float* xp = Xb + gp;
-            float acc = 0.f, sq = 0.f;
-            constexpr int XB = 32;                    // loads in flight per lane (64 were measured slower, also for the
-                                                      // sparse rounds of the later passes: profiles/r02_fps_speculation.txt)
-#pragma unroll 1
-            for (int k0 = 0; k0 < D; k0 += XB) {
-              float x[XB];
-#pragma unroll
-              for (int k = 0; k < XB; ++k) x[k] = __ldg(xp + (k0 + k) * p.sd);
-#pragma unroll
-              for (int k = 0; k < XB; ++k) {
-                acc = fmaf(x[k], seed[k0 + k], acc);
-                if (i == 0) sq = fmaf(x[k], x[k], sq);
-              }
-            }
+            float sq;
+            const float acc = exact_chain4<D, PM>(Xb + gp, p.sd, PM ? xfb + size_t(gp) * D : nullptr, seed, i == 0, sq);
             const float dist = 0.5f * (1.0f - acc);
             if (i == 0) {
               r[s] = dist;
@@ -442,7 +467,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
 // two-term split is needed); everything the screen cannot prove unchanged runs the canonical fp32 chain -> bit-identical
 // indices.  32-point tiles are dealt round-robin to all warps of the item, running minima live in registers.
 // ----------------------------------------------------------------------------------------------
-constexpr int kMaxSlots5 = 18;             // 32-point tiles per warp: n <= 148 * 16 * 32 * 18 = 1.36M points (4 x 640x480 on 37 CTAs each)
+constexpr int kMaxSlots5 = 12;             // 32-point tiles per warp: n <= 148 * 16 * 32 * 12 = 909k points
 
 // canonical fp32 chain over the channels of point xp (planar field, channel stride sd): out of line so that the twelve
 // unrolled slots of fps5_kernel do not each carry their own 32-register load batch
@@ -638,30 +663,29 @@ __global__ void __launch_bounds__(kThreads4, 1) fps5_kernel(Fps4Params p) {
 }  // namespace
 
 int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
-                           int64_t* selected_out, float* seeds_out, cudaStream_t stream_, bool* used) {
+                           int64_t* selected_out, float* seeds_out, cudaStream_t stream_, bool* used, const float* xf) {
   cudaStream_t stream = stream_;
   *used = false;
   if (!xb || (s.d != 64 && s.d != 128)) return UOC_OK;
   if (reinterpret_cast<uintptr_t>(xb) % 16 != 0) return UOC_OK;
-  if (const char* e = getenv("UOC_FPS_TC")) { if (atoi(e) == 0) return UOC_OK; }
+  if (knobs().fps_tc == 0) return UOC_OK;
   const int sms = sm_count();
   if (sms <= 0 || s.batch > sms) return UOC_OK;
   // a batch of fields that do not fit on chip together: the fields take turns in the resident-slice kernel
   // (launch_select_seeds); UOC_FPS_BATCH_STREAM=1 streams them side by side instead (A/B knob: slower)
   if (s.batch > 1) {
-    const char* e = getenv("UOC_FPS_BATCH_STREAM");
-    const bool side_by_side = e ? atoi(e) != 0 : false;   // measured (profiles/r02_fps_batch.txt): turns 0.72 ms / field, side by side 1.25 - 1.40
+    const bool side_by_side = knobs().fps_batch_stream != 0;   // measured (profiles/r02_fps_batch.txt): turns 0.72 ms / field, side by side 1.25 - 1.40
     const long long tiles_per_cta = ((s.n + 127) / 128 + (sms / s.batch) - 1) / (sms / s.batch);
     if (tiles_per_cta > 4 * kMaxSlots && !side_by_side) return UOC_OK;
   }
   const int nb = sms / s.batch;
   if (nb > 160) return UOC_OK;                      // the poll loop reads at most 5 keys per lane
   float rel_margin = kRelMargin4;
-  if (const char* e = getenv("UOC_FPS_RN_MARGIN")) { if (atoi(e) != 0) rel_margin = 0.00205f; }   // A/B: copy known to be round-to-nearest
+  if (knobs().fps_rn_margin != 0) rel_margin = 0.00205f;   // A/B: copy known to be round-to-nearest
   const long long total_tiles = (s.n + 127) / 128;
   const long long T = (total_tiles + nb - 1) / nb;  // tiles of the busiest CTA
   bool streaming = false;                           // the field does not fit on chip: stream the bf16 copy in every pass
-  if (const char* e = getenv("UOC_FPS_STREAM")) streaming = atoi(e) != 0;   // test knob: force the streaming variant
+  if (knobs().fps_stream != 0) streaming = true;            // test knob: force the streaming variant
   if (T > 4 * kMaxSlots) streaming = true;
   {
     const int acols0 = s.d / 2, kb0 = s.d / 64;
@@ -680,7 +704,7 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
     void* kern5 = s.d == 64 ? reinterpret_cast<void*>(&fps5_kernel<64>) : reinterpret_cast<void*>(&fps5_kernel<128>);
     const size_t smem5 = 0;
     Fps4Params p5;
-    p5.X = X; p5.xb = reinterpret_cast<const uint4*>(xb);
+    p5.X = X; p5.xb = reinterpret_cast<const uint4*>(xb); p5.xf = nullptr;
     p5.sb = s.stride_b; p5.sd = s.stride_d; p5.n = s.n; p5.d = s.d; p5.m = s.m; p5.batch = s.batch;
     p5.first = w.first;
     p5.selected_out = reinterpret_cast<long long*>(selected_out);
@@ -702,7 +726,7 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   int TA = int((512 - 16 * T) / acols);
   if (TA > T) TA = int(T);
   if (TA < 0) TA = 0;
-  if (const char* e = getenv("UOC_FPS_TC_TMEM_TILES")) { const int v = atoi(e); if (v >= 0 && v < TA) TA = v; }   // test / A-B knob
+  { const int v = knobs().fps_tmem_tiles; if (v >= 0 && v < TA) TA = v; }   // test / A-B knob
   const size_t smem = 1024 + 2 * size_t(kb) * 2048 + size_t(T - TA) * kb * 16384;
   if (smem > 225 * 1024) return UOC_OK;
   const size_t slot_need = size_t(s.batch) * s.m * nb * nb * 16;     // (first, second) key per CTA pair and pass
@@ -710,11 +734,13 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   unsigned int* err = device_error_word();
   if (!err) return fail(UOC_ERR_CUDA, "no device error word");
 
-  void* kern = s.d == 64 ? reinterpret_cast<void*>(&fps4_kernel<64>) : reinterpret_cast<void*>(&fps4_kernel<128>);
+  if (xf && reinterpret_cast<uintptr_t>(xf) % 16 != 0) xf = nullptr;
+  void* kern = s.d == 64 ? (xf ? reinterpret_cast<void*>(&fps4_kernel<64, true>) : reinterpret_cast<void*>(&fps4_kernel<64, false>))
+                         : (xf ? reinterpret_cast<void*>(&fps4_kernel<128, true>) : reinterpret_cast<void*>(&fps4_kernel<128, false>));
   UOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 
   Fps4Params p;
-  p.X = X; p.xb = reinterpret_cast<const uint4*>(xb);
+  p.X = X; p.xb = reinterpret_cast<const uint4*>(xb); p.xf = xf;
   p.sb = s.stride_b; p.sd = s.stride_d; p.n = s.n; p.d = s.d; p.m = s.m; p.batch = s.batch;
   p.first = w.first;
   p.selected_out = reinterpret_cast<long long*>(selected_out);
@@ -723,7 +749,7 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   p.slots = w.slots;
   p.nb = nb; p.T = int(T); p.TA = TA;
   p.rel_margin = rel_margin;
-  p.passlog = getenv("UOC_FPS_STATS") ? w.keys : nullptr;      // the key slots of the fp32 kernels are unused here
+  p.passlog = knobs().fps_stats ? w.keys : nullptr;      // the key slots of the fp32 kernels are unused here
   UOC_CUDA(cudaMemsetAsync(w.slots, 0, slot_need, stream));
   void* args[] = {&p};
   UOC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(nb * s.batch), dim3(kThreads4), args, smem, stream));

@@ -610,7 +610,7 @@ int launch_persistent(const CUtensorMap& tmap, const ClusterShape& s, const Clus
   long long n = s.n;
   unsigned int* err = device_error_word();
   long long* trace = nullptr;
-  const bool want_trace = getenv("UOC_LOOP_TRACE") != nullptr;     // debug: per-phase timeline on stderr (synchronises)
+  const bool want_trace = knobs().loop_trace != 0;                 // debug: per-phase timeline on stderr (synchronises)
   if (want_trace) {
     UOC_CUDA(cudaMalloc(&trace, sizeof(long long) * 20 * iters));
     UOC_CUDA(cudaMemsetAsync(trace, 0, sizeof(long long) * 20 * iters, stream));
@@ -657,11 +657,10 @@ int launch_hill_climb_tc(const __nv_bfloat16* xb, const ClusterShape& s, const C
   const long long tiles = (s.n + kTile - 1) / kTile;
   int P = w.max_partials;
   if (P > tiles) P = int(tiles);
-  // persistent single-launch variant (default): needs every CTA resident (cooperative launch) and cannot be captured
-  // into a CUDA graph; UOC_LOOP_PERSISTENT=0 or an ongoing stream capture select the launch-per-update form
+  // persistent single-launch variant: needs every CTA resident (cooperative launch) and cannot be captured into a CUDA
+  // graph; an ongoing stream capture, or more fields than SMs, select the launch-per-update form
   {
     bool persistent = true;
-    if (const char* e = getenv("UOC_LOOP_PERSISTENT")) persistent = atoi(e) != 0;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (persistent && cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) persistent = false;
     const int sms = sm_count();
@@ -669,15 +668,8 @@ int launch_hill_climb_tc(const __nv_bfloat16* xb, const ClusterShape& s, const C
     if (sms > 0 && (long long)Pp * s.batch > sms) Pp = sms / s.batch;
     if (Pp < 1 || iters < 1 || w.slot_bytes < 256 * size_t(s.batch)) persistent = false;
     if (persistent) {
-      int poly = kDefaultPoly;
-      if (const char* e = getenv("UOC_LOOP_POLY")) poly = atoi(e);
-      if (s.d == 64) {
-        if (poly >= 12) return launch_persistent<64, 12>(tmap, s, w, Z, Pp, kappa, iters, stream);
-        if (poly >= 8) return launch_persistent<64, 8>(tmap, s, w, Z, Pp, kappa, iters, stream);
-        return launch_persistent<64, 0>(tmap, s, w, Z, Pp, kappa, iters, stream);
-      }
-      if (poly >= 12) return launch_persistent<128, 12>(tmap, s, w, Z, Pp, kappa, iters, stream);
-      if (poly >= 8) return launch_persistent<128, 8>(tmap, s, w, Z, Pp, kappa, iters, stream);
+      // (POLY > 0 -- part of the exponentials on the FMA pipe -- was measured at -3 %: not instantiated)
+      if (s.d == 64) return launch_persistent<64, 0>(tmap, s, w, Z, Pp, kappa, iters, stream);
       return launch_persistent<128, 0>(tmap, s, w, Z, Pp, kappa, iters, stream);
     }
   }

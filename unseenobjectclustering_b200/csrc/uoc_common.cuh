@@ -26,6 +26,24 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (_e != cudaSuccess) return ::uoc::cuda_fail(_e, #expr, __FILE__, __LINE__); \
   } while (0)
 
+// Parity-test / measurement knobs: ONE struct, parsed once from UOC_* environment variables when the library is first
+// used and settable through uoc_set_knob (tests); the launch paths read plain ints (no getenv on any launch).
+struct Knobs {
+  int conv_pair = -1;        // UOC_CONV_PAIR        -1 per-layer choice, 0 / 1 force the one-tile-per-CTA / the CTA-pair kernel
+  int conv_debug = 0;        // UOC_CONV_DEBUG       pair kernel: 1 no A loads, 2 no B loads, 4 no MMA, 8 no stores (timing only)
+  int conv_trace = 0;        // UOC_CONV_TRACE       pair kernel: clock sums of pair 0 on stderr (synchronises)
+  int fps_tc = 1;            // UOC_FPS_TC           0: seed selection never uses the bf16 screen
+  int fps_stream = 0;        // UOC_FPS_STREAM       1: force the streaming screen (fields that do not fit on chip)
+  int fps_tmem_tiles = -1;   // UOC_FPS_TC_TMEM_TILES  cap of the tiles kept in tensor memory (both operand homes in tests)
+  int fps_batch_stream = 0;  // UOC_FPS_BATCH_STREAM 1: a batch of large fields is streamed side by side (slower: A/B)
+  int fps_rn_margin = 0;     // UOC_FPS_RN_MARGIN    1: screening margin of a round-to-nearest bf16 copy
+  int fps_stats = 0;         // UOC_FPS_STATS        exchange / speculation statistics of CTA 0 on stderr (synchronises)
+  int loop_trace = 0;        // UOC_LOOP_TRACE       per-phase timeline of the mean-shift loop on stderr (synchronises)
+  int assign_simt = 0;       // UOC_ASSIGN_SIMT      1: label pass on the fp32 kernel although a bf16 copy exists
+};
+const Knobs& knobs();
+int set_knob(const char* name, int value);   // UOC_OK, or UOC_ERR_INVALID for an unknown name
+
 void count_launch();        // every kernel launch of this library is counted (uoc_launch_count)
 #define UOC_CHECK_LAUNCH()            \
   do {                                \

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -14,6 +15,32 @@ static thread_local std::string g_last_error;
 static std::atomic<unsigned long long> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct KnobEntry { const char* name; const char* env; int Knobs::*field; };
+static const KnobEntry kKnobTable[] = {
+    {"conv_pair", "UOC_CONV_PAIR", &Knobs::conv_pair},          {"conv_debug", "UOC_CONV_DEBUG", &Knobs::conv_debug},
+    {"conv_trace", "UOC_CONV_TRACE", &Knobs::conv_trace},       {"fps_tc", "UOC_FPS_TC", &Knobs::fps_tc},
+    {"fps_stream", "UOC_FPS_STREAM", &Knobs::fps_stream},       {"fps_tmem_tiles", "UOC_FPS_TC_TMEM_TILES", &Knobs::fps_tmem_tiles},
+    {"fps_batch_stream", "UOC_FPS_BATCH_STREAM", &Knobs::fps_batch_stream},
+    {"fps_rn_margin", "UOC_FPS_RN_MARGIN", &Knobs::fps_rn_margin}, {"fps_stats", "UOC_FPS_STATS", &Knobs::fps_stats},
+    {"loop_trace", "UOC_LOOP_TRACE", &Knobs::loop_trace},       {"assign_simt", "UOC_ASSIGN_SIMT", &Knobs::assign_simt},
+};
+static Knobs& mutable_knobs() {
+  static Knobs k = [] {
+    Knobs v;
+    for (const KnobEntry& e : kKnobTable)
+      if (const char* s = getenv(e.env)) v.*(e.field) = atoi(s);
+    return v;
+  }();
+  return k;
+}
+const Knobs& knobs() { return mutable_knobs(); }
+int set_knob(const char* name, int value) {
+  if (!name) return fail(UOC_ERR_INVALID, "null knob name");
+  for (const KnobEntry& e : kKnobTable)
+    if (std::string(name) == e.name || std::string(name) == e.env) { mutable_knobs().*(e.field) = value; return UOC_OK; }
+  return fail(UOC_ERR_INVALID, std::string("unknown knob: ") + name);
+}
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -187,6 +214,8 @@ int uoc_device_info(int* sm_count_out, int* cc_major, int* cc_minor) {
   return uoc::require_sm100();
 }
 
+
+int uoc_set_knob(const char* name, int value) { return uoc::set_knob(name, value); }
 
 int uoc_check_device_error(uoc_stream_t stream) {
   int rc = uoc::require_sm100();
