@@ -233,7 +233,7 @@ def stage_split(lib, _lib, MS, dev, feats, xb, n, d, m, iters, firsts, flush, re
         first = (ctypes.c_int64 * batch)(*[int(firsts[(rep * batch + j) % len(firsts)]) for j in range(batch)])
         sb, sd = feats.stride(0), feats.stride(1)
         _lib.check(lib.uoc_select_seeds(_lib.ptr(feats), sb, sd, _lib.ptr(xb), batch, n, d, m, ctypes.cast(first, ctypes.c_void_p),
-                                        _lib.ptr(sel), _lib.ptr(Z), _lib.ptr(ws), ws.numel(), MS._side_flag(xb), sp), "select_seeds")
+                                        _lib.ptr(sel), _lib.ptr(Z), _lib.ptr(ws), ws.numel(), 0, sp), "select_seeds")
         ev[k + 1].record()
         _lib.check(lib.uoc_hill_climb(_lib.ptr(feats), sb, sd, _lib.ptr(xb), batch, n, d, m, KAPPA, iters, _lib.ptr(Z),
                                       _lib.ptr(ws), ws.numel(), 0, sp), "hill_climb")
@@ -591,7 +591,7 @@ def run_b200(args):
     # ---- config 2 on SURVEY 8(d)'s clustered field: the roofline of the loop kernel --------------------------
     fc, _ = synthetic.clustered_features(H, W, D, 6, 0.05, seed=0)
     fc = fc.to(dev)
-    xc = MS.pack_side(fc)
+    xc = MS.pack_bf16(fc)
     st_c = stage_split(lib, _lib, MS, dev, fc, xc, n, D, M, ITERS, firsts, flush, reps, 1)
     line["config2_clustered"] = {"workload": "SURVEY 8(d) config 2: 640x480x64 unit field, 6 objects + background, noise 0.05",
                                  "stages_ms": {k: round(v, 4) for k, v in st_c.items() if k != "clusters"},
@@ -601,7 +601,7 @@ def run_b200(args):
     roof["backbone_field"] = loop_roofline(st_bb["loop"], n, D, ITERS, peak, peak_src, None, kname)
     if extras:
         f4 = torch.cat([synthetic.clustered_features(H, W, D, 6, 0.05, seed=s)[0] for s in range(4)], 0).to(dev)
-        x4 = MS.pack_side(f4)
+        x4 = MS.pack_bf16(f4)
         st_4 = stage_split(lib, _lib, MS, dev, f4, x4, n, D, M, ITERS, firsts, flush, max(3, reps // 2), 4)
         roof["batched4"] = loop_roofline(st_4["loop"], n, D, ITERS, peak, peak_src, None, kname + ", 4 fields per launch", fields=4)
         roof["batched4"]["ms_per_frame"] = st_4["loop"] / 4

@@ -50,10 +50,6 @@ enum {
   UOC_FLAG_CONV_SIMT = 2,   /* backbone convolutions on the fp32 SIMT validation kernel instead of tcgen05 */
   UOC_FLAG_SYNC_CHECK = 4,  /* synchronise the stream and read back the device error word before returning */
   UOC_FLAG_FPS_FP32 = 8,    /* seed selection re-reads the fp32 field in every pass (no bf16 screening pass) */
-  UOC_FLAG_X_F32PM = 32,    /* the x_bf16 / features_bf16_out buffer is a SIDE BUFFER of two parts: the bf16 pixel-major copy
-                               [batch,n,d], then -- at the next multiple of 256 bytes -- an fp32 pixel-major copy [batch,n,d]
-                               (uoc_side_buffer_bytes).  uoc_backbone_forward writes both; the seed selection then reads a
-                               point's exact fp32 row as 256 contiguous bytes instead of d strided channel planes. */
   UOC_FLAG_EUCLIDEAN = 16   /* metric='euclidean' (cfg.TRAIN.EMBEDDING_METRIC, lib/fcn/config.py:261; the euclidean branches
                                of lib/utils/mean_shift.py:21-24,58-60,101-105,159-160,207-209): distances ||x - z||, weights
                                exp(-kappa ||x - z||^2), update divided by max(sum of weights, 1).  X need not be unit norm.
@@ -95,9 +91,6 @@ UOC_API int uoc_peek_device_error_async(uint32_t* word_host, uoc_stream_t stream
  * contiguous; the reference's `features[j].view(C,-1).t()` view, test_dataset.py:54-55).
  * Rows must be unit-norm (the network emits F.normalize'd features, lib/networks/SEG.py:114).
  * ------------------------------------------------------------------------------------------ */
-
-/* Bytes of the side buffer (bf16 pixel-major copy, + the fp32 pixel-major copy when with_f32pm) of `batch` fields. */
-UOC_API size_t uoc_side_buffer_bytes(int batch, int64_t n, int d, int with_f32pm);
 
 /* Bytes of device workspace uoc_meanshift_cluster / the stage functions need. */
 UOC_API size_t uoc_meanshift_workspace_bytes(int batch, int64_t n, int d, int m);

@@ -416,30 +416,3 @@ def test_bf16_side_channel_cannot_go_stale():
     assert MS._lookup_bf16(f) is None
     lab3, _ = MS.cluster_fields(f, 100, first_indices=[7], flags=_lib.FLAG_SYNC_CHECK)
     assert torch.equal(lab, lab3)
-
-
-@pytest.mark.parametrize("H,W,d,m", [(32, 48, 64, 100), (37, 41, 64, 100), (30, 44, 128, 100), (120, 160, 64, 100), (96, 128, 128, 60)])
-def test_select_seeds_pixel_major_rows_bit_exact(H, W, d, m):
-    """The resident-slice sampler with the fp32 PIXEL-MAJOR side copy (UOC_FLAG_X_F32PM: what the backbone writes next to the
-    features): exact rows are read as 4 d contiguous bytes; same canonical chain, so the indices equal the C oracle's and
-    the planar path's."""
-    feats, _ = _field(H, W, d, 4, 0.05, seed=H * 5 + d)
-    Xp = feats[0].reshape(d, -1).numpy()
-    first = (H * W) // 5
-    sel_o, seeds_o = C.select_seeds(Xp, m, first)
-    f = feats.to(DEV)
-    side = MS.pack_side(f, with_f32pm=True)
-    assert side._uoc_f32pm and torch.equal(MS.side_f32pm(side)[0], f[0].view(d, -1).t())
-    lab, sel, Z, sl = MS.cluster_fields(f, m, first_indices=[first], flags=_lib.FLAG_SYNC_CHECK, return_seeds=True, x_bf16=side)
-    assert np.array_equal(sel[0].cpu().numpy(), sel_o)
-    lab2, sel2, _, _ = MS.cluster_fields(f, m, first_indices=[first], flags=_lib.FLAG_SYNC_CHECK, return_seeds=True,
-                                         x_bf16=MS.pack_side(f, with_f32pm=False))
-    assert torch.equal(sel, sel2) and torch.equal(lab, lab2)
-
-
-def test_full_size_pixel_major_rows_match_reference_golden():
-    g, feats, gt = _full_case("full_cfg2")
-    f = feats.to(DEV)
-    labels, sel = MS.cluster_fields(f, 100, first_indices=[int(g["first_index"])], flags=_lib.FLAG_SYNC_CHECK, x_bf16=MS.pack_side(f))
-    assert np.array_equal(sel[0].cpu().numpy(), g["selected"])
-    assert np.array_equal(labels[0].cpu().numpy(), g["labels"].astype(np.int32))

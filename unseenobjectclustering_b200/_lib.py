@@ -14,7 +14,6 @@ FLAG_CONV_SIMT = 2
 FLAG_SYNC_CHECK = 4
 FLAG_FPS_FP32 = 8
 FLAG_EUCLIDEAN = 16
-FLAG_X_F32PM = 32
 MAX_SEEDS = 128
 
 
@@ -38,7 +37,6 @@ SIGNATURES = {
     "uoc_set_knob": (_i, [_c.c_char_p, _i]),
     "uoc_check_device_error": (_i, [_vp]),
     "uoc_peek_device_error_async": (_i, [_vp, _vp]),
-    "uoc_side_buffer_bytes": (_sz, [_i, _i64, _i, _i]),
     "uoc_meanshift_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "uoc_meanshift_cluster": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                    _i, _vp]),

@@ -374,12 +374,8 @@ int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, i
     if (rc != UOC_OK) return rc;
   }
   const int mode = (G == 1) ? HEAD_SINGLE : (bb->fusion == UOC_FUSION_CAT ? HEAD_CAT : HEAD_ADD);
-  float* f32pm = nullptr;
-  if ((flags & UOC_FLAG_X_F32PM) && features_bf16_out)       // side buffer: bf16 copy, then the fp32 pixel-major copy
-    f32pm = reinterpret_cast<float*>(static_cast<char*>(features_bf16_out) +
-                                     align_up(size_t(N) * H * W * bb->feat_dim * 2, 256));
   rc = launch_head(reinterpret_cast<const float*>(ws + wp.trunk[0]), reinterpret_cast<const float*>(ws + wp.trunk[1]), mode,
-                   bb->normalize, N, curH, curW, bb->feat_dim, H, W, features_out, features_bf16_out, st, f32pm);
+                   bb->normalize, N, curH, curW, bb->feat_dim, H, W, features_out, features_bf16_out, st);
   if (rc != UOC_OK) return rc;
   if (flags & UOC_FLAG_SYNC_CHECK) return check_device_error(st);
   return UOC_OK;

@@ -246,8 +246,7 @@ int launch_maxpool(const void* const* x, void* const* y, int groups, int N, int 
 template <int D, int MODE, int PX>
 __global__ void __launch_bounds__(256, 2) head_row_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w,
                                                        int H, int W, float sy, float sx, int normalize,
-                                                       float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_bf16,
-                                                       float* __restrict__ out_f32pm) {
+                                                       float* __restrict__ out_nchw, __nv_bfloat16* __restrict__ out_bf16) {
   constexpr int DU = (MODE == HEAD_CAT) ? D / 2 : D;     // channels of one trunk output
   constexpr int CPT = D / 4;                             // channels per thread
   constexpr int PITCH = D + 4;                           // floats per source pixel in shared memory (16-byte aligned, bank shift 4)
@@ -340,43 +339,34 @@ __global__ void __launch_bounds__(256, 2) head_row_kernel(const float* __restric
                              pack_bf16x2(f[i][8 * e + 6] * inv[i], f[i][8 * e + 7] * inv[i]));
       }
     }
-    if (out_f32pm) {                                     // fp32 pixel-major copy (exact rows for the seed selection)
-#pragma unroll
-      for (int i = 0; i < PX; ++i) {
-        float4* of = reinterpret_cast<float4*>(out_f32pm + (size_t(n) * HW + pix0 + i) * D + q * CPT);
-#pragma unroll
-        for (int e = 0; e < CPT / 4; ++e)
-          of[e] = make_float4(f[i][4 * e + 0] * inv[i], f[i][4 * e + 1] * inv[i], f[i][4 * e + 2] * inv[i], f[i][4 * e + 3] * inv[i]);
-      }
-    }
   }
 }
 
 template <int D, int MODE, int PX>
 static int launch_head_row(const float* a, const float* b, int normalize, int N, int h, int w, int H, int W, float sy, float sx,
-                           float* out_nchw, __nv_bfloat16* ob, cudaStream_t stream, float* of) {
+                           float* out_nchw, __nv_bfloat16* ob, cudaStream_t stream) {
   const size_t smem = size_t(2) * w * (D + 4) * sizeof(float);
   if (smem > 48 * 1024) {
     const int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&head_row_kernel<D, MODE, PX>), int(smem));
     if (rc != UOC_OK) return rc;
   }
-  head_row_kernel<D, MODE, PX><<<dim3(H, N), 256, smem, stream>>>(a, b, h, w, H, W, sy, sx, normalize, out_nchw, ob, of);
+  head_row_kernel<D, MODE, PX><<<dim3(H, N), 256, smem, stream>>>(a, b, h, w, H, W, sy, sx, normalize, out_nchw, ob);
   UOC_CHECK_LAUNCH();
   return UOC_OK;
 }
 
 int launch_head(const float* a, const float* b, int mode, int normalize, int N, int h, int w, int d, int H, int W,
-                float* out_nchw, void* out_bf16, cudaStream_t stream, float* out_f32pm) {
+                float* out_nchw, void* out_bf16, cudaStream_t stream) {
   const float sy = (H > 1) ? float(h - 1) / float(H - 1) : 0.f;
   const float sx = (W > 1) ? float(w - 1) / float(W - 1) : 0.f;
   __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
   const size_t smem_row = size_t(2) * w * (d + 4) * sizeof(float);
   if (W % 4 == 0 && smem_row <= 200 * 1024) {
-    if (mode == HEAD_ADD && d == 64) return launch_head_row<64, HEAD_ADD, 4>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream, out_f32pm);
-    if (mode == HEAD_ADD && d == 128) return launch_head_row<128, HEAD_ADD, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream, out_f32pm);
-    if (mode == HEAD_SINGLE && d == 64) return launch_head_row<64, HEAD_SINGLE, 4>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream, out_f32pm);
-    if (mode == HEAD_SINGLE && d == 128) return launch_head_row<128, HEAD_SINGLE, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream, out_f32pm);
-    if (mode == HEAD_CAT && d == 128) return launch_head_row<128, HEAD_CAT, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream, out_f32pm);
+    if (mode == HEAD_ADD && d == 64) return launch_head_row<64, HEAD_ADD, 4>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_ADD && d == 128) return launch_head_row<128, HEAD_ADD, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_SINGLE && d == 64) return launch_head_row<64, HEAD_SINGLE, 4>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_SINGLE && d == 128) return launch_head_row<128, HEAD_SINGLE, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_CAT && d == 128) return launch_head_row<128, HEAD_CAT, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
     return fail(UOC_ERR_UNSUPPORTED, "head supports 64 or 128 output channels (cat fusion: 2 x 64)");
   }
   return fail(UOC_ERR_UNSUPPORTED, "head: W must be a multiple of 4 and a source row pair must fit in shared memory");

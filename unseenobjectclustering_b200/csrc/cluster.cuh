@@ -40,12 +40,10 @@ int carve_cluster_workspace(void* ws, size_t ws_bytes, int batch, int64_t n, int
 // metric (all stages): METRIC_COSINE  d(x, z) = 0.5 (1 - x.z);  METRIC_EUCLIDEAN  d(x, z) = ||x - z||  (the 'euclidean'
 // branches of lib/utils/mean_shift.py:21-24,58-60,101-105,159-160,207-209; fp32 SIMT kernels only)
 enum { METRIC_COSINE = 0, METRIC_EUCLIDEAN = 1 };
-// xf (optional, with xb): fp32 pixel-major copy [batch][n][d] -- the exact rows of the resident-slice sampler come from it
 int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
-                        int64_t* selected_out, float* seeds_out, cudaStream_t stream, int metric = METRIC_COSINE,
-                        const float* xf = nullptr);
+                        int64_t* selected_out, float* seeds_out, cudaStream_t stream, int metric = METRIC_COSINE);
 int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
-                           int64_t* selected_out, float* seeds_out, cudaStream_t stream, bool* used, const float* xf = nullptr);
+                           int64_t* selected_out, float* seeds_out, cudaStream_t stream, bool* used);
 // K4  mean-shift iterations (lib/utils/mean_shift.py:79-109): fp32 SIMT validation kernel ...
 int launch_hill_climb_simt(const float* X, const ClusterShape& s, const ClusterWorkspace& w, float* Z, float kappa,
                            int iters, cudaStream_t stream, int metric = METRIC_COSINE);

@@ -25,11 +25,6 @@ static int upload_first(const int64_t* first_host, int batch, int64_t n, const C
 
 static inline int metric_of(int flags) { return (flags & UOC_FLAG_EUCLIDEAN) ? METRIC_EUCLIDEAN : METRIC_COSINE; }
 
-// the fp32 pixel-major part of a caller's side buffer (UOC_FLAG_X_F32PM), or nullptr
-static inline const float* side_f32pm(const void* x_bf16, int flags, int batch, int64_t n, int d) {
-  if (!x_bf16 || !(flags & UOC_FLAG_X_F32PM)) return nullptr;
-  return reinterpret_cast<const float*>(static_cast<const char*>(x_bf16) + align_up(size_t(batch) * n * d * 2, 256));
-}
 
 static int hill_climb(const float* X, const void* x_bf16, const ClusterShape& s, const ClusterWorkspace& w, float* Z,
                       float kappa, int iters, int flags, cudaStream_t st, const __nv_bfloat16** xb_used = nullptr) {
@@ -52,12 +47,6 @@ static int hill_climb(const float* X, const void* x_bf16, const ClusterShape& s,
 using namespace uoc;
 
 extern "C" {
-
-size_t uoc_side_buffer_bytes(int batch, int64_t n, int d, int with_f32pm) {
-  if (batch < 1 || n < 1 || d < 1) return 0;
-  const size_t bf = align_up(size_t(batch) * n * d * 2, 256);
-  return with_f32pm ? bf + size_t(batch) * n * d * 4 : bf;
-}
 
 size_t uoc_meanshift_workspace_bytes(int batch, int64_t n, int d, int m) {
   if (batch < 1 || n < 1 || d < 1 || m < 1) return 0;
@@ -93,14 +82,13 @@ int uoc_meanshift_cluster_ex(const float* X, int64_t stride_b, int64_t stride_d,
   // the bf16 pixel-major copy serves the screening pass of the seed selection, the tcgen05 loop and the label pass
   const int metric = metric_of(flags);
   const __nv_bfloat16* xb = (metric == METRIC_EUCLIDEAN) ? nullptr : static_cast<const __nv_bfloat16*>(x_bf16);
-  const float* xf = xb ? side_f32pm(x_bf16, flags, batch, n, d) : nullptr;
   if (!xb && !(flags & (UOC_FLAG_LOOP_SIMT | UOC_FLAG_EUCLIDEAN)) && (d == 64 || d == 128)) {
     rc = launch_pack_bf16(X, s, w.xb, st);
     if (rc != UOC_OK) return rc;
     xb = w.xb;
   }
   rc = launch_select_seeds(X, (flags & (UOC_FLAG_FPS_FP32 | UOC_FLAG_LOOP_SIMT)) ? nullptr : xb, s, w, selected_out, w.Z, st,
-                           metric, xf);
+                           metric);
   if (rc != UOC_OK) return rc;
   rc = hill_climb(X, xb, s, w, w.Z, kappa, iters, flags, st, &xb);
   if (rc != UOC_OK) return rc;
@@ -134,8 +122,7 @@ int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, const v
   rc = upload_first(first_seed_host, batch, n, w, st);
   if (rc != UOC_OK) return rc;
   rc = launch_select_seeds(X, (flags & (UOC_FLAG_FPS_FP32 | UOC_FLAG_EUCLIDEAN)) ? nullptr : static_cast<const __nv_bfloat16*>(x_bf16),
-                           s, w, selected_out, seeds_out, st, metric_of(flags),
-                           (flags & (UOC_FLAG_FPS_FP32 | UOC_FLAG_EUCLIDEAN)) ? nullptr : side_f32pm(x_bf16, flags, batch, n, d));
+                           s, w, selected_out, seeds_out, st, metric_of(flags));
   if (rc != UOC_OK) return rc;
   if (flags & UOC_FLAG_SYNC_CHECK) return check_device_error(st);
   return UOC_OK;

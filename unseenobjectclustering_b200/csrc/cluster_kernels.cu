@@ -551,10 +551,10 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
 }
 
 int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
-                        int64_t* selected_out, float* seeds_out, cudaStream_t stream, int metric, const float* xf) {
+                        int64_t* selected_out, float* seeds_out, cudaStream_t stream, int metric) {
   if (xb && metric == METRIC_COSINE) {
     bool used = false;
-    int rc = launch_select_seeds_tc(X, xb, s, w, selected_out, seeds_out, stream, &used, xf);
+    int rc = launch_select_seeds_tc(X, xb, s, w, selected_out, seeds_out, stream, &used);
     if (rc != UOC_OK || used) return rc;
     if (s.batch > 1) {
       // The resident-slice sampler keeps a whole field on chip (tensor + shared memory of all SMs); a batch of large
@@ -566,7 +566,7 @@ int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterSh
         ClusterWorkspace w1 = w;
         w1.first = w.first + b;
         rc = launch_select_seeds_tc(X + b * s.stride_b, xb + size_t(b) * s.n * s.d, s1, w1, selected_out + size_t(b) * s.m,
-                                    seeds_out + size_t(b) * s.m * s.d, stream, &used, xf ? xf + size_t(b) * s.n * s.d : nullptr);
+                                    seeds_out + size_t(b) * s.m * s.d, stream, &used);
         if (rc != UOC_OK) return rc;
         if (!used) break;
       }

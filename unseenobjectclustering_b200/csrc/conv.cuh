@@ -66,7 +66,7 @@ int launch_maxpool(const void* const* x, void* const* y, int groups, int N, int 
 //   mode HEAD_CAT: f = cat(a, b) over channels (d = 2 du; SEG.py:110)
 enum { HEAD_ADD = 0, HEAD_SINGLE = 1, HEAD_CAT = 2 };
 int launch_head(const float* a, const float* b, int mode, int normalize, int N, int h, int w, int d, int H, int W,
-                float* out_nchw, void* out_bf16, cudaStream_t stream, float* out_f32pm = nullptr);
+                float* out_nchw, void* out_bf16, cudaStream_t stream);
 // [N][h][w][d] fp32 NHWC -> [N][d][h][w] fp32 NCHW (debug / test hook)
 int launch_nhwc_to_nchw(const float* in, int N, int h, int w, int d, float* out, cudaStream_t stream);
 

@@ -47,7 +47,6 @@ constexpr float kAbsMargin4 = 2e-6f;
 struct Fps4Params {
   const float* X;
   const uint4* xb;          // bf16 pixel-major copy [batch][n][d], as 16-byte units
-  const float* xf;          // fp32 pixel-major copy [batch][n][d] or null (then exact rows come from the planar field X)
   long long sb, sd, n;
   int d, m, batch;
   const long long* first;
@@ -98,48 +97,30 @@ __device__ __forceinline__ float key_r(unsigned long long key) {      // inverse
 // list runs dry, or its best entry drops to the bound, a real exchange rebuilds it.  Indices are bit-identical by
 // construction: every decision is taken on exact keys.
 // canonical fp32 chain acc = fmaf(x_k, s_k, acc), k = 0 .. D-1 from +0 (bit-identical to fps_kernel / fps2_kernel / the
-// oracle) for ONE point.  PM: its row is 4 D contiguous bytes of the fp32 pixel-major copy -- 16 x 16-byte loads in one
-// batch, ONE L2 round trip and two cache lines per point instead of D strided planes in two dependent batches.
-template <int D, bool PM>
-__device__ __forceinline__ float exact_chain4(const float* __restrict__ xp, long long sd, const float* __restrict__ rowp,
-                                              const float* seed, bool want_sq, float& sq) {
+// oracle) for ONE point of the planar field.  (An fp32 pixel-major copy for these rows was built and measured: faster on
+// clustered fields, slower on the bench frame, and 21 us per frame in the head kernel: profiles/r02_fps_pixel_major.txt.)
+template <int D>
+__device__ __forceinline__ float exact_chain4(const float* __restrict__ xp, long long sd, const float* seed, bool want_sq,
+                                              float& sq) {
   float acc = 0.f;
   sq = 0.f;
-  if (PM) {
-#pragma unroll 1
-    for (int k0 = 0; k0 < D; k0 += 64) {
-      float4 x[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) x[k] = __ldg(reinterpret_cast<const float4*>(rowp + k0) + k);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        acc = fmaf(x[k].x, seed[k0 + 4 * k + 0], acc); acc = fmaf(x[k].y, seed[k0 + 4 * k + 1], acc);
-        acc = fmaf(x[k].z, seed[k0 + 4 * k + 2], acc); acc = fmaf(x[k].w, seed[k0 + 4 * k + 3], acc);
-        if (want_sq) {
-          sq = fmaf(x[k].x, x[k].x, sq); sq = fmaf(x[k].y, x[k].y, sq);
-          sq = fmaf(x[k].z, x[k].z, sq); sq = fmaf(x[k].w, x[k].w, sq);
-        }
-      }
-    }
-  } else {
-    constexpr int XB = 32;                    // loads in flight per lane (64 were measured slower, also for the sparse
+  constexpr int XB = 32;                      // loads in flight per lane (64 were measured slower, also for the sparse
                                               // rounds of the later passes: profiles/r02_fps_speculation.txt)
 #pragma unroll 1
-    for (int k0 = 0; k0 < D; k0 += XB) {
-      float x[XB];
+  for (int k0 = 0; k0 < D; k0 += XB) {
+    float x[XB];
 #pragma unroll
-      for (int k = 0; k < XB; ++k) x[k] = __ldg(xp + (k0 + k) * sd);
+    for (int k = 0; k < XB; ++k) x[k] = __ldg(xp + (k0 + k) * sd);
 #pragma unroll
-      for (int k = 0; k < XB; ++k) {
-        acc = fmaf(x[k], seed[k0 + k], acc);
-        if (want_sq) sq = fmaf(x[k], x[k], sq);
-      }
+    for (int k = 0; k < XB; ++k) {
+      acc = fmaf(x[k], seed[k0 + k], acc);
+      if (want_sq) sq = fmaf(x[k], x[k], sq);
     }
   }
   return acc;
 }
 
-template <int D, bool PM>
+template <int D>
 __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
   constexpr int KB = D / 64;                 // 64-channel blocks: one 128-byte swizzled row per point and block
   constexpr int NL = D / 8;                  // 16-byte units per point
@@ -168,7 +149,6 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
   const int TA = p.TA < T ? p.TA : T;
   const float* Xb = p.X + b * p.sb;
   const uint4* xbb = p.xb + size_t(b) * p.n * NL;
-  const float* xfb = PM ? p.xf + size_t(b) * p.n * D : nullptr;     // fp32 pixel-major copy of this field
   auto tile_base = [&](int t) { return ((long long)t * nb + rank) * 128; };       // first point of local tile t
   const uint32_t dcol0 = 0, acol0 = 16u * uint32_t(p.T);
 
@@ -224,9 +204,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
 #pragma unroll
     for (int h = 0; h < D / 64; ++h) {
       const int c0 = h * 64 + 2 * lane;
-      float v0, v1;
-      if (PM) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(xfb + idx * D + c0)); v0 = t2.x; v1 = t2.y; }
-      else { v0 = __ldg(Xb + c0 * p.sd + idx); v1 = __ldg(Xb + (c0 + 1) * p.sd + idx); }
+      const float v0 = __ldg(Xb + c0 * p.sd + idx), v1 = __ldg(Xb + (c0 + 1) * p.sd + idx);
       seedbuf[c0] = v0; seedbuf[c0 + 1] = v1;
       sq = fmaf(v0, v0, fmaf(v1, v1, sq));
       const float h0 = __bfloat162float(__float2bfloat16_rn(v0)), h1 = __bfloat162float(__float2bfloat16_rn(v1));
@@ -296,7 +274,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
         if (cand != 0ull) {
           const unsigned int idx = 0xFFFFFFFFu - static_cast<unsigned int>(cand & 0xFFFFFFFFull);
           float sq_unused;
-          const float acc = exact_chain4<D, PM>(Xb + idx, p.sd, PM ? xfb + size_t(idx) * D : nullptr, s_seed[i & 1], false, sq_unused);
+          const float acc = exact_chain4<D>(Xb + idx, p.sd, s_seed[i & 1], false, sq_unused);
           const float dist = 0.5f * (1.0f - acc);
           const float rq = key_r(cand);
           cand = pack_key4(dist < rq ? dist : rq, idx);
@@ -343,9 +321,8 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
         }
         if (__any_sync(0xffffffffu, need)) {
           if (need) {
-            // canonical fp32 chain (bit-identical to fps_kernel / fps2_kernel / the oracle)
             float sq;
-            const float acc = exact_chain4<D, PM>(Xb + gp, p.sd, PM ? xfb + size_t(gp) * D : nullptr, seed, i == 0, sq);
+            const float acc = exact_chain4<D>(Xb + gp, p.sd, seed, i == 0, sq);
             const float dist = 0.5f * (1.0f - acc);
             if (i == 0) {
               r[s] = dist;
@@ -663,7 +640,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps5_kernel(Fps4Params p) {
 }  // namespace
 
 int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
-                           int64_t* selected_out, float* seeds_out, cudaStream_t stream_, bool* used, const float* xf) {
+                           int64_t* selected_out, float* seeds_out, cudaStream_t stream_, bool* used) {
   cudaStream_t stream = stream_;
   *used = false;
   if (!xb || (s.d != 64 && s.d != 128)) return UOC_OK;
@@ -704,7 +681,7 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
     void* kern5 = s.d == 64 ? reinterpret_cast<void*>(&fps5_kernel<64>) : reinterpret_cast<void*>(&fps5_kernel<128>);
     const size_t smem5 = 0;
     Fps4Params p5;
-    p5.X = X; p5.xb = reinterpret_cast<const uint4*>(xb); p5.xf = nullptr;
+    p5.X = X; p5.xb = reinterpret_cast<const uint4*>(xb);
     p5.sb = s.stride_b; p5.sd = s.stride_d; p5.n = s.n; p5.d = s.d; p5.m = s.m; p5.batch = s.batch;
     p5.first = w.first;
     p5.selected_out = reinterpret_cast<long long*>(selected_out);
@@ -734,13 +711,11 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   unsigned int* err = device_error_word();
   if (!err) return fail(UOC_ERR_CUDA, "no device error word");
 
-  if (xf && reinterpret_cast<uintptr_t>(xf) % 16 != 0) xf = nullptr;
-  void* kern = s.d == 64 ? (xf ? reinterpret_cast<void*>(&fps4_kernel<64, true>) : reinterpret_cast<void*>(&fps4_kernel<64, false>))
-                         : (xf ? reinterpret_cast<void*>(&fps4_kernel<128, true>) : reinterpret_cast<void*>(&fps4_kernel<128, false>));
+  void* kern = s.d == 64 ? reinterpret_cast<void*>(&fps4_kernel<64>) : reinterpret_cast<void*>(&fps4_kernel<128>);
   UOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 
   Fps4Params p;
-  p.X = X; p.xb = reinterpret_cast<const uint4*>(xb); p.xf = xf;
+  p.X = X; p.xb = reinterpret_cast<const uint4*>(xb);
   p.sb = s.stride_b; p.sd = s.stride_d; p.n = s.n; p.d = s.d; p.m = s.m; p.batch = s.batch;
   p.first = w.first;
   p.selected_out = reinterpret_cast<long long*>(selected_out);

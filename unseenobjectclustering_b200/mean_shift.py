@@ -32,46 +32,6 @@ def _workspace(device, nbytes):
     return ws
 
 
-def new_side_buffer(N, n, C, device, with_f32pm=True):
-    """Side buffer of N fields (include/uoc.h, UOC_FLAG_X_F32PM): returns its bf16 part as a [N, n, C] bfloat16 tensor that
-    views the whole allocation; `._uoc_f32pm` says whether the fp32 pixel-major copy follows (at the next multiple of 256
-    bytes), `.uoc_f32pm()` returns that part as a [N, n, C] float32 view."""
-    lib = _lib.load()
-    nbytes = int(lib.uoc_side_buffer_bytes(int(N), int(n), int(C), 1 if with_f32pm else 0))
-    raw = torch.empty(nbytes, dtype=torch.uint8, device=device)
-    xb = raw[:N * n * C * 2].view(torch.bfloat16).view(N, n, C)
-    xb._uoc_f32pm = bool(with_f32pm)
-    xb._uoc_raw = raw
-    return xb
-
-
-def side_f32pm(xb):
-    """The fp32 pixel-major part of a side buffer made by new_side_buffer(with_f32pm=True)."""
-    N, n, C = xb.shape
-    off = (N * n * C * 2 + 255) // 256 * 256
-    return xb._uoc_raw[off:off + N * n * C * 4].view(torch.float32).view(N, n, C)
-
-
-def _side_flag(xb):
-    return _lib.FLAG_X_F32PM if (xb is not None and getattr(xb, "_uoc_f32pm", False)) else 0
-
-
-def pack_side(features, with_f32pm=True):
-    """Side buffer of a field that did not come from this package's backbone: bf16 copy by uoc_pack_bf16, fp32
-    pixel-major copy by a transposing copy."""
-    N, C, H, W = features.shape
-    features = features.contiguous()
-    lib = _lib.load()
-    dev = features.device
-    xb = new_side_buffer(N, H * W, C, dev, with_f32pm)
-    with torch.cuda.device(dev):
-        _lib.check(lib.uoc_pack_bf16(_lib.ptr(features), C * H * W, H * W, N, H * W, C, _lib.ptr(xb), _lib.stream_ptr(dev)),
-                   "uoc_pack_bf16")
-        if with_f32pm:
-            side_f32pm(xb).copy_(features.view(N, C, H * W).permute(0, 2, 1))
-    return xb
-
-
 def register_bf16_copy(features, xb):
     """Called by the backbone module: remember the bf16 [N, H*W, C] copy written next to `features`.
 
@@ -149,7 +109,6 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
         if xb is not None and (xb.dtype != torch.bfloat16 or tuple(xb.shape) != (N, n, C) or not xb.is_contiguous()
                                or xb.device != features.device):
             raise _lib.UocError("x_bf16 must be a contiguous bfloat16 [N, H*W, C] tensor on the features' device")
-        flags |= _side_flag(xb)
     if not (features.stride(3) == 1 and features.stride(2) == W and features.stride(1) == n):
         features = features.contiguous()
     lib = _lib.load()
@@ -179,7 +138,7 @@ def cluster_fields(features, num_seeds=100, kappa=20.0, max_iters=10, first_indi
             sb, sd_ = features.stride(0), features.stride(1)
             _lib.check(lib.uoc_select_seeds(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, fptr,
                                             _lib.ptr(selected), _lib.ptr(seeds), _lib.ptr(ws), ws.numel(),
-                                            int(flags) & (_lib.FLAG_FPS_FP32 | _lib.FLAG_EUCLIDEAN | _lib.FLAG_X_F32PM), sp),
+                                            int(flags) & (_lib.FLAG_FPS_FP32 | _lib.FLAG_EUCLIDEAN), sp),
                        "uoc_select_seeds")
             on_sampling_done()
             _lib.check(lib.uoc_hill_climb(_lib.ptr(features), sb, sd_, _lib.ptr(xb), N, n, C, num_seeds, float(kappa),

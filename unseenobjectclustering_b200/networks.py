@@ -160,7 +160,6 @@ class SEGNET_B200(nn.Module):
         self._ws = None
         self._ws_by_stream = {}
         self.keep_bf16 = True
-        self.keep_f32pm = True
         self.eval()
 
     # reference-format state_dict -------------------------------------------------------------
@@ -266,16 +265,9 @@ class SEGNET_B200(nn.Module):
             off = (-self._ws.data_ptr()) % 1024
             ws_ptr = ctypes.c_void_p(self._ws.data_ptr() + off)
             out = torch.empty((N, self.feature_dim, H, W), dtype=torch.float32, device=dev)
-            xb, flags = None, self.flags
-            if self.keep_bf16:
-                # side buffer written by the head kernel next to the features: the bf16 pixel-major copy (tcgen05 loop,
-                # label pass, screening of the seed selection) followed by an fp32 pixel-major copy (exact rows of the
-                # seed selection: 256 contiguous bytes per point instead of 64 strided planes)
-                xb = _ms.new_side_buffer(N, H * W, self.feature_dim, dev, with_f32pm=self.keep_f32pm)
-                if self.keep_f32pm:
-                    flags |= _lib.FLAG_X_F32PM
+            xb = torch.empty((N, H * W, self.feature_dim), dtype=torch.bfloat16, device=dev) if self.keep_bf16 else None
             st = lib.uoc_backbone_forward(handle, _lib.ptr(img), _lib.ptr(depth), N, H, W, _lib.ptr(out),
-                                          _lib.ptr(xb), ws_ptr, self._ws.numel() - off, flags,
+                                          _lib.ptr(xb), ws_ptr, self._ws.numel() - off, self.flags,
                                           _lib.stream_ptr(dev))
             _lib.check(st, "uoc_backbone_forward")
         return out, xb

@@ -140,8 +140,8 @@ class FramePipeline(object):
         f = slot.feats
         _lib.check(lib.uoc_select_seeds(_lib.ptr(f), f.stride(0), f.stride(1), _lib.ptr(slot.xb), B, n, C, m,
                                         ctypes.cast(first, ctypes.c_void_p),
-                                        _lib.ptr(slot.sel), _lib.ptr(slot.Z), _lib.ptr(slot.ws_fps), slot.ws_fps.numel(),
-                                        _ms._side_flag(slot.xb), _lib.stream_ptr(self.dev)), "uoc_select_seeds")
+                                        _lib.ptr(slot.sel), _lib.ptr(slot.Z), _lib.ptr(slot.ws_fps), slot.ws_fps.numel(), 0,
+                                        _lib.stream_ptr(self.dev)), "uoc_select_seeds")
         # the mean-shift loop is ONE persistent cooperative kernel (all updates): eager as well
         _lib.check(lib.uoc_hill_climb(_lib.ptr(f), f.stride(0), f.stride(1), _lib.ptr(slot.xb), B, n, C, m, self.kappa,
                                       self.max_iters, _lib.ptr(slot.Z), _lib.ptr(slot.ws_b), slot.ws_b.numel(), 0,
