@@ -34,6 +34,8 @@ CONV_CASES = [
     (128, 128, 3, 1, 1, 60, 80, 8),    # layer2, 4 frames x 2 branches: several stream-K segments per CTA pair
     (256, 512, 1, 1, 1, 60, 80, 8),    # 1x1 down-sample, 320 whole tiles dealt over 74 pairs (accumulator ring wraps)
     (256, 256, 3, 1, 2, 60, 80, 2),    # layer3 at 640x480: 38 tiles on 74 pairs, every tile split in two
+    (128, 128, 3, 1, 1, 28, 28, 3),    # layer2 on 224x224 crops (weights-resident kernel: ragged 16 x 8 tiles, 2 K blocks)
+    (64, 64, 3, 1, 1, 120, 160, 8),    # layer1, 4 frames: 9 tiles per CTA of the weights-resident kernel (accumulator ring wraps)
 ]
 
 
@@ -49,13 +51,22 @@ def _conv_call(x, w, bias, res, N, H, W, Cin, Cout, k, stride, dil, relu, flags)
     return y
 
 
-@pytest.mark.parametrize("variant", ["pair", "tc", "simt"])
+def _wres_case(case):
+    Cin, Cout, k, stride, dil = case[:5]
+    return k == 3 and stride == 1 and dil == 1 and Cin in (64, 128)
+
+
+@pytest.mark.parametrize("variant", ["pair", "tc", "wres", "simt"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
 def test_conv_matches_torch(case, variant, knob):
-    """The persistent CTA-pair stream-K kernel (conv_pair.cu, default), the first-generation one-tile-per-CTA kernel
-    (knob conv_pair = 0) and the SIMT validation kernel, against torch's convolution on the same bf16 operands."""
+    """The persistent CTA-pair stream-K kernel (conv_pair.cu), the one-tile-per-CTA kernel (conv_tc.cu), the
+    weights-resident halo kernel of layers 1 / 2 (conv_wres.cu; only the shapes it takes) and the SIMT validation kernel,
+    against torch's convolution on the same bf16 operands."""
     Cin, Cout, k, stride, dil, H, W, N = case
+    if variant == "wres" and not _wres_case(case):
+        pytest.skip("not a shape of the weights-resident kernel")
     flags = _lib.FLAG_CONV_SIMT if variant == "simt" else 0
+    knob("conv_wres", 1 if variant == "wres" else 0)
     knob("conv_pair", 0 if variant == "tc" else 1)
     g = torch.Generator().manual_seed(Cin + Cout + k + H)
     x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(torch.bfloat16)

@@ -16,7 +16,8 @@ LAYERS = [("l1 3x3 64", 120, 160, 64, 64, 3, 1, 1, 6), ("l2 3x3 s2 64>128", 120,
           ("l3 3x3 256 d2", 60, 80, 256, 256, 3, 1, 2, 11), ("l4 3x3 256>512 d4", 60, 80, 256, 512, 3, 1, 4, 1),
           ("l4 1x1 down", 60, 80, 256, 512, 1, 1, 1, 1), ("l4 3x3 512 d4", 60, 80, 512, 512, 3, 1, 4, 5),
           ("fc 1x1 512>64", 60, 80, 512, 64, 1, 1, 1, 1)]
-VARIANTS = [("auto", {}), ("pair", {"conv_pair": "1"}), ("tc", {"conv_pair": "0"})]
+VARIANTS = [("auto", {}), ("pair", {"conv_pair": "1", "conv_wres": "0"}), ("tc", {"conv_pair": "0", "conv_wres": "0"})]
+CHAIN = int(os.environ.get("UOC_CONV_LAYERS_CHAIN", "1"))   # > 1: that many launches back to back per measurement (warm L2, no launch gaps)
 if os.environ.get("UOC_CONV_LAYERS_VARIANTS"):
     VARIANTS = [(v, dict(kv.split("=") for kv in v.split(",") if "=" in kv)) for v in os.environ["UOC_CONV_LAYERS_VARIANTS"].split(";")]
 if os.environ.get("UOC_CONV_LAYERS_ONLY"):
@@ -35,7 +36,7 @@ for N in ([int(v) for v in sys.argv[1:]] or [2, 8]):
         flops = 2.0 * N * Ho * Wo * Cout * Cin * k * k
         row = {}
         for vname, env in VARIANTS:
-            for kk in ("conv_pair", "conv_debug", "conv_trace"):        # library knobs (uoc_set_knob), back to their defaults
+            for kk in ("conv_pair", "conv_wres", "conv_debug", "conv_trace"):        # library knobs (uoc_set_knob), back to their defaults
                 _lib.set_knob(kk, _lib.KNOB_DEFAULTS[kk])
             for kk, vv in env.items():
                 _lib.set_knob(kk, int(vv))
@@ -44,12 +45,13 @@ for N in ([int(v) for v in sys.argv[1:]] or [2, 8]):
                 flush.zero_()
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
-                _lib.check(lib.uoc_conv2d_bf16(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), None, _lib.ptr(y), N, H, W, Cin, Cout, k, stride,
-                                               dil, 1, 0, _lib.stream_ptr(dev)), "conv")
+                for _ in range(CHAIN):
+                    _lib.check(lib.uoc_conv2d_bf16(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), None, _lib.ptr(y), N, H, W, Cin, Cout, k, stride,
+                                                   dil, 1, 0, _lib.stream_ptr(dev)), "conv")
                 e.record()
                 torch.cuda.synchronize()
                 if rep >= 2:
-                    ts.append(s.elapsed_time(e) * 1e3)
+                    ts.append(s.elapsed_time(e) * 1e3 / CHAIN)
             us = sorted(ts)[len(ts) // 2]
             row[vname] = {"us": round(us, 2), "TFLOPs": round(flops / us / 1e6, 1)}
         out["N%d %s" % (N, name)] = dict(row, count=cnt, gflop=round(flops / 1e9, 2))

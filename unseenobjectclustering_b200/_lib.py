@@ -115,7 +115,7 @@ def raise_on_device_error(device=None):
         check(load().uoc_check_device_error(stream_ptr(device)), "device error check")
 
 
-KNOB_DEFAULTS = {"conv_pair": -1, "conv_debug": 0, "conv_trace": 0, "fps_tc": 1, "fps_stream": 0, "fps_tmem_tiles": -1,
+KNOB_DEFAULTS = {"conv_pair": -1, "conv_wres": -1, "conv_debug": 0, "conv_trace": 0, "fps_tc": 1, "fps_stream": 0, "fps_tmem_tiles": -1,
                  "fps_batch_stream": 0, "fps_rn_margin": 0, "fps_stats": 0, "loop_trace": 0, "assign_simt": 0}
 
 

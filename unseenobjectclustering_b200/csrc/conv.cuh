@@ -42,6 +42,10 @@ constexpr size_t kConvCounterBytes = 64 * 1024;
 size_t conv_pair_scratch_bytes();
 bool conv_pair_supported(const ConvProblem& p);
 int launch_conv_pair(const ConvProblem& p, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+// third kernel (conv_wres.cu): 3x3 / stride 1 / dilation 1 with Cin = 64 or 128 (layers 1 and 2): weights resident in shared
+// memory, one halo fetch per tile, persistent
+bool conv_wres_supported(const ConvProblem& p);
+int launch_conv_wres(const ConvProblem& p, cudaStream_t stream);
 // the default path: the pair kernel (scratch given and UOC_CONV_PAIR != 0), else the first generation
 int launch_conv_auto(const ConvProblem& p, void* scratch, size_t scratch_bytes, cudaStream_t stream);
 // fp32-accumulate SIMT validation convolution, same interface and data types

@@ -261,6 +261,8 @@ int launch_conv_auto(const ConvProblem& p, void* scratch, size_t scratch_bytes, 
   // stream-K kernel wins where a pair gets a long K range of a wide tile (layers 3 / 4; every layer-3 / 4 convolution when
   // several frames share a launch); the one-tile-per-CTA kernel wins on the small layers (Cout <= 128, and everything
   // short at batch 1), where fixed per-pair costs dominate.  UOC_CONV_PAIR=0 / 1 forces one of them (parity tests).
+  // layers 1 / 2 (3x3, stride 1, no dilation, Cin <= 128): the weights-resident halo kernel (UOC_CONV_WRES=0 disables it)
+  if (knobs().conv_wres != 0 && conv_wres_supported(p)) return launch_conv_wres(p, stream);
   int use_pair = knobs().conv_pair;
   if (!scratch || !conv_pair_supported(p)) use_pair = 0;
   if (use_pair < 0) {

@@ -30,6 +30,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // used and settable through uoc_set_knob (tests); the launch paths read plain ints (no getenv on any launch).
 struct Knobs {
   int conv_pair = -1;        // UOC_CONV_PAIR        -1 per-layer choice, 0 / 1 force the one-tile-per-CTA / the CTA-pair kernel
+  int conv_wres = -1;        // UOC_CONV_WRES        0 disables the weights-resident kernel of layers 1 / 2 (parity tests of the other two)
   int conv_debug = 0;        // UOC_CONV_DEBUG       pair kernel: 1 no A loads, 2 no B loads, 4 no MMA, 8 no stores (timing only)
   int conv_trace = 0;        // UOC_CONV_TRACE       pair kernel: clock sums of pair 0 on stderr (synchronises)
   int fps_tc = 1;            // UOC_FPS_TC           0: seed selection never uses the bf16 screen

@@ -18,7 +18,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct KnobEntry { const char* name; const char* env; int Knobs::*field; };
 static const KnobEntry kKnobTable[] = {
-    {"conv_pair", "UOC_CONV_PAIR", &Knobs::conv_pair},          {"conv_debug", "UOC_CONV_DEBUG", &Knobs::conv_debug},
+    {"conv_pair", "UOC_CONV_PAIR", &Knobs::conv_pair},          {"conv_wres", "UOC_CONV_WRES", &Knobs::conv_wres},
+    {"conv_debug", "UOC_CONV_DEBUG", &Knobs::conv_debug},
     {"conv_trace", "UOC_CONV_TRACE", &Knobs::conv_trace},       {"fps_tc", "UOC_FPS_TC", &Knobs::fps_tc},
     {"fps_stream", "UOC_FPS_STREAM", &Knobs::fps_stream},       {"fps_tmem_tiles", "UOC_FPS_TC_TMEM_TILES", &Knobs::fps_tmem_tiles},
     {"fps_batch_stream", "UOC_FPS_BATCH_STREAM", &Knobs::fps_batch_stream},
