@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
   // warp 1 (idle while warp 0 issues the MMAs of the screen), lane j: entry j of the candidate list (exact current key,
   // 0 = empty); `bound` is warp-uniform
   unsigned long long cand = 0ull, bound = ~0ull;
+  int nex = 0;                                // exchanges so far (the same in every CTA: all take the same decisions)
 
   // one warp: fetch seed `idx` = seed number i (fp32), its norm, and the B operand {bf16(s), bf16(s - bf16(s))} of the
   // screen into the buffers of parity i & 1
@@ -366,14 +367,21 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
           merge_top2(k1, k2, o1, o2);
         }
         // all-to-all: this CTA's pair goes into column `rank` of EVERY CTA's private row; then poll the own row
-        unsigned long long* mat = p.slots + (size_t(b) * p.m + (i + 1)) * nb * nb * 2;
+        // The key matrices form a RING of two (exchange number parity), not one per pass: a CTA can be at most one
+        // exchange ahead of another (it needs the other's keys of exchange c + 1 to get past it, and those are published
+        // after the other has read exchange c), so exchange c + 2 may reuse the matrix of exchange c.  Arrival is a TAG:
+        // bits 20..31 of a key's low word are all ones (index < 2^20), they carry the pass number on the wire.  700 KB
+        // per field instead of 35 MB to clear per launch and to push through L2 next to the field.
+        unsigned long long* mat = p.slots + (size_t(b) * 2 + (nex & 1)) * nb * nb * 2;
+        const unsigned long long tag = static_cast<unsigned long long>((i + 1) & 0xFFF) << 20;
+        const unsigned long long w1 = (k1 & ~0xFFF00000ull) | tag, w2 = (k2 & ~0xFFF00000ull) | tag;
 #pragma unroll
         for (int c5 = 0; c5 < 5; ++c5) {
           const int c = lane + 32 * c5;
           if (c < nb) {
             unsigned long long* dst = mat + (size_t(c) * nb + rank) * 2;
-            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst), "l"(k1) : "memory");
-            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(k2) : "memory");
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst), "l"(w1) : "memory");
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(w2) : "memory");
           }
         }
         const unsigned long long* row = mat + size_t(rank) * nb * 2;
@@ -384,15 +392,17 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
 #pragma unroll
           for (int c5 = 0; c5 < 5; ++c5) {
             const int c = lane + 32 * c5;
-            kv1[c5] = 1ull; kv2[c5] = 1ull;
+            kv1[c5] = tag; kv2[c5] = tag;
             if (c < nb) {
               asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(kv1[c5]) : "l"(row + 2 * c));
               asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(kv2[c5]) : "l"(row + 2 * c + 1));
             }
-            all = all && (kv1[c5] != 0ull) && (kv2[c5] != 0ull);
+            all = all && ((kv1[c5] & 0xFFF00000ull) == tag) && ((kv2[c5] & 0xFFF00000ull) == tag);
           }
           done = __all_sync(0xffffffffu, all);
         }
+#pragma unroll
+        for (int c5 = 0; c5 < 5; ++c5) { kv1[c5] |= 0xFFF00000ull; kv2[c5] |= 0xFFF00000ull; }   // back to plain keys
         if (done && ok) {
           // bound = the largest SECOND key: every point outside the CTAs' first keys is below it
           unsigned long long bk = 0ull, gmax = 0ull;
@@ -423,6 +433,7 @@ __global__ void __launch_bounds__(kThreads4, 1) fps4_kernel(Fps4Params p) {
       }
       tc_fence_before();
       __syncthreads();                        // the exchanged seed is staged
+      ++nex;
     }
     if (p.passlog && blockIdx.x == 0 && tid == 0)
       p.passlog[i] = (next < 0 ? (1ull << 63) : 0ull) | (static_cast<unsigned long long>(clock64()) & ~(1ull << 63));
@@ -706,7 +717,8 @@ int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const Cluste
   { const int v = knobs().fps_tmem_tiles; if (v >= 0 && v < TA) TA = v; }   // test / A-B knob
   const size_t smem = 1024 + 2 * size_t(kb) * 2048 + size_t(T - TA) * kb * 16384;
   if (smem > 225 * 1024) return UOC_OK;
-  const size_t slot_need = size_t(s.batch) * s.m * nb * nb * 16;     // (first, second) key per CTA pair and pass
+  if (s.n > (1ll << 20) || s.m > 4095) return UOC_OK;                 // key tags (pass number in the index word's free bits)
+  const size_t slot_need = size_t(s.batch) * 2 * nb * nb * 16;       // ring of two matrices of (first, second) keys per CTA pair
   if (slot_need > w.slot_bytes) return UOC_OK;
   unsigned int* err = device_error_word();
   if (!err) return fail(UOC_ERR_CUDA, "no device error word");
