@@ -69,7 +69,7 @@ UOC_API int uoc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Parity-test / measurement knobs (not part of the product contract): the same switches the UOC_* environment variables
  * set when the library is loaded -- conv_pair, conv_wres, fps_tc, fps_stream, fps_tmem_tiles, fps_batch_stream, fps_rn_margin,
- * fps_stats, conv_debug, conv_trace, loop_trace, loop_v2, assign_simt (csrc/uoc_common.cuh).  Used by tests/ to run both
+ * fps_stats, conv_debug, conv_trace, loop_trace, assign_simt (csrc/uoc_common.cuh).  Used by tests/ to run both
  * convolution kernels and every seed-selection variant on the same inputs. */
 UOC_API int uoc_set_knob(const char* name, int value);
 

@@ -116,7 +116,7 @@ def raise_on_device_error(device=None):
 
 
 KNOB_DEFAULTS = {"conv_pair": -1, "conv_wres": -1, "conv_debug": 0, "conv_trace": 0, "fps_tc": 1, "fps_stream": 0, "fps_tmem_tiles": -1,
-                 "fps_batch_stream": 0, "fps_rn_margin": 0, "fps_stats": 0, "loop_trace": 0, "loop_v2": 1, "assign_simt": 0}
+                 "fps_batch_stream": 0, "fps_rn_margin": 0, "fps_stats": 0, "loop_trace": 0, "assign_simt": 0}
 
 
 def set_knob(name, value):

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libuoc_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["uoc_runtime.cu", "cluster_kernels.cu", "fps_tc.cu", "meanshift_tc.cu", "meanshift_tc2.cu", "assign_tc.cu", "cluster_api.cu", "conv_tc.cu", "conv_pair.cu", "conv_wres.cu",
+SOURCES = ["uoc_runtime.cu", "cluster_kernels.cu", "fps_tc.cu", "meanshift_tc.cu", "assign_tc.cu", "cluster_api.cu", "conv_tc.cu", "conv_pair.cu", "conv_wres.cu",
            "backbone_kernels.cu", "backbone.cu", "input_prep.cu", "refine.cu", "metrics.cu"]
 HEADERS = ["uoc_common.cuh", "cluster.cuh", "conv.cuh", os.path.join(ROOT, "include", "uoc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler",

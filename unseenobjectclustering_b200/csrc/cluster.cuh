@@ -50,11 +50,6 @@ int launch_hill_climb_simt(const float* X, const ClusterShape& s, const ClusterW
 // ... and the tcgen05 kernel (meanshift_tc.cu) streaming the bf16 pixel-major copy
 int launch_hill_climb_tc(const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w, float* Z,
                          float kappa, int iters, cudaStream_t stream);
-// second generation of the persistent tcgen05 loop for d = 64 (meanshift_tc2.cu): two seed groups out of phase, so that one
-// group's grid-wide exchange hides behind the other's weights phase
-bool hill_climb_tc2_supported(const ClusterShape& s, int iters);
-int launch_hill_climb_tc2(const CUtensorMap& tmap, const ClusterShape& s, const ClusterWorkspace& w, float* Z, int P, float kappa,
-                          int iters, cudaStream_t stream);
 // sum the per-CTA partials and L2-normalise rows (F.normalize, mean_shift.py:107)
 // wsum != nullptr (euclidean): rows are divided by max(sum of weights, 1) instead (mean_shift.py:101-105)
 int launch_reduce_normalize(const float* partials, int batch, int P, int m, int d, int row_stride, float* Z,

@@ -667,9 +667,9 @@ int launch_hill_climb_tc(const __nv_bfloat16* xb, const ClusterShape& s, const C
     int Pp = P;
     if (sms > 0 && (long long)Pp * s.batch > sms) Pp = sms / s.batch;
     if (Pp < 1 || iters < 1 || w.slot_bytes < 256 * size_t(s.batch)) persistent = false;
-    if (persistent && knobs().loop_v2 != 0 && hill_climb_tc2_supported(s, iters))
-      return launch_hill_climb_tc2(tmap, s, w, Z, Pp, kappa, iters, stream);
     if (persistent) {
+      // (a points x seeds formulation with two seed groups out of phase hides the exchange but is shared-memory bound:
+      // profiles/r02_loop_two_groups.md)
       // (POLY > 0 -- part of the exponentials on the FMA pipe -- was measured at -3 %: not instantiated)
       if (s.d == 64) return launch_persistent<64, 0>(tmap, s, w, Z, Pp, kappa, iters, stream);
       return launch_persistent<128, 0>(tmap, s, w, Z, Pp, kappa, iters, stream);

@@ -39,7 +39,6 @@ struct Knobs {
   int fps_batch_stream = 0;  // UOC_FPS_BATCH_STREAM 1: a batch of large fields is streamed side by side (slower: A/B)
   int fps_rn_margin = 0;     // UOC_FPS_RN_MARGIN    1: screening margin of a round-to-nearest bf16 copy
   int fps_stats = 0;         // UOC_FPS_STATS        exchange / speculation statistics of CTA 0 on stderr (synchronises)
-  int loop_v2 = 1;           // UOC_LOOP_V2          0: first-generation persistent loop also at d = 64 (parity tests of both)
   int loop_trace = 0;        // UOC_LOOP_TRACE       per-phase timeline of the mean-shift loop on stderr (synchronises)
   int assign_simt = 0;       // UOC_ASSIGN_SIMT      1: label pass on the fp32 kernel although a bf16 copy exists
 };

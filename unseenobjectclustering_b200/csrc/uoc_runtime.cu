@@ -24,8 +24,7 @@ static const KnobEntry kKnobTable[] = {
     {"fps_stream", "UOC_FPS_STREAM", &Knobs::fps_stream},       {"fps_tmem_tiles", "UOC_FPS_TC_TMEM_TILES", &Knobs::fps_tmem_tiles},
     {"fps_batch_stream", "UOC_FPS_BATCH_STREAM", &Knobs::fps_batch_stream},
     {"fps_rn_margin", "UOC_FPS_RN_MARGIN", &Knobs::fps_rn_margin}, {"fps_stats", "UOC_FPS_STATS", &Knobs::fps_stats},
-    {"loop_trace", "UOC_LOOP_TRACE", &Knobs::loop_trace},       {"loop_v2", "UOC_LOOP_V2", &Knobs::loop_v2},
-          {"assign_simt", "UOC_ASSIGN_SIMT", &Knobs::assign_simt},
+    {"loop_trace", "UOC_LOOP_TRACE", &Knobs::loop_trace},       {"assign_simt", "UOC_ASSIGN_SIMT", &Knobs::assign_simt},
 };
 static Knobs& mutable_knobs() {
   static Knobs k = [] {
