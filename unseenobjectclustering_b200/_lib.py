@@ -119,9 +119,19 @@ KNOB_DEFAULTS = {"conv_pair": -1, "conv_wres": -1, "conv_debug": 0, "conv_trace"
                  "fps_batch_stream": 0, "fps_rn_margin": 0, "fps_stats": 0, "loop_trace": 0, "assign_simt": 0}
 
 
+_knob_epoch = 0
+
+
 def set_knob(name, value):
     """Parity-test / measurement switch of the library (include/uoc.h uoc_set_knob); not part of the product contract."""
+    global _knob_epoch
     check(load().uoc_set_knob(name.encode(), int(value)), "uoc_set_knob(%s)" % name)
+    _knob_epoch += 1
+
+
+def knob_epoch():
+    """Changes whenever a knob is set: captured launch sequences (networks._GraphedForward) are keyed on it."""
+    return _knob_epoch
 
 
 def ptr(t):

@@ -12,6 +12,7 @@ checkpoints load unchanged and .state_dict()/.cuda()/DataParallel behave), and r
 pass through uoc_backbone_forward: BN-folded bf16 implicit-GEMM convolutions on tcgen05, fused
 add + bilinear x8 + L2-normalise head.  Inference only.
 """
+import collections
 import ctypes
 import math
 
@@ -124,6 +125,32 @@ def _normalize_keys(data):
     return out
 
 
+_MAX_GRAPHS = 8
+
+
+class _GraphedForward(object):
+    """One captured CUDA graph of uoc_backbone_forward with its static buffers (SEGNET_B200.forward_ex)."""
+
+    def __init__(self, net, handle, dev, N, H, W):
+        need_img, need_depth = net.input_type != "DEPTH", net.input_type != "COLOR"
+        with torch.cuda.device(dev):
+            nbytes = _lib.load().uoc_backbone_workspace_bytes(handle, N, H, W)
+            self.ws = torch.empty(nbytes + 2048, dtype=torch.uint8, device=dev)
+            self.img = torch.zeros((N, 3, H, W), dtype=torch.float32, device=dev) if need_img else None
+            self.depth = torch.zeros((N, 3, H, W), dtype=torch.float32, device=dev) if need_depth else None
+            self.out = torch.empty((N, net.feature_dim, H, W), dtype=torch.float32, device=dev)
+            self.xb = torch.empty((N, H * W, net.feature_dim), dtype=torch.bfloat16, device=dev) if net.keep_bf16 else None
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                       # once eagerly: lazy per-kernel attributes are set outside the capture
+                net._launch(handle, dev, self.img, self.depth, N, H, W, self.out, self.xb, self.ws)
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                net._launch(handle, dev, self.img, self.depth, N, H, W, self.out, self.xb, self.ws)
+            torch.cuda.current_stream(dev).wait_stream(side)
+
+
 class SEGNET_B200(nn.Module):
     """Drop-in for the reference SEGNET built by seg_resnet34_8s_embedding[_early].  forward(img, label, depth)
     returns features [N, C, H, W] float32 on the input's device (C = num_units, or 2 * num_units for cat
@@ -159,6 +186,8 @@ class SEGNET_B200(nn.Module):
         self._owner = True          # replicas never destroy handles
         self._ws = None
         self._ws_by_stream = {}
+        self._graphs = collections.OrderedDict()
+        self.use_graphs = True
         self.keep_bf16 = True
         self.eval()
 
@@ -175,6 +204,7 @@ class SEGNET_B200(nn.Module):
         return res
 
     def _release(self):
+        self._graphs = collections.OrderedDict()      # captured graphs hold the handle's weights
         if not getattr(self, "_owner", False):
             return
         handles, self._handles = self._handles, {}
@@ -188,6 +218,8 @@ class SEGNET_B200(nn.Module):
         replica._owner = False
         replica._ws = None
         replica._ws_by_stream = {}
+        replica._graphs = collections.OrderedDict()
+        replica.use_graphs = False      # replicas live for one forward: nothing to amortise a capture over
         return replica
 
     def __del__(self):
@@ -239,8 +271,15 @@ class SEGNET_B200(nn.Module):
             _ms.register_bf16_copy(out, xb)
         return out
 
-    def forward_ex(self, img, label=None, depth=None):
-        """(features [N, C, H, W] float32, bf16 pixel-major copy [N, H*W, C] or None when keep_bf16 is off)."""
+    def forward_ex(self, img, label=None, depth=None, graph=None, static_outputs=False):
+        """(features [N, C, H, W] float32, bf16 pixel-major copy [N, H*W, C] or None when keep_bf16 is off).
+
+        graph (default: self.use_graphs): replay a captured CUDA graph of the ~45 launches of this (device, N, H, W)
+        instead of enqueueing them one by one -- the host cost of a forward drops from ~1.7 ms to one replay.  The graph
+        owns static input / output / workspace buffers: inputs are copied in, and the outputs are copied out into fresh
+        tensors unless static_outputs=True (then they are the graph's own buffers, valid until the next forward of the
+        same shape).  Inside somebody else's stream capture (pipeline.py) and under FLAG_SYNC_CHECK the launches are
+        enqueued directly."""
         need_img, need_depth = self.input_type != "DEPTH", self.input_type != "COLOR"
         if need_depth and depth is None:
             raise _lib.UocError("INPUT=%r needs the depth (XYZ) tensor" % self.input_type)
@@ -251,26 +290,50 @@ class SEGNET_B200(nn.Module):
             raise _lib.UocError("inputs must be CUDA tensors: there is no CPU path in this package")
         dev = lead.device
         handle = self._ensure_handle(dev)
-        lib = _lib.load()
+        N, _, H, W = lead.shape
+        use_graph = self.use_graphs if graph is None else graph
+        if use_graph and not (self.flags & _lib.FLAG_SYNC_CHECK) and not torch.cuda.is_current_stream_capturing():
+            g = self._graph_for(handle, dev, N, H, W)
+            if need_img:
+                g.img.copy_(img.detach(), non_blocking=True)
+            if need_depth:
+                g.depth.copy_(depth.detach(), non_blocking=True)
+            g.graph.replay()
+            self._ws = g.ws
+            if static_outputs:
+                return g.out, g.xb
+            return g.out.clone(), (g.xb.clone() if g.xb is not None else None)
         img = img.detach().to(device=dev, dtype=torch.float32).contiguous() if need_img else None
         depth = depth.detach().to(device=dev, dtype=torch.float32).contiguous() if need_depth else None
-        N, _, H, W = lead.shape
         with torch.cuda.device(dev):
-            nbytes = lib.uoc_backbone_workspace_bytes(handle, N, H, W)
             sid = torch.cuda.current_stream(dev).cuda_stream       # one activation workspace per stream in flight
             self._ws = self._ws_by_stream.get(sid)
+            nbytes = _lib.load().uoc_backbone_workspace_bytes(handle, N, H, W)
             if self._ws is None or self._ws.device != dev or self._ws.numel() < nbytes + 1024:
                 self._ws = torch.empty(nbytes + 2048, dtype=torch.uint8, device=dev)
                 self._ws_by_stream[sid] = self._ws
-            off = (-self._ws.data_ptr()) % 1024
-            ws_ptr = ctypes.c_void_p(self._ws.data_ptr() + off)
             out = torch.empty((N, self.feature_dim, H, W), dtype=torch.float32, device=dev)
             xb = torch.empty((N, H * W, self.feature_dim), dtype=torch.bfloat16, device=dev) if self.keep_bf16 else None
-            st = lib.uoc_backbone_forward(handle, _lib.ptr(img), _lib.ptr(depth), N, H, W, _lib.ptr(out),
-                                          _lib.ptr(xb), ws_ptr, self._ws.numel() - off, self.flags,
-                                          _lib.stream_ptr(dev))
-            _lib.check(st, "uoc_backbone_forward")
+            self._launch(handle, dev, img, depth, N, H, W, out, xb, self._ws)
         return out, xb
+
+    def _launch(self, handle, dev, img, depth, N, H, W, out, xb, ws):
+        off = (-ws.data_ptr()) % 1024
+        st = _lib.load().uoc_backbone_forward(handle, _lib.ptr(img), _lib.ptr(depth), N, H, W, _lib.ptr(out), _lib.ptr(xb),
+                                              ctypes.c_void_p(ws.data_ptr() + off), ws.numel() - off, self.flags,
+                                              _lib.stream_ptr(dev))
+        _lib.check(st, "uoc_backbone_forward")
+
+    def _graph_for(self, handle, dev, N, H, W):
+        """The captured forward of one (device, shape, flags, knob state); at most _MAX_GRAPHS are kept (least recently used out)."""
+        key = (dev, N, H, W, self.flags, self.keep_bf16, _lib.knob_epoch())
+        g = self._graphs.pop(key, None)
+        if g is None:
+            g = _GraphedForward(self, handle, dev, N, H, W)
+            while len(self._graphs) >= _MAX_GRAPHS:
+                self._graphs.pop(next(iter(self._graphs)))
+        self._graphs[key] = g                                      # most recently used last
+        return g
 
     def read_trunk(self, branch, N, H, W):
         """Test hook: trunk output [N, num_units, H/8, W/8] of one branch from the last forward."""

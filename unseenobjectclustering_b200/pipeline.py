@@ -75,7 +75,7 @@ class FramePipeline(object):
         """(features, bf16 copy or None): the network's explicit two-output form when it has one (SEGNET_B200)."""
         net = getattr(self.network, "module", self.network)
         if hasattr(net, "forward_ex"):
-            return net.forward_ex(slot.img_dev, None, slot.xyz_dev)
+            return net.forward_ex(slot.img_dev, None, slot.xyz_dev, graph=False)     # the pipeline captures its own graphs
         feats = self.network(slot.img_dev, None, slot.xyz_dev)
         return feats, _ms._lookup_bf16(feats)
 
