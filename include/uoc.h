@@ -135,6 +135,14 @@ UOC_API int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d,
                              int d, int m, const int64_t* first_seed_host, int64_t* selected_out, float* seeds_out,
                              void* workspace, size_t workspace_bytes, int flags, uoc_stream_t stream);
 
+/* select_smart_seeds continued from seeds chosen before (init_seeds / num_init_seeds, lib/utils/mean_shift.py:144-149,
+ * :164-169): init_seeds [batch,num_init,d] fp32 (device) are seeds 0 .. num_init-1; their distances enter the running
+ * minimum, the remaining m - num_init seeds are sampled as usual.  selected_out is -1 for the given seeds (:140),
+ * seeds_out [batch,m,d] holds all m.  fp32 passes (the continuation API is not on the hot path). */
+UOC_API int uoc_select_seeds_init(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
+                                  const float* init_seeds, int num_init, int64_t* selected_out, float* seeds_out,
+                                  void* workspace, size_t workspace_bytes, int flags, uoc_stream_t stream);
+
 /* seed_hill_climbing_ball (lib/utils/mean_shift.py:79-109, cosine): Z [batch,m,d] fp32 updated in place. */
 UOC_API int uoc_hill_climb(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch,
                            int64_t n, int d, int m, float kappa, int iters, float* Z, void* workspace,

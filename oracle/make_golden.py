@@ -222,6 +222,33 @@ FULL_CASES = [
 ]
 
 
+INIT_CASES = [
+    # name, H, W, d, objects, noise, seed, num_seeds, num_init, metric, scale
+    ("init_a", 32, 48, 64, 4, 0.05, 51, 60, 5, "cosine", 1.0),
+    ("init_b", 30, 40, 64, 3, 0.03, 52, 40, 12, "euclidean", 1.5),
+]
+
+
+def gen_init(ref):
+    """select_smart_seeds(init_seeds=, num_init_seeds=) of the unmodified reference (lib/utils/mean_shift.py:144-149, :164-169):
+    the given seeds are the object centres' first rows plus noise (NOT points of X)."""
+    for name, H, W, d, K, noise, seed, m, k, metric, scale in INIT_CASES:
+        feats, gt = O.synthetic_clustered_features(H, W, d, K, noise, seed)
+        feats = feats * scale
+        X = feats[0].view(d, -1).t().contiguous()
+        g = torch.Generator().manual_seed(seed + 1000)
+        given = torch.nn.functional.normalize(torch.randn(k, d, generator=g), dim=1) * scale
+        init = torch.zeros((m, d))
+        init[:k] = given
+        seeds, selected = ref.mean_shift.select_smart_seeds(X, m, return_selected_indices=True, init_seeds=init,
+                                                            num_init_seeds=k, metric=metric)
+        assert seeds is init
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), H=H, W=W, d=d, objects=K, noise=noise, seed=seed, scale=scale,
+                            num_seeds=m, num_init=k, metric=metric, given=given.numpy(), selected=selected.numpy(),
+                            seeds=seeds.numpy())
+        print(name, selected[:k + 4].tolist())
+
+
 def _planar_to_X(Xp):
     """[d, n] planar float32 -> the reference's X: a [n, d] view with strides (1, n) (test_dataset.py:54-55)."""
     return torch.from_numpy(Xp).t()
@@ -345,6 +372,8 @@ if __name__ == "__main__":
         gen_euclid(ref)
     if not only or "metrics" in only:
         gen_metrics(ref)
+    if not only or "init" in only:
+        gen_init(ref)
     if not only or "full" in only:
         gen_full(ref)
     if not only or "full_two_stage" in only:

@@ -121,6 +121,32 @@ def select_seeds(X, num_seeds, first_index, metric="cosine"):
     return seeds, selected
 
 
+def select_seeds_init(X, num_seeds, init_seeds, num_init_seeds, metric="cosine"):
+    """lib/utils/mean_shift.py:128-189 with init_seeds / num_init_seeds (:144-149, :164-169): the first num_init_seeds rows of
+    init_seeds are seeds chosen before; their distance columns are computed first, sampling continues from them.  Like the
+    reference, init_seeds is filled in place and returned; selected_indices stays -1 for the given rows (:140).
+    Returns (seeds [m,d] (= init_seeds), selected_indices [m] int64)."""
+    n, d = X.shape
+    selected = -torch.ones(num_seeds, dtype=torch.long)
+    seeds = init_seeds
+    distances = torch.empty((n, num_seeds))
+
+    def column(seed_row):                               # seed_row: [1, d]
+        if metric == "euclidean":
+            return torch.norm(X - seed_row, dim=1)
+        return 0.5 * (1 - torch.mm(X, seed_row.t())[:, 0])
+
+    for i in range(num_init_seeds):
+        distances[:, i] = column(seeds[i:i + 1, :])
+    for i in range(num_init_seeds, num_seeds):
+        nearest = torch.min(distances[:, :i], dim=1)[0]
+        idx = torch.argmax(nearest)
+        selected[i] = idx
+        seeds[i, :] = torch.index_select(X, 0, idx)[0, :]
+        distances[:, i] = column(seeds[i:i + 1, :])
+    return seeds, selected
+
+
 def assign_and_relabel(X, Z, seed_labels, metric="cosine"):
     """lib/utils/mean_shift.py:206-227.  Nearest-seed assignment (argmin of 0.5(1 - x.z), first
     minimum), then swap label 0 with the most populated label.  Reproduces the histogram quirk:

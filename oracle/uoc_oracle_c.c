@@ -11,7 +11,7 @@
  * through it against the reference) on inputs with margin.
  *
  * Follows lib/utils/mean_shift.py of NVlabs/UnseenObjectClustering @ f5a00c7:
- *   uoc_oracle_select_seeds   :128-189   farthest point sampling
+ *   uoc_oracle_select_seeds   :128-189   farthest point sampling (uoc_oracle_select_seeds_init: continued from given seeds)
  *   uoc_oracle_label_seeds    :41-76     greedy epsilon-neighbourhood labelling (+ :30-38 mode)
  *   uoc_oracle_assign         :206-227   nearest seed, histogram over range(len(unique)), label-0 swap
  *   uoc_oracle_hill_climb     :79-109    mean-shift updates (double accumulation: a tolerance oracle)
@@ -63,6 +63,37 @@ int uoc_oracle_select_seeds_metric(const float* X, int64_t n, int d, int64_t str
     int64_t bi = 0;
     for (int64_t p = 1; p < n; ++p)
       if (r[p] > best) { best = r[p]; bi = p; }                  /* first maximum, like torch.argmax */
+    idx = bi;
+  }
+  free(r);
+  free(s);
+  return 0;
+}
+
+/* mean_shift.py:128-189 continued from seeds chosen before (:144-149, :164-169): init [num_init][d].  selected = -1 for them. */
+int uoc_oracle_select_seeds_init(const float* X, int64_t n, int d, int64_t stride_d, int m, const float* init, int num_init,
+                                 int64_t* selected, float* seeds, int metric) {
+  if (num_init < 1 || num_init > m) return 1;
+  float* r = (float*)malloc(sizeof(float) * (size_t)n);
+  float* s = (float*)malloc(sizeof(float) * (size_t)d);
+  if (!r || !s) return 2;
+  int64_t idx = -1;
+  for (int i = 0; i < m; ++i) {
+    selected[i] = (i < num_init) ? -1 : idx;
+    for (int k = 0; k < d; ++k) {
+      s[k] = (i < num_init) ? init[(size_t)i * d + k] : X[k * stride_d + idx];
+      seeds[(size_t)i * d + k] = s[k];
+    }
+    if (i + 1 == m) break;
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < n; ++p) {
+      const float dist = distance(X + p, stride_d, s, 1, d, metric);
+      r[p] = (i == 0) ? dist : (dist < r[p] ? dist : r[p]);
+    }
+    float best = r[0];
+    int64_t bi = 0;
+    for (int64_t p = 1; p < n; ++p)
+      if (r[p] > best) { best = r[p]; bi = p; }
     idx = bi;
   }
   free(r);

@@ -44,6 +44,19 @@ def select_seeds(X_planar, m, first, metric="cosine"):
     return sel, seeds
 
 
+def select_seeds_init(X_planar, m, init_seeds, metric="cosine"):
+    """Continue from the rows of init_seeds [num_init, d].  Returns (selected int64 [m] with -1 for the given rows, seeds [m, d])."""
+    X = _f32(X_planar)
+    init = _f32(init_seeds)
+    d, n = X.shape
+    sel = np.empty(m, dtype=np.int64)
+    seeds = np.empty((m, d), dtype=np.float32)
+    rc = load().uoc_oracle_select_seeds_init(_p(X), ctypes.c_int64(n), d, ctypes.c_int64(n), m, _p(init), init.shape[0],
+                                             _p(sel), _p(seeds), METRICS[metric])
+    assert rc == 0, rc
+    return sel, seeds
+
+
 def label_seeds(Z, eps, metric="cosine"):
     Z = _f32(Z)
     m, d = Z.shape

@@ -144,6 +144,30 @@ def test_backbone_full_frame_vs_oracle_and_bf16_copy():
     assert torch.equal(net(i2.to(DEV), None, x2.to(DEV)).cpu(), f2)
 
 
+def test_graphed_forward_equals_eager_and_returns_fresh_tensors():
+    """forward_ex replays a captured CUDA graph from the second call of a shape on: results are bit-identical to the
+    launch-by-launch path, returned tensors are fresh (an earlier result is not overwritten by a later call), the bf16
+    copy belongs to the returned tensor, and static_outputs=True hands out the graph's own buffers."""
+    from unseenobjectclustering_b200 import mean_shift as MS
+    net = NW.seg_resnet34_8s_embedding(2, 64, O.randomise_bn_(NW.random_state_dict(64, seed=5), 1005)).to(DEV)
+    frames = [O.synthetic_rgbd_frame(96, 128, seed=s) for s in (11, 12, 13)]
+    net.use_graphs = False
+    eager = [net(i.to(DEV), None, x.to(DEV)).clone() for i, x in frames]
+    net.use_graphs = True
+    got = [net(i.to(DEV), None, x.to(DEV)) for i, x in frames]          # eager, capture + replay, replay
+    assert len(net._graphs) == 1
+    for a, b in zip(eager, got):
+        assert torch.equal(a, b)
+    assert got[1].data_ptr() != got[2].data_ptr()
+    xb = MS._lookup_bf16(got[2])
+    assert xb is not None and (xb.float().view(1, 96, 128, 64).permute(0, 3, 1, 2) - got[2]).abs().max().item() < 1e-2
+    f_static, xb_static = net.forward_ex(frames[0][0].to(DEV), None, frames[0][1].to(DEV), static_outputs=True)
+    assert torch.equal(f_static, eager[0])
+    g = next(iter(net._graphs.values()))
+    assert f_static.data_ptr() == g.out.data_ptr() and xb_static.data_ptr() == g.xb.data_ptr()
+    assert torch.equal(got[1], eager[1])                                  # untouched by the later replays
+
+
 def test_module_drop_in_behaviour():
     net = NW.seg_resnet34_8s_embedding(2, 64, None).cuda(0)
     dp = torch.nn.DataParallel(net, device_ids=[0]).cuda(0)

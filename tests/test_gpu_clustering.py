@@ -383,6 +383,25 @@ def test_full_size_loop_vs_double_oracle():
     assert np.abs(cosd).max() < 5e-5, np.abs(cosd).max()
 
 
+@pytest.mark.parametrize("name", ["init_a", "init_b"])
+def test_select_seeds_with_init_seeds(name):
+    """select_smart_seeds(init_seeds=, num_init_seeds=) (lib/utils/mean_shift.py:144-149, :164-169): indices bit-exact against
+    the fixture written by the unmodified reference and against the C oracle; init_seeds is filled in place and returned."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d, m, k, metric = int(g["d"]), int(g["num_seeds"]), int(g["num_init"]), str(g["metric"])
+    feats, _ = O.synthetic_clustered_features(int(g["H"]), int(g["W"]), d, int(g["objects"]), float(g["noise"]), int(g["seed"]))
+    feats = feats * float(g["scale"])
+    X = feats.to(DEV)[0].view(d, -1).t()
+    init = torch.zeros((m, d), device=DEV)
+    init[:k] = torch.from_numpy(g["given"]).to(DEV)
+    seeds, sel = MS.select_smart_seeds(X, m, return_selected_indices=True, init_seeds=init, num_init_seeds=k, metric=metric)
+    assert seeds is init
+    assert np.array_equal(sel.numpy(), g["selected"])
+    assert np.array_equal(seeds.cpu().numpy(), g["seeds"])
+    sel_c, seeds_c = C.select_seeds_init(feats[0].reshape(d, -1).numpy(), m, g["given"], metric)
+    assert np.array_equal(sel.numpy(), sel_c) and np.array_equal(seeds.cpu().numpy(), seeds_c)
+
+
 def test_bf16_side_channel_cannot_go_stale():
     """the bf16 copy of a backbone output must never be served for a different tensor that happens to get the
     same address.  Free a backbone output, allocate a same-shape foreign field, cluster it: the lookup must miss and the

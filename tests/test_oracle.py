@@ -89,6 +89,47 @@ def test_euclidean_torch_oracle_is_bit_identical_to_the_live_reference():
     assert torch.equal(lr, lo) and torch.equal(sr, so)
 
 
+INIT_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "init_*.npz")))
+
+
+def _init_case(g):
+    d, m, k = int(g["d"]), int(g["num_seeds"]), int(g["num_init"])
+    feats, _ = O.synthetic_clustered_features(int(g["H"]), int(g["W"]), d, int(g["objects"]), float(g["noise"]), int(g["seed"]))
+    feats = feats * float(g["scale"])
+    return feats, d, m, k, str(g["metric"])
+
+
+@pytest.mark.parametrize("path", INIT_FIXTURES, ids=[os.path.basename(p) for p in INIT_FIXTURES])
+def test_select_seeds_with_init_seeds_matches_reference_golden(path):
+    """select_smart_seeds(init_seeds=, num_init_seeds=) (lib/utils/mean_shift.py:144-149, :164-169): torch oracle bit-identical
+    to the fixture written by the unmodified reference; C oracle (canonical chain) picks the same indices."""
+    g = _load(path)
+    feats, d, m, k, metric = _init_case(g)
+    X = feats[0].view(d, -1).t().contiguous()
+    init = torch.zeros((m, d))
+    init[:k] = torch.from_numpy(g["given"])
+    seeds, sel = O.select_seeds_init(X, m, init, k, metric)
+    assert seeds is init
+    assert np.array_equal(sel.numpy(), g["selected"]) and (sel[:k] == -1).all()
+    assert np.array_equal(seeds.numpy(), g["seeds"])
+    sel_c, seeds_c = C.select_seeds_init(feats[0].reshape(d, -1).numpy(), m, g["given"], metric)
+    assert np.array_equal(sel_c, g["selected"])
+    assert np.array_equal(seeds_c, g["seeds"])
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not present (GPU box)")
+def test_select_seeds_with_init_seeds_is_bit_identical_to_the_live_reference():
+    ref = rh.load()
+    feats, _ = O.synthetic_clustered_features(28, 36, 64, 3, 0.04, seed=91)
+    X = feats[0].view(64, -1).t().contiguous()
+    given = torch.nn.functional.normalize(torch.randn(7, 64, generator=torch.Generator().manual_seed(5)), dim=1)
+    a, b = torch.zeros((30, 64)), torch.zeros((30, 64))
+    a[:7], b[:7] = given, given
+    sr, ir = ref.mean_shift.select_smart_seeds(X, 30, return_selected_indices=True, init_seeds=a, num_init_seeds=7, metric='cosine')
+    so, io = O.select_seeds_init(X, 30, b, 7, "cosine")
+    assert torch.equal(ir, io) and torch.equal(sr, so)
+
+
 def test_two_stage_oracle_matches_golden():
     g = _load(os.path.join(GOLDEN, "two_stage.npz"))
     H, W = int(g["H"]), int(g["W"])

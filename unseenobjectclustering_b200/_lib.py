@@ -44,6 +44,7 @@ SIGNATURES = {
                                       _sz, _i, _vp]),
     "uoc_assign_labels_typed": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "uoc_select_seeds": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "uoc_select_seeds_init": (_i, [_vp, _i64, _i64, _i, _i64, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "uoc_hill_climb": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _f, _i, _vp, _vp, _sz, _i, _vp]),
     "uoc_label_seeds": (_i, [_vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "uoc_assign_labels": (_i, [_vp, _i64, _i64, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -42,6 +42,8 @@ int carve_cluster_workspace(void* ws, size_t ws_bytes, int batch, int64_t n, int
 enum { METRIC_COSINE = 0, METRIC_EUCLIDEAN = 1 };
 int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
                         int64_t* selected_out, float* seeds_out, cudaStream_t stream, int metric = METRIC_COSINE);
+int launch_select_seeds_init(const float* X, const ClusterShape& s, const ClusterWorkspace& w, const float* init_seeds,
+                             int num_init, int64_t* selected_out, float* seeds_out, cudaStream_t stream, int metric = METRIC_COSINE);
 int launch_select_seeds_tc(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
                            int64_t* selected_out, float* seeds_out, cudaStream_t stream, bool* used);
 // K4  mean-shift iterations (lib/utils/mean_shift.py:79-109): fp32 SIMT validation kernel ...

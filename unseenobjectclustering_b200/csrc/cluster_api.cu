@@ -128,6 +128,25 @@ int uoc_select_seeds(const float* X, int64_t stride_b, int64_t stride_d, const v
   return UOC_OK;
 }
 
+int uoc_select_seeds_init(const float* X, int64_t stride_b, int64_t stride_d, int batch, int64_t n, int d, int m,
+                          const float* init_seeds, int num_init, int64_t* selected_out, float* seeds_out, void* workspace,
+                          size_t workspace_bytes, int flags, uoc_stream_t stream) {
+  int rc = require_sm100();
+  if (rc != UOC_OK) return rc;
+  rc = check_shape(X, batch, n, d, m, stride_b, stride_d);
+  if (rc != UOC_OK) return rc;
+  if (!selected_out || !seeds_out) return fail(UOC_ERR_INVALID, "selected_out / seeds_out is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ClusterWorkspace w;
+  rc = carve_cluster_workspace(workspace, workspace_bytes, batch, n, d, m, &w);
+  if (rc != UOC_OK) return rc;
+  ClusterShape s{batch, n, d, m, stride_b, stride_d};
+  rc = launch_select_seeds_init(X, s, w, init_seeds, num_init, selected_out, seeds_out, st, metric_of(flags));
+  if (rc != UOC_OK) return rc;
+  if (flags & UOC_FLAG_SYNC_CHECK) return check_device_error(st);
+  return UOC_OK;
+}
+
 int uoc_hill_climb(const float* X, int64_t stride_b, int64_t stride_d, const void* x_bf16, int batch, int64_t n, int d,
                    int m, float kappa, int iters, float* Z, void* workspace, size_t workspace_bytes, int flags,
                    uoc_stream_t stream) {

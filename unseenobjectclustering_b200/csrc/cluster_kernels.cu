@@ -122,6 +122,8 @@ struct FpsParams {
   long long* trace;       // optional (debug): per pass {start, after local arg-max, after exchange} clock64 of CTA `trace_cta`
   int trace_cta;
   int debug_mode;         // 0 normal; 1 = skip the inter-CTA exchange (each CTA follows its own arg-max); 2 = skip the streaming loop
+  const float* init_seeds = nullptr;   // [batch][num_init][d]: seeds chosen already (mean_shift.py:144-149, :164-169); fps_kernel only
+  int num_init = 0;
 };
 
 __device__ __forceinline__ unsigned int orderable(float f) {
@@ -169,14 +171,21 @@ __global__ void __launch_bounds__(256) fps_kernel(FpsParams p) {
   for (int i = 0; i < p.m; ++i) {
     for (int b = my_first_item; b < p.batch; b += item_step) {
       long long idx;
-      if (i == 0) {
-        idx = p.first[b];
-      } else {
-        unsigned long long key = __ldcg(p.keys + size_t(b) * p.m + i);
-        idx = static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(key & 0xFFFFFFFFull));
-      }
       const float* Xb = p.X + b * p.sb;
-      for (int k = tid; k < p.d; k += blockDim.x) s_seed[k] = __ldg(Xb + k * p.sd + idx);
+      if (i < p.num_init) {
+        // a seed the caller chose before (mean_shift.py:164-169): its distances enter the running minimum like any
+        // other column; there is no index for it (selected_indices stays -1, :140)
+        idx = -1;
+        for (int k = tid; k < p.d; k += blockDim.x) s_seed[k] = __ldg(p.init_seeds + (size_t(b) * p.num_init + i) * p.d + k);
+      } else {
+        if (i == 0) {
+          idx = p.first[b];
+        } else {
+          unsigned long long key = __ldcg(p.keys + size_t(b) * p.m + i);
+          idx = static_cast<long long>(0xFFFFFFFFu - static_cast<unsigned int>(key & 0xFFFFFFFFull));
+        }
+        for (int k = tid; k < p.d; k += blockDim.x) s_seed[k] = __ldg(Xb + k * p.sd + idx);
+      }
       __syncthreads();
       if (rank == 0) {
         if (tid == 0) p.selected_out[size_t(b) * p.m + i] = idx;
@@ -550,6 +559,30 @@ static int launch_select_seeds_v2(FpsParams p, const ClusterShape& s, unsigned l
   return UOC_OK;
 }
 
+// the generic cooperative fp32 sampler (any d, both metrics, optional seeds chosen before)
+static int launch_fps_generic(FpsParams p, const ClusterShape& s, bool vec4, int metric, cudaStream_t stream) {
+  void* kern = vec4 ? reinterpret_cast<void*>(&fps_kernel<4, METRIC_COSINE>) : reinterpret_cast<void*>(&fps_kernel<1, METRIC_COSINE>);
+  if (metric == METRIC_EUCLIDEAN)
+    kern = vec4 ? reinterpret_cast<void*>(&fps_kernel<4, METRIC_EUCLIDEAN>) : reinterpret_cast<void*>(&fps_kernel<1, METRIC_EUCLIDEAN>);
+  const int threads = 256;
+  const size_t smem = sizeof(float) * size_t(s.d);
+  int per_sm = 0;
+  UOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) return fail(UOC_ERR_CUDA, "fps kernel does not fit on an SM");
+  int want = 2;
+  if (want > per_sm) want = per_sm;
+  const int sms = sm_count();
+  long long groups_total = (s.n / (vec4 ? 4 : 1)) * (long long)s.batch;
+  int grid = sms * want;
+  long long needed = (groups_total + threads - 1) / threads;
+  if (needed < grid) grid = int(needed < 1 ? 1 : needed);
+  if (grid < s.batch && s.batch <= sms * per_sm) grid = s.batch;
+  void* args[] = {&p};
+  UOC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, stream));
+  count_launch();
+  return UOC_OK;
+}
+
 int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterShape& s, const ClusterWorkspace& w,
                         int64_t* selected_out, float* seeds_out, cudaStream_t stream, int metric) {
   if (xb && metric == METRIC_COSINE) {
@@ -592,26 +625,30 @@ int launch_select_seeds(const float* X, const __nv_bfloat16* xb, const ClusterSh
     int rc = launch_select_seeds_v2(p, s, w.slots, w.slot_bytes, stream, &used);
     if (rc != UOC_OK || used) return rc;
   }
-  void* kern = vec4 ? reinterpret_cast<void*>(&fps_kernel<4, METRIC_COSINE>) : reinterpret_cast<void*>(&fps_kernel<1, METRIC_COSINE>);
-  if (metric == METRIC_EUCLIDEAN)
-    kern = vec4 ? reinterpret_cast<void*>(&fps_kernel<4, METRIC_EUCLIDEAN>) : reinterpret_cast<void*>(&fps_kernel<1, METRIC_EUCLIDEAN>);
-  const int threads = 256;
-  const size_t smem = sizeof(float) * size_t(s.d);
-  int per_sm = 0;
-  UOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-  if (per_sm < 1) return fail(UOC_ERR_CUDA, "fps kernel does not fit on an SM");
-  int want = 2;
-  if (want > per_sm) want = per_sm;
-  const int sms = sm_count();
-  long long groups_total = (s.n / (vec4 ? 4 : 1)) * (long long)s.batch;
-  int grid = sms * want;
-  long long needed = (groups_total + threads - 1) / threads;
-  if (needed < grid) grid = int(needed < 1 ? 1 : needed);
-  if (grid < s.batch && s.batch <= sms * per_sm) grid = s.batch;
-  void* args[] = {&p};
-  UOC_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, stream));
-  count_launch();
-  return UOC_OK;
+  return launch_fps_generic(p, s, vec4, metric, stream);
+}
+
+// select_smart_seeds with init_seeds (mean_shift.py:144-149, :164-169): the first num_init seeds are given as vectors
+int launch_select_seeds_init(const float* X, const ClusterShape& s, const ClusterWorkspace& w, const float* init_seeds,
+                             int num_init, int64_t* selected_out, float* seeds_out, cudaStream_t stream, int metric) {
+  if (num_init < 1 || num_init > s.m || !init_seeds) return fail(UOC_ERR_INVALID, "init_seeds: 1 <= num_init_seeds <= num_seeds");
+  FpsParams p;
+  p.X = X; p.sb = s.stride_b; p.sd = s.stride_d; p.n = s.n; p.d = s.d; p.m = s.m; p.batch = s.batch;
+  p.first = w.first; p.r = w.r; p.keys = w.keys; p.barrier = w.barrier;
+  p.selected_out = reinterpret_cast<long long*>(selected_out);
+  p.seeds_out = seeds_out;
+  p.err = device_error_word();
+  if (!p.err) return fail(UOC_ERR_CUDA, "no device error word");
+  p.trace = nullptr;
+  p.trace_cta = 0;
+  p.debug_mode = 0;
+  p.init_seeds = init_seeds;
+  p.num_init = num_init;
+  UOC_CUDA(cudaMemsetAsync(w.keys, 0, sizeof(unsigned long long) * size_t(s.batch) * s.m, stream));
+  UOC_CUDA(cudaMemsetAsync(w.barrier, 0, sizeof(unsigned int), stream));
+  const bool vec4 = (s.n % 4 == 0) && (s.stride_d % 4 == 0) && (s.stride_b % 4 == 0) &&
+                    (reinterpret_cast<uintptr_t>(X) % 16 == 0);
+  return launch_fps_generic(p, s, vec4, metric, stream);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -189,15 +189,30 @@ def mean_shift_smart_init(X, kappa, num_seeds=100, max_iters=10, metric='cosine'
 
 def select_smart_seeds(X, num_seeds, return_selected_indices=False, init_seeds=None, num_init_seeds=None,
                        metric='cosine', first_index=None, bf16_screen=True):
-    """lib/utils/mean_shift.py:128-189 (fresh start only: init_seeds is not supported).
-    bf16_screen: screen every pass with a bf16 copy of X (d = 64/128; same indices, see fps_tc.cu)."""
-    if init_seeds is not None:
-        raise NotImplementedError("fresh start only: init_seeds is not supported")
+    """lib/utils/mean_shift.py:128-189.  init_seeds [num_seeds, d] with its first num_init_seeds rows chosen already
+    (:144-149): sampling continues from them; like the reference, the remaining rows of init_seeds are filled IN PLACE, the
+    same tensor is returned, and selected_indices is -1 for the given rows.
+    bf16_screen: screen every pass with a bf16 copy of X (d = 64/128; same indices, see fps_tc.cu; fresh starts only)."""
     mflag = _metric_flag(metric)
     n, d = X.shape
     Xp, stride_d = _as_planar(X)
     lib = _lib.load()
     dev = X.device
+    if init_seeds is not None and num_init_seeds:
+        k = int(num_init_seeds)
+        given = init_seeds[:k].detach().to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            ws = _workspace(dev, lib.uoc_meanshift_workspace_bytes(1, n, d, num_seeds))
+            selected = torch.empty((num_seeds,), dtype=torch.int64, device=dev)
+            seeds = torch.empty((num_seeds, d), dtype=torch.float32, device=dev)
+            st = lib.uoc_select_seeds_init(_lib.ptr(Xp), d * stride_d, stride_d, 1, n, d, num_seeds, _lib.ptr(given), k,
+                                           _lib.ptr(selected), _lib.ptr(seeds), _lib.ptr(ws), ws.numel(),
+                                           _lib.FLAG_SYNC_CHECK | mflag, _lib.stream_ptr(dev))
+            _lib.check(st, "uoc_select_seeds_init")
+        init_seeds[k:num_seeds] = seeds[k:].to(init_seeds.device, init_seeds.dtype)      # seeds = init_seeds (:147)
+        if return_selected_indices:
+            return init_seeds, selected.cpu()
+        return (init_seeds,)
     if first_index is None:
         first_index = np.random.randint(0, n)
     first = (ctypes.c_int64 * 1)(int(first_index))

@@ -125,7 +125,7 @@ def _normalize_keys(data):
     return out
 
 
-_MAX_GRAPHS = 8
+_MAX_GRAPHS = 16         # captured shapes kept per network (least recently used out)
 
 
 class _GraphedForward(object):
@@ -187,6 +187,7 @@ class SEGNET_B200(nn.Module):
         self._ws = None
         self._ws_by_stream = {}
         self._graphs = collections.OrderedDict()
+        self._seen = {}
         self.use_graphs = True
         self.keep_bf16 = True
         self.eval()
@@ -205,6 +206,7 @@ class SEGNET_B200(nn.Module):
 
     def _release(self):
         self._graphs = collections.OrderedDict()      # captured graphs hold the handle's weights
+        self._seen = {}
         if not getattr(self, "_owner", False):
             return
         handles, self._handles = self._handles, {}
@@ -219,6 +221,7 @@ class SEGNET_B200(nn.Module):
         replica._ws = None
         replica._ws_by_stream = {}
         replica._graphs = collections.OrderedDict()
+        replica._seen = {}
         replica.use_graphs = False      # replicas live for one forward: nothing to amortise a capture over
         return replica
 
@@ -294,6 +297,9 @@ class SEGNET_B200(nn.Module):
         use_graph = self.use_graphs if graph is None else graph
         if use_graph and not (self.flags & _lib.FLAG_SYNC_CHECK) and not torch.cuda.is_current_stream_capturing():
             g = self._graph_for(handle, dev, N, H, W)
+        else:
+            g = None
+        if g is not None:
             if need_img:
                 g.img.copy_(img.detach(), non_blocking=True)
             if need_depth:
@@ -329,6 +335,14 @@ class SEGNET_B200(nn.Module):
         key = (dev, N, H, W, self.flags, self.keep_bf16, _lib.knob_epoch())
         g = self._graphs.pop(key, None)
         if g is None:
+            # a shape is captured when it comes back (the crop network sees a different batch size per frame: capturing
+            # every one-off shape would cost more than it saves)
+            seen = self._seen.get(key, 0) + 1
+            if len(self._seen) > 256:
+                self._seen.clear()
+            self._seen[key] = seen
+            if seen < 2:
+                return None
             g = _GraphedForward(self, handle, dev, N, H, W)
             while len(self._graphs) >= _MAX_GRAPHS:
                 self._graphs.pop(next(iter(self._graphs)))
