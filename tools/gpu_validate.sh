@@ -11,7 +11,7 @@ for w in $what; do
       timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ;;
     sanitize)
       K1='test_conv_matches_torch and (44 or 28 or 45) and not simt and not 60 and not 120'
-      K2='(test_select_seeds_bit_exact and 32-48-64-100) or (test_full_clustering_matches_reference_golden and cluster_d) or (test_select_seeds_test_assign_tensor_core_certificate_on_marginless_input'
+      K2='(test_select_seeds_bit_exact and 32-48-64-100) or (test_full_clustering_matches_reference_golden and cluster_d) or test_assign_tensor_core_certificate_on_marginless_input or test_select_seeds_with_init_seeds or (test_hill_climb_vs_double_oracle and 32-48-64-100)'
       for tool in memcheck racecheck; do
         timeout 1200 compute-sanitizer --tool $tool --error-exitcode 86 python -m pytest tests/test_gpu_backbone.py -m gpu -q -x -k "$K1" > gpurun_out/sanitizer_${tool}_conv.log 2>&1
         echo "$tool conv rc=$?"; tail -4 gpurun_out/sanitizer_${tool}_conv.log
