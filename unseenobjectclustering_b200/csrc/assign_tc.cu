@@ -4,8 +4,10 @@
 // The output must equal the canonical fp32 arg-min bit for bit, but a pixel's LABEL only depends on which
 // cluster of seeds wins, and clusters are separated by far more than bf16 rounding.  So:
 //   pass 1 (this kernel): S^T[128 points x 128 seeds] = Xtile . Zs^T on tcgen05 (bf16 operands, fp32 accumulate) from the
-//           bf16 pixel-major copy of X; every point tracks, in one sweep over its row, the best dot v1 (label l1) and the
-//           best dot v2 among seeds whose label differs from l1.  |bf16 dot - canonical fp32 dot| <= E = 2^-8 (|x||z| = 1)
+//           bf16 pixel-major copy of X; every point finds the best dot v1 (label l1) and the best dot v2 among seeds whose
+//           label differs from l1.  The seed COLUMNS are sorted by label first, so a label is a run of consecutive columns:
+//           per run one max-reduction straight from tensor memory (runtime column address), then a top-2 over the runs --
+//           no label logic per element (the element-wise sweep was ~14 instructions per seed and point: 44 us per field).  |bf16 dot - canonical fp32 dot| <= E = 2^-8 (|x||z| = 1)
 //           plus accumulation noise, so v1 - v2 > 2E + slack PROVES that the canonical arg-min carries label l1.
 //   pass 2 (assign_fix_kernel): the few uncertified points (cluster borders) are recomputed with the canonical fp32 chain.
 // Result: identical labels to the fp32 kernel (tests/test_gpu_clustering.py::test_assign_bit_exact), one pass over
@@ -49,8 +51,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __rest
   uint64_t* s_full = bars + 2 * Cfg::kStages;
   uint64_t* s_empty = s_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
-  __shared__ int s_lab[UOC_MAX_SEEDS];
+  __shared__ int s_lab[UOC_MAX_SEEDS];         // label of seed i
   __shared__ int s_hist[UOC_MAX_SEEDS];
+  __shared__ int s_perm[UOC_MAX_SEEDS];        // column (sorted position) -> seed
+  __shared__ int s_sorted[UOC_MAX_SEEDS];      // label of column
+  __shared__ int s_run_start[UOC_MAX_SEEDS + 1];   // first column of run r; [nruns] = m
+  __shared__ int s_run_lab[UOC_MAX_SEEDS];
+  __shared__ int s_nruns;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, b = blockIdx.y;
@@ -64,15 +71,49 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __rest
     mbar_init(&s_empty[0], 128); mbar_init(&s_empty[1], 128);
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
+  // (8-column loads of a run that ends near column 128 may read up to 7 columns past the buffer: more columns then)
+  const uint32_t tmem_cols = (m > 120) ? 512u : Cfg::kTmemCols;
+  if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   if (threadIdx.x < UOC_MAX_SEEDS) {
     s_lab[threadIdx.x] = threadIdx.x < m ? seed_labels[size_t(b) * m + threadIdx.x] : -1;
     s_hist[threadIdx.x] = 0;
   }
+  __syncthreads();
+  if (warp >= 2 && warp < 6) {
+    // stable sort of the seeds by label: column of seed t = number of seeds that sort before it
+    const int t = threadIdx.x - 64;
+    if (t < m) {
+      const int lt = s_lab[t];
+      int pos = 0;
+      for (int i = 0; i < m; ++i) {
+        const int li = s_lab[i];
+        pos += (li < lt || (li == lt && i < t)) ? 1 : 0;
+      }
+      s_perm[pos] = t;
+      s_sorted[pos] = lt;
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    // runs of equal labels
+    int count = 0;
+    for (int base = 0; base < UOC_MAX_SEEDS; base += 32) {
+      const int pos = base + lane;
+      const bool st = pos < m && (pos == 0 || s_sorted[pos] != s_sorted[pos - 1]);
+      const unsigned int bal = __ballot_sync(0xffffffffu, st);
+      if (st) {
+        const int r = count + __popc(bal & ((1u << lane) - 1u));
+        s_run_start[r] = pos;
+        s_run_lab[r] = s_sorted[pos];
+      }
+      count += __popc(bal);
+    }
+    if (lane == 0) { s_nruns = count; s_run_start[count] = m; }
+  }
   if (warp >= 2) {
     const int r = (threadIdx.x - 64) & 127;
     const int half = (threadIdx.x - 64) >> 7;
-    const float* zr = Z + (size_t(b) * m + (r < m ? r : 0)) * D;
+    const float* zr = Z + (size_t(b) * m + (r < m ? s_perm[r] : 0)) * D;     // column r holds seed s_perm[r]
 #pragma unroll
     for (int c = half * (D / 16); c < (half + 1) * (D / 16); ++c) {
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -137,27 +178,37 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __rest
       tc_fence_after();
       float v1 = -INFINITY, v2 = -INFINITY;
       int l1 = -1;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c * 32 < m) {
+      const uint32_t sbase = lane_addr + grp * 128;
+      const int nruns = s_nruns;
+      for (int r = 0; r < nruns; ++r) {
+        const int c0 = s_run_start[r], len = s_run_start[r + 1] - c0;
+        float cur = -INFINITY;
+        int g = 0;
+        for (; len - g >= 32; g += 32) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(lane_addr + grp * 128 + c * 32, v);
+          tmem_ld_32x32b_x32(sbase + c0 + g, v);
           tmem_wait_ld();
+          float t8[8];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int jj = c * 32 + e;
-            if (jj < m) {
-              const float val = __uint_as_float(v[e]);
-              const int lab = s_lab[jj];
-              if (val > v1) {
-                if (lab != l1) v2 = v1;
-                v1 = val; l1 = lab;
-              } else if (lab != l1 && val > v2) {
-                v2 = val;
-              }
-            }
-          }
+          for (int e = 0; e < 8; ++e)
+            t8[e] = fmaxf(fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 8])), fmaxf(__uint_as_float(v[e + 16]), __uint_as_float(v[e + 24])));
+          cur = fmaxf(cur, fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7]))));
         }
+        for (; g < len; g += 8) {
+          uint32_t v[8];
+          tmem_ld_32x32b_x8(sbase + c0 + g, v);
+          tmem_wait_ld();
+          const int left = len - g;                       // columns of this load that belong to the run
+          float t8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t8[e] = (e < left) ? __uint_as_float(v[e]) : -INFINITY;
+          cur = fmaxf(cur, fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7]))));
+        }
+        // top-2 over the runs (their labels are distinct); an exact tie of two labels leaves v1 == v2: not certified
+        const bool gt = cur > v1;
+        v2 = gt ? v1 : fmaxf(v2, cur);
+        l1 = gt ? s_run_lab[r] : l1;
+        v1 = gt ? cur : v1;
       }
       tc_fence_before();
       mbar_arrive(&s_empty[grp]);
@@ -182,7 +233,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __rest
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < UOC_MAX_SEEDS && s_hist[threadIdx.x] != 0) atomicAdd(hist + size_t(b) * m + threadIdx.x, s_hist[threadIdx.x]);
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // pass 2: canonical fp32 evaluation of the uncertified points (same arithmetic as assign_kernel)

@@ -39,9 +39,11 @@ template <int D>
 struct MsCfg {
   static constexpr int kKBlocks = D / 64;
   static constexpr int kStageBytes = kKBlocks * kBoxBytes;
-  static constexpr int kStages = (D == 64) ? 6 : 5;
+  static constexpr int kStages = (D == 64) ? 12 : 5;   // X tiles in flight: several fields per launch stream from HBM (latency x bandwidth)
   static constexpr int kZBytes = kKBlocks * kBoxBytes;
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kZBytes + kStages * kStageBytes + 256 /*barriers*/;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kZBytes + kStages * kStageBytes + 512 /*barriers*/;
+  static_assert((2 * kStages + 3 + 3 + 1 + 3) * 8 + 8 <= 512, "barrier region");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   static constexpr uint32_t kTmemCols = 512;
   static constexpr uint32_t kColS3 = 128, kColO3 = 384;   // three S/P buffers of 128 columns (tile j -> j % 3), then O
 };
