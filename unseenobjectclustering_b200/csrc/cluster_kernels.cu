@@ -814,12 +814,12 @@ int launch_hill_climb_simt(const float* X, const ClusterShape& s, const ClusterW
 template <int DREG>   // channels held in registers (0 = generic d)
 __global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restrict__ Z, int m, int d, float eps, int metric,
                                                           int* __restrict__ seed_labels, int* __restrict__ num_unique) {
-  extern __shared__ float zs[];  // [m][d+1]
+  extern __shared__ __align__(16) float zs[];  // [m][d+4]: rows 16-byte aligned (float4 broadcast reads), 4-way bank conflicts at most on the per-lane row reads
   __shared__ unsigned int adj[UOC_MAX_SEEDS][4];
   __shared__ int labels[UOC_MAX_SEEDS];
   __shared__ int cnt[UOC_MAX_SEEDS];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int ld = d + 1;
+  const int ld = d + 4;
   const float* Zb = Z + size_t(b) * m * d;
   for (int e = tid; e < m * d; e += blockDim.x) zs[(e / d) * ld + (e % d)] = Zb[e];
   if (tid < UOC_MAX_SEEDS) { labels[tid] = -1; cnt[tid] = 0; }
@@ -844,8 +844,15 @@ __global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restric
       } else {
         for (int i = iq; i < m; i += 4) {
           float acc = 0.f;
+          const float4* zi = reinterpret_cast<const float4*>(zs + i * ld);     // broadcast reads, same fmaf order as before
 #pragma unroll
-          for (int k = 0; k < DREG; ++k) acc = fmaf(zj[k], zs[i * ld + k], acc);
+          for (int k4 = 0; k4 < DREG / 4; ++k4) {
+            const float4 z4 = zi[k4];
+            acc = fmaf(zj[4 * k4 + 0], z4.x, acc);
+            acc = fmaf(zj[4 * k4 + 1], z4.y, acc);
+            acc = fmaf(zj[4 * k4 + 2], z4.z, acc);
+            acc = fmaf(zj[4 * k4 + 3], z4.w, acc);
+          }
           const bool in = (j < m) && ((0.5f * (1.0f - acc)) <= eps);
           const unsigned int bits = __ballot_sync(0xffffffffu, in);
           if ((tid & 31) == 0) adj[i][w4] = bits;
@@ -927,7 +934,7 @@ __global__ void __launch_bounds__(512) label_seeds_kernel(const float* __restric
 
 int launch_label_seeds(const float* Z, int batch, int m, int d, float epsilon, int* seed_labels, int* num_unique,
                        cudaStream_t stream, int metric) {
-  const size_t smem = sizeof(float) * size_t(m) * (d + 1);
+  const size_t smem = sizeof(float) * size_t(m) * (d + 4);
   {
     const void* kern = d == 64 ? reinterpret_cast<const void*>(&label_seeds_kernel<64>)
                      : d == 128 ? reinterpret_cast<const void*>(&label_seeds_kernel<128>)
