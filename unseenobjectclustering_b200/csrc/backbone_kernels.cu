@@ -407,35 +407,48 @@ struct StemTcParams {
   __nv_bfloat16* y[2];
   int N, H, W, Ho, Wo, tiles_x, tiles_y, tiles_per_group, groups;
   unsigned int* err;
+  int use_tma;                   // input patches by TMA (fp32 3-D maps over [W][H][3 N], OOB zero fill = the padding), double buffered
+  CUtensorMap tmap_x[2];
+  CUtensorMap tmap_x2[2];
 };
 
 constexpr int kStemPatchH = 8 * 2 + 5;     // 21
 constexpr int kStemPatchW = 16 * 2 + 5;    // 37
+constexpr int kStemPitch = 44;             // floats per patch row in shared memory: the TMA box starts one pixel early (x0 - 4) so that
+                                           // its first byte is 16-byte aligned in global memory, and spans 44 floats = 176 bytes
+constexpr int kStemShift = 1;              // column of the patch's own first pixel (x0 - 3) inside a row
+constexpr int kStemHalfFloats = ((3 * kStemPatchH * kStemPitch * 4 + 127) / 128) * 128 / 4;   // channels 0..2 | 3..5: 128-byte aligned halves
+__host__ __device__ constexpr int stem_patch_index(int c, int row, int col) {
+  return (c / 3) * kStemHalfFloats + ((c % 3) * kStemPatchH + row) * kStemPitch + col;
+}
 
 template <int CIN>
 struct StemTcCfg {
   static constexpr int K = 49 * CIN;                 // 147 | 294
   static constexpr int KB = (K + 63) / 64;           // 3 | 5 K-blocks of 64
   static constexpr int NCH = (K + 7) / 8;            // 19 | 37 16-byte chunks per im2col row that hold data
-  static constexpr int kSmem = 1024 + KB * 16384 + KB * 8192 + CIN * kStemPatchH * 38 * 4 + 64;
+  static constexpr int kPatchBytes = (CIN / 3) * kStemHalfFloats * 4;     // one patch buffer
+  static constexpr int kSmem = 1024 + KB * 16384 + KB * 8192 + 2 * kPatchBytes + 256 /*bias*/ + 64;
 };
 
 template <int CIN>
-__global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(StemTcParams p) {
+__global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(const __grid_constant__ StemTcParams p) {
   using Cfg = StemTcCfg<CIN>;
   constexpr int KB = Cfg::KB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_s = smem;                                  // KB x 16 KB : [kb][128 rows][128 B]
   uint8_t* w_s = smem + KB * 16384;                     // KB x  8 KB : [kb][ 64 rows][128 B]
-  float* patch = reinterpret_cast<float*>(w_s + KB * 8192);         // [CIN][21][38]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(patch + CIN * kStemPatchH * 38);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* patch_raw = w_s + KB * 8192;                             // 2 x [CIN][21][40] fp32
+  float* s_bias = reinterpret_cast<float*>(patch_raw + 2 * Cfg::kPatchBytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_bias + 64);
+  uint64_t* p_full = bar + 1;                                       // 2: patch buffers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int total_tiles = p.groups * p.tiles_per_group;
   int cur_g = -1;
 
-  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(&p_full[0], 1); mbar_init(&p_full[1], 1); fence_mbar_init(); }
   if (warp == 0) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
   for (int e = tid; e < KB * 16384 / 16; e += 128) reinterpret_cast<uint4*>(a_s)[e] = make_uint4(0u, 0u, 0u, 0u);
   tc_fence_before();
@@ -444,13 +457,36 @@ __global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(StemTc
   const uint32_t tmem = *tmem_slot;
   const uint32_t a_addr = smem_u32(a_s), w_addr = smem_u32(w_s);
   uint32_t phase = 0;
+  constexpr uint32_t kPatchTx = CIN * kStemPatchH * kStemPitch * 4;
+  // one thread: the input patch of tile t -> patch buffer buf  (a macro, not a lambda: the tensor maps must be addressed
+  // in the kernel's parameter space, which a by-reference capture of `p` does not guarantee)
+#define UOC_STEM_FETCH(T_, BUF_)                                                                                          \
+  do {                                                                                                                    \
+    const int fg = (T_) / p.tiles_per_group;                                                                              \
+    int fr = (T_) - fg * p.tiles_per_group;                                                                               \
+    const int ftx = fr % p.tiles_x; fr /= p.tiles_x;                                                                      \
+    const int fty = fr % p.tiles_y;                                                                                       \
+    const int fn = fr / p.tiles_y;                                                                                        \
+    uint8_t* fdst = patch_raw + (BUF_) * Cfg::kPatchBytes;                                                                \
+    mbar_arrive_expect_tx(&p_full[(BUF_)], kPatchTx);                                                                     \
+    tma_load_3d(fdst, &p.tmap_x[fg], &p_full[(BUF_)], ftx * 32 - 3 - kStemShift, fty * 16 - 3, fn * 3);                                \
+    if (CIN == 6)                                                                                                         \
+      tma_load_3d(fdst + kStemHalfFloats * 4, &p.tmap_x2[fg], &p_full[(BUF_)], ftx * 32 - 3 - kStemShift, fty * 16 - 3, fn * 3); \
+  } while (0)
+  if (p.use_tma && tid == 0 && int(blockIdx.x) < total_tiles) UOC_STEM_FETCH(int(blockIdx.x), 0);
+  int it = 0;
 
-  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
     const int g = t / p.tiles_per_group;
     int r = t - g * p.tiles_per_group;
     const int tx = r % p.tiles_x; r /= p.tiles_x;
     const int ty = r % p.tiles_y;
     const int n = r / p.tiles_y;
+    const int buf = p.use_tma ? (it & 1) : 0;
+    float* patch = reinterpret_cast<float*>(patch_raw + buf * Cfg::kPatchBytes);
+    // the next tile's patch travels while this one is processed (its buffer was last read before the barrier that ended
+    // the previous iteration)
+    if (p.use_tma && tid == 0 && t + int(gridDim.x) < total_tiles) UOC_STEM_FETCH(t + int(gridDim.x), buf ^ 1);
     if (g != cur_g) {                                   // (re)load this branch's weights, K-major 128B-swizzled rows
       const uint4* wg = reinterpret_cast<const uint4*>(p.w[g]);
       for (int e = tid; e < 64 * KB * 8; e += 128) {
@@ -458,9 +494,13 @@ __global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(StemTc
         const int kb = j >> 3, cc = j & 7;
         *reinterpret_cast<uint4*>(w_s + kb * 8192 + row * 128 + ((cc ^ (row & 7)) << 4)) = __ldg(wg + e);
       }
+      if (tid < 64) s_bias[tid] = __ldg(p.bias[g] + tid);
       cur_g = g;
     }
-    // stage the fp32 input patch
+    if (p.use_tma) {
+      if (!mbar_wait(&p_full[buf], uint32_t(it >> 1) & 1u, p.err)) break;
+    } else {
+    // stage the fp32 input patch (unaligned input / W % 4 != 0)
     const int iy0 = ty * 16 - 3, ix0 = tx * 32 - 3;
     const float* xa = p.x[g] + size_t(n) * 3 * p.H * p.W;                     // channels 0..2
     const float* xb = (CIN == 6) ? p.x2[g] + size_t(n) * 3 * p.H * p.W : xa;  // channels 3..5 (early fusion)
@@ -472,13 +512,14 @@ __global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(StemTc
       const float* xg = (CIN == 6 && c >= 3) ? xb + size_t(c - 3) * p.H * p.W : xa + size_t(c) * p.H * p.W;
       float v = 0.f;
       if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xg + size_t(iy) * p.W + ix);
-      patch[(c * kStemPatchH + py) * 38 + px] = v;
+      patch[stem_patch_index(c, py, px + kStemShift)] = v;
+    }
     }
     __syncthreads();
     // im2col row of pixel `tid` -> NCH chunks of 8 bf16 (k >= K is zero)
     {
       const int ly = tid >> 4, lx = tid & 15;
-      const float* pb = patch + (ly * 2) * 38 + lx * 2;
+      const float* pb = patch + (ly * 2) * kStemPitch + lx * 2 + kStemShift;     // + stem_patch_index(c, kr, ks)
       float vals[8];
 #pragma unroll
       for (int j = 0; j < Cfg::NCH; ++j) {
@@ -489,7 +530,7 @@ __global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(StemTc
           if (k < Cfg::K) {
             const int tap = k / CIN, c = k - tap * CIN;
             const int kr = tap / 7, ks = tap - kr * 7;
-            v = pb[(c * kStemPatchH + kr) * 38 + ks];
+            v = pb[stem_patch_index(c, kr, ks)];
           }
           vals[q] = v;
         }
@@ -525,7 +566,6 @@ __global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(StemTc
       const int oy = ty * 8 + (tid >> 4), ox = tx * 16 + (tid & 15);
       const bool inb = (oy < p.Ho) && (ox < p.Wo);
       const uint32_t ta = tmem + (uint32_t(warp * 32) << 16);
-      const float* bias = p.bias[g];
       uint4* op = reinterpret_cast<uint4*>(p.y[g] + ((size_t(n) * p.Ho + oy) * p.Wo + ox) * 64);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -536,8 +576,11 @@ __global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(StemTc
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float f[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 32 + 8 * e);          // broadcast
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 32 + 8 * e + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int h = 0; h < 8; ++h) f[h] = fmaxf(__uint_as_float(v[8 * e + h]) + __ldg(bias + c * 32 + 8 * e + h), 0.f);
+            for (int h = 0; h < 8; ++h) f[h] = fmaxf(__uint_as_float(v[8 * e + h]) + bb[h], 0.f);
             op[c * 4 + e] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                                        pack_bf16x2(f[6], f[7]));
           }
@@ -552,6 +595,8 @@ __global__ void __launch_bounds__(128, (CIN == 3 ? 2 : 1)) stem_tc_kernel(StemTc
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 64);
 }
+
+#undef UOC_STEM_FETCH
 
 template <int CIN>
 static int launch_stem_tc_t(const StemTcParams& p, cudaStream_t stream) {
@@ -589,6 +634,25 @@ int launch_stem_tc(const StemGroup* g, const void* const* w_bf16, int groups, in
   p.groups = groups;
   p.err = device_error_word();
   if (!p.err) return fail(UOC_ERR_CUDA, "no device error word");
+  // input patches by TMA when the planes allow it (16-byte aligned base, rows a multiple of 16 bytes)
+  p.use_tma = (W % 4 == 0) ? 1 : 0;
+  for (int i = 0; i < groups && p.use_tma; ++i) {
+    if (reinterpret_cast<uintptr_t>(g[i].x) % 16 != 0 || (cin == 6 && reinterpret_cast<uintptr_t>(g[i].x2) % 16 != 0)) p.use_tma = 0;
+  }
+  if (p.use_tma) {
+    const uint64_t dims[3] = {uint64_t(W), uint64_t(H), uint64_t(3) * N};
+    const uint64_t strides[2] = {uint64_t(W) * 4, uint64_t(H) * W * 4};
+    const uint32_t box[3] = {uint32_t(kStemPitch), uint32_t(kStemPatchH), 3};
+    for (int i = 0; i < 2; ++i) {
+      const int j = i < groups ? i : 0;
+      int rc = make_tmap_f32(&p.tmap_x[i], g[j].x, 3, dims, strides, box);
+      if (rc != UOC_OK) return rc;
+      if (cin == 6) {
+        rc = make_tmap_f32(&p.tmap_x2[i], g[j].x2, 3, dims, strides, box);
+        if (rc != UOC_OK) return rc;
+      }
+    }
+  }
   return cin == 3 ? launch_stem_tc_t<3>(p, stream) : launch_stem_tc_t<6>(p, stream);
 }
 

@@ -68,6 +68,8 @@ EncodeTiledFn get_encode_tiled();
 // rank-r bf16 tensor map with 128B swizzle; dims/strides innermost first; strides in BYTES for dims 1..r-1
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const uint32_t* elem_strides);
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

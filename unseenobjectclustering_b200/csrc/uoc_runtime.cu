@@ -195,6 +195,29 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return UOC_OK;
 }
 
+// fp32 tensor map without swizzle (the stem's input patches: box rows land linearly in shared memory, OOB -> zero)
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(UOC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1u; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, cuuint32_t(rank), const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled (fp32) failed with CUresult %d (rank %d, dims %llu %llu ..)", int(r), rank,
+             (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0));
+    return fail(UOC_ERR_CUDA, buf);
+  }
+  return UOC_OK;
+}
+
 }  // namespace uoc
 
 extern "C" {
