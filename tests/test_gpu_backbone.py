@@ -168,6 +168,23 @@ def test_graphed_forward_equals_eager_and_returns_fresh_tensors():
     assert torch.equal(got[1], eager[1])                                  # untouched by the later replays
 
 
+def test_stem_without_tma_for_unaligned_inputs():
+    """The stem fetches its input patches by TMA when the planes are 16-byte aligned; an input view that starts 4 bytes into
+    its storage takes the thread-staged path: same result, bit for bit."""
+    net = NW.seg_resnet34_8s_embedding(2, 64, O.randomise_bn_(NW.random_state_dict(64, seed=6), 1006)).to(DEV)
+    img, xyz = O.synthetic_rgbd_frame(96, 128, seed=21)
+    n = img.numel()
+    ref, _ = net.forward_ex(img.to(DEV), None, xyz.to(DEV), graph=False)
+    buf_i = torch.empty(n + 1, dtype=torch.float32, device=DEV)
+    buf_x = torch.empty(n + 1, dtype=torch.float32, device=DEV)
+    vi, vx = buf_i[1:].view(img.shape), buf_x[1:].view(xyz.shape)
+    vi.copy_(img)
+    vx.copy_(xyz)
+    assert vi.data_ptr() % 16 == 4 and vi.is_contiguous()
+    got, _ = net.forward_ex(vi, None, vx, graph=False)
+    assert torch.equal(got, ref)
+
+
 def test_module_drop_in_behaviour():
     net = NW.seg_resnet34_8s_embedding(2, 64, None).cuda(0)
     dp = torch.nn.DataParallel(net, device_ids=[0]).cuda(0)
