@@ -249,6 +249,40 @@ def gen_init(ref):
         print(name, selected[:k + 4].tolist())
 
 
+def gen_munkres(ref):
+    """Assignments of the reference's own utils.munkres.Munkres on tie-heavy rectangular cost matrices (the way
+    lib/utils/evaluation.py:220-221 calls it: F.max() - F)."""
+    import importlib
+    mk = importlib.import_module("utils.munkres")
+    rng = np.random.default_rng(1234)
+    mats, shapes, pairs, counts = [], [], [], []
+    for t in range(400):
+        r, c = int(rng.integers(1, 10)), int(rng.integers(1, 10))
+        mode = t % 4
+        if mode == 0:
+            F = rng.random((r, c))
+        elif mode == 1:
+            F = rng.integers(0, 4, (r, c)).astype(np.float64) / 3.0
+        elif mode == 2:
+            F = np.round(rng.random((r, c)), 1)
+            F[rng.random((r, c)) < 0.5] = 0
+        else:
+            F = rng.integers(0, 2, (r, c)).astype(np.float64)
+        cost = F.max() - F.copy()
+        a = mk.Munkres().compute(cost.copy())
+        pad = np.zeros((9, 9))
+        pad[:r, :c] = cost
+        mats.append(pad)
+        shapes.append((r, c))
+        pa = -np.ones((9, 2), dtype=np.int64)
+        pa[:len(a)] = np.array(a, dtype=np.int64).reshape(-1, 2)
+        pairs.append(pa)
+        counts.append(len(a))
+    np.savez_compressed(os.path.join(OUT, "munkres.npz"), cost=np.stack(mats), shape=np.array(shapes), pairs=np.stack(pairs),
+                        count=np.array(counts))
+    print("munkres", len(mats), "matrices")
+
+
 def _planar_to_X(Xp):
     """[d, n] planar float32 -> the reference's X: a [n, d] view with strides (1, n) (test_dataset.py:54-55)."""
     return torch.from_numpy(Xp).t()
@@ -374,6 +408,8 @@ if __name__ == "__main__":
         gen_metrics(ref)
     if not only or "init" in only:
         gen_init(ref)
+    if not only or "munkres" in only:
+        gen_munkres(ref)
     if not only or "full" in only:
         gen_full(ref)
     if not only or "full_two_stage" in only:

@@ -654,10 +654,81 @@ def boundary_overlap(predicted_mask, gt_mask, bound_th=0.003):
     return np.sum(np.logical_and(fg_boundary, gt_dil)), np.sum(np.logical_and(gt_boundary, fg_dil))
 
 
+def munkres_assignment(cost):
+    """lib/utils/munkres.py:320-372 (Munkres.compute) restated with plain loops: the Kuhn-Munkres steps in the reference's
+    scan orders (zero padding to a square :301-316, row minima only :385-399, row-major greedy stars :401-418, the zero to
+    prime = LAST uncovered zero of the first uncovered row that has one :536-560, update = add to covered rows then subtract
+    from uncovered columns :510-524, first star in column / first prime in row :562-599), so that ties are broken alike.
+    Returns the (row, col) pairs inside the original matrix, row-major."""
+    cost = np.asarray(cost, dtype=np.float64)
+    R, Cn = cost.shape
+    n = max(R, Cn)
+    C = [[float(cost[i, j]) if (i < R and j < Cn) else 0.0 for j in range(n)] for i in range(n)]
+    for i in range(n):
+        mv = min(C[i])
+        for j in range(n):
+            C[i][j] -= mv
+    mark = [[0] * n for _ in range(n)]               # 1 star, 2 prime
+    rc, cc = [False] * n, [False] * n
+    for i in range(n):
+        for j in range(n):
+            if C[i][j] == 0 and not rc[i] and not cc[j]:
+                mark[i][j] = 1
+                rc[i] = cc[j] = True
+    rc, cc = [False] * n, [False] * n
+    while True:
+        count = 0
+        for i in range(n):
+            for j in range(n):
+                if mark[i][j] == 1:
+                    cc[j] = True
+                    count += 1
+        if count >= n:
+            break
+        while True:
+            zr = zc = -1
+            for i in range(n):
+                found = False
+                for j in range(n):
+                    if C[i][j] == 0 and not rc[i] and not cc[j]:
+                        zr, zc, found = i, j, True    # keeps scanning the row: the last zero wins
+                if found:
+                    break
+            if zr < 0:
+                mv = min(C[i][j] for i in range(n) for j in range(n) if not rc[i] and not cc[j])
+                for i in range(n):
+                    for j in range(n):
+                        if rc[i]:
+                            C[i][j] += mv
+                        if not cc[j]:
+                            C[i][j] -= mv
+                continue
+            mark[zr][zc] = 2
+            sc = next((j for j in range(n) if mark[zr][j] == 1), -1)
+            if sc < 0:
+                break
+            rc[zr] = True
+            cc[sc] = False
+        path = [(zr, zc)]
+        while True:
+            r = next((i for i in range(n) if mark[i][path[-1][1]] == 1), -1)
+            if r < 0:
+                break
+            path.append((r, path[-1][1]))
+            path.append((r, next(j for j in range(n) if mark[r][j] == 2)))
+        for (i, j) in path:
+            mark[i][j] = 0 if mark[i][j] == 1 else 1
+        rc, cc = [False] * n, [False] * n
+        for i in range(n):
+            for j in range(n):
+                if mark[i][j] == 2:
+                    mark[i][j] = 0
+    return [(i, j) for i in range(R) for j in range(Cn) if mark[i][j] == 1]
+
+
 def multilabel_metrics(prediction, gt, obj_detect_threshold=0.75):
     """lib/utils/evaluation.py:109-257, statement by statement; the Hungarian step (utils.munkres, :221-223) through
-    scipy.optimize.linear_sum_assignment (same optimum; the pairs can differ only between equally good assignments)."""
-    from scipy.optimize import linear_sum_assignment
+    munkres_assignment above (the reference's procedure and tie-breaking)."""
     labels_gt = np.unique(gt)
     labels_gt = labels_gt[~np.isin(labels_gt, [0])]
     labels_pred = np.unique(prediction)
@@ -692,8 +763,7 @@ def multilabel_metrics(prediction, gt, obj_detect_threshold=0.75):
     boundary_prec_denom = sum(float(np.sum(seg2bmap(prediction == pred_j))) for pred_j in labels_pred)
     boundary_rec_denom = sum(float(np.sum(seg2bmap(gt == gt_i))) for gt_i in labels_gt)
     F[np.isnan(F)] = 0
-    r, c = linear_sum_assignment(F.max() - F.copy())
-    assignments = list(zip(r.tolist(), c.tolist()))
+    assignments = munkres_assignment(F.max() - F.copy())
     num_obj_detected = sum(1 for a in assignments if F[a] > obj_detect_threshold)
     idx = tuple(np.array(assignments).T)
     with np.errstate(divide='ignore', invalid='ignore'):

@@ -130,6 +130,36 @@ def test_select_seeds_with_init_seeds_is_bit_identical_to_the_live_reference():
     assert torch.equal(ir, io) and torch.equal(sr, so)
 
 
+def test_assignment_matches_the_reference_munkres_golden():
+    """The Hungarian step of the evaluation tail (lib/utils/evaluation.py:220-221): the product's host implementation and
+    the oracle's restatement both reproduce the assignments the reference's own Munkres class returned on 400 tie-heavy
+    rectangular matrices (fixture written by oracle/make_golden.py) -- the pairs, not just the optimum."""
+    from unseenobjectclustering_b200 import evaluation as EV
+    g = _load(os.path.join(GOLDEN, "munkres.npz"))
+    for k in range(g["cost"].shape[0]):
+        r, c = int(g["shape"][k][0]), int(g["shape"][k][1])
+        cost = g["cost"][k][:r, :c]
+        want = [tuple(int(v) for v in p) for p in g["pairs"][k][:int(g["count"][k])]]
+        assert EV._assignment(cost.copy()) == want, k
+        assert O.munkres_assignment(cost.copy()) == want, k
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference tree not present (GPU box)")
+def test_assignment_matches_the_live_reference_munkres():
+    import importlib
+    from unseenobjectclustering_b200 import evaluation as EV
+    rh.load()
+    mk = importlib.import_module("utils.munkres")
+    rng = np.random.default_rng(7)
+    for t in range(600):
+        r, c = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        F = rng.integers(0, 3, (r, c)).astype(np.float64) / 2.0 if t % 2 else np.round(rng.random((r, c)), 1)
+        cost = F.max() - F.copy()
+        want = [tuple(int(v) for v in p) for p in mk.Munkres().compute(cost.copy())]
+        assert EV._assignment(cost.copy()) == want
+        assert O.munkres_assignment(cost.copy()) == want
+
+
 def test_two_stage_oracle_matches_golden():
     g = _load(os.path.join(GOLDEN, "two_stage.npz"))
     H, W = int(g["H"]), int(g["W"])

@@ -21,11 +21,72 @@ _KL = 256
 
 def _assignment(cost):
     """Minimum-cost assignment of a rectangular matrix as a list of (row, col) pairs -- what
-    utils.munkres.Munkres().compute returns (evaluation.py:221-223).  The optimum is the same; when several
-    assignments are optimal the pairs may differ from the reference's implementation."""
-    from scipy.optimize import linear_sum_assignment
-    r, c = linear_sum_assignment(cost)
-    return list(zip(r.tolist(), c.tolist()))
+    utils.munkres.Munkres().compute returns (lib/utils/evaluation.py:220-221, lib/utils/munkres.py:320-372) INCLUDING its
+    choice among equally good assignments: the Kuhn-Munkres procedure with the reference's scan orders and float64
+    arithmetic, restated on numpy state arrays.  What decides ties (lib/utils/munkres.py):
+      * the smaller side is zero-padded to a square (:301-316); only ROW minima are subtracted (:385-399);
+      * initial stars: row-major greedy over uncovered zeros (:401-418);
+      * the zero to prime is taken in the FIRST uncovered row that has an uncovered zero, and in that row it is the LAST
+        such zero -- the scan does not stop at the first hit (:536-560);
+      * the matrix update adds the smallest uncovered value to covered rows, THEN subtracts it from uncovered columns,
+        element by element (:510-524): the same two float64 operations in the same order here, so the exact == 0 tests see
+        the same bits;
+      * augmenting path: first star in the column, first prime in the row (:474-508, :562-599).
+    Pinned against the reference's own class on thousands of tie-heavy matrices (tests/test_oracle.py) and against a
+    fixture it wrote (tests/golden/munkres.npz)."""
+    cost = np.asarray(cost, dtype=np.float64)
+    rows, cols = cost.shape
+    n = max(rows, cols)
+    C = np.zeros((n, n), dtype=np.float64)
+    C[:rows, :cols] = cost
+    C -= C.min(axis=1, keepdims=True)
+    star = np.zeros((n, n), dtype=bool)
+    prime = np.zeros((n, n), dtype=bool)
+    row_cov = np.zeros(n, dtype=bool)
+    col_cov = np.zeros(n, dtype=bool)
+    for i in range(n):                                   # initial stars
+        free = np.flatnonzero((C[i] == 0) & ~col_cov)
+        if free.size:
+            star[i, free[0]] = True
+            col_cov[free[0]] = True
+    col_cov[:] = False
+    while True:
+        col_cov |= star.any(axis=0)
+        if int(star.sum()) >= n:
+            break
+        z_row = z_col = -1
+        while True:                                      # prime zeros until one has no star in its row
+            open_zero = (C == 0) & ~row_cov[:, None] & ~col_cov[None, :]
+            hit_rows = np.flatnonzero(open_zero.any(axis=1))
+            if hit_rows.size == 0:                       # no uncovered zero: shift the matrix by the smallest uncovered value
+                m = C[np.ix_(~row_cov, ~col_cov)].min()
+                C[row_cov, :] += m
+                C[:, ~col_cov] -= m
+                continue
+            i = int(hit_rows[0])
+            j = int(np.flatnonzero(open_zero[i])[-1])
+            prime[i, j] = True
+            starred = np.flatnonzero(star[i])
+            if starred.size:
+                row_cov[i] = True
+                col_cov[starred[0]] = False
+            else:
+                z_row, z_col = i, j
+                break
+        path = [(z_row, z_col)]                          # alternate: star in the column, prime in that star's row
+        while True:
+            above = np.flatnonzero(star[:, path[-1][1]])
+            if above.size == 0:
+                break
+            r = int(above[0])
+            path.append((r, path[-1][1]))
+            path.append((r, int(np.flatnonzero(prime[r])[0])))
+        for r, c in path:
+            star[r, c] = not star[r, c]
+        row_cov[:] = False
+        col_cov[:] = False
+        prime[:] = False
+    return [(i, j) for i in range(rows) for j in range(cols) if star[i, j]]
 
 
 def multilabel_counts(prediction, gt, device=None):
