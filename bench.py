@@ -476,17 +476,11 @@ def run_b200(args):
     if world > 1:
         multi = {}
         sl = pipe.slots[(pipe.next - 1) % len(pipe.slots)]          # the last step: its labels and the last gather
-        mine = sl.lab_u8.view(-1).to(torch.int64)
-        w = torch.arange(1, mine.numel() + 1, device=dev, dtype=torch.int64) % 65521
-        local_sum = torch.stack([mine.sum(), (mine * w).sum()])
-        sums = torch.empty((world, 2), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(sums, local_sum)
-        g64 = gathered_u8.to(torch.int64)
-        got = torch.stack([g64.sum(1), (g64 * w[None]).sum(1)], 1)
-        same_as_f32 = bool(torch.equal(sl.lab_u8.view(B, H, W).to(torch.float32), sl.lab_f32))
-        ok = torch.tensor([int(torch.equal(got, sums) and same_as_f32)], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        multi["gather_verified"] = bool(ok.item())
+        from unseenobjectclustering_b200 import distributed as UD
+        arrived = UD.verify_gathered_labels(sl.lab_u8.view(-1), gathered_u8)     # checksums all-gathered, verdict MIN-reduced
+        same_as_f32 = torch.tensor([int(torch.equal(sl.lab_u8.view(B, H, W).to(torch.float32), sl.lab_f32))], device=dev)
+        dist.all_reduce(same_as_f32, op=dist.ReduceOp.MIN)
+        multi["gather_verified"] = bool(arrived and same_as_f32.item())
         multi["gather_dtype"] = "uint8 on the wire (%d bytes per frame), widened by the receiver" % n
         # config 4: 8 frames per GPU (8 / S steps of S), ONE gather of all 8*N label maps, inside the timed region
         per_gpu = 8

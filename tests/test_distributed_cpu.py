@@ -67,3 +67,38 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     for r in range(2):
         got = np.load(os.path.join(str(tmp_path), "rank%d.npy" % r))
         assert np.array_equal(got, single.numpy())
+
+
+def _verify_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    from unseenobjectclustering_b200 import distributed as UD
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(10 + rank)
+    mine = torch.randint(0, 9, (2, 12 * 16), generator=g, dtype=torch.uint8)       # two frames per rank
+    gathered = UD.gather_labels(mine).view(world, -1)
+    good = UD.verify_gathered_labels(mine.view(-1), gathered)
+    broken = gathered.clone()
+    if rank == 1:                                                                  # one rank, one pixel: every rank must say no
+        broken[0, 7] += 1
+    bad = UD.verify_gathered_labels(mine.view(-1), broken)
+    swapped = gathered.flip(0)                                                     # same sums overall, wrong rank order
+    swp = UD.verify_gathered_labels(mine.view(-1), swapped)
+    np.save(os.path.join(out_dir, "verdict%d.npy" % rank), np.array([good, bad, swp]))
+    dist.destroy_process_group()
+
+
+def test_label_checksums_see_value_and_position():
+    from unseenobjectclustering_b200 import distributed as UD
+    a = torch.tensor([[0, 1, 2, 3]], dtype=torch.uint8)
+    assert UD.label_checksums(a).tolist() == [[6, 0 * 1 + 1 * 2 + 2 * 3 + 3 * 4]]
+    assert UD.label_checksums(a.flip(1))[0, 0] == 6 and UD.label_checksums(a.flip(1))[0, 1] != 20
+    assert UD.label_checksums(torch.zeros((2, 0), dtype=torch.uint8)).tolist() == [[0, 0], [0, 0]]
+
+
+def test_two_rank_gloo_gather_verification(tmp_path):
+    port = _free_port()
+    mp.spawn(_verify_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert np.load(os.path.join(str(tmp_path), "verdict%d.npy" % r)).tolist() == [True, False, False]

@@ -37,6 +37,35 @@ def gather_labels(local_labels, num_frames=None, group=None):
     return out if num_frames is None else out[:num_frames]
 
 
+def _all_gather_rows(row, group=None):
+    """[L] per rank -> [world, L] on every rank (NCCL: one all_gather_into_tensor; gloo: all_gather of the chunks)."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(row.shape), dtype=row.dtype, device=row.device)
+    if row.is_cuda:
+        dist.all_gather_into_tensor(out, row.contiguous(), group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), row.contiguous(), group=group)
+    return out
+
+
+def label_checksums(labels_u8):
+    """[R, L] uint8 label maps (one flattened row per rank) -> [R, 2] int64: plain sum and position-weighted sum."""
+    v = labels_u8.reshape(labels_u8.shape[0], -1).to(torch.int64)
+    w = torch.arange(1, v.shape[1] + 1, device=v.device, dtype=torch.int64) % 65521
+    return torch.stack([v.sum(1), (v * w[None]).sum(1)], 1)
+
+
+def verify_gathered_labels(local_u8, gathered_u8, group=None):
+    """True on every rank iff every rank's uint8 label maps arrived intact in `gathered_u8` [world, L] on every rank:
+    the checksums of the local maps are all-gathered and compared with the checksums of the gathered rows; the verdicts
+    are MIN-reduced.  (bench.py runs this once per multi-GPU run; tests/test_distributed_cpu.py on gloo.)"""
+    mine = label_checksums(local_u8.reshape(1, -1))[0]
+    sums = _all_gather_rows(mine, group)
+    ok = torch.tensor([int(torch.equal(label_checksums(gathered_u8), sums))], device=local_u8.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    return bool(ok.item())
+
+
 def segment_frames(images, depths, network, first_indices, cluster_fn, rank=0, world_size=1, pad_to=None):
     """Shard [F,3,H,W] host frames over ranks, run network + clustering on the local shard with the
     pre-drawn first-seed indices, all-gather the label maps.  `cluster_fn(features, firsts)` returns
