@@ -221,7 +221,8 @@ UOC_API size_t uoc_backbone_workspace_bytes(const uoc_backbone* bb, int N, int H
  * lib/fcn/test_dataset.py:235-239); rgb may be NULL for UOC_INPUT_DEPTH, xyz for UOC_INPUT_COLOR.
  * features_out: [N,C,H,W] fp32 NCHW, C = uoc_backbone_feature_dim(), unit L2 norm over channels (unless
  * normalize == 0).  features_bf16_out (optional, may be NULL): [N,H*W,C] bf16 copy for
- * uoc_meanshift_cluster.  H and W must be multiples of 8.
+ * uoc_meanshift_cluster.  Any H, W >= 16, like the reference (the stride-2 stages round as PyTorch's convolutions do,
+ * the head interpolates back to H x W); widths that are multiples of 4 take the TMA-fed stem and 16-byte planar stores.
  */
 UOC_API int uoc_backbone_forward(uoc_backbone* bb, const float* rgb, const float* xyz, int N, int H, int W,
                                  float* features_out, void* features_bf16_out, void* workspace,

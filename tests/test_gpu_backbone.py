@@ -144,6 +144,34 @@ def test_backbone_full_frame_vs_oracle_and_bf16_copy():
     assert torch.equal(net(i2.to(DEV), None, x2.to(DEV)).cpu(), f2)
 
 
+@pytest.mark.parametrize("H,W", [(100, 132), (90, 124), (75, 100), (61, 83), (33, 50)])
+def test_backbone_takes_any_frame_size(H, W):
+    """The reference takes every frame size (resnet_dilated.py:293,325: the trunk's stride-2 stages round as PyTorch's
+    convolutions do, the head interpolates back to the input size).  Sizes that are not multiples of 8: ragged tiles in
+    every layer, odd stem / max-pool / stride-2 extents; widths that are not multiples of 4 take the thread-staged stem and
+    the one-pixel-per-thread head.  Same bars as the full frame: <= 1e-3 cosine distance, bf16 copy = the field."""
+    sd = O.randomise_bn_(NW.random_state_dict(64, seed=4), 1004)
+    net = NW.seg_resnet34_8s_embedding(2, 64, sd).to(DEV)
+    net.flags = _lib.FLAG_SYNC_CHECK
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed=H + W)
+    f, xb = net.forward_ex(img.to(DEV), None, xyz.to(DEV), graph=False)
+    want = O.OracleSegNet(sd)(img, None, xyz)
+    assert f.shape == want.shape == (1, 64, H, W)
+    assert bool(torch.isfinite(f).all())
+    cosd = (1.0 - (f.cpu() * want).sum(1)).abs().max().item()
+    assert cosd < 1e-3, cosd
+    assert xb.shape == (1, H * W, 64)
+    back = xb.float().view(1, H, W, 64).permute(0, 3, 1, 2)
+    assert (back - f).abs().max().item() < 1e-2
+    # and straight into the clustering with that bf16 copy: labels of a valid partition, every stage ran
+    from unseenobjectclustering_b200 import mean_shift as MS
+    import uoc_oracle_c as C
+    labels, sel = MS.cluster_fields(f, 100, 20.0, 10, [H * W // 2], x_bf16=xb, flags=_lib.FLAG_SYNC_CHECK)[:2]
+    sel_o, _ = C.select_seeds(f.cpu()[0].reshape(64, -1).numpy(), 100, H * W // 2)
+    assert np.array_equal(sel.cpu().numpy()[0], sel_o)                   # the bf16 screen never changes an index
+    assert labels.shape == (1, H * W) and int(labels.min()) >= 0
+
+
 def test_graphed_forward_equals_eager_and_returns_fresh_tensors():
     """forward_ex replays a captured CUDA graph from the second call of a shape on: results are bit-identical to the
     launch-by-launch path, returned tensors are fresh (an earlier result is not overwritten by a later call), the bf16

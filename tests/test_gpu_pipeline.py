@@ -51,14 +51,15 @@ def test_no_objects_returns_none_refined():
     assert refined is None
 
 
-def test_end_to_end_with_real_backbone_runs():
+@pytest.mark.parametrize("H,W", [(240, 320), (123, 170), (77, 101)])
+def test_end_to_end_with_real_backbone_runs(H, W):
     """Random-init weights collapse to one cluster, so this only checks the plumbing
-    end to end through both CUDA stages."""
+    end to end through both CUDA stages -- also at frame sizes that are not multiples of 8 / 4 / 2."""
     from unseenobjectclustering_b200 import networks as NW
     net = NW.seg_resnet34_8s_embedding(2, 64, None).cuda(0)
-    img, xyz = O.synthetic_rgbd_frame(240, 320, seed=0)
-    out_label, refined = TD.test_sample({'image_color': img, 'depth': xyz}, net, None, [17])
-    assert out_label.shape == (1, 240, 320) and refined is None
+    img, xyz = O.synthetic_rgbd_frame(H, W, seed=0)
+    out_label, refined = TD.test_sample({'image_color': img, 'depth': xyz}, net, None, [17], flags=_lib.FLAG_SYNC_CHECK)
+    assert out_label.shape == (1, H, W) and refined is None
 
 
 def test_frame_pipeline_equals_serial_calls():

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256, 2) head_row_kernel(const float* __restric
   const int lane = tid & 31, warp = tid >> 5;
   const int q = lane >> 3, gi = lane & 7;                // channel quarter, pixel group inside the warp
   const size_t HW = size_t(H) * W;
-  const int groups = W / PX;                             // W % PX == 0 (W is a multiple of 8)
+  const int groups = W / PX;                             // W % PX == 0 (launch_head picks PX = 1 for any other width)
   for (int g0 = warp * 8; g0 < groups; g0 += 8 * 8) {
     const int grp = g0 + gi;
     const bool live = grp < groups;
@@ -323,8 +323,10 @@ __global__ void __launch_bounds__(256, 2) head_row_kernel(const float* __restric
       if (PX == 4) {
         __stcs(reinterpret_cast<float4*>(o + size_t(c) * HW),
                make_float4(f[0][c] * inv[0], f[1][c] * inv[1], f[2 % PX][c] * inv[2 % PX], f[3 % PX][c] * inv[3 % PX]));
-      } else {
+      } else if (PX == 2) {
         __stcs(reinterpret_cast<float2*>(o + size_t(c) * HW), make_float2(f[0][c] * inv[0], f[1 % PX][c] * inv[1 % PX]));
+      } else {
+        __stcs(o + size_t(c) * HW, f[0][c] * inv[0]);       // PX == 1: frames whose width is not a multiple of 4
       }
     }
     if (out_bf16) {
@@ -369,7 +371,17 @@ int launch_head(const float* a, const float* b, int mode, int normalize, int N, 
     if (mode == HEAD_CAT && d == 128) return launch_head_row<128, HEAD_CAT, 2>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
     return fail(UOC_ERR_UNSUPPORTED, "head supports 64 or 128 output channels (cat fusion: 2 x 64)");
   }
-  return fail(UOC_ERR_UNSUPPORTED, "head: W must be a multiple of 4 and a source row pair must fit in shared memory");
+  if (smem_row <= 200 * 1024) {
+    // any other width (the reference takes every frame size, resnet_dilated.py:293,325): one pixel per thread, so that
+    // no planar store straddles a row end or needs more than 4-byte alignment (H * W need not be a multiple of 4)
+    if (mode == HEAD_ADD && d == 64) return launch_head_row<64, HEAD_ADD, 1>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_ADD && d == 128) return launch_head_row<128, HEAD_ADD, 1>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_SINGLE && d == 64) return launch_head_row<64, HEAD_SINGLE, 1>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_SINGLE && d == 128) return launch_head_row<128, HEAD_SINGLE, 1>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    if (mode == HEAD_CAT && d == 128) return launch_head_row<128, HEAD_CAT, 1>(a, b, normalize, N, h, w, H, W, sy, sx, out_nchw, ob, stream);
+    return fail(UOC_ERR_UNSUPPORTED, "head supports 64 or 128 output channels (cat fusion: 2 x 64)");
+  }
+  return fail(UOC_ERR_UNSUPPORTED, "head: a source row pair must fit in shared memory (W <= ~2900 at 64 channels)");
 }
 
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ in, int hw, int d, float* __restrict__ out) {
