@@ -613,6 +613,16 @@ def run_b200(args):
         roof["batched4"]["field"] = "four bf16 fields = 157 MB > L2: streamed from HBM in every update (DRAM traffic ~ algorithmic bytes)"
         line["config2_clustered"]["stages_ms_per_frame_4_fields"] = {k: round(v / 4, 4) for k, v in st_4.items() if k != "clusters"}
         del f4, x4
+        if B not in (1, 4):
+            # the launch shape of the timed region itself: B fields per persistent launch (frames_per_gpu_per_step)
+            fB = torch.cat([synthetic.clustered_features(H, W, D, 6, 0.05, seed=s)[0] for s in range(B)], 0).to(dev)
+            xB = MS.pack_bf16(fB)
+            st_B = stage_split(lib, _lib, MS, dev, fB, xB, n, D, M, ITERS, firsts, flush, max(3, reps // 2), B)
+            roof["as_in_timed_region"] = loop_roofline(st_B["loop"], n, D, ITERS, peak, peak_src, None,
+                                                       kname + ", %d fields per launch" % B, fields=B)
+            roof["as_in_timed_region"]["ms_per_frame"] = st_B["loop"] / B
+            line["config2_clustered"]["stages_ms_per_frame_%d_fields" % B] = {k: round(v / B, 4) for k, v in st_B.items() if k != "clusters"}
+            del fB, xB
     roof["note"] = "algorithmic bytes = n*d*2 per mean-shift update (the bf16 copy actually streamed); fp32-equivalent (n*d*4) is 2x"
     line["roofline"] = roof
     del fc, xc

@@ -133,11 +133,12 @@ def test_frame_pipeline_with_cuda_graphs_equals_serial_calls():
         assert len(torch.unique(want)) >= 3
 
 
-def test_frame_pipeline_raw_frames_equal_prepared_frames():
-    """submit_raw (uint8 BGR + uint16 depth, inputs built on the device) == submit with the reference's fp32 inputs."""
+@pytest.mark.parametrize("H,W", [(96, 128), (77, 101)])
+def test_frame_pipeline_raw_frames_equal_prepared_frames(H, W):
+    """submit_raw (uint8 BGR + uint16 depth, inputs built on the device) == submit with the reference's fp32 inputs
+    (also at a frame size that is a multiple of nothing)."""
     from unseenobjectclustering_b200.pipeline import FramePipeline
     from unseenobjectclustering_b200 import networks
-    H, W = 96, 128
     net = networks.seg_resnet34_8s_embedding(2, 64, networks.random_state_dict(64, seed=2)).to(DEV)
     cam = {"fx": 120.0, "fy": 121.5, "x_offset": 63.2, "y_offset": 47.9}
     rng = np.random.RandomState(4)
