@@ -9,6 +9,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+collect_ignore_glob = ["ref_layout/*"]      # a stand-in tree with the reference's module names (fcn/test_dataset.py), not tests
 
 
 def pytest_configure(config):
