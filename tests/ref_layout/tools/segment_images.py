@@ -19,8 +19,8 @@ from fcn.config import cfg, cfg_from_file
 import networks
 
 
-def parse_args():
-    p = argparse.ArgumentParser()
+def options():
+    p = argparse.ArgumentParser(description="stand-in for the reference's tools/test_images.py (same option names)")
     p.add_argument('--gpu', dest='gpu_id', default=0, type=int)
     p.add_argument('--pretrained', default=None, type=str)
     p.add_argument('--pretrained_crop', default=None, type=str)
@@ -34,65 +34,74 @@ def parse_args():
     return p.parse_args()
 
 
-def compute_xyz(depth, fx, fy, px, py):
-    h, w = depth.shape
-    ix = np.tile(np.arange(w, dtype=np.float32)[None, :], (h, 1))
-    iy = np.tile(np.arange(h, dtype=np.float32)[:, None], (1, w))
-    return np.stack([(ix - px) * depth / fx, (iy - py) * depth / fy, depth], axis=-1).astype(np.float32)
+def back_project(depth, cam):
+    """metric depth [H,W] -> XYZ [H,W,3] with the pinhole model of camera_params.json"""
+    rows, cols = depth.shape
+    u = np.tile(np.arange(cols, dtype=np.float32)[None, :], (rows, 1))
+    v = np.tile(np.arange(rows, dtype=np.float32)[:, None], (1, cols))
+    return np.stack([(u - cam['x_offset']) * depth / cam['fx'], (v - cam['y_offset']) * depth / cam['fy'], depth],
+                    axis=-1).astype(np.float32)
 
 
-def read_sample(file_color, file_depth, camera_params):
-    """color: BGR / 255 - PIXEL_MEANS / 255, [1,3,H,W]; depth: millimetres -> metres -> XYZ [1,3,H,W]"""
-    im = cv2.imread(file_color)
-    depth = cv2.imread(file_depth, cv2.IMREAD_ANYDEPTH).astype(np.float32) / 1000.0
-    xyz = compute_xyz(depth, camera_params['fx'], camera_params['fy'], camera_params['x_offset'], camera_params['y_offset'])
-    im_tensor = torch.from_numpy(im) / 255.0
-    im_tensor -= torch.tensor(cfg.PIXEL_MEANS / 255.0).float()
-    sample = {'image_color': im_tensor.permute(2, 0, 1).unsqueeze(0)}
+def load_frame(color_png, depth_png, cam):
+    """What the reference tool's read_sample hands to test_sample: BGR / 255 - PIXEL_MEANS / 255 as [1,3,H,W]; depth in
+    millimetres -> metres -> XYZ as [1,3,H,W] (only for the DEPTH / RGBD inputs)."""
+    bgr = torch.from_numpy(cv2.imread(color_png)) / 255.0
+    bgr -= torch.tensor(cfg.PIXEL_MEANS / 255.0).float()
+    frame = {'image_color': bgr.permute(2, 0, 1).unsqueeze(0)}
     if cfg.INPUT in ('DEPTH', 'RGBD'):
-        sample['depth'] = torch.from_numpy(xyz).permute(2, 0, 1).unsqueeze(0)
-    return sample
+        metres = cv2.imread(depth_png, cv2.IMREAD_ANYDEPTH).astype(np.float32) / 1000.0
+        frame['depth'] = torch.from_numpy(back_project(metres, cam)).permute(2, 0, 1).unsqueeze(0)
+    return frame
+
+
+def construct(name, checkpoint):
+    """factory call of the reference tool: networks.__dict__[name](num_classes, num_units, checkpoint dict)"""
+    return networks.__dict__[name](2, cfg.TRAIN.NUM_UNITS, torch.load(checkpoint))
+
+
+def deploy(net):
+    """.cuda -> DataParallel on the one device -> .cuda -> eval, the wrapping the reference tool applies"""
+    net = net.cuda(device=cfg.device)
+    net = torch.nn.DataParallel(net, device_ids=[cfg.gpu_id]).cuda(device=cfg.device)
+    net.eval()
+    return net
+
+
+def main():
+    opts = options()
+    if opts.cfg_file:
+        cfg_from_file(opts.cfg_file)                     # AFTER the imports: the factories must read cfg at construction
+    np.random.seed(cfg.RNG_SEED)
+    cfg.gpu_id, cfg.MODE = 0, 'TEST'
+    cfg.device = torch.device('cuda:%d' % cfg.gpu_id)
+    colors = sorted(glob.glob(os.path.join(opts.imgdir, opts.color_name)))
+    depths = sorted(glob.glob(os.path.join(opts.imgdir, opts.depth_name)))
+    with open(os.path.join(opts.imgdir, 'camera_params.json')) as fh:
+        cam = json.load(fh)
+    if not opts.pretrained:
+        sys.exit("no pretrained network specified")
+    net = construct(opts.network_name, opts.pretrained)
+    net_crop = construct(opts.network_name, opts.pretrained_crop) if opts.pretrained_crop else None
+    if opts.stop_after_build:
+        print("built:", type(net).__name__, getattr(net, "input_type", "?"), getattr(net, "feature_dim", "?"),
+              "test_sample from", test_sample.__module__)
+        return
+    cudnn.benchmark = True
+    net = deploy(net)
+    if net_crop is not None:
+        net_crop = deploy(net_crop)
+    maps = {}
+    for k, (c, d) in enumerate(zip(colors, depths)):
+        print(c)
+        first_stage, second_stage = test_sample(load_frame(c, d, cam), net, net_crop)
+        maps["out_label_%d" % k] = first_stage.numpy()
+        if second_stage is not None:
+            maps["out_label_refined_%d" % k] = second_stage.numpy()
+    if opts.out:
+        np.savez(opts.out, **maps)
+    print("segmented %d frames" % len(colors))
 
 
 if __name__ == '__main__':
-    args = parse_args()
-    if args.cfg_file is not None:
-        cfg_from_file(args.cfg_file)                     # AFTER the imports: the factories must read cfg at construction
-    np.random.seed(cfg.RNG_SEED)
-    cfg.gpu_id = 0
-    cfg.device = torch.device('cuda:{:d}'.format(cfg.gpu_id))
-    cfg.MODE = 'TEST'
-    images_color = sorted(glob.glob(os.path.join(args.imgdir, args.color_name)))
-    images_depth = sorted(glob.glob(os.path.join(args.imgdir, args.depth_name)))
-    with open(os.path.join(args.imgdir, 'camera_params.json')) as f:
-        camera_params = json.load(f)
-    if not args.pretrained:
-        sys.exit("no pretrained network specified")
-    network_data = torch.load(args.pretrained)
-    network = networks.__dict__[args.network_name](2, cfg.TRAIN.NUM_UNITS, network_data)
-    network_crop = None
-    if args.pretrained_crop:
-        network_crop = networks.__dict__[args.network_name](2, cfg.TRAIN.NUM_UNITS, torch.load(args.pretrained_crop))
-    if args.stop_after_build:
-        print("built:", type(network).__name__, getattr(network, "input_type", "?"), getattr(network, "feature_dim", "?"),
-              "test_sample from", test_sample.__module__)
-        sys.exit(0)
-    network = network.cuda(device=cfg.device)
-    network = torch.nn.DataParallel(network, device_ids=[cfg.gpu_id]).cuda(device=cfg.device)
-    cudnn.benchmark = True
-    network.eval()
-    if network_crop is not None:
-        network_crop = network_crop.cuda(device=cfg.device)
-        network_crop = torch.nn.DataParallel(network_crop, device_ids=[cfg.gpu_id]).cuda(device=cfg.device)
-        network_crop.eval()
-    results = {}
-    for i in range(len(images_color)):
-        print(images_color[i])
-        sample = read_sample(images_color[i], images_depth[i], camera_params)
-        out_label, out_label_refined = test_sample(sample, network, network_crop)
-        results["out_label_%d" % i] = out_label.numpy()
-        if out_label_refined is not None:
-            results["out_label_refined_%d" % i] = out_label_refined.numpy()
-    if args.out:
-        np.savez(args.out, **results)
-    print("segmented %d frames" % len(images_color))
+    main()

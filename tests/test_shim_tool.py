@@ -85,3 +85,20 @@ def test_unmodified_reference_tool_under_shim_reaches_this_packages_forward(tmp_
     assert "tools/test_images.py" in tb and "out_label, out_label_refined = test_sample(sample, network, network_crop)" in tb
     assert "unseenobjectclustering_b200/test_dataset.py" in tb and "unseenobjectclustering_b200/networks.py" in tb
     assert "there is no CPU path in this package" in tb.strip().splitlines()[-1]
+
+
+def test_stand_in_tool_under_shim_reaches_this_packages_forward_on_cpu(tmp_path):
+    """The whole call sequence of the stand-in tool (factory -> .cuda -> DataParallel -> .eval -> cv2 frames -> test_sample)
+    with Tensor.cuda() as a no-op: it must arrive in SEGNET_B200.forward and fail loudly there (no CPU path)."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU half; the GPU half is tests/test_gpu_zz_shim_tool.py")
+    from unseenobjectclustering_b200 import networks as N
+    _frames(tmp_path)
+    torch.save(N.random_state_dict(64, seed=0), str(tmp_path / "ckpt.pth"))
+    code = ("import sys; sys.path[:0] = [%r, %r]; import ref_harness as rh; from unseenobjectclustering_b200 import shim\n"
+            "with rh.cpu_cuda_identity():\n    shim.main(sys.argv[1:])\n" % (ROOT, os.path.join(ROOT, "oracle")))
+    r = subprocess.run([sys.executable, "-c", code, TOOL, "--pretrained", str(tmp_path / "ckpt.pth"), "--pretrained_crop",
+                        str(tmp_path / "ckpt.pth"), "--imgdir", str(tmp_path)], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "000-color.png" in r.stdout
+    assert "segment_images.py" in r.stderr and "unseenobjectclustering_b200/test_dataset.py" in r.stderr
+    assert "there is no CPU path in this package" in r.stderr.strip().splitlines()[-1]
