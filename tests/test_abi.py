@@ -55,3 +55,46 @@ def test_product_package_never_imports_the_oracle():
                 bad = re.findall(r"^\s*(?:import|from)\s+\S*(?:uoc_oracle|ref_harness|oracle)\b|#include[^\n]*oracle|"
                                  r"CDLL\([^\n]*oracle", src, flags=re.M)
                 assert not bad, (f, bad)
+
+
+C_CALLER = r'''
+#include <stdio.h>
+#include <string.h>
+#include "uoc.h"
+/* a plain C99 caller of the boundary: sizes, one compute call, the error text */
+int main(void) {
+  float x[2 * 8];
+  int64_t first = 0, selected[2];
+  int32_t labels[8];
+  size_t ws = uoc_meanshift_workspace_bytes(1, 8, 2, 2);
+  int rc;
+  memset(x, 0, sizeof(x));
+  if (ws == 0 || uoc_meanshift_workspace_bytes(0, 8, 2, 2) != 0) return 10;
+  if (uoc_version() < 100) return 11;
+  rc = uoc_meanshift_cluster(x, 16, 8, NULL, 1, 8, 2, 2, 20.0f, 10, 0.04f, &first, labels, selected, NULL, NULL,
+                             (void*)x, ws, 0, NULL);
+  printf("rc=%d err=%s\n", rc, uoc_last_error());
+  return rc == UOC_OK ? 12 : 0;          /* host pointers / no device: the call must refuse, not compute */
+}
+'''
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """include/uoc.h is the drop-in boundary: it must compile as C99 (no C++-isms, no torch / CUDA headers) and a C program
+    must link against the shared library alone.  On a box without a GPU the compute call returns an error code with a text."""
+    import subprocess
+    import torch
+    from unseenobjectclustering_b200 import _lib, build
+    build.build_cuda()
+    src = tmp_path / "caller.c"
+    src.write_text(C_CALLER)
+    exe = str(tmp_path / "caller")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    libname = os.path.basename(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", exe, "-L", libdir, "-l:" + libname, "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+    if torch.cuda.is_available():
+        return                                            # the compute half of this test is for the CPU-only box
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "rc=" in r.stdout and "err=" in r.stdout and not r.stdout.strip().endswith("err=")
