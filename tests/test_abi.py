@@ -98,3 +98,55 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "rc=" in r.stdout and "err=" in r.stdout and not r.stdout.strip().endswith("err=")
+
+
+def test_integration_stub_matches_the_header():
+    """The reference-side ctypes stub printed in INTEGRATION.md section 2 is executable as written (against the built
+    library) and its argtypes have exactly the parameters include/uoc.h declares for the entry point it binds."""
+    from unseenobjectclustering_b200 import _lib, build
+    build.build_cuda()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# lib/utils/mean_shift_b200\.py.*?)```", doc, flags=re.S).group(1)
+    assert 'ctypes.CDLL("libuoc_b200.so")' in block
+    ns = {}
+    exec(compile(block.replace('ctypes.CDLL("libuoc_b200.so")', "ctypes.CDLL(%r)" % _lib.LIB_PATH), "INTEGRATION.md", "exec"), ns)
+    header = open(os.path.join(ROOT, "include", "uoc.h")).read()
+    decl = re.search(r"UOC_API\s+int\s+uoc_meanshift_cluster\s*\((.*?)\)\s*;", header, flags=re.S).group(1)
+    n_params = len([p for p in decl.split(",") if p.strip()])
+    assert len(ns["_lib"].uoc_meanshift_cluster.argtypes) == n_params == len(_lib.SIGNATURES["uoc_meanshift_cluster"][1])
+    assert callable(ns["clustering_features"])
+
+
+def test_binding_table_has_the_headers_parameter_counts_and_kinds():
+    """Every entry of the ctypes table (_lib.SIGNATURES) has as many parameters as its declaration in include/uoc.h, and
+    pointer / integer / float kinds agree position by position (a mismatch would corrupt the call frame silently)."""
+    from unseenobjectclustering_b200 import _lib
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "uoc.h")).read(), flags=re.S)
+    decls = dict(re.findall(r"UOC_API\s+[^;(]*?\b(uoc_[a-z0-9_]+)\s*\((.*?)\)\s*;", header, flags=re.S))
+    assert sorted(decls) == sorted(_lib.SIGNATURES)
+
+    def kind_of_c(param):
+        p = " ".join(param.split())
+        if "*" in p or "uoc_stream_t" in p:
+            return "ptr"
+        if re.search(r"\b(float|double)\b", p):
+            return "float"
+        if re.search(r"\b(int64_t|uint64_t|size_t|long long)\b", p):
+            return "int64"
+        return "int"
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_float, ctypes.c_double):
+            return "float"
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) == "P":
+            return "ptr"
+        if ctypes.sizeof(t) == 8:
+            return "int64"
+        return "int"
+
+    for name, params in decls.items():
+        plist = [p for p in params.split(",") if p.strip() and p.strip() != "void"]
+        args = _lib.SIGNATURES[name][1]
+        assert len(plist) == len(args), (name, len(plist), len(args))
+        for i, (p, a) in enumerate(zip(plist, args)):
+            assert kind_of_c(p) == kind_of_ctypes(a), (name, i, p.strip(), a)
